@@ -1,0 +1,533 @@
+/*
+ * sdf_b200.h — C-ABI of libsdf_b200.so: hand-written sm_100a kernels for the SDformerFlow
+ * spiking spatiotemporal Swin encoder hot path.
+ *
+ * The reference (yitian97/SDformerFlow) has no FFI of its own: its "native" code is what
+ * spikingjelly JIT-compiles through cupy when the scripts call
+ *   functional.set_backend(model, "cupy", neurontype)
+ *     (train_flow_parallel_supervised_SNN.py:118-119, eval_DSEC_flow_SNN.py:118-119)
+ * plus the ATen ops behind models/STSwinNet_SNN/Spiking_swin_transformer3D.py.  Every entry
+ * point below cites the reference interface (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain structs of raw DEVICE pointers + int64 sizes + a cudaStream_t passed
+ *    as void*.  No torch types.
+ *  - The caller owns every buffer including workspaces; the library never allocates or
+ *    frees device memory and never synchronises the stream.
+ *  - Every function returns 0 on success or a negative sdf_status; sdf_last_error() returns
+ *    a thread-local message for the last failure on the calling thread.
+ *  - All float scalars cross the ABI as double and are narrowed to fp32 inside (the
+ *    reference promotes python floats to the tensor dtype the same way).
+ *  - "channels-last rows": a tensor viewed as [rows, C] with C contiguous, C % 4 == 0,
+ *    base pointers 16-byte aligned.
+ */
+#ifndef SDF_B200_H
+#define SDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDF_VERSION_MAJOR 0
+#define SDF_VERSION_MINOR 1
+
+typedef enum {
+  SDF_OK = 0,
+  SDF_ERR_INVALID_ARG = -1,
+  SDF_ERR_UNSUPPORTED = -2,
+  SDF_ERR_CUDA = -3,
+  SDF_ERR_WORKSPACE = -4
+} sdf_status;
+
+/* neuron dynamics — reference Spiking_modules.py:26-99 (Spiking_neuron switch) over
+ * spikingjelly neuron.{LIFNode, IFNode, ParametricLIFNode}. */
+typedef enum {
+  SDF_NEURON_LIF = 0,  /* h = v + (x - (v - v_reset))/tau   (decay_input=True)            */
+  SDF_NEURON_IF = 1,   /* h = v + x                                                       */
+  SDF_NEURON_PLIF = 2  /* h = v + (x - (v - v_reset)) * k,  k = sigmoid(w) passed as 1/tau */
+} sdf_neuron_kind;
+
+/* spike output element type */
+typedef enum {
+  SDF_SPIKE_F32 = 0,  /* {0.0f, 1.0f}: the reference's dtype (parity mode, fp32 GEMM input) */
+  SDF_SPIKE_U8 = 1,   /* {0, 1} bytes: inference contract, 5 B per neuron-timestep          */
+  SDF_SPIKE_BF16 = 2  /* {0, 1} bf16: exact operand of the bf16x3-split spike GEMM          */
+} sdf_spike_dtype;
+
+/* surrogate gradient — spikingjelly surrogate.ATan / surrogate.Sigmoid */
+typedef enum { SDF_SG_ATAN = 0, SDF_SG_SIGMOID = 1 } sdf_surrogate_kind;
+
+typedef struct {
+  int32_t kind;         /* sdf_neuron_kind */
+  int32_t hard_reset;   /* 0: soft reset v = h - s*v_th (v_reset None); 1: v = (1-s)h + s*v_reset */
+  int32_t detach_reset; /* 1: spike detached in the reset path (reference default True) */
+  int32_t surrogate;    /* sdf_surrogate_kind */
+  double v_th;
+  double v_reset;       /* used when hard_reset; also the initial v */
+  double tau;           /* LIF: tau; PLIF: 1/sigmoid(w) */
+  double sg_alpha;      /* surrogate alpha (ATan default 2.0) */
+} sdf_neuron_cfg;
+
+/* Addressing of a multi-step neuron tensor.  Neuron n in [0, n_neurons), time t in [0, T):
+ *   b = n / inner, r = n % inner, element offset = b*stride_b + t*stride_t + r.
+ * Plain [T, N]:              inner = N,       stride_b = 0,        stride_t = N.
+ * (B, D, H, W, C), time = D: inner = H*W*C,   stride_b = D*H*W*C,  stride_t = H*W*C
+ *   (replaces the x.permute(1,0,2,3,4) copies of Spiking_swin_transformer3D.py:845,932,970). */
+typedef struct {
+  int64_t T;
+  int64_t n_neurons;
+  int64_t inner;
+  int64_t stride_b;
+  int64_t stride_t;
+} sdf_seq_layout;
+
+/* ---- K1 / K2: multi-step LIF/IF/PLIF forward and surrogate-gradient backward ---------------
+ * Replaces spikingjelly LIFNode.multi_step_forward (torch loop / cupy LIFNodeFPTTKernel,
+ * LIFNodeBPTTKernel) reached through Spiking_neuron.forward (Spiking_modules.py:98-99),
+ * fused with the preceding BatchNorm apply (SpikingNormLayer, Spiking_modules.py:101-146):
+ *   x_t = u_t * scale[c] + shift[c]   (c = channel, channels-last: n % C; NCHW: (n / hw) % C)
+ * One thread keeps the membrane potential of 4 neurons in registers across all T steps. */
+typedef struct {
+  const float* u;      /* input, fp32 */
+  void* spike;         /* output spikes, spike_dtype, same addressing as u */
+  float* h_seq;        /* optional: membrane potential after charge, fp32 (tests / monitors) */
+  const float* v_init; /* optional [n_neurons] initial membrane (NULL: 0 or v_reset) */
+  float* v_final;      /* optional [n_neurons] membrane after the last step */
+  const float* scale;  /* optional [C] */
+  const float* shift;  /* optional [C] */
+  int64_t C;           /* channels (ignored when scale == NULL) */
+  int64_t hw;          /* 1: channels-last (c = n % C); >1: NCHW, c = (n / hw) % C */
+  sdf_seq_layout lay;
+  sdf_neuron_cfg neuron;
+  int32_t spike_dtype;
+  int32_t _pad;
+  void* stream;
+} sdf_lif_fwd_args;
+
+int sdf_lif_fwd(const sdf_lif_fwd_args* a);
+
+typedef struct {
+  const float* u;       /* forward input (re-read; h is recomputed, nothing else was saved) */
+  const void* grad_spike; /* dL/ds, fp32 */
+  float* grad_u;        /* dL/du, fp32 (already multiplied by scale[c] when scale != NULL) */
+  float* grad_x;        /* optional: dL/dx (before the scale multiply); needed for BN-train backward */
+  const float* v_init;
+  const float* scale;
+  const float* shift;
+  float* bn_partials;   /* optional [n_partial_blocks, 2, C]: per-block sum(dx), sum(dx*u) */
+  int64_t n_partial_blocks; /* in: capacity; the launcher uses min(capacity, its grid) and zero-fills the rest */
+  float* plif_partials; /* optional [n_partial_blocks]: PLIF d(1/tau) partial sums */
+  int64_t C;
+  int64_t hw;
+  sdf_seq_layout lay;
+  sdf_neuron_cfg neuron;
+  void* stream;
+} sdf_lif_bwd_args;
+
+int sdf_lif_bwd(const sdf_lif_bwd_args* a);
+
+/* number of partial blocks sdf_lif_bwd / sdf_bn_stats / ... will write for a [rows, C] problem */
+int64_t sdf_partial_blocks(int64_t rows, int64_t C);
+
+/* ---- K1p: PSN (parallel spiking neuron) — reference Spiking_submodules.py:183-211 ----------
+ * h[t] = sum_k W[t,k] * x[k] + b[t]; s = (h >= 0).  T <= 32. */
+typedef struct {
+  const float* u;
+  void* spike;
+  float* h_seq;        /* optional */
+  const float* weight; /* [T, T] */
+  const float* bias;   /* [T] */
+  const float* scale;
+  const float* shift;
+  int64_t C;
+  int64_t hw;
+  sdf_seq_layout lay;
+  int32_t spike_dtype;
+  int32_t _pad;
+  void* stream;
+} sdf_psn_fwd_args;
+
+int sdf_psn_fwd(const sdf_psn_fwd_args* a);
+
+typedef struct {
+  const float* u;
+  const float* grad_spike;
+  float* grad_u;
+  float* grad_h;       /* [T, n_neurons] contiguous: dL/dh, consumed by the host for dW = dh x^T, db */
+  float* x_out;        /* optional [T, n_neurons] contiguous: the post-affine input x (for dW) */
+  const float* weight;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  float* bn_partials;  /* optional [n_partial_blocks, 2, C]: per-block sum(dx), sum(dx*u) */
+  int64_t n_partial_blocks;
+  int64_t C;
+  int64_t hw;
+  sdf_seq_layout lay;
+  int32_t surrogate;
+  int32_t _pad;
+  double sg_alpha;
+  void* stream;
+} sdf_psn_bwd_args;
+
+int sdf_psn_bwd(const sdf_psn_bwd_args* a);
+
+/* ---- K6: BatchNorm statistics over channels-last rows ---------------------------------------
+ * Replaces the statistics half of sj_layer.BatchNorm2d on permuted views
+ * (Spiking_swin_transformer3D.py:153,159,310,314,318,367,673,677,714,933,972). */
+typedef struct {
+  const float* x;      /* [rows, ld] fp32, channel c of row r at x[r*ld + c] */
+  int64_t rows;
+  int64_t C;
+  int64_t ld;          /* row stride in elements (>= C, % 4 == 0) */
+  float* partials;     /* [n_partial_blocks, 2, C] workspace */
+  int64_t n_partial_blocks;
+  void* stream;
+} sdf_bn_stats_args;
+
+int sdf_bn_stats(const sdf_bn_stats_args* a);
+
+/* Finalise statistics: mean/var from partials, scale = w*rstd, shift = b - mean*scale,
+ * running-stat update exactly like torch (momentum, unbiased running_var). */
+typedef struct {
+  const float* partials; /* [n_partial_blocks, 2, C]; NULL in eval mode */
+  int64_t n_partial_blocks;
+  int64_t count;         /* rows that contributed */
+  int64_t C;
+  const float* weight;   /* [C] or NULL (=1) */
+  const float* bias;     /* [C] or NULL (=0) */
+  float* running_mean;   /* [C] or NULL */
+  float* running_var;    /* [C] or NULL */
+  double momentum;
+  double eps;
+  int32_t training;      /* 1: batch statistics (+ running update); 0: running statistics */
+  int32_t _pad;
+  float* scale;          /* out [C] */
+  float* shift;          /* out [C] */
+  float* mean;           /* out [C] (saved for backward), optional */
+  float* rstd;           /* out [C] (saved for backward), optional */
+  void* stream;
+} sdf_bn_finalize_args;
+
+int sdf_bn_finalize(const sdf_bn_finalize_args* a);
+
+/* BN backward, second half.  Given dy = dL/d(BN output) and the forward input u:
+ *   train: du = w*rstd * (dy - sum(dy)/n - xhat * sum(dy*xhat)/n),  xhat = (u - mean)*rstd
+ *   eval : du = w*rstd * dy
+ * plus dweight = sum(dy*xhat), dbias = sum(dy) from the partial sums (sum(dy), sum(dy*u)). */
+typedef struct {
+  const float* partials; /* [n_partial_blocks, 2, C]: sum(dy), sum(dy*u) per block */
+  int64_t n_partial_blocks;
+  int64_t count;
+  int64_t C;
+  const float* weight;
+  const float* mean;
+  const float* rstd;
+  float* grad_weight;    /* out [C] */
+  float* grad_bias;      /* out [C] */
+  float* coef;           /* out [3, C]: a, b, c with du = a*dy + b*u + c */
+  int32_t training;
+  int32_t _pad;
+  void* stream;
+} sdf_bn_bwd_finalize_args;
+
+int sdf_bn_bwd_finalize(const sdf_bn_bwd_finalize_args* a);
+
+/* elementwise over channels-last rows: out = a[c]*dy + b[c]*u + c[c]  (BN-train backward apply) */
+typedef struct {
+  const float* dy;
+  const float* u;
+  int64_t ld_u;
+  float* du;
+  int64_t ld_du;
+  const float* coef;     /* [3, C] */
+  int64_t rows;
+  int64_t C;
+  void* stream;
+} sdf_bn_bwd_apply_args;
+
+int sdf_bn_bwd_apply(const sdf_bn_bwd_apply_args* a);
+
+/* partial sums (sum(dy), sum(dy*u)) over channels-last rows, for BN sites not preceded by a neuron */
+typedef struct {
+  const float* dy;
+  const float* u;
+  int64_t ld_u;
+  int64_t rows;
+  int64_t C;
+  float* partials;
+  int64_t n_partial_blocks;
+  void* stream;
+} sdf_bn_bwd_reduce_args;
+
+int sdf_bn_bwd_reduce(const sdf_bn_bwd_reduce_args* a);
+
+/* out = res + alpha * (u*scale[c] + shift[c]) over channels-last rows
+ * (MLP tail: Spiking_swin_transformer3D.py:177-178 + :845 residual add) */
+typedef struct {
+  const float* u;
+  int64_t ld_u;
+  const float* res;      /* optional */
+  float* out;
+  const float* scale;    /* optional */
+  const float* shift;
+  int64_t rows;
+  int64_t C;
+  void* stream;
+} sdf_bn_apply_args;
+
+int sdf_bn_apply(const sdf_bn_apply_args* a);
+
+/* ---- window index algebra ---------------------------------
+ * Replaces F.pad + torch.roll + window_partition_v2 + window_reverse + roll + crop
+ * (Spiking_swin_transformer3D.py:781-821, :100-113; swin_transformer3D_v2.py:52-81) and the
+ * region ids behind compute_mask (:980-993).  Window-buffer row rho = (w*wd + dd)*P + pos. */
+typedef struct {
+  int64_t B, D, H, W;    /* unpadded feature map (tokens) */
+  int64_t wd, wh, ww;    /* window, already clamped by get_window_size */
+  int64_t sd, sh, sw;    /* shift, already clamped (0 on unshifted blocks) */
+} sdf_window_geom;
+
+typedef struct {
+  sdf_window_geom g;
+  int32_t* win2x;        /* out [B*nW*N]: token row in the (B,D,H,W) map or -1 for padding */
+  uint8_t* region;       /* out [nW*N] (first sample): compute_mask region id 0..26; optional */
+  void* stream;
+} sdf_window_index_args;
+
+int sdf_window_index(const sdf_window_index_args* a);
+/* rows of the window buffer for a geometry: B * ceil(D/wd)*wd * ceil(H/wh)*wh * ceil(W/ww)*ww */
+int64_t sdf_window_rows(const sdf_window_geom* g);
+
+/* plain gather: xw[rho, :] = x[win2x[rho], :] or 0 (SEW attention input, :804) */
+typedef struct {
+  const float* x;
+  float* xw;
+  const int32_t* win2x;
+  int64_t rows;          /* window rows */
+  int64_t C;
+  void* stream;
+} sdf_window_gather_args;
+
+int sdf_window_gather(const sdf_window_gather_args* a);
+
+/* out[win2x[rho], :] = res[win2x[rho], :] + alpha[b] * (y[rho,:]*scale + shift)   (skip pads)
+ * = proj_bn + window_reverse + roll back + crop + DropPath scale + shortcut add (:810-820,:840) */
+typedef struct {
+  const float* y;        /* [rows, C] window-ordered */
+  const float* res;      /* optional (B,D,H,W,C) shortcut */
+  float* out;            /* (B,D,H,W,C) */
+  const int32_t* win2x;
+  const float* scale;    /* optional [C] */
+  const float* shift;
+  const float* alpha;    /* optional [B] DropPath keep/scale factors */
+  int64_t rows;
+  int64_t rows_per_sample; /* window rows per batch element */
+  int64_t C;
+  void* stream;
+} sdf_window_scatter_args;
+
+int sdf_window_scatter(const sdf_window_scatter_args* a);
+
+/* backward of the scatter: dy[rho,:] = alpha[b] * dout[win2x[rho], :] (0 at pads), optional
+ * BN partial sums (sum(dy), sum(dy*u)) for the proj_bn backward. */
+typedef struct {
+  const float* dout;
+  float* dy;
+  const float* u;        /* optional forward y (pre-BN) for the partial sums */
+  const int32_t* win2x;
+  const float* alpha;
+  float* bn_partials;    /* optional */
+  int64_t n_partial_blocks;
+  int64_t rows;
+  int64_t rows_per_sample;
+  int64_t C;
+  void* stream;
+} sdf_window_scatter_bwd_args;
+
+int sdf_window_scatter_bwd(const sdf_window_scatter_bwd_args* a);
+
+/* gather backward: dx[win2x[rho], :] = dxw[rho, :] */
+typedef struct {
+  const float* dxw;
+  float* dx;             /* (B,D,H,W,C), fully overwritten (every token has exactly one row) */
+  const int32_t* win2x;
+  int64_t rows;
+  int64_t C;
+  void* stream;
+} sdf_window_gather_bwd_args;
+
+int sdf_window_gather_bwd(const sdf_window_gather_bwd_args* a);
+
+/* ---- LIF over the window "fake time" axis with the gather folded in -------------------------
+ * proj_sn(x_windows) of Spiking_QK_WindowAttention3D.forward (:670) / SDSA (:425): neuron
+ * time step t = slice // M (Appendix B.1), input read straight from the (B,D,H,W,C) map. */
+typedef struct {
+  const float* x;        /* (B,D,H,W,C) */
+  void* spike;           /* [wd*M*P, C] window-ordered */
+  float* h_seq;          /* optional */
+  const int32_t* win2x;
+  int64_t wd;            /* fake T */
+  int64_t MP;            /* M * P = rows / wd */
+  int64_t C;
+  sdf_neuron_cfg neuron;
+  int32_t spike_dtype;
+  int32_t _pad;
+  void* stream;
+} sdf_lif_window_fwd_args;
+
+int sdf_lif_window_fwd(const sdf_lif_window_fwd_args* a);
+
+typedef struct {
+  const float* x;
+  const float* grad_spike; /* [wd*M*P, C] */
+  float* grad_x;           /* (B,D,H,W,C) fully overwritten */
+  const int32_t* win2x;
+  int64_t wd;
+  int64_t MP;
+  int64_t C;
+  sdf_neuron_cfg neuron;
+  void* stream;
+} sdf_lif_window_bwd_args;
+
+int sdf_lif_window_bwd(const sdf_lif_window_bwd_args* a);
+
+/* ---- LIF with the 2x2 patch-merging gather folded in (MS_SpikingPatchMerging, :952-974) ----
+ * xm[b,d,h2,w2, k*C + c] = x[b,d,2*h2 + (k&1), 2*w2 + (k>>1), c] (zero beyond H/W), time = D. */
+typedef struct {
+  const float* x;        /* (B,D,H,W,C) */
+  void* spike;           /* (B,D,H2,W2,4C) */
+  float* h_seq;          /* optional */
+  int64_t B, D, H, W, C;
+  sdf_neuron_cfg neuron;
+  int32_t spike_dtype;
+  int32_t apply_neuron;  /* 0: plain gather (SEW SpikingPatchMerging, :926-930), fp32 out */
+  void* stream;
+} sdf_lif_merge_fwd_args;
+
+int sdf_lif_merge_fwd(const sdf_lif_merge_fwd_args* a);
+
+typedef struct {
+  const float* x;
+  const float* grad_spike; /* (B,D,H2,W2,4C) */
+  float* grad_x;           /* (B,D,H,W,C) */
+  int64_t B, D, H, W, C;
+  sdf_neuron_cfg neuron;
+  int32_t apply_neuron;
+  int32_t _pad;
+  void* stream;
+} sdf_lif_merge_bwd_args;
+
+int sdf_lif_merge_bwd(const sdf_lif_merge_bwd_args* a);
+
+/* ---- K5: QK token-gate attention core (Spiking_QK_WindowAttention3D.forward :671-710) ------
+ * q = LIF(bn_q(q_pre)); a = LIF2(sum_{d<32} q); k = LIF(bn_k(k_pre) + pos); g = k * a;
+ * output written in the proj-input order of :709-710 (Appendix B.3).  All neurons run over
+ * the fake time axis wd.  Mask is ignored by the reference (:700-703). */
+typedef struct {
+  const float* q_pre;    /* [wd*M*P, ld] */
+  const float* k_pre;    /* [wd*M*P, ld] */
+  int64_t ld;            /* row stride of q_pre / k_pre (C, or 2C when they share one GEMM output) */
+  const float* q_scale;  /* [C] bn_q folded */
+  const float* q_shift;
+  const float* k_scale;  /* [C] bn_k folded */
+  const float* k_shift;
+  const float* pos;      /* [wd*P*C]: positional_encoding (1,nH,N,32) flat-reshaped to (wd,1,wh,ww,C) (:678) */
+  void* gate;            /* out [wd*M*P, C] spikes g, permuted (B.3) */
+  float* q_h;            /* optional debug: membrane of sn_q  [wd*M*P, C] */
+  float* k_h;            /* optional debug: membrane of sn_k */
+  float* a_h;            /* optional debug: membrane of sn2_q [wd*M*P*nH] */
+  int64_t wd, M, P, C, nH;
+  sdf_neuron_cfg neuron;
+  int32_t spike_dtype;
+  int32_t _pad;
+  void* stream;
+} sdf_attn_qkgate_fwd_args;
+
+int sdf_attn_qkgate_fwd(const sdf_attn_qkgate_fwd_args* a);
+
+typedef struct {
+  const float* q_pre;
+  const float* k_pre;
+  int64_t ld;
+  const float* q_scale;
+  const float* q_shift;
+  const float* k_scale;
+  const float* k_shift;
+  const float* pos;
+  const float* grad_gate; /* [wd*M*P, C] in the permuted (proj-input) order */
+  float* grad_q;          /* dL/d(bn_q output) [wd*M*P, C] */
+  float* grad_k;          /* dL/d(bn_k output + pos) [wd*M*P, C] */
+  float* bn_partials_q;   /* optional [n_partial_blocks, 2, C] sum(dq), sum(dq*q_pre) */
+  float* bn_partials_k;
+  int64_t n_partial_blocks;
+  int64_t wd, M, P, C, nH;
+  sdf_neuron_cfg neuron;
+  void* stream;
+} sdf_attn_qkgate_bwd_args;
+
+int sdf_attn_qkgate_bwd(const sdf_attn_qkgate_bwd_args* a);
+
+/* grad of positional_encoding: dpos[t*P*C + j] = sum_m grad_k[(t*M + m)*P*C + j] */
+typedef struct {
+  const float* grad_k;
+  float* grad_pos;
+  int64_t wd, M, PC;
+  void* stream;
+} sdf_pos_grad_args;
+
+int sdf_pos_grad(const sdf_pos_grad_args* a);
+
+/* ---- K3 / K4: QK^T V spiking window attention on tcgen05 tensor cores -----------------------
+ * Replaces Spiking_BN_WindowAttention3D.forward :320-363 and SDSA_WindowAttention3D.forward
+ * :438-485:  O = (scale * Q K^T + Bias[h'] + Mask[w]) @ V on the raw [M*nH, N, 32]
+ * reinterpretation (Appendix B.4).  Q, K, V are {0,1} bytes; S = Q K^T are exact integer
+ * counts (kind::i8 MMA, int32 accumulate in TMEM).  hd must be 32. */
+typedef struct {
+  const uint8_t* q;      /* [M*nH*N, 32] spikes as bytes (flat view of the (wd,M,wh,ww,C) buffer) */
+  const uint8_t* k;
+  const uint8_t* v;
+  const float* bias_table; /* [(2wd-1)(2wh-1)(2ww-1), nH] relative_position_bias_table (:246-248) */
+  const uint8_t* region;   /* [nW*N] region ids, NULL on unshifted blocks (mask None, :801) */
+  float* out;            /* [wd*M*P, C] in proj-input order (:362-363) */
+  int32_t* s_dbg;        /* optional [M*nH, N, N] integer Q K^T counts (bit-exact parity tests) */
+  float* attn_dbg;       /* optional [M*nH, N, N] fp32 attn (return_attention path) */
+  int64_t M, nH, nW;
+  int64_t wd, wh, ww;
+  double scale;
+  void* stream;
+} sdf_attn_qktv_fwd_args;
+
+int sdf_attn_qktv_fwd(const sdf_attn_qktv_fwd_args* a);
+
+typedef struct {
+  const uint8_t* q;
+  const uint8_t* k;
+  const uint8_t* v;
+  const float* bias_table;
+  const uint8_t* region;
+  const float* grad_out; /* [wd*M*P, C] proj-input order */
+  float* grad_q;         /* [M*nH*N, 32] fp32 */
+  float* grad_k;
+  float* grad_v;
+  float* grad_bias_table; /* [(2wd-1)(2wh-1)(2ww-1), nH] accumulated with atomics; caller zero-fills */
+  int64_t M, nH, nW;
+  int64_t wd, wh, ww;
+  double scale;
+  void* stream;
+} sdf_attn_qktv_bwd_args;
+
+int sdf_attn_qktv_bwd(const sdf_attn_qktv_bwd_args* a);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+int sdf_version(void);             /* major*100 + minor */
+const char* sdf_last_error(void);  /* thread-local, never NULL */
+/* kernel launches issued through this library by the calling process (bench gpu_launches) */
+int64_t sdf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDF_B200_H */

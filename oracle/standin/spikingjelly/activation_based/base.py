@@ -1,0 +1,138 @@
+"""Stand-in for spikingjelly.activation_based.base (0.0.0.0.14).  TEST INFRASTRUCTURE ONLY.
+
+StepModule / MemoryModule protocol: memories are python attributes that are NOT part of
+``state_dict``; ``reset()`` restores the registered initial value; ``forward`` dispatches
+on ``step_mode``.
+"""
+import copy
+import torch
+from torch import nn
+
+
+class StepModule:
+    def supported_step_mode(self):
+        return ('s', 'm')
+
+    @property
+    def step_mode(self):
+        return self._step_mode
+
+    @step_mode.setter
+    def step_mode(self, value: str):
+        if value not in self.supported_step_mode():
+            raise ValueError(f'step_mode can only be {self.supported_step_mode()}, but got "{value}"!')
+        self._step_mode = value
+
+
+class SingleModule(StepModule):
+    def supported_step_mode(self):
+        return ('s',)
+
+
+class MultiStepModule(StepModule):
+    def supported_step_mode(self):
+        return ('m',)
+
+    @property
+    def step_mode(self):
+        return 'm'
+
+    @step_mode.setter
+    def step_mode(self, value: str):
+        if value not in self.supported_step_mode():
+            raise ValueError(f'step_mode can only be {self.supported_step_mode()}, but got "{value}"!')
+
+
+class MemoryModule(nn.Module, StepModule):
+    def __init__(self):
+        super().__init__()
+        self._memories = {}
+        self._memories_rv = {}
+        self._backend = 'torch'
+        self._step_mode = 's'
+
+    @property
+    def supported_backends(self):
+        return ('torch',)
+
+    @property
+    def backend(self):
+        return self._backend
+
+    @backend.setter
+    def backend(self, value: str):
+        if value not in self.supported_backends:
+            raise NotImplementedError(f'{value} is not a supported backend of {self._get_name()}!')
+        self._backend = value
+
+    def single_step_forward(self, x, *args, **kwargs):
+        raise NotImplementedError
+
+    def multi_step_forward(self, x_seq, *args, **kwargs):
+        T = x_seq.shape[0]
+        y_seq = []
+        for t in range(T):
+            y_seq.append(self.single_step_forward(x_seq[t], *args, **kwargs).unsqueeze(0))
+        return torch.cat(y_seq, 0)
+
+    def forward(self, *args, **kwargs):
+        if self.step_mode == 's':
+            return self.single_step_forward(*args, **kwargs)
+        elif self.step_mode == 'm':
+            return self.multi_step_forward(*args, **kwargs)
+        raise ValueError(self.step_mode)
+
+    def extra_repr(self):
+        return f'step_mode={self.step_mode}, backend={self.backend}'
+
+    def register_memory(self, name: str, value):
+        assert not hasattr(self, name), f'{name} has been set as a member variable!'
+        self._memories[name] = value
+        self._memories_rv[name] = copy.deepcopy(value)
+
+    def reset(self):
+        for key in self._memories.keys():
+            self._memories[key] = copy.deepcopy(self._memories_rv[key])
+
+    def set_reset_value(self, name: str, value):
+        self._memories_rv[name] = copy.deepcopy(value)
+
+    def __getattr__(self, name: str):
+        if '_memories' in self.__dict__:
+            memories = self.__dict__['_memories']
+            if name in memories:
+                return memories[name]
+        return super().__getattr__(name)
+
+    def __setattr__(self, name: str, value) -> None:
+        _memories = self.__dict__.get('_memories')
+        if _memories is not None and name in _memories:
+            _memories[name] = value
+        else:
+            super().__setattr__(name, value)
+
+    def __delattr__(self, name):
+        if name in self._memories:
+            del self._memories[name]
+            del self._memories_rv[name]
+        else:
+            return super().__delattr__(name)
+
+    def memories(self):
+        for value in self._memories.values():
+            yield value
+
+    def named_memories(self):
+        for name, value in self._memories.items():
+            yield name, value
+
+    def detach(self):
+        for key in self._memories.keys():
+            if isinstance(self._memories[key], torch.Tensor):
+                self._memories[key].detach_()
+
+    def _apply(self, fn):
+        for key, value in self._memories.items():
+            if isinstance(value, torch.Tensor):
+                self._memories[key] = fn(value)
+        return super()._apply(fn)
