@@ -111,8 +111,9 @@ int sdf_lif_fwd(const sdf_lif_fwd_args* a);
 typedef struct {
   const float* u;       /* forward input (re-read; h is recomputed, nothing else was saved) */
   const void* grad_spike; /* dL/ds, fp32 */
-  float* grad_u;        /* dL/du, fp32 (already multiplied by scale[c] when scale != NULL) */
-  float* grad_x;        /* optional: dL/dx (before the scale multiply); needed for BN-train backward */
+  float* grad_u;        /* optional: dL/du, fp32 (already multiplied by scale[c] when scale != NULL) */
+  float* grad_x;        /* optional: dL/dx (before the scale multiply); needed for BN-train backward.
+                           At least one of grad_u / grad_x must be given. */
   const float* v_init;
   const float* scale;
   const float* shift;
@@ -154,7 +155,8 @@ int sdf_psn_fwd(const sdf_psn_fwd_args* a);
 typedef struct {
   const float* u;
   const float* grad_spike;
-  float* grad_u;
+  float* grad_u;       /* optional: dL/du = dL/dx * scale[c] */
+  float* grad_x;       /* optional: dL/dx (BN-train backward needs it before the scale multiply) */
   float* grad_h;       /* [T, n_neurons] contiguous: dL/dh, consumed by the host for dW = dh x^T, db */
   float* x_out;        /* optional [T, n_neurons] contiguous: the post-affine input x (for dW) */
   const float* weight;

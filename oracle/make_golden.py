@@ -1,0 +1,155 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.pt by running the UNMODIFIED reference
+(/root/reference, imported through oracle/standin) on the deterministic recipe of oracle/synth.py.
+
+Run in the build container:  python oracle/make_golden.py
+The fixtures pin the CPU port (oracle/port.py) — and through it the CUDA path — to the reference's
+own outputs; /root/reference is not needed to consume them.
+"""
+import copy
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reference_loader as rl  # noqa: E402
+from oracle import synth  # noqa: E402
+
+rl._activate()  # puts oracle/standin and /root/reference on sys.path
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _load_synth(model, seed=0):
+    sd = synth.synth_state_dict(model.state_dict(), seed)
+    model.load_state_dict(sd, strict=True)
+    return sd
+
+
+def _summ(t, step=8):
+    """Sub-sampled copy + moments: keeps fixtures small while still pinning every region."""
+    return {"sub": t[..., ::step, ::step].clone(), "sum": t.double().sum().item(), "abs": t.double().abs().sum().item(),
+            "shape": tuple(t.shape)}
+
+
+def golden_small_model(neuron_type, train):
+    """MS 3-encoder model, 96x128, window (2,3,4): flows (+ loss and a few gradients in train mode)."""
+    from spikingjelly.activation_based import functional
+    mc, sc = synth.small_config(neuron_type)
+    model = rl.build_reference_model(mc, sc, seed=0, train=train)
+    _load_synth(model)
+    B = 2
+    x = synth.synth_voxels(B, 10, 96, 128)
+    out = {"neuron_type": neuron_type, "train": train}
+    functional.reset_net(model)
+    if not train:
+        with torch.no_grad():
+            flows = model(x)["flow"]
+        out["flows"] = [f.clone() for f in flows]
+        return out
+    # train mode: BN batch statistics, DropPath with injected masks (so CPU/GPU RNG need not agree)
+    scales = synth.synth_drop_scales(sc["swin_depths"], B)
+    blocks = [b for lyr in model.sttmultires_unet.encoders.swin3d.layers for b in lyr.swin_blocks]
+
+    class Forced(torch.nn.Module):
+        def __init__(self, s):
+            super().__init__()
+            self.s = s
+
+        def forward(self, t):
+            return t if self.s is None else t * self.s.view(-1, 1, 1, 1, 1)
+
+    for b, s in zip(blocks, scales):
+        b.drop_path = Forced(s)
+    flows = model(x)["flow"]
+    gt, mask = synth.synth_labels(B, 96, 128)
+    sys.path.insert(0, rl.REFERENCE_ROOT)
+    from loss.flow_supervised import flow_loss_supervised
+    crit = flow_loss_supervised({"metrics": {"flow_scaling": 1}, "loss": {"lambda_mod": 1, "lambda_ang": 0}}, "cpu")
+    loss = crit(flows, gt, mask)
+    loss.backward()
+    out["flows"] = [f.detach().clone() for f in flows]
+    out["loss"] = loss.item()
+    grads = {}
+    named = dict(model.named_parameters())
+    for k in ["sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.0.attn.linear_q.weight",
+              "sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.1.attn.positional_encoding",
+              "sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.1.attn.bn_k.norm_layer.weight",
+              "sttmultires_unet.encoders.swin3d.layers.1.swin_blocks.0.mlp.fc1.weight",
+              "sttmultires_unet.encoders.swin3d.layers.1.swin_blocks.1.attn.proj.bias",
+              "sttmultires_unet.encoders.swin3d.layers.0.downsample.reduction.weight",
+              "sttmultires_unet.encoders.swin3d.patch_embed.head.conv.0.weight",
+              "sttmultires_unet.preds.2.conv.0.weight"]:
+        grads[k] = named[k].grad.clone()
+    out["grads"] = grads
+    out["running_mean_after"] = model.state_dict()[
+        "sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.0.mlp.bn1.norm_layer.running_mean"].clone()
+    out["running_var_after"] = model.state_dict()[
+        "sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.0.mlp.bn1.norm_layer.running_var"].clone()
+    return out
+
+
+def golden_en4(neuron_type="lif"):
+    """The shipped model/config (MS en4, window (2,9,9)) at its smallest legal size 288x384, eval."""
+    from spikingjelly.activation_based import functional
+    mc, sc = rl.default_config(neuron_type=neuron_type, input_size=(288, 384))
+    model = rl.build_reference_model(mc, sc, seed=0, train=False)
+    _load_synth(model)
+    x = synth.synth_voxels(1, 10, 288, 384)
+    functional.reset_net(model)
+    with torch.no_grad():
+        flows = model(x)["flow"]
+    return {"neuron_type": neuron_type, "flows": [_summ(f) for f in flows]}
+
+
+def golden_sew_stage():
+    """SEW family: one Spiking_Swin_BasicLayer (QK^T V attention, shifted + unshifted block, with
+    SpikingPatchMerging) and the SDSA attention variant, eval and train."""
+    swin, mods, sub, functional = rl.reference_modules()
+    out = {}
+    kw = {"num_steps": 4, "v_reset": None, "v_th": 0.3, "neuron_type": "lif", "surrogate_fun": "surrogate.ATan()",
+          "tau": 2.0, "detach_reset": True, "spike_norm": "BN"}
+    for variant in ("bn", "sdsa"):
+        class Blk(swin.Spiking_SwinTransformerBlock3D):
+            attn_module = swin.Spiking_BN_WindowAttention3D if variant == "bn" else swin.SDSA_WindowAttention3D
+
+        class Lyr(swin.Spiking_Swin_BasicLayer):
+            swin_block_type = Blk
+        torch.manual_seed(0)
+        lyr = Lyr(dim=64, input_resolution=(7, 10), depth=2, num_heads=2, window_size=(2, 3, 4),
+                  pretrained_window_size=(0, 0, 0), mlp_ratio=4.0, version="swinv1", qk_scale=0.125,
+                  drop_path=[0.0, 0.0], norm_layer="BN", downsample=swin.SpikingPatchMerging, **kw)
+        lyr.load_state_dict(synth.synth_state_dict(lyr.state_dict(), seed=3))
+        functional.set_step_mode(lyr, "m")
+        g = torch.Generator().manual_seed(5)
+        x = (torch.rand(2, 64, 4, 7, 10, generator=g) < 0.3).float() * torch.randint(1, 3, (2, 64, 4, 7, 10), generator=g)
+        for train in (False, True):
+            lyr.train(train)
+            functional.reset_net(lyr)
+            xo, xb = lyr(x.clone())
+            out[f"{variant}_{'train' if train else 'eval'}"] = {"x_out": xo.detach().clone(), "x_pre": xb.detach().clone()}
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 8)
+    jobs = {
+        "small_lif_eval.pt": lambda: golden_small_model("lif", False),
+        "small_psn_eval.pt": lambda: golden_small_model("psn", False),
+        "small_lif_train.pt": lambda: golden_small_model("lif", True),
+        "small_psn_train.pt": lambda: golden_small_model("psn", True),
+        "en4_lif_eval.pt": lambda: golden_en4("lif"),
+        "sew_stage.pt": golden_sew_stage,
+    }
+    only = set(sys.argv[1:])
+    for name, fn in jobs.items():
+        if only and name not in only:
+            continue
+        torch.save(fn(), os.path.join(OUT, name))
+        print("wrote", name, os.path.getsize(os.path.join(OUT, name)) // 1024, "KiB", flush=True)
+
+
+if __name__ == "__main__":
+    main()

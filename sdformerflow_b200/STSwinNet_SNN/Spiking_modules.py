@@ -1,0 +1,367 @@
+"""Neuron switch, spike norm layer and the convolutional layers around the Swin encoder
+(host-side mirror of reference models/STSwinNet_SNN/Spiking_modules.py).
+
+Only what the three SNN FlowNets with the shipped patch embedding need is built:
+Spiking_neuron (:26-99), SpikingNormLayer (:101-146), SpikingConvEncoderLayer (:250-296),
+MS_SpikingConvEncoderLayer (:298-347), (MS_)SpikingTransposeDecoderLayer (:398-474),
+(MS_)SpikingPredLayer (:568-647), SpikingPEDLayer (:772-825), SEWResBlock / MS_ResBlock
+(:827-933), the residual feature generators (:935-973) and
+MS_PED_Spiking_PatchEmbed_Conv_sfn (:1710-1790).  Convolutions stay cuDNN calls (out of the
+hot-path scope); every neuron runs on the K1 kernel.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..sj import surrogate, neuron, functional, base, layer  # noqa: F401  (`surrogate` is eval()'d below)
+from .. import capi, ops
+from .Spiking_submodules import *  # noqa: F401,F403
+from .Spiking_submodules import PSN, GatedLIFNode, SLTTLIFNode
+
+
+class Spiking_neuron(nn.Module):
+    """Switch over neuron types; `surrogate_fun` is a string eval()'d with `surrogate` in scope,
+    as in the reference (:44).  State handling: the reference scripts call
+    functional.reset_net(model) before every sample, so by default the membrane potential is
+    not written back after a forward (saves 4 B/neuron); calling forward twice without a reset
+    raises instead of silently diverging.  Set ``persist_state = True`` for spikingjelly's
+    carry-over semantics."""
+    persist_state = False
+
+    def __init__(self, num_steps, spike_norm=None, neuron_type="plif", v_th=1.0, v_reset=0,
+                 surrogate_fun="surrogate.ATan()", tau=2.0, detach_reset=True):
+        super().__init__()
+        assert neuron_type in ["lif", "if", "plif", "SLTTlif", "glif", "psn"]
+        sf = eval(surrogate_fun) if isinstance(surrogate_fun, str) else surrogate_fun
+        self.neuron_type = neuron_type
+        if neuron_type == "lif":
+            self.spiking_neuron = neuron.LIFNode(v_threshold=v_th, v_reset=v_reset, surrogate_function=sf, tau=tau,
+                                                 detach_reset=detach_reset)
+        elif neuron_type == "if":
+            self.spiking_neuron = neuron.IFNode(v_threshold=v_th, v_reset=v_reset, surrogate_function=sf,
+                                                detach_reset=detach_reset)
+        elif neuron_type == "plif":
+            self.spiking_neuron = neuron.ParametricLIFNode(v_threshold=v_th, v_reset=v_reset, surrogate_function=sf,
+                                                           init_tau=tau, detach_reset=detach_reset)
+        elif neuron_type == "psn":
+            self.spiking_neuron = PSN(T=num_steps, surrogate_function=sf)
+        elif neuron_type == "glif":
+            self.spiking_neuron = GatedLIFNode(T=num_steps, surrogate_function=sf)
+        else:
+            self.spiking_neuron = SLTTLIFNode(v_threshold=v_th, v_reset=v_reset, surrogate_function=sf, tau=tau,
+                                              detach_reset=detach_reset)
+        self._dirty = False
+
+    # ---- protocol -------------------------------------------------------------------------
+    def reset(self):
+        self._dirty = False
+
+    @property
+    def is_psn(self):
+        return self.neuron_type == "psn"
+
+    def cfg(self):
+        return self.spiking_neuron.neuron_cfg()
+
+    def plif_w(self):
+        return getattr(self.spiking_neuron, "w", None)
+
+    def mark(self):
+        """Called by fused operators that run this neuron inside a kernel."""
+        if self._dirty and not self.is_psn:
+            raise RuntimeError("Spiking_neuron called twice without functional.reset_net(model); the reference "
+                               "scripts reset before every sample (train_flow_parallel_supervised_SNN.py:238)")
+        self._dirty = True
+
+    def forward(self, x, time_dim=0):
+        if self.is_psn:
+            return ops.psn(x, self.spiking_neuron.weight, self.spiking_neuron.bias, self.cfg(), time_dim)
+        if self.persist_state and time_dim == 0:
+            return self.spiking_neuron(x)
+        self.mark()
+        return ops.neuron(x, self.cfg(), time_dim, self.plif_w())
+
+
+class SpikingNormLayer(nn.Module):
+    """Multi-step spike normalisation (reference :101-146).  The Swin blocks read `.norm_layer`'s
+    tensors and fold the apply into the consuming kernel; called directly it normalises
+    [T,B,C,H,W] like spikingjelly (statistics over T*B*H*W)."""
+
+    def __init__(self, out_channels, num_steps, norm="BN", v_th=1.0):
+        super().__init__()
+        self.num_steps, self.norm = num_steps, norm
+        if norm == "BN":
+            self.norm_layer = layer.BatchNorm2d(out_channels)
+        if norm == "BN_notrack":
+            self.norm_layer = layer.BatchNorm2d(out_channels, track_running_stats=False)
+        if norm == "GN":
+            self.norm_layer = layer.GroupNorm(out_channels // 16, out_channels)
+        if norm == "IN":
+            self.norm_layer = layer.GroupNorm(out_channels, out_channels)
+        if norm == "LN":
+            self.norm_layer = layer.GroupNorm(1, out_channels)
+        elif norm == "BNTT":
+            self.norm_layer = nn.ModuleList([nn.BatchNorm2d(out_channels, eps=1e-4, momentum=0.1, affine=True)
+                                             for _ in range(num_steps)])
+        elif norm == "TDBN":
+            self.norm_layer = layer.ThresholdDependentBatchNorm2d(alpha=1, v_th=v_th, num_features=out_channels)
+
+    @property
+    def is_batchnorm(self):
+        return isinstance(self.norm_layer, nn.BatchNorm2d)
+
+    def forward(self, x):
+        if self.norm == "BNTT":
+            return torch.cat([self.norm_layer[i](x[i]).unsqueeze(0) for i in range(self.num_steps)], dim=0)
+        return self.norm_layer(x)
+
+
+def _conv(cin, cout, k, stride, padding, bias):
+    return nn.Sequential(layer.Conv2d(in_channels=cin, out_channels=cout, kernel_size=k, stride=stride, padding=padding,
+                                      bias=bias))
+
+
+class SpikingConvEncoderLayer(nn.Module):
+    """conv -> norm -> neuron (SEW ordering, reference :250-296)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, spike_norm=None,
+                 **spiking_kwargs):
+        super().__init__()
+        self.norm = spike_norm
+        self.conv = _conv(in_channels, out_channels, kernel_size, stride, padding, self.norm is None)
+        if self.norm is not None:
+            self.norm_layer = SpikingNormLayer(out_channels, spiking_kwargs["num_steps"], self.norm,
+                                               v_th=spiking_kwargs["v_th"])
+        self.sn = Spiking_neuron(**spiking_kwargs)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.norm is not None:
+            x = self.norm_layer(x)
+        return self.sn(x)
+
+
+class MS_SpikingConvEncoderLayer(nn.Module):
+    """[neuron ->] conv -> norm (membrane-shortcut ordering, reference :298-347)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, first_layer=True,
+                 spike_norm=None, **spiking_kwargs):
+        super().__init__()
+        self.first_layer, self.norm = first_layer, spike_norm
+        if not first_layer:
+            self.sn = Spiking_neuron(**spiking_kwargs)
+        self.conv = _conv(in_channels, out_channels, kernel_size, stride, padding, self.norm is None)
+        if self.norm is not None:
+            self.norm_layer = SpikingNormLayer(out_channels, spiking_kwargs["num_steps"], self.norm,
+                                               v_th=spiking_kwargs["v_th"])
+
+    def forward(self, x):
+        if not self.first_layer:
+            x = self.sn(x)
+        x = self.conv(x)
+        return self.norm_layer(x) if self.norm is not None else x
+
+
+class SpikingTransposeDecoderLayer(nn.Module):
+    """x2 (or x4) transposed-conv upsampling: deconv -> norm -> neuron (reference :398-459)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, spike_norm=None, scale=2, **spiking_kwargs):
+        super().__init__()
+        self.scale, self.norm = scale, spike_norm
+        bias = self.norm is None
+        if scale == 2:
+            dc = layer.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=2, padding=kernel_size // 2,
+                                       output_padding=1, bias=bias)
+        elif scale == 4:
+            dc = layer.ConvTranspose2d(in_channels, out_channels, 7, stride=4, padding=2, output_padding=1, bias=bias)
+        else:
+            raise ValueError(scale)
+        self.deconv = nn.Sequential(dc)
+        if self.norm is not None:
+            self.norm_layer = SpikingNormLayer(out_channels, spiking_kwargs["num_steps"], self.norm,
+                                               v_th=spiking_kwargs["v_th"])
+        self.sn = Spiking_neuron(**spiking_kwargs)
+
+    def forward(self, x):
+        x = self.deconv(x)
+        if self.norm is not None:
+            x = self.norm_layer(x)
+        return self.sn(x)
+
+
+class MS_SpikingTransposeDecoderLayer(SpikingTransposeDecoderLayer):
+    """neuron -> deconv -> norm (reference :461-474)."""
+
+    def forward(self, x):
+        x = self.deconv(self.sn(x))
+        return self.norm_layer(x) if self.norm is not None else x
+
+
+class SpikingPredLayer(nn.Module):
+    """1x1 prediction conv with bias (reference :568-605)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, **spiking_kwargs):
+        super().__init__()
+        self.norm = None
+        self.conv = _conv(in_channels, out_channels, kernel_size, stride, kernel_size // 2, True)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class MS_SpikingPredLayer(nn.Module):
+    """neuron -> 1x1 prediction conv with bias (reference :607-647)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, **spiking_kwargs):
+        super().__init__()
+        self.norm = None
+        self.sn = Spiking_neuron(**spiking_kwargs)
+        self.conv = _conv(in_channels, out_channels, kernel_size, stride, kernel_size // 2, True)
+
+    def forward(self, x):
+        return self.conv(self.sn(x))
+
+
+class SpikingPEDLayer(nn.Module):
+    """Patch embedding with deformed shortcut, /2 (reference :772-825): 1x1 s2 shortcut on the membrane
+    input + neuron -> 3x3 s2 conv -> BN."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, norm=None,
+                 patch_resolution=(120, 160), **spiking_kwargs):
+        super().__init__()
+        self.norm, self.patch = norm, patch_resolution
+        bias = norm is None
+        self.conv_res = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=2, padding=0, bias=bias)
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=1, bias=bias)
+        if self.norm is not None:
+            self.norm_layer = nn.BatchNorm2d(out_channels)
+        self.sn = Spiking_neuron(**spiking_kwargs)
+
+    def forward(self, x):
+        T, B, C, H, W = x.shape
+        x_res = self.conv_res(x.flatten(0, 1))
+        y = self.conv(self.sn(x).flatten(0, 1))
+        if self.norm is not None:
+            y = self.norm_layer(y)
+        return (y + x_res).reshape(T, B, -1, self.patch[0], self.patch[1]).contiguous()
+
+
+def _connect(out, identity, fn):
+    if fn == "ADD":
+        return out + identity
+    if fn in ("MUL", "AND"):
+        return out * identity
+    if fn == "OR":
+        return surrogate.ATan(spiking=True)(out + identity)
+    if fn == "NMUL":
+        return identity * (1.0 - out)
+    raise NotImplementedError(fn)
+
+
+class _ResBlockBase(nn.Module):
+    def __init__(self, in_channels, out_channels, stride=1, connect_function="ADD", spike_norm=None,
+                 **spiking_kwargs):
+        super().__init__()
+        self.norm = spike_norm
+        bias = self.norm is None
+        self.conv1 = _conv(in_channels, out_channels, 3, stride, 1, bias)
+        self.conv2 = _conv(in_channels, in_channels, 3, 1, 1, bias)
+        if self.norm is not None:
+            # reference quirk kept: SpikingNormLayer(out_channels, self.norm, v_th=...) => num_steps = "BN",
+            # norm = default 'BN' (:848-849, :901-902)
+            self.norm1 = SpikingNormLayer(out_channels, self.norm, v_th=spiking_kwargs["v_th"])
+            self.norm2 = SpikingNormLayer(out_channels, self.norm, v_th=spiking_kwargs["v_th"])
+        self.sn1 = Spiking_neuron(**spiking_kwargs)
+        self.sn2 = Spiking_neuron(**spiking_kwargs)
+        self.connect_function = connect_function
+
+
+class SEWResBlock(_ResBlockBase):
+    """conv-norm-neuron x2, spike-element-wise shortcut (reference :827-878)."""
+
+    def forward(self, x):
+        identity = x
+        x = self.conv1(x)
+        if self.norm is not None:
+            x = self.norm1(x)
+        x = self.conv2(self.sn1(x))
+        if self.norm is not None:
+            x = self.norm2(x)
+        return _connect(self.sn2(x), identity, self.connect_function)
+
+
+class MS_ResBlock(_ResBlockBase):
+    """neuron-conv-norm x2, membrane shortcut (reference :880-933)."""
+
+    def forward(self, x):
+        identity = x
+        x = self.conv1(self.sn1(x))
+        if self.norm is not None:
+            x = self.norm1(x)
+        x = self.conv2(self.sn2(x))
+        if self.norm is not None:
+            x = self.norm2(x)
+        return _connect(x, identity, self.connect_function)
+
+
+class spiking_residual_feature_generator(nn.Module):
+    res_block_type = SEWResBlock
+
+    def __init__(self, dim, norm, num_resblocks=4, cnt_fun="ADD", **spiking_kwargs):
+        super().__init__()
+        self.dim, self.num_resblocks = dim, num_resblocks
+        self.resblocks = nn.ModuleList([
+            self.res_block_type(dim, dim, stride=1, spike_norm=norm, connect_function=cnt_fun, **spiking_kwargs)
+            for _ in range(num_resblocks)])
+
+    def forward(self, x):
+        for blk in self.resblocks:
+            x = blk(x)
+        return x
+
+
+class MS_spiking_residual_feature_generator(spiking_residual_feature_generator):
+    res_block_type = MS_ResBlock
+
+
+def regroup_bins_to_steps(x, num_bins, num_steps):
+    """(B, bins, 2, H, W) -> (steps, B, num_ch, H, W) with new[:, i, ..., t] = x[:, (i//2)*steps + t, i%2]
+    (reference :1772-1786), as one permute instead of a zero-fill + per-channel copy loop."""
+    if x.size(1) > num_bins:
+        x = x[:, :num_bins]
+    B, _, _, H, W = x.shape
+    g = num_bins // num_steps
+    return x.reshape(B, g, num_steps, 2, H, W).permute(2, 0, 1, 3, 4, 5).reshape(num_steps, B, g * 2, H, W)
+
+
+class MS_PED_Spiking_PatchEmbed_Conv_sfn(nn.Module):
+    """Spiking patch embedding with PED, membrane shortcut (reference :1710-1790)."""
+    use_MS = True
+    num_res = 2
+    first_conv_k = 3
+
+    def __init__(self, img_size=(240, 320), patch_size=(2, 4, 4), in_chans=10, embed_dim=96, patch_norm=None, norm=None,
+                 spiking_proj=False, spike_norm=None, **spiking_kwargs):
+        super().__init__()
+        self.patch_size, self.image_size = patch_size, img_size
+        self.patches_resolution = [img_size[0] // patch_size[2] // 2, img_size[1] // patch_size[3] // 2]
+        self.embed_dim, self.patch_norm = embed_dim, patch_norm
+        self.num_bins, self.num_steps = in_chans, spiking_kwargs["num_steps"]
+        self.num_ch = in_chans * 2 // self.num_steps
+        self.spike_norm = spike_norm
+        self.head = SpikingConvEncoderLayer(self.num_ch, embed_dim // 2, kernel_size=3, stride=1, padding=1,
+                                            spike_norm=spike_norm, **spiking_kwargs)
+        self.conv = MS_SpikingConvEncoderLayer(embed_dim // 2, embed_dim, kernel_size=self.first_conv_k, stride=2,
+                                               padding=self.first_conv_k // 2, spike_norm=spike_norm, **spiking_kwargs)
+        self.residual_encoding = MS_spiking_residual_feature_generator(dim=embed_dim, norm=spike_norm,
+                                                                       num_resblocks=self.num_res, cnt_fun="ADD",
+                                                                       **spiking_kwargs)
+        self.proj = SpikingPEDLayer(embed_dim, embed_dim, kernel_size=3, stride=patch_size[2:], padding=1,
+                                    norm=spike_norm, patch_resolution=self.patches_resolution, **spiking_kwargs)
+
+    def forward(self, x):
+        x = regroup_bins_to_steps(x, self.num_bins, self.num_steps)
+        return self.proj(self.residual_encoding(self.conv(self.head(x))))
+
+    def extra_repr(self):
+        return f" num_steps={self.num_steps}, patches_resolution={self.patches_resolution}"

@@ -126,10 +126,52 @@ def struct(name, **kw):
     return obj
 
 
-def call(fn_name, args_struct):
+class KernelTimer:
+    """Optional per-launch device timing (CUDA events on torch's current stream, which is the stream
+    every kernel is launched on) + algorithmic bytes, used by bench.py for the roofline line."""
+
+    def __init__(self, only=None):
+        self.only = None if only is None else set(only)
+        self.records = []
+
+    def wants(self, name):
+        return self.only is None or name in self.only
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, nbytes in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+        for d in out.values():
+            d["gbps"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+        return out
+
+
+_timer = None
+
+
+def set_timer(timer):
+    global _timer
+    _timer = timer
+
+
+def call(fn_name, args_struct, algo_bytes=0):
     """Calls an ``int sdf_*(const args*)`` entry point; raises with sdf_last_error() on failure."""
     L = lib()
-    rc = getattr(L, fn_name)(ctypes.byref(args_struct))
+    t = _timer
+    if t is not None and t.wants(fn_name):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(L, fn_name)(ctypes.byref(args_struct))
+        e1.record()
+        t.records.append((fn_name, e0, e1, algo_bytes))
+    else:
+        rc = getattr(L, fn_name)(ctypes.byref(args_struct))
     if rc != 0:
         raise RuntimeError(f"{fn_name} failed ({rc}): {L.sdf_last_error().decode()}")
 

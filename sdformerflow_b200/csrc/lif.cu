@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) lif_bwd_kernel(const LifBwdP p) {
             plif_acc += gh * (xx - (vp - vr));
           }
         }
-        stv<V>(p.gu + off + t * s.stride_t, du);
+        if (p.gu) stv<V>(p.gu + off + t * s.stride_t, du);
         if (p.gx) stv<V>(p.gx + off + t * s.stride_t, dx);
       }
     }
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) lif_bwd_kernel(const LifBwdP p) {
 // ---- K1p: PSN ---------------------------------------------------------------------------------
 struct PsnP {
   const float* u; void* spike; float* h_seq;
-  const float* gs; float* gu; float* gh; float* x_out;
+  const float* gs; float* gu; float* gx; float* gh; float* x_out;
   const float* weight; const float* bias;
   const float* scale; const float* shift;
   float* bn_partials;
@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(256) psn_bwd_kernel(const PsnP p) {
             acc[1][i] += dx[i] * u[k][i];
           }
         }
-        stv<V>(p.gu + off + k * s.stride_t, du);
+        if (p.gu) stv<V>(p.gu + off + k * s.stride_t, du);
+        if (p.gx) stv<V>(p.gx + off + k * s.stride_t, dx);
       }
     }
   }
@@ -498,7 +499,7 @@ extern "C" int sdf_lif_fwd(const sdf_lif_fwd_args* a) {
 }
 
 extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
-  SDF_REQUIRE(a && a->u && a->grad_spike && a->grad_u, "sdf_lif_bwd: null argument");
+  SDF_REQUIRE(a && a->u && a->grad_spike && (a->grad_u || a->grad_x), "sdf_lif_bwd: null argument");
   int st = validate_neuron(a->neuron);
   if (st) return st;
   const bool affine = a->scale != nullptr;
@@ -574,17 +575,17 @@ extern "C" int sdf_psn_fwd(const sdf_psn_fwd_args* a) {
 }
 
 extern "C" int sdf_psn_bwd(const sdf_psn_bwd_args* a) {
-  SDF_REQUIRE(a && a->u && a->grad_spike && a->grad_u && a->grad_h && a->weight && a->bias, "sdf_psn_bwd: null argument");
+  SDF_REQUIRE(a && a->u && a->grad_spike && (a->grad_u || a->grad_x) && a->grad_h && a->weight && a->bias, "sdf_psn_bwd: null argument");
   const bool affine = a->scale != nullptr;
   SDF_REQUIRE(!affine || a->shift, "sdf_psn_bwd: scale without shift");
   if (a->lay.n_neurons == 0) return SDF_OK;
   PsnP p = {};
-  p.u = a->u; p.gs = a->grad_spike; p.gu = a->grad_u; p.gh = a->grad_h; p.x_out = a->x_out;
+  p.u = a->u; p.gs = a->grad_spike; p.gu = a->grad_u; p.gx = a->grad_x; p.gh = a->grad_h; p.x_out = a->x_out;
   p.weight = a->weight; p.bias = a->bias; p.scale = a->scale; p.shift = a->shift; p.bn_partials = a->bn_partials;
   sdf_neuron_cfg nc = {};
   nc.kind = SDF_NEURON_IF; nc.surrogate = a->surrogate; nc.sg_alpha = a->sg_alpha; nc.tau = 2.0; nc.v_th = 0.0;
   p.nrn = make_neuron(nc);
-  const void* ptrs[] = {a->u, a->grad_spike, a->grad_u, a->grad_h, a->x_out};
+  const void* ptrs[] = {a->u, a->grad_spike, a->grad_u, a->grad_h, a->x_out, a->grad_x};
   const int T = (int)a->lay.T;
   const bool fastT = (T == 2 || T == 4 || T == 5 || T == 10);
   int64_t max_blocks = (int64_t)kNumSMs * 2;
@@ -593,7 +594,7 @@ extern "C" int sdf_psn_bwd(const sdf_psn_bwd_args* a) {
     if (a->n_partial_blocks < max_blocks) max_blocks = a->n_partial_blocks;
   }
   SeqLaunch L;
-  int st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, fastT ? 4 : 1,
+  int st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 6, fastT ? 4 : 1,
                      256, max_blocks, &L);
   if (st) return st;
   p.s = L.s;

@@ -1,0 +1,653 @@
+"""Host-side operators: thin autograd wrappers over the C-ABI of libsdf_b200.so.
+
+Every function here takes CUDA fp32 tensors, allocates outputs/workspaces with torch (the
+library never allocates) and launches on torch's current stream.  There is NO CPU path: a
+non-CUDA tensor raises.  Shapes follow the reference's tensors; comments cite the reference
+lines each operator replaces.
+"""
+from dataclasses import dataclass
+import math
+import torch
+
+from . import capi
+
+N_PARTIAL = 296  # == sdf_partial_blocks(): 2 CTAs per SM x 148 SMs
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sdformerflow_b200: operators run on CUDA tensors only (there is no CPU fallback)")
+        if t is not None and t.dtype != torch.float32 and t.dtype not in (torch.int32, torch.uint8, torch.bfloat16):
+            raise RuntimeError(f"sdformerflow_b200: unexpected dtype {t.dtype}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_SPIKE_TORCH = {capi.SDF_SPIKE_F32: torch.float32, capi.SDF_SPIKE_U8: torch.uint8, capi.SDF_SPIKE_BF16: torch.bfloat16}
+
+
+@dataclass(frozen=True)
+class NeuronCfg:
+    """Device-independent description of a spikingjelly neuron."""
+    kind: int = capi.SDF_NEURON_LIF
+    v_th: float = 1.0
+    v_reset: object = 0.0          # None = soft reset
+    tau: float = 2.0               # LIF tau; PLIF: 1/sigmoid(w) (set per call)
+    detach_reset: bool = False
+    surrogate: int = capi.SDF_SG_ATAN
+    sg_alpha: float = 2.0
+
+    def c(self, tau=None):
+        return dict(kind=self.kind, hard_reset=0 if self.v_reset is None else 1,
+                    detach_reset=1 if self.detach_reset else 0, surrogate=self.surrogate,
+                    v_th=float(self.v_th), v_reset=0.0 if self.v_reset is None else float(self.v_reset),
+                    tau=float(self.tau if tau is None else tau), sg_alpha=float(self.sg_alpha))
+
+
+def seq_layout(shape, time_dim=0):
+    """sdf_seq_layout for a contiguous tensor whose time axis is dim 0 ([T, ...]) or dim 1
+    ((B, T, ...): replaces the x.permute(1,0,2,3,4) views of Spiking_swin_transformer3D.py:845)."""
+    numel = 1
+    for s in shape:
+        numel *= s
+    if time_dim == 0:
+        T = shape[0]
+        n = numel // T
+        return dict(T=T, n_neurons=n, inner=n, stride_b=0, stride_t=n)
+    if time_dim == 1:
+        B, T = shape[0], shape[1]
+        inner = numel // (B * T)
+        return dict(T=T, n_neurons=B * inner, inner=inner, stride_b=T * inner, stride_t=inner)
+    raise ValueError("time_dim must be 0 or 1")
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm bookkeeping shared by the fused operators
+# ---------------------------------------------------------------------------------------------
+class BNParams:
+    """Bundle of a BatchNorm2d's tensors + hyper-parameters handed to fused operators."""
+    __slots__ = ("weight", "bias", "running_mean", "running_var", "num_batches_tracked", "momentum", "eps",
+                 "training")
+
+    def __init__(self, bn: torch.nn.modules.batchnorm._BatchNorm):
+        self.weight, self.bias = bn.weight, bn.bias
+        self.running_mean, self.running_var = bn.running_mean, bn.running_var
+        self.num_batches_tracked = bn.num_batches_tracked
+        self.momentum = 0.1 if bn.momentum is None else bn.momentum
+        self.eps = bn.eps
+        # torch: batch statistics when training or when no running stats are tracked
+        self.training = bn.training or bn.running_mean is None
+
+
+def _bn_forward_affine(u2d, rows, C, ld, bn: BNParams):
+    """-> scale, shift, mean, rstd (all [C]).  Train: batch stats + running update like torch."""
+    dev = u2d.device
+    scale = torch.empty(C, device=dev, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale)
+    rstd = torch.empty_like(scale)
+    partials = None
+    if bn.training:
+        partials = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
+        capi.call("sdf_bn_stats", capi.struct("sdf_bn_stats_args", x=_ptr(u2d), rows=rows, C=C, ld=ld,
+                                              partials=_ptr(partials), n_partial_blocks=N_PARTIAL, stream=_stream()),
+                  algo_bytes=4 * rows * C)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    with torch.no_grad():
+        capi.call("sdf_bn_finalize", capi.struct(
+            "sdf_bn_finalize_args", partials=_ptr(partials), n_partial_blocks=N_PARTIAL if bn.training else 0,
+            count=rows, C=C, weight=_ptr(bn.weight), bias=_ptr(bn.bias),
+            running_mean=_ptr(bn.running_mean), running_var=_ptr(bn.running_var),
+            momentum=float(bn.momentum), eps=float(bn.eps), training=1 if bn.training else 0,
+            scale=_ptr(scale), shift=_ptr(shift), mean=_ptr(mean), rstd=_ptr(rstd), stream=_stream()))
+    return scale, shift, mean, rstd
+
+
+def _bn_backward(partials, dy, u2d, ld_u, rows, C, weight, mean, rstd, training, need_du=True, du_ld=None):
+    """partials = per-block (sum dy, sum dy*u).  -> du [rows, C], grad_weight, grad_bias."""
+    dev = dy.device
+    gw = torch.empty(C, device=dev, dtype=torch.float32)
+    gb = torch.empty_like(gw)
+    coef = torch.empty((3, C), device=dev, dtype=torch.float32)
+    capi.call("sdf_bn_bwd_finalize", capi.struct(
+        "sdf_bn_bwd_finalize_args", partials=_ptr(partials), n_partial_blocks=N_PARTIAL, count=rows, C=C,
+        weight=_ptr(weight), mean=_ptr(mean), rstd=_ptr(rstd), grad_weight=_ptr(gw), grad_bias=_ptr(gb),
+        coef=_ptr(coef), training=1 if training else 0, stream=_stream()))
+    du = None
+    if need_du:
+        du = torch.empty((rows, C), device=dev, dtype=torch.float32)
+        capi.call("sdf_bn_bwd_apply", capi.struct(
+            "sdf_bn_bwd_apply_args", dy=_ptr(dy), u=_ptr(u2d), ld_u=ld_u, du=_ptr(du), ld_du=C, coef=_ptr(coef),
+            rows=rows, C=C, stream=_stream()))
+    return du, gw, gb
+
+
+# ---------------------------------------------------------------------------------------------
+# K1/K2: multi-step neuron (optionally fused with the preceding BatchNorm)
+# ---------------------------------------------------------------------------------------------
+def _lif_fwd_raw(u, lay, cfg_c, spike_dtype, scale=None, shift=None, C=0, hw=1, want_h=False, v_init=None,
+                 want_v=False):
+    spike = torch.empty(u.shape, device=u.device, dtype=_SPIKE_TORCH[spike_dtype])
+    h = torch.empty_like(u) if want_h else None
+    v_final = torch.empty(lay["n_neurons"], device=u.device, dtype=torch.float32) if want_v else None
+    capi.call("sdf_lif_fwd", capi.struct(
+        "sdf_lif_fwd_args", u=_ptr(u), spike=_ptr(spike), h_seq=_ptr(h), v_init=_ptr(v_init), v_final=_ptr(v_final),
+        scale=_ptr(scale), shift=_ptr(shift), C=C, hw=hw, lay=lay, neuron=cfg_c, spike_dtype=spike_dtype,
+        stream=_stream()), algo_bytes=u.numel() * (4 + spike.element_size()))
+    return spike, h, v_final
+
+
+class _NeuronFn(torch.autograd.Function):
+    """Plain multi-step LIF/IF/PLIF: spikingjelly LIFNode.multi_step_forward via Spiking_neuron.forward
+    (reference Spiking_modules.py:98-99)."""
+
+    @staticmethod
+    def forward(ctx, u, plif_w, cfg, time_dim, v_init, want_state):
+        _need_cuda(u)
+        u = u.contiguous()
+        lay = seq_layout(u.shape, time_dim)
+        tau = None
+        if cfg.kind == capi.SDF_NEURON_PLIF:
+            tau = 1.0 / torch.sigmoid(plif_w.detach()).item()
+        cc = cfg.c(tau)
+        spike, _, v_final = _lif_fwd_raw(u, lay, cc, capi.SDF_SPIKE_F32, v_init=v_init, want_v=want_state)
+        ctx.save_for_backward(u, plif_w, v_init)
+        ctx.lay, ctx.cc, ctx.cfg = lay, cc, cfg
+        if want_state:
+            ctx.mark_non_differentiable(v_final)
+            return spike, v_final
+        return spike, None
+
+    @staticmethod
+    def backward(ctx, gs, _gv):
+        u, plif_w, v_init = ctx.saved_tensors
+        gs = gs.contiguous()
+        gu = torch.empty_like(u)
+        plif_part = None
+        if ctx.cfg.kind == capi.SDF_NEURON_PLIF:
+            plif_part = torch.empty(N_PARTIAL, device=u.device, dtype=torch.float32)
+        capi.call("sdf_lif_bwd", capi.struct(
+            "sdf_lif_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=_ptr(gu), v_init=_ptr(v_init),
+            plif_partials=_ptr(plif_part), n_partial_blocks=N_PARTIAL, C=0, hw=1, lay=ctx.lay, neuron=ctx.cc,
+            stream=_stream()), algo_bytes=12 * u.numel())
+        gw = None
+        if plif_part is not None:
+            s = torch.sigmoid(plif_w.detach())
+            gw = (plif_part.sum() * s * (1 - s)).reshape(plif_w.shape)
+        return gu, gw, None, None, None, None
+
+
+def neuron(u, cfg: NeuronCfg, time_dim=0, plif_w=None, v_init=None, want_state=False):
+    """spikes (fp32 {0,1}) of a multi-step neuron over dim `time_dim`; optionally the final membrane."""
+    spike, v = _NeuronFn.apply(u, plif_w, cfg, time_dim, v_init, want_state)
+    return (spike, v) if want_state else spike
+
+
+def neuron_debug(u, cfg: NeuronCfg, time_dim=0, scale=None, shift=None, C=0, hw=1, spike_dtype=capi.SDF_SPIKE_F32):
+    """(spikes, membrane-after-charge h) without autograd — for parity tests and monitors."""
+    _need_cuda(u)
+    u = u.contiguous()
+    spike, h, _ = _lif_fwd_raw(u, seq_layout(u.shape, time_dim), cfg.c(), spike_dtype, scale, shift, C, hw, want_h=True)
+    return spike, h
+
+
+class _PSNFn(torch.autograd.Function):
+    """Parallel spiking neuron: s = heaviside(W x + b) over the time axis
+    (reference Spiking_submodules.py:207-211: addmm + surrogate)."""
+
+    @staticmethod
+    def forward(ctx, u, weight, bias, cfg, time_dim):
+        _need_cuda(u, weight, bias)
+        u = u.contiguous()
+        lay = seq_layout(u.shape, time_dim)
+        if weight.shape[0] != lay["T"]:
+            raise RuntimeError(f"PSN: weight is {tuple(weight.shape)} but the input has T={lay['T']}")
+        spike = torch.empty_like(u)
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        capi.call("sdf_psn_fwd", capi.struct(
+            "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), weight=_ptr(w), bias=_ptr(b), C=0, hw=1, lay=lay,
+            spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()))
+        ctx.save_for_backward(u, w, b)
+        ctx.lay, ctx.cfg = lay, cfg
+        return spike
+
+    @staticmethod
+    def backward(ctx, gs):
+        u, w, b = ctx.saved_tensors
+        gs = gs.contiguous()
+        T, n = ctx.lay["T"], ctx.lay["n_neurons"]
+        gu = torch.empty_like(u)
+        gh = torch.empty((T, n), device=u.device, dtype=torch.float32)
+        xo = u.view(T, n) if ctx.lay["stride_b"] == 0 else torch.empty((T, n), device=u.device, dtype=torch.float32)
+        capi.call("sdf_psn_bwd", capi.struct(
+            "sdf_psn_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=_ptr(gu), grad_h=_ptr(gh),
+            x_out=None if ctx.lay["stride_b"] == 0 else _ptr(xo), weight=_ptr(w), bias=_ptr(b), C=0, hw=1,
+            lay=ctx.lay, surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
+        return gu, gh @ xo.t(), gh.sum(1, keepdim=True), None, None
+
+
+def psn(u, weight, bias, cfg: NeuronCfg, time_dim=0):
+    return _PSNFn.apply(u, weight, bias, cfg, time_dim)
+
+
+class _BNNeuronFn(torch.autograd.Function):
+    """y = neuron(BN(u)) on channels-last rows: `sn(bn(linear(x)).permute..)` sites, e.g. reference
+    Spiking_swin_transformer3D.py:171-174 (bn1 -> sn2), :310-311, :933-934."""
+
+    @staticmethod
+    def forward(ctx, u, weight, bias, bn, cfg, time_dim, psn_w, psn_b):
+        _need_cuda(u)
+        u = u.contiguous()
+        C = u.shape[-1]
+        rows = u.numel() // C
+        scale, shift, mean, rstd = _bn_forward_affine(u, rows, C, C, bn)
+        lay = seq_layout(u.shape, time_dim)
+        if psn_w is None:
+            cc = cfg.c()
+            spike, _, _ = _lif_fwd_raw(u, lay, cc, capi.SDF_SPIKE_F32, scale, shift, C, 1)
+        else:
+            cc = None
+            spike = torch.empty_like(u)
+            capi.call("sdf_psn_fwd", capi.struct(
+                "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), weight=_ptr(psn_w), bias=_ptr(psn_b),
+                scale=_ptr(scale), shift=_ptr(shift), C=C, hw=1, lay=lay, spike_dtype=capi.SDF_SPIKE_F32,
+                stream=_stream()))
+        ctx.save_for_backward(u, weight, scale, shift, mean, rstd, psn_w, psn_b)
+        ctx.lay, ctx.cc, ctx.cfg, ctx.training, ctx.rows, ctx.C = lay, cc, cfg, bn.training, rows, C
+        return spike
+
+    @staticmethod
+    def backward(ctx, gs):
+        u, weight, scale, shift, mean, rstd, psn_w, psn_b = ctx.saved_tensors
+        gs = gs.contiguous()
+        rows, C = ctx.rows, ctx.C
+        dev = u.device
+        partials = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
+        dx = torch.empty_like(u)
+        g_psn_w = g_psn_b = None
+        if psn_w is None:
+            capi.call("sdf_lif_bwd", capi.struct(
+                "sdf_lif_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=None, grad_x=_ptr(dx), scale=_ptr(scale),
+                shift=_ptr(shift), bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=ctx.lay,
+                neuron=ctx.cc, stream=_stream()), algo_bytes=12 * u.numel())
+        else:
+            T, n = ctx.lay["T"], ctx.lay["n_neurons"]
+            gh = torch.empty((T, n), device=dev, dtype=torch.float32)
+            xo = torch.empty((T, n), device=dev, dtype=torch.float32)
+            capi.call("sdf_psn_bwd", capi.struct(
+                "sdf_psn_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=None, grad_x=_ptr(dx), grad_h=_ptr(gh),
+                x_out=_ptr(xo), weight=_ptr(psn_w), bias=_ptr(psn_b), scale=_ptr(scale), shift=_ptr(shift),
+                bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=ctx.lay,
+                surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
+            g_psn_w = gh @ xo.t()
+            g_psn_b = gh.sum(1, keepdim=True)
+        du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, weight, mean, rstd, ctx.training)
+        return du.view(u.shape), gw, gb, None, None, None, g_psn_w, g_psn_b
+
+
+def _seq_to_layout(seq, shape, lay):
+    """[T, n] contiguous -> tensor laid out like the original input (inverse of the kernel's addressing)."""
+    T = lay["T"]
+    if lay["stride_b"] == 0:
+        return seq.reshape(shape).contiguous()
+    B = lay["n_neurons"] // lay["inner"]
+    return seq.view(T, B, lay["inner"]).permute(1, 0, 2).contiguous().view(shape)
+
+
+def bn_neuron(u, bn_module, cfg: NeuronCfg, time_dim=0, psn=None):
+    """neuron(BN(u)); u is channels-last [..., C]; BN statistics over all leading dims (the
+    spikingjelly multi-step BN flattens (T,B): SURVEY.md Appendix A)."""
+    bn = BNParams(bn_module)
+    pw, pb = (psn.weight, psn.bias) if psn is not None else (None, None)
+    return _BNNeuronFn.apply(u, bn.weight, bn.bias, bn, cfg, time_dim, pw, pb)
+
+
+class _BNResidualFn(torch.autograd.Function):
+    """out = res + BN(u) on channels-last rows (MS MLP tail: Spiking_swin_transformer3D.py:176-178 + :845)."""
+
+    @staticmethod
+    def forward(ctx, u, res, weight, bias, bn):
+        _need_cuda(u, res)
+        u = u.contiguous()
+        C = u.shape[-1]
+        rows = u.numel() // C
+        scale, shift, mean, rstd = _bn_forward_affine(u, rows, C, C, bn)
+        out = torch.empty_like(u)
+        if res is not None:
+            res = res.contiguous()
+        capi.call("sdf_bn_apply", capi.struct(
+            "sdf_bn_apply_args", u=_ptr(u), ld_u=C, res=_ptr(res), out=_ptr(out), scale=_ptr(scale), shift=_ptr(shift),
+            rows=rows, C=C, stream=_stream()))
+        ctx.save_for_backward(u, weight, mean, rstd)
+        ctx.training, ctx.rows, ctx.C, ctx.has_res = bn.training, rows, C, res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        u, weight, mean, rstd = ctx.saved_tensors
+        go = go.contiguous()
+        rows, C = ctx.rows, ctx.C
+        partials = torch.empty((N_PARTIAL, 2, C), device=u.device, dtype=torch.float32)
+        capi.call("sdf_bn_bwd_reduce", capi.struct(
+            "sdf_bn_bwd_reduce_args", dy=_ptr(go), u=_ptr(u), ld_u=C, rows=rows, C=C, partials=_ptr(partials),
+            n_partial_blocks=N_PARTIAL, stream=_stream()))
+        du, gw, gb = _bn_backward(partials, go, u, C, rows, C, weight, mean, rstd, ctx.training)
+        return du.view(u.shape), (go if ctx.has_res else None), gw, gb, None
+
+
+def bn_residual(u, bn_module, res=None):
+    bn = BNParams(bn_module)
+    return _BNResidualFn.apply(u, res, bn.weight, bn.bias, bn)
+
+
+# ---------------------------------------------------------------------------------------------
+# window index algebra
+# ---------------------------------------------------------------------------------------------
+class WindowGeom:
+    """Geometry of one (feature map, window, shift) combination and its cached index tables.
+    get_window_size clamping (reference swin_transformer3D_v2.py:68-81) is applied here."""
+    _cache = {}
+
+    def __init__(self, B, D, H, W, window, shift):
+        ws, ss = list(window), list(shift)
+        for i, x in enumerate((D, H, W)):
+            if x <= ws[i]:
+                ws[i] = x
+                ss[i] = 0
+        self.B, self.D, self.H, self.W = B, D, H, W
+        self.window, self.shift = tuple(ws), tuple(ss)
+        wd, wh, ww = self.window
+        self.nD, self.nHw, self.nWw = -(-D // wd), -(-H // wh), -(-W // ww)
+        self.Dp, self.Hp, self.Wp = self.nD * wd, self.nHw * wh, self.nWw * ww
+        self.P = wh * ww
+        self.N = wd * self.P
+        self.nW = self.nD * self.nHw * self.nWw
+        self.M = B * self.nW
+        self.rows = self.M * self.N
+        self.shifted = any(s > 0 for s in self.shift)
+        self.win2x = None
+        self.region = None
+
+    def c(self):
+        return dict(B=self.B, D=self.D, H=self.H, W=self.W, wd=self.window[0], wh=self.window[1], ww=self.window[2],
+                    sd=self.shift[0], sh=self.shift[1], sw=self.shift[2])
+
+    @classmethod
+    def get(cls, B, D, H, W, window, shift, device):
+        key = (B, D, H, W, tuple(window), tuple(shift), str(device))
+        g = cls._cache.get(key)
+        if g is None:
+            g = cls(B, D, H, W, window, shift)
+            g.build(device)
+            cls._cache[key] = g
+        return g
+
+    def build(self, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("sdformerflow_b200: window tables are built on the GPU (no CPU fallback)")
+        self.win2x = torch.empty(self.rows, device=device, dtype=torch.int32)
+        self.region = torch.empty(self.nW * self.N, device=device, dtype=torch.uint8)
+        capi.call("sdf_window_index", capi.struct("sdf_window_index_args", g=self.c(), win2x=_ptr(self.win2x),
+                                                  region=_ptr(self.region), stream=_stream()))
+        return self
+
+
+class _WindowGatherFn(torch.autograd.Function):
+    """x_windows = window_partition_v2(roll(pad(x))) (reference Spiking_swin_transformer3D.py:793-804)."""
+
+    @staticmethod
+    def forward(ctx, x, geom):
+        _need_cuda(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        wd, wh, ww = geom.window
+        xw = torch.empty((wd, geom.M, wh, ww, C), device=x.device, dtype=torch.float32)
+        capi.call("sdf_window_gather", capi.struct("sdf_window_gather_args", x=_ptr(x), xw=_ptr(xw),
+                                                   win2x=_ptr(geom.win2x), rows=geom.rows, C=C, stream=_stream()))
+        ctx.geom, ctx.xshape = geom, x.shape
+        return xw
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        geom = ctx.geom
+        dx = torch.empty(ctx.xshape, device=g.device, dtype=torch.float32)
+        capi.call("sdf_window_gather_bwd", capi.struct("sdf_window_gather_bwd_args", dxw=_ptr(g), dx=_ptr(dx),
+                                                       win2x=_ptr(geom.win2x), rows=geom.rows, C=ctx.xshape[-1],
+                                                       stream=_stream()))
+        return dx, None
+
+
+def window_gather(x, geom):
+    return _WindowGatherFn.apply(x, geom)
+
+
+class _LifWindowFn(torch.autograd.Function):
+    """proj_sn(x_windows) with the pad/roll/partition gather folded in (reference :670 / :425)."""
+
+    @staticmethod
+    def forward(ctx, x, geom, cfg):
+        _need_cuda(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        wd, wh, ww = geom.window
+        spike = torch.empty((wd, geom.M, wh, ww, C), device=x.device, dtype=torch.float32)
+        cc = cfg.c()
+        capi.call("sdf_lif_window_fwd", capi.struct(
+            "sdf_lif_window_fwd_args", x=_ptr(x), spike=_ptr(spike), win2x=_ptr(geom.win2x), wd=wd,
+            MP=geom.M * geom.P, C=C, neuron=cc, spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()),
+            algo_bytes=4 * x.numel() + 4 * spike.numel())
+        ctx.save_for_backward(x)
+        ctx.geom, ctx.cc = geom, cc
+        return spike
+
+    @staticmethod
+    def backward(ctx, gs):
+        (x,) = ctx.saved_tensors
+        gs = gs.contiguous()
+        geom = ctx.geom
+        gx = torch.empty_like(x)
+        capi.call("sdf_lif_window_bwd", capi.struct(
+            "sdf_lif_window_bwd_args", x=_ptr(x), grad_spike=_ptr(gs), grad_x=_ptr(gx), win2x=_ptr(geom.win2x),
+            wd=geom.window[0], MP=geom.M * geom.P, C=x.shape[-1], neuron=ctx.cc, stream=_stream()))
+        return gx, None, None
+
+
+def lif_window(x, geom, cfg: NeuronCfg):
+    return _LifWindowFn.apply(x, geom, cfg)
+
+
+def lif_window_debug(x, geom, cfg: NeuronCfg):
+    x = x.contiguous()
+    C = x.shape[-1]
+    wd, wh, ww = geom.window
+    spike = torch.empty((wd, geom.M, wh, ww, C), device=x.device, dtype=torch.float32)
+    h = torch.empty_like(spike)
+    capi.call("sdf_lif_window_fwd", capi.struct(
+        "sdf_lif_window_fwd_args", x=_ptr(x), spike=_ptr(spike), h_seq=_ptr(h), win2x=_ptr(geom.win2x), wd=wd,
+        MP=geom.M * geom.P, C=C, neuron=cfg.c(), spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()))
+    return spike, h
+
+
+class _WindowScatterFn(torch.autograd.Function):
+    """out = shortcut + alpha_b * BN(y)[window -> token]: proj_bn + window_reverse + roll back + crop +
+    DropPath + residual (reference Spiking_swin_transformer3D.py:713-715, :810-820, :840)."""
+
+    @staticmethod
+    def forward(ctx, y, res, weight, bias, bn, geom, alpha):
+        _need_cuda(y, res)
+        y = y.contiguous()
+        C = y.shape[-1]
+        rows = geom.rows
+        assert y.numel() == rows * C
+        scale = shift = mean = rstd = None
+        if bn is not None:
+            scale, shift, mean, rstd = _bn_forward_affine(y, rows, C, C, bn)
+        out = torch.empty((geom.B, geom.D, geom.H, geom.W, C), device=y.device, dtype=torch.float32)
+        if res is not None:
+            res = res.contiguous()
+        capi.call("sdf_window_scatter", capi.struct(
+            "sdf_window_scatter_args", y=_ptr(y), res=_ptr(res), out=_ptr(out), win2x=_ptr(geom.win2x),
+            scale=_ptr(scale), shift=_ptr(shift), alpha=_ptr(alpha), rows=rows, rows_per_sample=geom.nW * geom.N, C=C,
+            stream=_stream()))
+        ctx.save_for_backward(y, weight, mean, rstd, alpha)
+        ctx.geom, ctx.C, ctx.has_bn, ctx.training = geom, C, bn is not None, (bn.training if bn is not None else False)
+        ctx.has_res = res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        y, weight, mean, rstd, alpha = ctx.saved_tensors
+        go = go.contiguous()
+        geom, C = ctx.geom, ctx.C
+        rows = geom.rows
+        dy = torch.empty((rows, C), device=go.device, dtype=torch.float32)
+        partials = torch.empty((N_PARTIAL, 2, C), device=go.device, dtype=torch.float32) if ctx.has_bn else None
+        capi.call("sdf_window_scatter_bwd", capi.struct(
+            "sdf_window_scatter_bwd_args", dout=_ptr(go), dy=_ptr(dy), u=_ptr(y) if ctx.has_bn else None,
+            win2x=_ptr(geom.win2x), alpha=_ptr(alpha), bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL,
+            rows=rows, rows_per_sample=geom.nW * geom.N, C=C, stream=_stream()))
+        gw = gb = None
+        if ctx.has_bn:
+            dy, gw, gb = _bn_backward(partials, dy, y, C, rows, C, weight, mean, rstd, ctx.training)
+        return dy.view(y.shape), (go if ctx.has_res else None), gw, gb, None, None, None
+
+
+def window_scatter(y, geom, res=None, bn_module=None, alpha=None):
+    bn = BNParams(bn_module) if bn_module is not None else None
+    w = bn.weight if bn is not None else None
+    b = bn.bias if bn is not None else None
+    return _WindowScatterFn.apply(y, res, w, b, bn, geom, alpha)
+
+
+# ---------------------------------------------------------------------------------------------
+# patch merging gather (+ LIF over D)
+# ---------------------------------------------------------------------------------------------
+class _LifMergeFn(torch.autograd.Function):
+    """MS_SpikingPatchMerging: sn(cat(x0..x3)) (reference :958-970); apply_neuron=False gives the
+    plain 2x2 gather of SpikingPatchMerging (:919-930)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, apply_neuron):
+        _need_cuda(x)
+        x = x.contiguous()
+        B, D, H, W, C = x.shape
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        out = torch.empty((B, D, H2, W2, 4 * C), device=x.device, dtype=torch.float32)
+        cc = cfg.c() if apply_neuron else NeuronCfg().c()
+        capi.call("sdf_lif_merge_fwd", capi.struct(
+            "sdf_lif_merge_fwd_args", x=_ptr(x), spike=_ptr(out), B=B, D=D, H=H, W=W, C=C, neuron=cc,
+            spike_dtype=capi.SDF_SPIKE_F32, apply_neuron=1 if apply_neuron else 0, stream=_stream()))
+        ctx.save_for_backward(x)
+        ctx.cc, ctx.apply_neuron = cc, apply_neuron
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.contiguous()
+        B, D, H, W, C = x.shape
+        gx = torch.empty_like(x)
+        capi.call("sdf_lif_merge_bwd", capi.struct(
+            "sdf_lif_merge_bwd_args", x=_ptr(x), grad_spike=_ptr(g), grad_x=_ptr(gx), B=B, D=D, H=H, W=W, C=C,
+            neuron=ctx.cc, apply_neuron=1 if ctx.apply_neuron else 0, stream=_stream()))
+        return gx, None, None
+
+
+def lif_merge(x, cfg: NeuronCfg, apply_neuron=True):
+    return _LifMergeFn.apply(x, cfg, apply_neuron)
+
+
+# ---------------------------------------------------------------------------------------------
+# K5: QK token-gate attention core
+# ---------------------------------------------------------------------------------------------
+class _QKGateFn(torch.autograd.Function):
+    """g = sn_k(bn_k(k_pre)+pos) * sn2_q(sum_d sn_q(bn_q(q_pre))), permuted to proj-input order
+    (reference Spiking_swin_transformer3D.py:671-710).  qk_pre: [wd*M*P, 2C] = [q_pre | k_pre]."""
+
+    @staticmethod
+    def forward(ctx, qk_pre, wq, bq, wk, bk, pos, bn_q, bn_k, cfg, wd, M, P, nH):
+        _need_cuda(qk_pre, pos)
+        qk_pre = qk_pre.contiguous()
+        rows = wd * M * P
+        C = nH * 32
+        assert qk_pre.shape == (rows, 2 * C)
+        q_pre, k_pre = qk_pre[:, :C], qk_pre[:, C:]
+        qs, qh, qm, qr = _bn_forward_affine(q_pre, rows, C, 2 * C, bn_q)
+        ks, kh, km, kr = _bn_forward_affine(k_pre, rows, C, 2 * C, bn_k)
+        posc = pos.detach().contiguous()
+        gate = torch.empty((rows, C), device=qk_pre.device, dtype=torch.float32)
+        cc = cfg.c()
+        capi.call("sdf_attn_qkgate_fwd", capi.struct(
+            "sdf_attn_qkgate_fwd_args", q_pre=_ptr(q_pre), k_pre=_ptr(k_pre), ld=2 * C, q_scale=_ptr(qs), q_shift=_ptr(qh),
+            k_scale=_ptr(ks), k_shift=_ptr(kh), pos=_ptr(posc), gate=_ptr(gate), wd=wd, M=M, P=P, C=C, nH=nH,
+            neuron=cc, spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()), algo_bytes=12 * rows * C)
+        ctx.save_for_backward(qk_pre, wq, wk, pos, qs, qh, qm, qr, ks, kh, km, kr)
+        ctx.dims, ctx.cc, ctx.tq, ctx.tk = (wd, M, P, C, nH), cc, bn_q.training, bn_k.training
+        return gate
+
+    @staticmethod
+    def backward(ctx, gg):
+        qk_pre, wq, wk, pos, qs, qh, qm, qr, ks, kh, km, kr = ctx.saved_tensors
+        wd, M, P, C, nH = ctx.dims
+        rows = wd * M * P
+        dev = gg.device
+        gg = gg.contiguous()
+        q_pre, k_pre = qk_pre[:, :C], qk_pre[:, C:]
+        gq = torch.empty((rows, C), device=dev, dtype=torch.float32)
+        gk = torch.empty_like(gq)
+        pq = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
+        pk = torch.empty_like(pq)
+        capi.call("sdf_attn_qkgate_bwd", capi.struct(
+            "sdf_attn_qkgate_bwd_args", q_pre=_ptr(q_pre), k_pre=_ptr(k_pre), ld=2 * C, q_scale=_ptr(qs), q_shift=_ptr(qh),
+            k_scale=_ptr(ks), k_shift=_ptr(kh), pos=_ptr(pos.detach().contiguous()), grad_gate=_ptr(gg), grad_q=_ptr(gq),
+            grad_k=_ptr(gk), bn_partials_q=_ptr(pq), bn_partials_k=_ptr(pk), n_partial_blocks=N_PARTIAL, wd=wd, M=M,
+            P=P, C=C, nH=nH, neuron=ctx.cc, stream=_stream()), algo_bytes=20 * rows * C)
+        gpos = torch.empty(pos.numel(), device=dev, dtype=torch.float32)
+        capi.call("sdf_pos_grad", capi.struct("sdf_pos_grad_args", grad_k=_ptr(gk), grad_pos=_ptr(gpos), wd=wd, M=M,
+                                              PC=P * C, stream=_stream()))
+        # BN backward of both halves, written into one [rows, 2C] buffer for the shared GEMM backward
+        dqk = torch.empty((rows, 2 * C), device=dev, dtype=torch.float32)
+        outs = []
+        for half, (g, u, w, m, r, tr) in enumerate(((gq, q_pre, wq, qm, qr, ctx.tq), (gk, k_pre, wk, km, kr, ctx.tk))):
+            gw = torch.empty(C, device=dev, dtype=torch.float32)
+            gb = torch.empty_like(gw)
+            coef = torch.empty((3, C), device=dev, dtype=torch.float32)
+            capi.call("sdf_bn_bwd_finalize", capi.struct(
+                "sdf_bn_bwd_finalize_args", partials=_ptr(pq if half == 0 else pk), n_partial_blocks=N_PARTIAL,
+                count=rows, C=C, weight=_ptr(w), mean=_ptr(m), rstd=_ptr(r), grad_weight=_ptr(gw), grad_bias=_ptr(gb),
+                coef=_ptr(coef), training=1 if tr else 0, stream=_stream()))
+            capi.call("sdf_bn_bwd_apply", capi.struct(
+                "sdf_bn_bwd_apply_args", dy=_ptr(g), u=_ptr(u), ld_u=2 * C, du=_ptr(dqk[:, half * C:]), ld_du=2 * C,
+                coef=_ptr(coef), rows=rows, C=C, stream=_stream()))
+            outs += [gw, gb]
+        return (dqk, outs[0], outs[1], outs[2], outs[3], gpos.view(pos.shape), None, None, None, None, None, None, None)
+
+
+def qkgate(qk_pre, bn_q_module, bn_k_module, pos, cfg: NeuronCfg, wd, M, P, nH):
+    bq, bk = BNParams(bn_q_module), BNParams(bn_k_module)
+    return _QKGateFn.apply(qk_pre, bq.weight, bq.bias, bk.weight, bk.bias, pos, bq, bk, cfg, wd, M, P, nH)
+
+
+def qkgate_debug(q_pre, k_pre, q_scale, q_shift, k_scale, k_shift, pos, cfg, wd, M, P, nH):
+    """forward only, returning (gate, q membrane, k membrane, sn2_q membrane) for parity tests."""
+    rows, C = wd * M * P, nH * 32
+    dev = q_pre.device
+    gate = torch.empty((rows, C), device=dev, dtype=torch.float32)
+    qh = torch.empty_like(gate)
+    kh = torch.empty_like(gate)
+    ah = torch.empty((rows, nH), device=dev, dtype=torch.float32)
+    capi.call("sdf_attn_qkgate_fwd", capi.struct(
+        "sdf_attn_qkgate_fwd_args", q_pre=_ptr(q_pre), k_pre=_ptr(k_pre), ld=q_pre.stride(0), q_scale=_ptr(q_scale),
+        q_shift=_ptr(q_shift), k_scale=_ptr(k_scale), k_shift=_ptr(k_shift), pos=_ptr(pos.contiguous()), gate=_ptr(gate),
+        q_h=_ptr(qh), k_h=_ptr(kh), a_h=_ptr(ah), wd=wd, M=M, P=P, C=C, nH=nH, neuron=cfg.c(),
+        spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()))
+    return gate, qh, kh, ah

@@ -1,0 +1,135 @@
+"""CPU tests of the host side: C-ABI library loads and exports what include/sdf_b200.h declares,
+ctypes layouts match the C compiler's, argument validation fails loudly, the product has no CPU
+fallback, module surface / state_dict layout match the reference contract."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+from oracle import synth
+
+
+def test_library_exports_every_declared_symbol():
+    from sdformerflow_b200 import capi
+    L = capi.lib()
+    names = capi.declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), n
+    assert capi.version() == 1
+    assert L.sdf_last_error() is not None
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc not available")
+def test_ctypes_layouts_match_c(tmp_path):
+    from sdformerflow_b200 import capi
+    st, _ = capi.parse_header()
+    src = f'#include "{capi.HEADER}"\n#include <stdio.h>\n#include <stddef.h>\nint main(){{\n'
+    for k, v in st.items():
+        src += f'printf("{k} %zu", sizeof({k}));\n'
+        for f, _t in v["fields"]:
+            src += f'printf(" %zu", offsetof({k},{f}));\n'
+        src += 'printf("\\n");\n'
+    src += "return 0;}\n"
+    c = tmp_path / "sz.c"
+    c.write_text(src)
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", str(c), "-o", str(exe)])
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        parts = line.split()
+        cls = st[parts[0]]["ctype"]
+        mine = [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f, _ in st[parts[0]]["fields"]]
+        assert mine == list(map(int, parts[1:])), parts[0]
+
+
+def test_argument_validation_fails_loudly():
+    from sdformerflow_b200 import capi
+    with pytest.raises(RuntimeError, match="null argument"):
+        capi.call("sdf_lif_fwd", capi.struct("sdf_lif_fwd_args"))
+    with pytest.raises(RuntimeError, match="shift must be in"):
+        capi.call("sdf_window_index", capi.struct("sdf_window_index_args", win2x=16,
+                                                  g=dict(B=1, D=2, H=4, W=4, wd=2, wh=2, ww=2, sd=2, sh=0, sw=0)))
+    g = capi.struct("sdf_window_geom", B=2, D=5, H=16, W=16, wd=2, wh=8, ww=8, sd=1, sh=4, sw=4)
+    assert capi.lib().sdf_window_rows(ctypes.byref(g)) == 2 * 6 * 16 * 16
+
+
+def test_no_cpu_fallback():
+    from sdformerflow_b200 import ops, capi
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.neuron(torch.zeros(2, 8), ops.NeuronCfg())
+    from helpers import build_product
+    mc, sc = synth.small_config("lif")
+    model = build_product(mc, sc, "cpu")
+    with pytest.raises(RuntimeError):
+        model(synth.synth_voxels(1, 10, 96, 128))
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sdformerflow_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, os.path.join(dp, f)
+
+
+@pytest.mark.parametrize("nt,n_entries", [("lif", 501), ("psn", 711), ("plif", 606)])
+def test_state_dict_layout_en4(nt, n_entries):
+    """Appendix D of SURVEY.md: entry counts and key shapes of MS_SpikingformerFlowNet_en4."""
+    from oracle import reference_loader as rl
+    from helpers import product_template_sd
+    mc, sc = rl.default_config(nt, input_size=(288, 384))
+    sd = product_template_sd(mc, sc)
+    assert len(sd) == n_entries
+    p = "sttmultires_unet.encoders.swin3d."
+    assert tuple(sd[p + "patch_embed.head.conv.0.weight"].shape) == (48, 2, 3, 3)
+    assert tuple(sd[p + "layers.0.swin_blocks.0.attn.positional_encoding"].shape) == (1, 3, 162, 32)
+    assert tuple(sd[p + "layers.2.swin_blocks.5.mlp.fc1.weight"].shape) == (1536, 384)
+    assert tuple(sd[p + "layers.1.downsample.reduction.weight"].shape) == (384, 768)
+    assert p + "layers.3.downsample.reduction.weight" not in sd
+    assert tuple(sd["sttmultires_unet.preds.3.conv.0.bias"].shape) == (2,)
+    if nt == "psn":
+        assert tuple(sd[p + "layers.0.swin_blocks.0.attn.sn_q.spiking_neuron.weight"].shape) == (2, 2)
+        assert tuple(sd[p + "layers.0.swin_blocks.0.mlp.sn1.spiking_neuron.bias"].shape) == (10, 1)
+    n_params = sum(v.numel() for k, v in sd.items()
+                   if not any(s in k for s in ("running_", "num_batches", "relative_position_index")))
+    assert n_params == {"lif": 54913928, "psn": 54919238}.get(nt, n_params)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("nt", ["lif", "psn"])
+def test_state_dict_keys_equal_reference(nt):
+    from oracle import reference_loader as rl
+    from helpers import product_template_sd
+    mc, sc = rl.default_config(nt, input_size=(288, 384))
+    ours = product_template_sd(mc, sc)
+    ref = rl.build_reference_model(mc, sc).state_dict()
+    assert list(ours.keys()) == list(ref.keys())
+    for k in ref:
+        assert ours[k].shape == ref[k].shape and ours[k].dtype == ref[k].dtype, k
+
+
+def test_spikingjelly_protocol():
+    from sdformerflow_b200.sj import functional, neuron
+    from helpers import build_product
+    mc, sc = synth.small_config("lif")
+    model = build_product(mc, sc, "cpu")
+    functional.reset_net(model)
+    functional.set_step_mode(model, "m")
+    functional.set_backend(model, "cupy", neuron.LIFNode)   # accepted no-op, as in the reference scripts
+    lifs = [m for m in model.modules() if isinstance(m, neuron.LIFNode)]
+    assert lifs and all(m.step_mode == "m" and m.backend == "cupy" for m in lifs)
+    assert not any("spiking_neuron.v" in k for k in model.state_dict())
+
+
+def test_window_geometry_host_math():
+    from sdformerflow_b200 import ops
+    g = ops.WindowGeom(8, 10, 120, 160, (2, 9, 9), (1, 4, 4))
+    assert (g.Dp, g.Hp, g.Wp, g.nW, g.N, g.M) == (10, 126, 162, 1260, 162, 8 * 1260)
+    g = ops.WindowGeom(1, 10, 9, 12, (2, 9, 9), (1, 4, 4))      # 288x384 stage 4: shift_h clamps to 0
+    assert g.window == (2, 9, 9) and g.shift == (1, 0, 4) and g.nW == 5 * 1 * 2
+    g = ops.WindowGeom(1, 5, 8, 8, (2, 8, 8), (1, 4, 4))        # MDR stage 4
+    assert g.shift == (1, 0, 0) and g.Dp == 6

@@ -1,0 +1,112 @@
+"""Kernel micro-bench sweep (BASELINE.json configs[4] / SURVEY.md §8d cfg5): LIF kernel T in {5,10,20}
+on [T, N] fp32 with N = 8*120*160*384 (cfg2 stage-1 mlp.sn2), BN stats, QK-gate, window kernels.
+Prints one JSON line per kernel: achieved GB/s (algorithmic bytes / CUDA-event time) vs the measured
+HBM peak of MEASURED_PEAKS.json.  Inputs are far larger than L2 (126 MB)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sdformerflow_b200 import ops, capi  # noqa: E402
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, nbytes, ms, **extra):
+    pk, how = peak_gbs()
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "algo_GB": round(nbytes / 1e9, 3), "GBps": round(gbs, 1),
+                      "frac_of_hbm_peak": round(gbs / pk, 3), "peak": pk, "peak_kind": how, **extra}), flush=True)
+
+
+def main():
+    dev = "cuda"
+    N = 8 * 120 * 160 * 384
+    cfg = ops.NeuronCfg(kind=capi.SDF_NEURON_LIF, v_th=0.1, v_reset=None, tau=2.0, detach_reset=True)
+    for T in (5, 10, 20):
+        x = torch.randn(T, N, device=dev) * 0.1 + 0.03
+        lay = ops.seq_layout(x.shape, 0)
+        for dt, nm, ob in ((capi.SDF_SPIKE_U8, "u8", 1), (capi.SDF_SPIKE_F32, "f32", 4)):
+            ms = timeit(lambda: ops._lif_fwd_raw(x, lay, cfg.c(), dt))
+            report(f"lif_fwd T={T} out={nm}", T * N * (4 + ob), ms, T=T, N=N)
+        C = 384
+        scale, shift = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1
+        ms = timeit(lambda: ops._lif_fwd_raw(x, lay, cfg.c(), capi.SDF_SPIKE_U8, scale, shift, C, 1))
+        report(f"lif_fwd+bn T={T} out=u8", T * N * 5, ms, T=T, N=N)
+        if T <= 10:
+            gs = torch.randn(T, N, device=dev)
+            gx = torch.empty_like(x)
+            part = torch.empty(ops.N_PARTIAL, 2, C, device=dev)
+
+            def bwd():
+                capi.call("sdf_lif_bwd", capi.struct(
+                    "sdf_lif_bwd_args", u=x.data_ptr(), grad_spike=gs.data_ptr(), grad_x=gx.data_ptr(),
+                    scale=scale.data_ptr(), shift=shift.data_ptr(), bn_partials=part.data_ptr(),
+                    n_partial_blocks=ops.N_PARTIAL, C=C, hw=1, lay=lay, neuron=cfg.c(),
+                    stream=torch.cuda.current_stream().cuda_stream))
+            ms = timeit(bwd)
+            report(f"lif_bwd+bn T={T}", T * N * 12, ms, T=T, N=N)
+            del gs, gx
+        del x
+        torch.cuda.empty_cache()
+    # time-strided (B, D, H, W, C) layout, the MLP sn1 site of cfg2 stage 1
+    x = torch.randn(8, 10, 120, 160, 96, device=dev) * 0.1
+    lay = ops.seq_layout(x.shape, 1)
+    ms = timeit(lambda: ops._lif_fwd_raw(x, lay, cfg.c(), capi.SDF_SPIKE_F32))
+    report("lif_fwd (B,D,H,W,C) time-strided out=f32", x.numel() * 8, ms)
+    # BN stats
+    rows, C = 8 * 10 * 120 * 160, 384
+    u = torch.randn(rows, C, device=dev)
+    part = torch.empty(ops.N_PARTIAL, 2, C, device=dev)
+    ms = timeit(lambda: capi.call("sdf_bn_stats", capi.struct(
+        "sdf_bn_stats_args", x=u.data_ptr(), rows=rows, C=C, ld=C, partials=part.data_ptr(), n_partial_blocks=ops.N_PARTIAL,
+        stream=torch.cuda.current_stream().cuda_stream)))
+    report("bn_stats rows x 384", rows * C * 4, ms)
+    del u
+    # window LIF gather + QK-gate + scatter at cfg2 stage 1 (B=8, 120x160, C=96, window (2,9,9), shifted)
+    B, D, H, W, C, nH = 8, 10, 120, 160, 96, 3
+    geom = ops.WindowGeom.get(B, D, H, W, (2, 9, 9), (1, 4, 4), dev)
+    x = torch.randn(B, D, H, W, C, device=dev) * 0.2
+    ms = timeit(lambda: ops.lif_window_debug(x, geom, cfg)[0])
+    report("lif_window_fwd (with h_seq)", x.numel() * 4 + geom.rows * C * 8, ms)
+    qk = torch.randn(geom.rows, 2 * C, device=dev)
+    sc, sh = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    pos = torch.randn(1, nH, geom.N, 32, device=dev) * 0.1
+    gate = torch.empty(geom.rows, C, device=dev)
+
+    def qkf():
+        capi.call("sdf_attn_qkgate_fwd", capi.struct(
+            "sdf_attn_qkgate_fwd_args", q_pre=qk.data_ptr(), k_pre=qk[:, C:].data_ptr(), ld=2 * C, q_scale=sc.data_ptr(),
+            q_shift=sh.data_ptr(), k_scale=sc.data_ptr(), k_shift=sh.data_ptr(), pos=pos.data_ptr(), gate=gate.data_ptr(),
+            wd=2, M=geom.M, P=geom.P, C=C, nH=nH, neuron=cfg.c(), spike_dtype=capi.SDF_SPIKE_F32,
+            stream=torch.cuda.current_stream().cuda_stream))
+    ms = timeit(qkf)
+    report("attn_qkgate_fwd", geom.rows * C * 12, ms, rows=geom.rows)
+    y = torch.randn(geom.rows, C, device=dev)
+    ms = timeit(lambda: ops.window_scatter(y, geom, res=x))
+    report("window_scatter+residual", geom.rows * C * 4 + x.numel() * 8, ms)
+
+
+if __name__ == "__main__":
+    main()
