@@ -28,7 +28,8 @@ def synth_tensor(key, like, seed=0):
         return torch.randn(shape, generator=g) * 0.1
     if key.endswith("running_var"):
         return torch.rand(shape, generator=g) * 0.5 + 0.75
-    if "norm" in key.split(".")[-2] or ".bn" in key or "_bn" in key:
+    parts = key.split(".")
+    if (len(parts) >= 2 and "norm" in parts[-2]) or ".bn" in key or "_bn" in key:
         if key.endswith("weight") and len(shape) == 1:
             return torch.rand(shape, generator=g) * 0.5 + 0.75
         if key.endswith("bias") and len(shape) == 1:

@@ -181,7 +181,7 @@ def test_bn_residual_fwd_bwd(train):
     go = torch.randn(2, 10, 5, 4, 192, generator=g)
     bn_ref = _bn(192, 2, train)
     bn_gpu = copy.deepcopy(bn_ref).to(DEV)
-    ref = bn_ref(u.permute(0, 4, 1, 2, 3)).permute(0, 2, 3, 4, 1) + r
+    ref = bn_ref(u.permute(0, 4, 1, 2, 3).reshape(2, 192, 50, 4)).view(2, 192, 10, 5, 4).permute(0, 2, 3, 4, 1) + r
     ref.backward(go)
     ug, rg = (t.detach().to(DEV).requires_grad_(True) for t in (u, r))
     out = ops.bn_residual(ug, bn_gpu, rg)
