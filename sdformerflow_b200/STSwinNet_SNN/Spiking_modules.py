@@ -151,6 +151,7 @@ class MS_SpikingConvEncoderLayer(nn.Module):
         if not first_layer:
             self.sn = Spiking_neuron(**spiking_kwargs)
         self.conv = _conv(in_channels, out_channels, kernel_size, stride, padding, self.norm is None)
+        self.conv[0].spike_input = not first_layer
         if self.norm is not None:
             self.norm_layer = SpikingNormLayer(out_channels, spiking_kwargs["num_steps"], self.norm,
                                                v_th=spiking_kwargs["v_th"])
@@ -193,6 +194,7 @@ class MS_SpikingTransposeDecoderLayer(SpikingTransposeDecoderLayer):
     """neuron -> deconv -> norm (reference :461-474)."""
 
     def forward(self, x):
+        self.deconv[0].spike_input = True
         x = self.deconv(self.sn(x))
         return self.norm_layer(x) if self.norm is not None else x
 
@@ -217,6 +219,7 @@ class MS_SpikingPredLayer(nn.Module):
         self.norm = None
         self.sn = Spiking_neuron(**spiking_kwargs)
         self.conv = _conv(in_channels, out_channels, kernel_size, stride, kernel_size // 2, True)
+        self.conv[0].spike_input = True
 
     def forward(self, x):
         return self.conv(self.sn(x))
@@ -239,8 +242,8 @@ class SpikingPEDLayer(nn.Module):
 
     def forward(self, x):
         T, B, C, H, W = x.shape
-        x_res = self.conv_res(x.flatten(0, 1))
-        y = self.conv(self.sn(x).flatten(0, 1))
+        x_res = ops.spike_conv2d(x.flatten(0, 1), self.conv_res.weight, self.conv_res.bias, 2, 0, exact_input=False)
+        y = ops.spike_conv2d(self.sn(x).flatten(0, 1), self.conv.weight, self.conv.bias, self.conv.stride, 1)
         if self.norm is not None:
             y = self.norm_layer(y)
         return (y + x_res).reshape(T, B, -1, self.patch[0], self.patch[1]).contiguous()
@@ -280,6 +283,7 @@ class SEWResBlock(_ResBlockBase):
     """conv-norm-neuron x2, spike-element-wise shortcut (reference :827-878)."""
 
     def forward(self, x):
+        self.conv1[0].spike_input = self.conv2[0].spike_input = True   # spikes (+ integer SEW sums)
         identity = x
         x = self.conv1(x)
         if self.norm is not None:
@@ -294,6 +298,7 @@ class MS_ResBlock(_ResBlockBase):
     """neuron-conv-norm x2, membrane shortcut (reference :880-933)."""
 
     def forward(self, x):
+        self.conv1[0].spike_input = self.conv2[0].spike_input = True
         identity = x
         x = self.conv1(self.sn1(x))
         if self.norm is not None:

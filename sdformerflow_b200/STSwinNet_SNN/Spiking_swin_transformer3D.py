@@ -108,9 +108,9 @@ class Spiking_Mlp(nn.Module):
 
     def forward(self, x, time_dim=0):
         """x: [T, B, H, W, C] (time_dim 0, the reference's call) or (B, D, H, W, C) (time_dim 1)."""
-        h = F.linear(x, self.fc1.weight)
+        h = ops.spike_linear(x, self.fc1.weight)           # SEW stream: spikes + residual adds = small integers
         s = self._bn_sn(h, self.bn1, self.sn1, time_dim)
-        h = F.linear(s, self.fc2.weight)
+        h = ops.spike_linear(s, self.fc2.weight)
         return self._bn_sn(h, self.bn2, self.sn2, time_dim)
 
     def fused(self, x):
@@ -123,9 +123,9 @@ class MS_Spiking_Mlp(Spiking_Mlp):
 
     def forward(self, x, time_dim=0, res=None):
         s = self.sn1(x, time_dim)
-        h = F.linear(s, self.fc1.weight)
+        h = ops.spike_linear(s, self.fc1.weight)
         s = self._bn_sn(h, self.bn1, self.sn2, time_dim)
-        h = F.linear(s, self.fc2.weight)
+        h = ops.spike_linear(s, self.fc2.weight)
         return ops.bn_residual(h, _bn_of(self.bn2), res)
 
     def fused(self, x):
@@ -187,24 +187,24 @@ class Spiking_QK_WindowAttention3D(_WindowAttentionBase):
         for sn in (self.sn_q, self.sn_k, self.sn2_q):
             sn.mark()
         wqk = torch.cat([self.linear_q.weight, self.linear_k.weight], 0)
-        qk_pre = F.linear(s, wqk)                                               # [rows, 2C], one GEMM
+        qk_pre = ops.spike_linear(s, wqk)                                       # [rows, 2C], one GEMM
         g = ops.qkgate(qk_pre, _bn_of(self.bn_q), _bn_of(self.bn_k), self.positional_encoding, self.sn_q.cfg(),
                        wd, M, P, nH)
-        return g, F.linear(g, self.proj.weight, self.proj.bias)
+        return g, ops.spike_linear(g, self.proj.weight, self.proj.bias)
 
     def _core_psn(self, s, wd, M, P):
         """PSN variant: the generic K1p kernel per neuron site + library elementwise glue."""
         C, nH = self.dim, self.num_heads
         s5 = s.view(wd, M, P, C)
-        q = ops.bn_neuron(F.linear(s5, self.linear_q.weight), _bn_of(self.bn_q), self.sn_q.cfg(), 0,
+        q = ops.bn_neuron(ops.spike_linear(s5, self.linear_q.weight), _bn_of(self.bn_q), self.sn_q.cfg(), 0,
                           psn=self.sn_q.spiking_neuron)
-        k = ops.bn_residual(F.linear(s5, self.linear_k.weight), _bn_of(self.bn_k),
+        k = ops.bn_residual(ops.spike_linear(s5, self.linear_k.weight), _bn_of(self.bn_k),
                             self.positional_encoding.reshape(wd, 1, P, C).expand(wd, M, P, C))
         k = self.sn_k(k)
         att = self.sn2_q(q.reshape(wd, M, nH, -1, 32).sum(dim=-1, keepdim=True))
         g = k.reshape(M, nH, -1, 32) * att.reshape(M, nH, -1, 1)
         g = g.reshape(M, nH, wd, P, 32).permute(2, 0, 3, 1, 4).reshape(wd * M * P, C)
-        return g, F.linear(g, self.proj.weight, self.proj.bias)
+        return g, ops.spike_linear(g, self.proj.weight, self.proj.bias)
 
     def forward(self, x, mask=None):
         """Reference call: x = x_windows (wd, B_, wh, ww, C) -> (x (B_, N, C), attention-score spikes)."""
@@ -269,7 +269,7 @@ class Spiking_BN_WindowAttention3D(_WindowAttentionBase):
         for name in ("q", "k", "v"):
             sn = getattr(self, f"sn_{name}")
             sn.mark()
-            h = F.linear(xin, getattr(self, f"linear_{name}").weight)
+            h = ops.spike_linear(xin, getattr(self, f"linear_{name}").weight)
             outs.append(ops.bn_neuron(h, _bn_of(getattr(self, f"bn_{name}")), sn.cfg(), 0,
                                       psn=sn.spiking_neuron if sn.is_psn else None))
         return outs
@@ -281,7 +281,7 @@ class Spiking_BN_WindowAttention3D(_WindowAttentionBase):
             raise NotImplementedError("relative position bias needs an unclamped window (stage >= window size)")
         o, attn = ops.qktv_attention(q, k, v, self.relative_position_bias_table, region, M, self.num_heads, nW,
                                      ws, float(self.scale), want_attn)
-        return F.linear(o, self.proj.weight, self.proj.bias), attn
+        return ops.spike_linear(o, self.proj.weight, self.proj.bias, exact_input=False), attn   # O is real-valued
 
     def forward(self, x, mask=None, region=None, nW=1):
         """Reference call on x_windows (wd, B_, wh, ww, C).  The additive mask of the reference is
@@ -396,10 +396,10 @@ class SpikingPatchMerging(nn.Module):
             else:
                 self.sn.mark()
                 s = ops.lif_merge(x, self.sn.cfg())
-            return ops.bn_residual(F.linear(s, self.reduction.weight), _bn_of(self.norm))
+            return ops.bn_residual(ops.spike_linear(s, self.reduction.weight), _bn_of(self.norm))
         g = ops.lif_merge(x, self.sn.cfg(), apply_neuron=False)
         self.sn.mark()
-        return ops.bn_neuron(F.linear(g, self.reduction.weight), _bn_of(self.norm), self.sn.cfg(), 1,
+        return ops.bn_neuron(ops.spike_linear(g, self.reduction.weight), _bn_of(self.norm), self.sn.cfg(), 1,
                              psn=self.sn.spiking_neuron if self.sn.is_psn else None)
 
 

@@ -349,6 +349,116 @@ def bn_residual(u, bn_module, res=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# fp32-faithful spike GEMM / convolution on tensor cores (library calls)
+# ---------------------------------------------------------------------------------------------
+# A spike operand is exactly representable in TF32 (so is a small-integer SEW residual sum), hence
+# every product spike * w_tf32 is exact and accumulates in fp32.  Splitting W = hi + lo with both
+# parts TF32-representable (|W - hi - lo| <= 2^-22 |W|) turns one fp32 GEMM/conv on the SIMT pipe
+# into two TF32 tensor-core calls with fp32-grade results.  Backward runs single-pass TF32 (the
+# reference trains under fp16 autocast, train_flow_parallel_supervised_SNN.py:248, so this is at
+# least as precise).  GEMM_MODE = "fp32" restores plain SIMT fp32 everywhere.
+GEMM_MODE = "tf32x2"
+
+
+def split_tf32(w):
+    """w (fp32) -> hi, lo, both exactly representable in TF32, hi + lo == w up to 2^-22 |w|."""
+    wi = w.contiguous().view(torch.int32)
+    hi = ((wi + 0x1000) & ~0x1FFF).view(torch.float32)      # round-to-nearest on the 13 dropped bits
+    lo = w - hi                                              # exact in fp32
+    lo = ((lo.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, lo
+
+
+class _tf32:
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = self.on
+        torch.backends.cudnn.allow_tf32 = self.on
+
+    def __exit__(self, *a):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.prev
+
+
+class _SpikeLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, weight, bias):
+        s2 = s.reshape(-1, s.shape[-1])
+        hi, lo = split_tf32(weight.detach())
+        with _tf32(True):
+            y = torch.addmm(bias.detach(), s2, hi.t()) if bias is not None else torch.mm(s2, hi.t())
+            y.addmm_(s2, lo.t())
+        ctx.save_for_backward(s, weight)
+        ctx.has_bias = bias is not None
+        return y.view(*s.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        s, weight = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        s2 = s.reshape(-1, s.shape[-1])
+        gs = gw = gb = None
+        with _tf32(True):
+            if ctx.needs_input_grad[0]:
+                gs = torch.mm(g2, weight).view(s.shape)
+            if ctx.needs_input_grad[1]:
+                gw = torch.mm(g2.t(), s2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gs, gw, gb
+
+
+def spike_linear(s, weight, bias=None, exact_input=True):
+    """F.linear(s, weight, bias) for a spike (or small-integer) operand s with fp32-grade results on
+    tensor cores; exact_input=False (real-valued s) keeps the plain fp32 GEMM."""
+    if GEMM_MODE == "fp32" or not exact_input:
+        with _tf32(False):
+            return torch.nn.functional.linear(s, weight, bias)
+    return _SpikeLinearFn.apply(s, weight, bias)
+
+
+class _SpikeConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, transposed, output_padding):
+        conv = torch.nn.functional.conv_transpose2d if transposed else torch.nn.functional.conv2d
+        kw = dict(stride=stride, padding=padding)
+        if transposed:
+            kw["output_padding"] = output_padding
+        hi, lo = split_tf32(weight.detach())
+        with _tf32(True):
+            y = conv(x, hi, None if bias is None else bias.detach(), **kw)
+            y += conv(x, lo, None, **kw)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding, transposed, output_padding, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        stride, padding, transposed, output_padding, has_bias = ctx.cfg
+        two = lambda v: [v, v] if isinstance(v, int) else list(v)  # noqa: E731
+        with _tf32(True):
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                g.contiguous(), x, weight, [weight.shape[1] if transposed else weight.shape[0]] if has_bias else None,
+                two(stride), two(padding), [1, 1], transposed, two(output_padding), 1,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]])
+        return gx, gw, gb, None, None, None, None
+
+
+def spike_conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_padding=0, exact_input=True):
+    """conv2d / conv_transpose2d on a spike operand, fp32-grade on tensor cores (see split_tf32)."""
+    if GEMM_MODE == "fp32" or not exact_input:
+        with _tf32(False):
+            if transposed:
+                return torch.nn.functional.conv_transpose2d(x, weight, bias, stride=stride, padding=padding,
+                                                            output_padding=output_padding)
+            return torch.nn.functional.conv2d(x, weight, bias, stride=stride, padding=padding)
+    return _SpikeConvFn.apply(x, weight, bias, stride, padding, transposed, output_padding)
+
+
+# ---------------------------------------------------------------------------------------------
 # window index algebra
 # ---------------------------------------------------------------------------------------------
 class WindowGeom:

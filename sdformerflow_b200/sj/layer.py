@@ -24,22 +24,47 @@ class _Seq5D(base.StepModule):
         return functional.seq_to_ann_forward(x, op)
 
 
+def _plain(conv):
+    return (conv.groups == 1 and tuple(conv.dilation) == (1, 1) and conv.padding_mode == "zeros"
+            and not isinstance(conv.padding, str))
+
+
 class Conv2d(nn.Conv2d, _Seq5D):
+    """`spike_input = True` (set by the module that feeds it a neuron output) routes the call through
+    ops.spike_conv2d: fp32-grade result from two TF32 tensor-core convolutions (exact for {0,1} inputs)."""
+    spike_input = False
+
     def __init__(self, *a, step_mode="s", **k):
         super().__init__(*a, **k)
         self.step_mode = step_mode
 
+    def _op(self, x):
+        from .. import ops
+        if self.spike_input and _plain(self):
+            return ops.spike_conv2d(x, self.weight, self.bias, self.stride, self.padding)
+        return ops.spike_conv2d(x, self.weight, self.bias, self.stride, self.padding, exact_input=False) \
+            if _plain(self) else nn.Conv2d.forward(self, x)
+
     def forward(self, x):
-        return self._fwd(x, super().forward)
+        return self._fwd(x, self._op)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d, _Seq5D):
+    spike_input = False
+
     def __init__(self, *a, step_mode="s", **k):
         super().__init__(*a, **k)
         self.step_mode = step_mode
 
+    def _op(self, x):
+        from .. import ops
+        if _plain(self):
+            return ops.spike_conv2d(x, self.weight, self.bias, self.stride, self.padding, True, self.output_padding,
+                                    exact_input=self.spike_input)
+        return nn.ConvTranspose2d.forward(self, x)
+
     def forward(self, x):
-        return self._fwd(x, super().forward)
+        return self._fwd(x, self._op)
 
 
 class BatchNorm2d(nn.BatchNorm2d, _Seq5D):

@@ -352,3 +352,51 @@ def test_qk_attention_module_fwd_bwd(train, wd, wh, ww, nH, M):
     for name in ("linear_q.weight", "proj.weight", "positional_encoding", "bn_k.norm_layer.weight"):
         a, b = dict(m.named_parameters())[name].grad.cpu(), P["a." + name].grad
         assert ((a - b).abs() > 2e-2 * b.abs().max()).float().mean().item() <= 1e-2, name
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32-faithful spike GEMM / conv on tensor cores (TF32 x 2 weight split)
+# ---------------------------------------------------------------------------------------------
+def test_split_tf32_is_exactly_representable_and_tight():
+    ops, capi = _ops()
+    w = torch.randn(4096, generator=torch.Generator().manual_seed(0)).to(DEV) * 0.1
+    hi, lo = ops.split_tf32(w)
+    for t in (hi, lo):
+        assert int((t.view(torch.int32) & 0x1FFF).abs().max()) == 0          # 13 low mantissa bits clear
+    assert ((w - hi - lo).abs() <= w.abs() * 2.0 ** -21).all()
+
+
+@pytest.mark.parametrize("mode", ["tf32x2", "fp32"])
+def test_spike_linear_and_conv_are_fp32_grade(mode):
+    ops, capi = _ops()
+    old = ops.GEMM_MODE
+    ops.GEMM_MODE = mode
+    try:
+        g = torch.Generator().manual_seed(1)
+        s = (torch.rand(4000, 384, generator=g) < 0.35).float().to(DEV)
+        W = (torch.randn(1536, 384, generator=g) * 0.07).to(DEV)
+        b = torch.randn(1536, generator=g).to(DEV)
+        ref = (s.double() @ W.double().t() + b.double())
+        y = ops.spike_linear(s, W, b)
+        assert ((y.double() - ref).abs().max() / ref.abs().max()).item() <= 2e-6
+        x = (torch.rand(6, 96, 36, 48, generator=g) < 0.3).float().to(DEV)
+        Wc = (torch.randn(96, 96, 3, 3, generator=g) * 0.05).to(DEV)
+        refc = F.conv2d(x.double(), Wc.double(), None, stride=2, padding=1)
+        yc = ops.spike_conv2d(x, Wc, None, 2, 1)
+        assert ((yc.double() - refc).abs().max() / refc.abs().max()).item() <= 2e-6
+        Wt = (torch.randn(96, 48, 3, 3, generator=g) * 0.05).to(DEV)
+        reft = F.conv_transpose2d(x.double(), Wt.double(), None, stride=2, padding=1, output_padding=1)
+        yt = ops.spike_conv2d(x, Wt, None, 2, 1, True, 1)
+        assert ((yt.double() - reft).abs().max() / reft.abs().max()).item() <= 2e-6
+        # backward (single-pass TF32): gradients within 2e-3 of fp64
+        s.requires_grad_(True)
+        Wp = W.clone().requires_grad_(True)
+        go = torch.randn(4000, 1536, generator=g).to(DEV)
+        ops.spike_linear(s, Wp, b).backward(go)
+        gs_ref = go.double() @ W.double()
+        gw_ref = go.double().t() @ s.detach().double()
+        tol = 3e-3 if mode == "tf32x2" else 1e-5
+        assert ((s.grad.double() - gs_ref).abs().max() / gs_ref.abs().max()).item() <= tol
+        assert ((Wp.grad.double() - gw_ref).abs().max() / gw_ref.abs().max()).item() <= tol
+    finally:
+        ops.GEMM_MODE = old

@@ -85,8 +85,30 @@ def _teacher_forced(model, mc, sc, x, train):
         return out.cpu()
 
     with torch.no_grad():
-        pe = port.patch_embed_ms_ped(x, P, f"{u}.encoders.swin3d.patch_embed", spec, mode(), cfg.num_bins)
-        yield "patch_embed", run(swin.patch_embed, x), pe
+        # patch embedding, layer by layer (it is five neuron layers deep on its own)
+        pp = f"{u}.encoders.swin3d.patch_embed"
+        pem = swin.patch_embed
+        t = port.regroup_events(x, cfg.num_bins, spec.num_steps)
+        ref = port.conv_seq(t, P[pp + ".head.conv.0.weight"], None, 1, 1)
+        ref = port.batchnorm_seq(ref, P, pp + ".head.norm_layer.norm_layer", mode())
+        ref = port.spiking_neuron(ref, P, pp + ".head.sn", spec)
+        yield "patch_embed.head", run(pem.head, t), ref
+        t = ref
+        ref = port.conv_seq(t, P[pp + ".conv.conv.0.weight"], None, 2, 1)
+        ref = port.batchnorm_seq(ref, P, pp + ".conv.norm_layer.norm_layer", mode())
+        yield "patch_embed.conv", run(pem.conv, t), ref
+        t = ref
+        for i in range(2):
+            ref = port.ms_resblock(t, P, f"{pp}.residual_encoding.resblocks.{i}", spec, mode())
+            yield f"patch_embed.resblocks.{i}", run(pem.residual_encoding.resblocks[i], t), ref
+            t = ref
+        T_, B_, C_, H_, W_ = t.shape
+        x_res = torch.nn.functional.conv2d(t.flatten(0, 1), P[pp + ".proj.conv_res.weight"], None, stride=2, padding=0)
+        y = port.spiking_neuron(t, P, pp + ".proj.sn", spec)
+        y = torch.nn.functional.conv2d(y.flatten(0, 1), P[pp + ".proj.conv.weight"], None, stride=2, padding=1)
+        y = port.batchnorm_4d(y, P, pp + ".proj.norm_layer", mode())
+        pe = (y + x_res).reshape(T_, B_, -1, y.shape[-2], y.shape[-1]).contiguous()
+        yield "patch_embed.proj", run(pem.proj, t), pe
         xs = pe.permute(1, 0, 3, 4, 2).contiguous()
         outs = []
         shift_full = tuple(s // 2 for s in swc.window_size)
@@ -138,7 +160,7 @@ def test_model_teacher_forced_every_module(nt, train):
         bad = _frac_bad(got, ref)
         assert bad <= 5e-3, (name, bad, (got - ref).abs().max().item())
         seen += 1
-    assert seen == 1 + 6 + 2 + 2 + 3 + 3
+    assert seen == 5 + 6 + 2 + 2 + 3 + 3
 
 
 @pytest.mark.parametrize("nt", ["lif", "psn"])
@@ -153,8 +175,12 @@ def test_small_model_eval_end_to_end(golden, nt):
         flows = model(x.to(DEV))["flow"]
     sd = synth.synth_state_dict(model.state_dict(), 0)
     P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-    with torch.no_grad():
-        f64 = port.ms_flownet_forward(x.double(), P64, port_cfg(mc, sc), port_spec(mc), port.BNMode(False))
+    port.KEEP_DTYPE = True
+    try:
+        with torch.no_grad():
+            f64 = port.ms_flownet_forward(x.double(), P64, port_cfg(mc, sc), port_spec(mc), port.BNMode(False))
+    finally:
+        port.KEEP_DTYPE = False
     assert len(flows) == 3
     for a, b, c in zip(flows, g["flows"], f64):
         assert a.shape == b.shape
