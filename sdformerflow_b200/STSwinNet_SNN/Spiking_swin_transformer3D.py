@@ -263,24 +263,19 @@ class Spiking_BN_WindowAttention3D(_WindowAttentionBase):
         self.proj_drop = sj_layer.Dropout(proj_drop)
         self.softmax = nn.Softmax(dim=-1)
 
-    def _qkv(self, xin, wd, M, P):
-        """xin [wd, M, P, C] -> q, k, v spikes [wd, M, P, C]."""
-        outs = []
-        for name in ("q", "k", "v"):
-            sn = getattr(self, f"sn_{name}")
-            sn.mark()
-            h = ops.spike_linear(xin, getattr(self, f"linear_{name}").weight)
-            outs.append(ops.bn_neuron(h, _bn_of(getattr(self, f"bn_{name}")), sn.cfg(), 0,
-                                      psn=sn.spiking_neuron if sn.is_psn else None))
-        return outs
-
     def _attend(self, xin, wd, M, P, region, nW, want_attn=False):
-        q, k, v = self._qkv(xin, wd, M, P)
+        """xin [wd, M, P, C] -> proj output rows [wd*M*P, C] (q,k,v neurons + attention in one fused operator)."""
         ws = self.window_size
         if (wd, P) != (ws[0], ws[1] * ws[2]):
             raise NotImplementedError("relative position bias needs an unclamped window (stage >= window size)")
-        o, attn = ops.qktv_attention(q, k, v, self.relative_position_bias_table, region, M, self.num_heads, nW,
-                                     ws, float(self.scale), want_attn)
+        sns = (self.sn_q, self.sn_k, self.sn_v)
+        for sn in sns:
+            sn.mark()
+        pres = [ops.spike_linear(xin, getattr(self, f"linear_{n}").weight) for n in ("q", "k", "v")]
+        psn = [sn.spiking_neuron for sn in sns] if self.sn_q.is_psn else None
+        o, attn = ops.qktv_attention(pres[0], pres[1], pres[2], _bn_of(self.bn_q), _bn_of(self.bn_k), _bn_of(self.bn_v),
+                                     self.relative_position_bias_table, self.sn_q.cfg(), region, wd, M, P, self.num_heads,
+                                     nW, ws, float(self.scale), psn, want_attn)
         return ops.spike_linear(o, self.proj.weight, self.proj.bias, exact_input=False), attn   # O is real-valued
 
     def forward(self, x, mask=None, region=None, nW=1):

@@ -1,13 +1,478 @@
-// attn_qktv.cu — K3/K4 placeholder translation unit (tcgen05 kernel lands in a later commit).
+// attn_qktv.cu — K3/K4: Q K^T V spiking window attention on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Replaces reference models/STSwinNet_SNN/Spiking_swin_transformer3D.py:320-363 / :438-485
+// (Spiking_BN_WindowAttention3D / SDSA_WindowAttention3D):
+//     attn = (q*scale) @ k^T + relative_position_bias[h'] + mask[w]        (no softmax, :356-358)
+//     x    = (attn @ v).reshape(B_,nH,T,H,W,hd).permute(2,0,3,4,1,5)        (:362-363)
+// on the raw [M*nH, N, 32] reinterpretation of the (wd,M,wh,ww,C) spike buffers (Appendix B.4):
+// the rows of one (window m', pseudo-head h') pair are 32 contiguous bytes each, N*32 B in all.
+//
+// One persistent CTA per SM walks pairs with a fixed pseudo-head.  Per pair:
+//   stage  Q, K (row-major -> UMMA canonical K-major, no swizzle) and V^T into shared memory,
+//          u8 {0,1} -> fp16 (exact);
+//   MMA 1  S = Q K^T           tcgen05.mma kind::f16, M=128, N<=192, K=16 x2, fp32 accum in TMEM
+//                              (S are exact integer counts 0..32);
+//   epi 1  T = scale*S + bias[lin_i - lin_j + off] + (-100)[region_i != region_j], in registers
+//          (tcgen05.ld), split T = hi + lo in fp16 (22 significant bits) and written back IN PLACE
+//          over S (tcgen05.st) as the A operand of the second contraction — the N x N matrix never
+//          leaves the SM;
+//   MMA 2  O += T_hi V + T_lo V   tcgen05.mma kind::f16 with A from TMEM, B = V^T from smem;
+//   epi 2  O rows -> global in the proj-input order of :362-363 (128 B per row).
+// The backward (K4) is three more passes of the same two-contraction structure:
+//   dA = dO V^T  -> dQ = scale*dA K        (+ d(bias table) accumulated in shared memory)
+//   dA^T = V dO^T -> dK = scale*dA^T Q
+//   T^T = (K Q^T ...) -> dV = T^T dO
+// with bf16 operands (gradients need range, not 22 bits).
+//
+// Arithmetic intensity: 4*N^2*32 algorithmic FLOP per pair against 3*N*32 B in and
+// N*128 B out — HBM-bound at N=162, tensor-bound from N~576; bench reports both.
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "sdf_common.cuh"
-using namespace sdf;
-extern "C" int sdf_attn_qktv_fwd(const sdf_attn_qktv_fwd_args* a) {
-  (void)a;
-  set_error("sdf_attn_qktv_fwd: not built yet");
-  return SDF_ERR_UNSUPPORTED;
+
+namespace sdf {
+
+constexpr int kThreads = 256;      // 8 warps: two 128-lane TMEM slots
+constexpr int kKT = 192;           // key tile (TMEM columns of S per slot)
+constexpr int kSlotCols = 256;     // TMEM columns per slot: [0,192) S/T, [192,224) O
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows x 16 B
+// contiguous; SBO = byte distance between 8-row groups, LBO = byte distance between 16-B K chunks.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, format 0 = F16, 1 = BF16
+__device__ __forceinline__ uint32_t make_idesc(int fmt, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- 16-bit operand helpers ---------------------------------------------------------------------
+template <int BF>
+__device__ __forceinline__ uint16_t one16() { return BF ? 0x3F80 : 0x3C00; }
+template <int BF>
+__device__ __forceinline__ uint16_t f2h(float x) {
+  if (BF) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  return __half_as_ushort(__float2half_rn(x));
+}
+template <int BF>
+__device__ __forceinline__ float h2f(uint16_t h) {
+  if (BF) return __uint_as_float((uint32_t)h << 16);
+  return __half2float(__ushort_as_half(h));
+}
+
+// ---- kernel parameters ----------------------------------------------------------------------------
+struct QktvP {
+  const uint8_t* q; const uint8_t* k; const uint8_t* v;
+  const float* bias_table; const uint8_t* region;
+  float* out; int32_t* s_dbg; float* attn_dbg;
+  const float* grad_out; float* grad_q; float* grad_k; float* grad_v; float* grad_table;
+  int64_t M, nH, nW, P;
+  int N, wd, wh, ww, Rpad, n_mt, n_kt, tab;
+  float scale;
+  int has_mask;
+};
+
+// shared-memory carve-up (bytes), all operand arrays 16-bit
+struct SmemPlan {
+  uint32_t a, b, bt, lin, reg, tab, dtab, bars, tmem_slot, total;
+};
+__host__ __device__ inline SmemPlan plan_smem(int Rpad, int tab, bool bwd) {
+  SmemPlan s;
+  uint32_t o = 0;
+  s.a = o; o += (uint32_t)Rpad * 64;          // [4 chunks][Rpad rows][16 B]
+  s.b = o; o += (uint32_t)Rpad * 64;
+  s.bt = o; o += (uint32_t)Rpad * 64;         // [Rpad/8 key chunks][32 dims][16 B]
+  s.lin = o; o += (uint32_t)Rpad * 4;
+  s.reg = o; o += (uint32_t)((Rpad + 15) / 16 * 16);
+  s.tab = o; o += (uint32_t)((tab * 4 + 15) / 16 * 16);
+  s.dtab = o; o += bwd ? (uint32_t)((tab * 4 + 15) / 16 * 16) : 0;
+  s.bars = o; o += 32;
+  s.tmem_slot = o; o += 16;
+  s.total = o;
+  return s;
+}
+
+// plain operand: element (row r, dim d) at chunk (d/8), row r  -> [c][r][16 B]
+__device__ __forceinline__ uint32_t plain_off(int Rpad, int r, int c16) { return (uint32_t)(c16 * Rpad + r) * 16; }
+// transposed operand (rows = 32 dims, K = tokens): element (dim d, token n) -> [n/8][d][ (n%8)*2 ]
+__device__ __forceinline__ uint32_t trans_off(int d, int n) { return (uint32_t)((n >> 3) * 32 + d) * 16 + (n & 7) * 2; }
+
+// stage rows [0, N) of a u8 {0,1} [N, 32] block
+template <int BF>
+__device__ __forceinline__ void stage_plain_u8(uint8_t* smem, uint32_t base, int Rpad, const uint8_t* src, int N) {
+  for (int i = threadIdx.x; i < N * 2; i += kThreads) {       // one 16-byte half-row per item
+    const int r = i >> 1, hf = i & 1;
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * 32 + hf * 16));
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t b = ws[j];
+      o[2 * j] = ((b & 0xFF) ? one16<BF>() : 0) | (((b >> 8) & 0xFF) ? (uint32_t)one16<BF>() << 16 : 0);
+      o[2 * j + 1] = (((b >> 16) & 0xFF) ? one16<BF>() : 0) | (((b >> 24) & 0xFF) ? (uint32_t)one16<BF>() << 16 : 0);
+    }
+    *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+template <int BF>
+__device__ __forceinline__ void stage_trans_u8(uint8_t* smem, uint32_t base, const uint8_t* src, int N) {
+  for (int i = threadIdx.x; i < N * 2; i += kThreads) {
+    const int r = i >> 1, hf = i & 1;
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * 32 + hf * 16));
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t b = (ws[j >> 2] >> ((j & 3) * 8)) & 0xFF;
+      *reinterpret_cast<uint16_t*>(smem + base + trans_off(hf * 16 + j, r)) = b ? one16<BF>() : (uint16_t)0;
+    }
+  }
+}
+// fp32 rows gathered from the proj-input layout: token n of pair (m', h') lives at row (t*M + m')*P + pos, col h'*32
+__device__ __forceinline__ const float* go_row(const QktvP& p, int64_t mwin, int64_t head, int n) {
+  const int64_t t = n / p.P, pos = n - t * p.P;
+  return p.grad_out + ((t * p.M + mwin) * p.P + pos) * (p.nH * 32) + head * 32;
+}
+template <int BF>
+__device__ __forceinline__ void stage_plain_f32(uint8_t* smem, uint32_t base, int Rpad, const QktvP& p, int64_t mwin, int64_t head) {
+  for (int i = threadIdx.x; i < p.N * 4; i += kThreads) {     // 8 floats -> one 16-byte chunk
+    const int r = i >> 2, c = i & 3;
+    const float* src = go_row(p, mwin, head, r) + c * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+    uint4 o;
+    o.x = f2h<BF>(a.x) | ((uint32_t)f2h<BF>(a.y) << 16); o.y = f2h<BF>(a.z) | ((uint32_t)f2h<BF>(a.w) << 16);
+    o.z = f2h<BF>(b.x) | ((uint32_t)f2h<BF>(b.y) << 16); o.w = f2h<BF>(b.z) | ((uint32_t)f2h<BF>(b.w) << 16);
+    *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, c)) = o;
+  }
+}
+template <int BF>
+__device__ __forceinline__ void stage_trans_f32(uint8_t* smem, uint32_t base, const QktvP& p, int64_t mwin, int64_t head) {
+  for (int i = threadIdx.x; i < p.N * 8; i += kThreads) {
+    const int r = i >> 3, c = i & 7;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(go_row(p, mwin, head, r) + c * 4));
+    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 0, r)) = f2h<BF>(a.x);
+    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 1, r)) = f2h<BF>(a.y);
+    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 2, r)) = f2h<BF>(a.z);
+    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 3, r)) = f2h<BF>(a.w);
+  }
+}
+
+// PHASE 0: forward O = T V           A=Q  B=K  Bt=V^T   out -> p.out (permuted rows)
+// PHASE 1: dQ = scale*(dO V^T) K     A=dO B=V  Bt=K^T   out -> grad_q, side effect d(bias table)
+// PHASE 2: dK = scale*(V dO^T) Q     A=V  B=dO Bt=Q^T   out -> grad_k
+// PHASE 3: dV = T^T dO               A=K  B=Q  Bt=dO^T  out -> grad_v      (T^T[j][i]: roles of i, j swapped)
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
+  constexpr int BF = PHASE == 0 ? 0 : 1;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const SmemPlan sp = plan_smem(p.Rpad, p.tab, PHASE == 1);
+  int* lin_s = reinterpret_cast<int*>(smem + sp.lin);
+  uint8_t* reg_s = smem + sp.reg;
+  float* tab_s = reinterpret_cast<float*>(smem + sp.tab);
+  float* dtab_s = reinterpret_cast<float*>(smem + sp.dtab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_slot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, Rpad = p.Rpad;
+  const int64_t head = blockIdx.x % p.nH;      // fixed pseudo-head per CTA (gridDim.x is a multiple of nH)
+
+  // ---- one-time setup ----
+  for (uint32_t i = tid * 16; i < sp.lin; i += kThreads * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  const int A_ = (2 * p.wh - 1) * (2 * p.ww - 1), B_ = 2 * p.ww - 1;
+  for (int n = tid; n < Rpad; n += kThreads) {
+    const int d = n / (p.wh * p.ww), rem = n - d * (p.wh * p.ww), hh = rem / p.ww, w = rem - hh * p.ww;
+    lin_s[n] = n < N ? d * A_ + hh * B_ + w : 0;
+    reg_s[n] = 0;
+  }
+  for (int i = tid; i < p.tab; i += kThreads) {
+    tab_s[i] = (PHASE == 0 || PHASE == 3) ? __ldg(p.bias_table + (int64_t)i * p.nH + head) : 0.f;
+    if (PHASE == 1) dtab_s[i] = 0.f;
+  }
+  const int lin_off = (p.wd - 1) * A_ + (p.wh - 1) * B_ + (p.ww - 1);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  uint32_t ph_s = 0, ph_o = 0;
+
+  const int slot = warp >> 2;                                   // which M-tile of the current pair of M-tiles
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16; // this warp's TMEM lanes
+  const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b), bt_base = smem_u32(smem + sp.bt);
+  const uint32_t lbo_plain = (uint32_t)Rpad * 16, sbo = 128, lbo_t = 512;
+
+  const int64_t n_pairs = p.M * p.nH;
+  for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    const int64_t mwin = pair / p.nH;                            // pair % nH == head by construction
+    const uint8_t* qp = p.q + pair * N * 32;
+    const uint8_t* kp = p.k + pair * N * 32;
+    const uint8_t* vp = p.v + pair * N * 32;
+    // ---- stage operands ----
+    if (PHASE == 0) { stage_plain_u8<BF>(smem, sp.a, Rpad, qp, N); stage_plain_u8<BF>(smem, sp.b, Rpad, kp, N); stage_trans_u8<BF>(smem, sp.bt, vp, N); }
+    if (PHASE == 1) { stage_plain_f32<BF>(smem, sp.a, Rpad, p, mwin, head); stage_plain_u8<BF>(smem, sp.b, Rpad, vp, N); stage_trans_u8<BF>(smem, sp.bt, kp, N); }
+    if (PHASE == 2) { stage_plain_u8<BF>(smem, sp.a, Rpad, vp, N); stage_plain_f32<BF>(smem, sp.b, Rpad, p, mwin, head); stage_trans_u8<BF>(smem, sp.bt, qp, N); }
+    if (PHASE == 3) { stage_plain_u8<BF>(smem, sp.a, Rpad, kp, N); stage_plain_u8<BF>(smem, sp.b, Rpad, qp, N); stage_trans_f32<BF>(smem, sp.bt, p, mwin, head); }
+    if (p.has_mask && (PHASE == 0 || PHASE == 3)) {
+      const uint8_t* rp = p.region + (mwin % p.nW) * N;
+      for (int n = tid; n < N; n += kThreads) reg_s[n] = __ldg(rp + n);
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    for (int mt0 = 0; mt0 < p.n_mt; mt0 += 2) {
+      const int n_slots = (p.n_mt - mt0) >= 2 ? 2 : 1;
+      const int mt = mt0 + slot;
+      const int row = mt * 128 + (warp & 3) * 32 + lane;         // A-operand row handled by this thread
+      const bool row_ok = slot < n_slots && row < N;
+      const int lin_i = row_ok ? lin_s[row] : 0;
+      const int reg_i = row_ok ? reg_s[row] : 0;
+      for (int kt = 0; kt < p.n_kt; ++kt) {
+        const int key0 = kt * kKT;
+        int nk = N - key0;
+        nk = nk > kKT ? kKT : ((nk + 15) & ~15);
+        // ---- MMA 1: S[128 x nk] = A[128 x 32] * B[nk x 32]^T, both slots ----
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t idesc = make_idesc(BF, 128, nk);
+          for (int s = 0; s < n_slots; ++s) {
+            const uint32_t d = tmem_base + s * kSlotCols;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t ad = make_desc(a_base + ks * 2 * lbo_plain + (uint32_t)(mt0 + s) * 128 * 16, lbo_plain, sbo);
+              const uint64_t bd = make_desc(b_base + ks * 2 * lbo_plain + (uint32_t)key0 * 16, lbo_plain, sbo);
+              mma_ss(d, ad, bd, idesc, ks);
+            }
+          }
+          tc_commit(&bars[0]);
+        }
+        mbar_wait(&bars[0], ph_s);
+        ph_s ^= 1;
+        tc_fence_after();
+        // ---- epilogue 1: S -> T = hi + lo (in place) ----
+        if (slot < n_slots) {
+          const uint32_t tcol = tmem_base + lane_base + slot * kSlotCols;
+          for (int c0 = 0; c0 < nk; c0 += 16) {
+            uint32_t r[16], o[16];
+            tmem_ld16(tcol + c0, r);
+            uint16_t hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int j = key0 + c0 + e;
+              const float s = __uint_as_float(r[e]);
+              float t;
+              if (PHASE == 0 || PHASE == 3) {
+                // PHASE 0: this thread is query i = row, column j is the key.  PHASE 3: thread row is the KEY j',
+                // column is the query i' (T^T): bias[i'][j'] = tab[lin_i' - lin_j' + off], mask symmetric.
+                const int lj = lin_s[j < Rpad ? j : 0];
+                const int idx = PHASE == 0 ? (lin_i - lj + lin_off) : (lj - lin_i + lin_off);
+                t = __fadd_rn(__fmul_rn(s, p.scale), tab_s[(idx >= 0 && idx < p.tab) ? idx : 0]);
+                if (p.has_mask && reg_s[j < Rpad ? j : 0] != reg_i) t = __fadd_rn(t, -100.f);
+                if (PHASE == 0 && row_ok && j < N) {
+                  const int64_t o2 = (pair * N + row) * N + j;
+                  if (p.s_dbg) p.s_dbg[o2] = (int32_t)s;
+                  if (p.attn_dbg) p.attn_dbg[o2] = t;
+                }
+              } else {
+                // s = dA[i][j] (PHASE 1, thread row = query i) or dA^T[j][i] (PHASE 2)
+                if (PHASE == 1 && row_ok && j < N) atomicAdd(&dtab_s[lin_i - lin_s[j] + lin_off], s);
+                t = s * p.scale;
+              }
+              if (!row_ok || j >= N) t = 0.f;
+              hi[e] = f2h<BF>(t);
+              lo[e] = f2h<BF>(t - h2f<BF>(hi[e]));
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              o[c] = hi[2 * c] | ((uint32_t)hi[2 * c + 1] << 16);
+              o[8 + c] = lo[2 * c] | ((uint32_t)lo[2 * c + 1] << 16);
+            }
+            tmem_st16(tcol + c0, o);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 2: O[128 x 32] (+)= T_hi * Bt + T_lo * Bt over the 16-key chunks of this tile ----
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t idesc = make_idesc(BF, 128, 32);
+          for (int s = 0; s < n_slots; ++s) {
+            const uint32_t d = tmem_base + s * kSlotCols + kKT;
+            for (int c0 = 0; c0 < nk; c0 += 16) {
+              const uint64_t bd = make_desc(bt_base + (uint32_t)((key0 + c0) >> 3) * lbo_t, lbo_t, sbo);
+              const uint32_t a_hi = tmem_base + s * kSlotCols + c0;
+              mma_ts(d, a_hi, bd, idesc, (kt > 0 || c0 > 0) ? 1u : 0u);
+              mma_ts(d, a_hi + 8, bd, idesc, 1u);
+            }
+          }
+          if (kt == p.n_kt - 1) tc_commit(&bars[1]);
+        }
+      }
+      // ---- epilogue 2: O rows -> global ----
+      mbar_wait(&bars[1], ph_o);
+      ph_o ^= 1;
+      tc_fence_after();
+      if (slot < n_slots) {
+        const uint32_t tcol = tmem_base + lane_base + slot * kSlotCols + kKT;
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tcol, r0);
+        tmem_ld16(tcol + 16, r1);
+        if (row_ok) {
+          float* dst;
+          if (PHASE == 0) {
+            const int64_t t = row / p.P, pos = row - t * p.P;
+            dst = p.out + ((t * p.M + mwin) * p.P + pos) * (p.nH * 32) + head * 32;
+          } else {
+            float* base = PHASE == 1 ? p.grad_q : (PHASE == 2 ? p.grad_k : p.grad_v);
+            dst = base + (pair * N + row) * 32;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            st_stream4(dst + c * 4, make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
+                                                __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3])));
+            st_stream4(dst + 16 + c * 4, make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
+                                                     __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3])));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();   // TMEM and smem free for the next M-tile pair / next pair
+    }
+  }
+  if (PHASE == 1) {
+    __syncthreads();
+    for (int i = tid; i < p.tab; i += kThreads)
+      if (dtab_s[i] != 0.f) atomicAdd(p.grad_table + (int64_t)i * p.nH + head, dtab_s[i]);
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+static int qktv_setup(int64_t M, int64_t nH, int64_t nW, int64_t wd, int64_t wh, int64_t ww, double scale, bool bwd,
+                      QktvP* p, SmemPlan* sp, int* grid) {
+  SDF_REQUIRE(M > 0 && nH > 0 && wd > 0 && wh > 0 && ww > 0, "qktv: bad dims");
+  const int64_t N = wd * wh * ww;
+  SDF_REQUIRE(N >= 8 && N <= 1024, "qktv: window tokens N=%lld must be in [8, 1024]", (long long)N);
+  SDF_REQUIRE(nW > 0 && M % nW == 0, "qktv: M must be a multiple of windows-per-sample nW");
+  p->M = M; p->nH = nH; p->nW = nW; p->P = wh * ww; p->N = (int)N; p->wd = (int)wd; p->wh = (int)wh; p->ww = (int)ww;
+  p->Rpad = (int)((N + 127) / 128 * 128);
+  p->n_mt = p->Rpad / 128;
+  p->n_kt = (int)((N + kKT - 1) / kKT);
+  p->tab = (int)((2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1));
+  p->scale = (float)scale;
+  *sp = plan_smem(p->Rpad, p->tab, bwd);
+  SDF_REQUIRE(sp->total <= 227 * 1024, "qktv: window too large for shared memory (%u B)", sp->total);
+  int g = kNumSMs / (int)nH * (int)nH;
+  if (g < nH) g = (int)nH;
+  if ((int64_t)g > M * nH) g = (int)(M * nH);
+  *grid = g;
+  return SDF_OK;
+}
+
+}  // namespace sdf
+
+using namespace sdf;
+
+extern "C" int sdf_attn_qktv_fwd(const sdf_attn_qktv_fwd_args* a) {
+  SDF_REQUIRE(a && a->q && a->k && a->v && a->bias_table && a->out, "sdf_attn_qktv_fwd: null argument");
+  SDF_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->out), "sdf_attn_qktv_fwd: 16-byte alignment");
+  QktvP p = {};
+  SmemPlan sp;
+  int grid;
+  int st = qktv_setup(a->M, a->nH, a->nW, a->wd, a->wh, a->ww, a->scale, false, &p, &sp, &grid);
+  if (st) return st;
+  p.q = a->q; p.k = a->k; p.v = a->v; p.bias_table = a->bias_table; p.region = a->region; p.has_mask = a->region != nullptr;
+  p.out = a->out; p.s_dbg = a->s_dbg; p.attn_dbg = a->attn_dbg;
+  cudaFuncSetAttribute(qktv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+  qktv_kernel<0><<<grid, kThreads, sp.total, (cudaStream_t)a->stream>>>(p);
+  return finish_launch("sdf_attn_qktv_fwd");
+}
+
 extern "C" int sdf_attn_qktv_bwd(const sdf_attn_qktv_bwd_args* a) {
-  (void)a;
-  set_error("sdf_attn_qktv_bwd: not built yet");
-  return SDF_ERR_UNSUPPORTED;
+  SDF_REQUIRE(a && a->q && a->k && a->v && a->bias_table && a->grad_out && a->grad_q && a->grad_k && a->grad_v && a->grad_bias_table,
+              "sdf_attn_qktv_bwd: null argument");
+  SDF_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->grad_out) && aligned16(a->grad_q) &&
+                  aligned16(a->grad_k) && aligned16(a->grad_v), "sdf_attn_qktv_bwd: 16-byte alignment");
+  QktvP p = {};
+  SmemPlan sp;
+  int grid;
+  int st = qktv_setup(a->M, a->nH, a->nW, a->wd, a->wh, a->ww, a->scale, true, &p, &sp, &grid);
+  if (st) return st;
+  p.q = a->q; p.k = a->k; p.v = a->v; p.bias_table = a->bias_table; p.region = a->region; p.has_mask = a->region != nullptr;
+  p.grad_out = a->grad_out; p.grad_q = a->grad_q; p.grad_k = a->grad_k; p.grad_v = a->grad_v; p.grad_table = a->grad_bias_table;
+  cudaStream_t stream = (cudaStream_t)a->stream;
+  cudaFuncSetAttribute(qktv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+  cudaFuncSetAttribute(qktv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+  cudaFuncSetAttribute(qktv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+  qktv_kernel<1><<<grid, kThreads, sp.total, stream>>>(p);
+  st = finish_launch("sdf_attn_qktv_bwd(dQ)");
+  if (st) return st;
+  qktv_kernel<2><<<grid, kThreads, sp.total, stream>>>(p);
+  st = finish_launch("sdf_attn_qktv_bwd(dK)");
+  if (st) return st;
+  qktv_kernel<3><<<grid, kThreads, sp.total, stream>>>(p);
+  return finish_launch("sdf_attn_qktv_bwd(dV)");
 }

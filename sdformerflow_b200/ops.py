@@ -761,3 +761,141 @@ def qkgate_debug(q_pre, k_pre, q_scale, q_shift, k_scale, k_shift, pos, cfg, wd,
         q_h=_ptr(qh), k_h=_ptr(kh), a_h=_ptr(ah), wd=wd, M=M, P=P, C=C, nH=nH, neuron=cfg.c(),
         spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()))
     return gate, qh, kh, ah
+
+
+# ---------------------------------------------------------------------------------------------
+# K3/K4: Q K^T V attention on tcgen05 (with its three input neurons, so spikes stay 1 byte)
+# ---------------------------------------------------------------------------------------------
+def _neuron_u8(u, lay, cfg, scale, shift, C, psn):
+    """spikes as uint8 {0,1} of neuron(BN(u)) — LIF family or PSN."""
+    spike = torch.empty(u.shape, device=u.device, dtype=torch.uint8)
+    if psn is None:
+        capi.call("sdf_lif_fwd", capi.struct(
+            "sdf_lif_fwd_args", u=_ptr(u), spike=_ptr(spike), scale=_ptr(scale), shift=_ptr(shift), C=C, hw=1, lay=lay,
+            neuron=cfg.c(), spike_dtype=capi.SDF_SPIKE_U8, stream=_stream()), algo_bytes=5 * u.numel())
+    else:
+        capi.call("sdf_psn_fwd", capi.struct(
+            "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), weight=_ptr(psn[0]), bias=_ptr(psn[1]), scale=_ptr(scale),
+            shift=_ptr(shift), C=C, hw=1, lay=lay, spike_dtype=capi.SDF_SPIKE_U8, stream=_stream()),
+            algo_bytes=5 * u.numel())
+    return spike
+
+
+class _QKTVFn(torch.autograd.Function):
+    """O = (scale * Q K^T + Bias + Mask) @ V with Q,K,V = sn(bn(x_pre)) (reference
+    Spiking_swin_transformer3D.py:308-363); output rows in proj-input order."""
+
+    @staticmethod
+    def forward(ctx, q_pre, k_pre, v_pre, wq, bq, wk, bk, wv, bv, table, bns, cfg, region, dims, scale, want_attn,
+                *psn_params):
+        wd, M, P, nH, nW, ws = dims
+        C, N = nH * 32, wd * P
+        rows = wd * M * P
+        _need_cuda(q_pre, k_pre, v_pre, table)
+        pres = [t.contiguous() for t in (q_pre, k_pre, v_pre)]
+        lay = seq_layout((wd, M * P * C), 0)
+        spikes, saved = [], []
+        for i, (u, bn) in enumerate(zip(pres, bns)):
+            sc, sh, mean, rstd = _bn_forward_affine(u, rows, C, C, bn)
+            psn = None if not psn_params else (psn_params[2 * i].detach().contiguous(), psn_params[2 * i + 1].detach().contiguous())
+            spikes.append(_neuron_u8(u, lay, cfg, sc, sh, C, psn))
+            saved += [sc, sh, mean, rstd]
+        out = torch.empty((rows, C), device=q_pre.device, dtype=torch.float32)
+        attn = torch.empty((M * nH, N, N), device=q_pre.device, dtype=torch.float32) if want_attn else None
+        tab = table.detach().contiguous()
+        capi.call("sdf_attn_qktv_fwd", capi.struct(
+            "sdf_attn_qktv_fwd_args", q=_ptr(spikes[0]), k=_ptr(spikes[1]), v=_ptr(spikes[2]), bias_table=_ptr(tab),
+            region=_ptr(region), out=_ptr(out), attn_dbg=_ptr(attn), M=M, nH=nH, nW=nW, wd=ws[0], wh=ws[1], ww=ws[2],
+            scale=float(scale), stream=_stream()), algo_bytes=3 * rows * C + 4 * rows * C)
+        ctx.save_for_backward(*pres, *spikes, wq, wk, wv, tab, *saved, *psn_params)
+        ctx.meta = (dims, scale, cfg, region, lay, [b.training for b in bns], len(psn_params) > 0)
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, go, _ga):
+        dims, scale, cfg, region, lay, trains, has_psn = ctx.meta
+        wd, M, P, nH, nW, ws = dims
+        C, N = nH * 32, wd * P
+        rows = wd * M * P
+        sv = ctx.saved_tensors
+        pres, spikes, ws_bn, tab = sv[0:3], sv[3:6], sv[6:9], sv[9]
+        stats = sv[10:22]
+        psn_params = sv[22:] if has_psn else None
+        dev = go.device
+        go = go.contiguous()
+        gq = torch.empty((rows, C), device=dev, dtype=torch.float32)
+        gk, gv = torch.empty_like(gq), torch.empty_like(gq)
+        gtab = torch.zeros_like(tab)
+        capi.call("sdf_attn_qktv_bwd", capi.struct(
+            "sdf_attn_qktv_bwd_args", q=_ptr(spikes[0]), k=_ptr(spikes[1]), v=_ptr(spikes[2]), bias_table=_ptr(tab),
+            region=_ptr(region), grad_out=_ptr(go), grad_q=_ptr(gq), grad_k=_ptr(gk), grad_v=_ptr(gv),
+            grad_bias_table=_ptr(gtab), M=M, nH=nH, nW=nW, wd=ws[0], wh=ws[1], ww=ws[2], scale=float(scale),
+            stream=_stream()))
+        outs, bn_grads, psn_grads = [], [], []
+        for i, (u, g) in enumerate(zip(pres, (gq, gk, gv))):
+            sc, sh, mean, rstd = stats[4 * i:4 * i + 4]
+            partials = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
+            dx = torch.empty_like(u)
+            if not has_psn:
+                capi.call("sdf_lif_bwd", capi.struct(
+                    "sdf_lif_bwd_args", u=_ptr(u), grad_spike=_ptr(g), grad_x=_ptr(dx), scale=_ptr(sc), shift=_ptr(sh),
+                    bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=lay, neuron=cfg.c(),
+                    stream=_stream()), algo_bytes=12 * u.numel())
+            else:
+                pw, pb = psn_params[2 * i].detach().contiguous(), psn_params[2 * i + 1].detach().contiguous()
+                T, n = lay["T"], lay["n_neurons"]
+                gh = torch.empty((T, n), device=dev, dtype=torch.float32)
+                xo = torch.empty((T, n), device=dev, dtype=torch.float32)
+                capi.call("sdf_psn_bwd", capi.struct(
+                    "sdf_psn_bwd_args", u=_ptr(u), grad_spike=_ptr(g), grad_x=_ptr(dx), grad_h=_ptr(gh), x_out=_ptr(xo),
+                    weight=_ptr(pw), bias=_ptr(pb), scale=_ptr(sc), shift=_ptr(sh), bn_partials=_ptr(partials),
+                    n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=lay, surrogate=cfg.surrogate, sg_alpha=float(cfg.sg_alpha),
+                    stream=_stream()))
+                psn_grads += [gh @ xo.t(), gh.sum(1, keepdim=True)]
+            du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, ws_bn[i], mean, rstd, trains[i])
+            outs.append(du.view(u.shape))
+            bn_grads += [gw, gb]
+        return (outs[0], outs[1], outs[2], bn_grads[0], bn_grads[1], bn_grads[2], bn_grads[3], bn_grads[4], bn_grads[5],
+                gtab, None, None, None, None, None, None, *psn_grads)
+
+
+def qktv_attention(q_pre, k_pre, v_pre, bn_q, bn_k, bn_v, table, cfg, region, wd, M, P, nH, nW, window, scale,
+                   psn_modules=None, want_attn=False):
+    bns = [BNParams(b) for b in (bn_q, bn_k, bn_v)]
+    dims = (wd, M, P, nH, nW, tuple(window))
+    psn = [] if psn_modules is None else [t for m in psn_modules for t in (m.weight, m.bias)]
+    return _QKTVFn.apply(q_pre, k_pre, v_pre, bns[0].weight, bns[0].bias, bns[1].weight, bns[1].bias, bns[2].weight,
+                         bns[2].bias, table, bns, cfg, region, dims, scale, want_attn, *psn)
+
+
+def qktv_debug(q, k, v, table, region, M, nH, nW, window, scale):
+    """Raw forward call on uint8 spikes [M*nH*N, 32]: returns (out [wd*M*P, C], S int32 [M*nH,N,N], attn fp32)."""
+    wd, wh, ww = window
+    N, P = wd * wh * ww, wh * ww
+    rows, C = wd * M * P, nH * 32
+    dev = q.device
+    out = torch.empty((rows, C), device=dev, dtype=torch.float32)
+    s_dbg = torch.empty((M * nH, N, N), device=dev, dtype=torch.int32)
+    attn = torch.empty((M * nH, N, N), device=dev, dtype=torch.float32)
+    capi.call("sdf_attn_qktv_fwd", capi.struct(
+        "sdf_attn_qktv_fwd_args", q=_ptr(q), k=_ptr(k), v=_ptr(v), bias_table=_ptr(table.contiguous()), region=_ptr(region),
+        out=_ptr(out), s_dbg=_ptr(s_dbg), attn_dbg=_ptr(attn), M=M, nH=nH, nW=nW, wd=wd, wh=wh, ww=ww, scale=float(scale),
+        stream=_stream()))
+    return out, s_dbg, attn
+
+
+def qktv_bwd_debug(q, k, v, table, region, grad_out, M, nH, nW, window, scale):
+    wd, wh, ww = window
+    N, P = wd * wh * ww, wh * ww
+    rows, C = wd * M * P, nH * 32
+    dev = q.device
+    gq = torch.empty((rows, C), device=dev, dtype=torch.float32)
+    gk, gv = torch.empty_like(gq), torch.empty_like(gq)
+    gtab = torch.zeros_like(table)
+    capi.call("sdf_attn_qktv_bwd", capi.struct(
+        "sdf_attn_qktv_bwd_args", q=_ptr(q), k=_ptr(k), v=_ptr(v), bias_table=_ptr(table.contiguous()), region=_ptr(region),
+        grad_out=_ptr(grad_out.contiguous()), grad_q=_ptr(gq), grad_k=_ptr(gk), grad_v=_ptr(gv), grad_bias_table=_ptr(gtab),
+        M=M, nH=nH, nW=nW, wd=wd, wh=wh, ww=ww, scale=float(scale), stream=_stream()))
+    return gq, gk, gv, gtab
