@@ -17,6 +17,14 @@ def skip_concat(x1, x2, dim=1):
     return torch.cat([F.pad(x1, (dX // 2, dX - dX // 2, dY // 2, dY - dY // 2)), x2], dim=dim)
 
 
+def skip_concat_cl(x1, x2):
+    """skip_concat on channels-last (B, T, H, W, C) tensors: pad x1's H, W to x2's, concatenate channels."""
+    dY, dX = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
+    if dY or dX:
+        x1 = F.pad(x1, (0, 0, dX // 2, dX - dX // 2, dY // 2, dY - dY // 2))
+    return torch.cat([x1, x2], dim=-1)
+
+
 def skip_sum(x1, x2, dim=None):
     dY, dX = x2.size(-2) - x1.size(-2), x2.size(-1) - x1.size(-1)
     return F.pad(x1, (dX // 2, dX - dX // 2, dY // 2, dY - dY // 2)) + x2

@@ -12,7 +12,7 @@ from torch import nn
 from ..sj import layer, functional, neuron  # noqa: F401
 from .Spiking_swin_transformer3D import Spiking_SwinTransformer3D_v2, MS_Spiking_SwinTransformer3D_v2
 from .SNN_models import *  # noqa: F401,F403
-from .SNN_models import SpikingMultiResUNet
+from .SNN_models import SpikingMultiResUNet, skip_concat_cl
 from .Spiking_modules import (MS_SpikingConvEncoderLayer, MS_ResBlock, MS_SpikingTransposeDecoderLayer,
                               MS_SpikingPredLayer)
 
@@ -39,6 +39,9 @@ class spiking_former_encoder(nn.Module):
             pretrained_window_size=pretrained_window_size, mlp_ratio=mlp_ratio, drop_rate=0.0, attn_drop_rate=0.0,
             drop_path_rate=0.2, norm_layer=spikformer_norm, out_indices=out_indices, frozen_stages=frozen_stages,
             norm=norm, **spiking_kwargs)
+
+    def forward_cl(self, inputs):
+        return self.swin3d.features_cl(inputs)                        # (B, D, Hi, Wi, Ci) per stage
 
     def forward(self, inputs):
         feats = self.swin3d(inputs)                                   # (B, C, D, H, W) views
@@ -84,19 +87,26 @@ class Spikingformer_MultiResUNet(SpikingMultiResUNet):
         self.preds_out = nn.ModuleList([neuron.IFNode(v_threshold=float("inf"), v_reset=0.0)
                                         for _ in range(self.num_encoders)])
 
-    def forward(self, x):
-        blocks = self.encoders(x)
+    def forward_cl(self, x):
+        """voxels (B, bins, 2, H, W) -> multi-resolution predictions, each (B, T, Hi, Wi, 2) channels-last."""
+        blocks = self.encoders.forward_cl(x)
         x = blocks[-1]
         for resblock in self.resblocks:
-            x = resblock(x)
+            x = resblock.forward_cl(x)
         predictions = []
         for i, (decoder, pred) in enumerate(zip(self.decoders, self.preds)):
-            x = self.skip_ftn(x, blocks[self.num_encoders - i - 1], dim=2)
+            x = skip_concat_cl(x, blocks[self.num_encoders - i - 1])
             if i > 0:
-                x = self.skip_ftn(predictions[-1], x, dim=2)
-            x = decoder(x)
-            predictions.append(pred(x))
+                x = skip_concat_cl(predictions[-1], x)
+            x = decoder.forward_cl(x)
+            predictions.append(pred.forward_cl(x))
         return predictions
+
+    def forward(self, x):
+        """Reference layout: list of (T, B, 2, Hi, Wi)."""
+        if self.skip_type != "concat":
+            raise NotImplementedError("skip_type 'sum' is not built (FlowNets hard-code 'concat', STSwinNet.py:336)")
+        return [p.permute(1, 0, 4, 2, 3) for p in self.forward_cl(x)]
 
 
 class MS_Spikingformer_MultiResUNet(Spikingformer_MultiResUNet):
@@ -165,8 +175,8 @@ class SpikingformerFlowNet(nn.Module):
             raise NotImplementedError("log=True (attention-score dump) is not built; see Spiking_SwinTransformerBlock3D")
         H, W = x.shape[-2], x.shape[-1]
         flow_list = []
-        for flow in self.sttmultires_unet.forward(x):
-            flow = torch.sum(flow, dim=0)
+        for pred in self.sttmultires_unet.forward_cl(x):               # (B, T, h, w, 2)
+            flow = torch.sum(pred, dim=1).permute(0, 3, 1, 2)           # sum over time -> (B, 2, h, w)
             flow_list.append(torch.nn.functional.interpolate(
                 flow, scale_factor=(H / flow.shape[-2], W / flow.shape[-1])))
         return {"flow": flow_list, "attn": None}

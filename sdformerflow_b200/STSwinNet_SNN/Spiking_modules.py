@@ -116,6 +116,41 @@ class SpikingNormLayer(nn.Module):
         return self.norm_layer(x)
 
 
+
+# ---------------------------------------------------------------------------------------------
+# channels-last execution of the convolutional layers
+# ---------------------------------------------------------------------------------------------
+# Internally every layer below runs on ONE layout, (B, T, H, W, C) contiguous ("cl"): cuDNN gets NHWC
+# tensors (tensor-core kernels without NCHW<->NHWC transforms), BatchNorm + neuron sites become
+# channels-last rows for the fused K1/K2/K6 kernels (time axis = dim 1, no permute copies), and the
+# Swin stages consume / produce the same layout.  `forward` keeps the reference's (T, B, C, H, W)
+# signature as a thin adapter around `forward_cl`.
+def to_cl(x):
+    """(T, B, C, H, W) -> (B, T, H, W, C) contiguous."""
+    return x.permute(1, 0, 3, 4, 2).contiguous()
+
+
+def from_cl(y):
+    """(B, T, H, W, C) -> logical (T, B, C, H, W) view."""
+    return y.permute(1, 0, 4, 2, 3)
+
+
+def conv_cl(x, conv, spike_input, transposed=False):
+    """x (B, T, H, W, Cin) -> (B, T, H', W', Cout); `conv` is an nn.Conv2d / nn.ConvTranspose2d parameter holder."""
+    B, T, H, W, C = x.shape
+    x4 = x.view(B * T, H, W, C).permute(0, 3, 1, 2)                # logical NCHW with channels_last strides
+    y4 = ops.spike_conv2d(x4, conv.weight, conv.bias, conv.stride, conv.padding, transposed,
+                          conv.output_padding if transposed else 0, exact_input=spike_input)
+    y = y4.permute(0, 2, 3, 1).contiguous()                        # no-op when cuDNN returned NHWC
+    return y.view(B, T, y.shape[1], y.shape[2], y.shape[3])
+
+
+def _bn_sn(h, norm_layer, sn):
+    """neuron(BN(h)) on channels-last rows, time axis = dim 1."""
+    sn.mark()
+    return ops.bn_neuron(h, norm_layer.norm_layer, sn.cfg(), 1, psn=sn.spiking_neuron if sn.is_psn else None)
+
+
 def _conv(cin, cout, k, stride, padding, bias):
     return nn.Sequential(layer.Conv2d(in_channels=cin, out_channels=cout, kernel_size=k, stride=stride, padding=padding,
                                       bias=bias))
@@ -134,11 +169,16 @@ class SpikingConvEncoderLayer(nn.Module):
                                                v_th=spiking_kwargs["v_th"])
         self.sn = Spiking_neuron(**spiking_kwargs)
 
-    def forward(self, x):
-        x = self.conv(x)
+    def forward_cl(self, x, spike_input=False):
+        h = conv_cl(x, self.conv[0], spike_input)
+        if self.norm is not None and self.norm_layer.is_batchnorm:
+            return _bn_sn(h, self.norm_layer, self.sn)
         if self.norm is not None:
-            x = self.norm_layer(x)
-        return self.sn(x)
+            h = to_cl(self.norm_layer(from_cl(h)))
+        return self.sn(h, 1)
+
+    def forward(self, x):
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class MS_SpikingConvEncoderLayer(nn.Module):
@@ -156,11 +196,18 @@ class MS_SpikingConvEncoderLayer(nn.Module):
             self.norm_layer = SpikingNormLayer(out_channels, spiking_kwargs["num_steps"], self.norm,
                                                v_th=spiking_kwargs["v_th"])
 
-    def forward(self, x):
+    def forward_cl(self, x):
         if not self.first_layer:
-            x = self.sn(x)
-        x = self.conv(x)
-        return self.norm_layer(x) if self.norm is not None else x
+            x = self.sn(x, 1)
+        h = conv_cl(x, self.conv[0], not self.first_layer)
+        if self.norm is None:
+            return h
+        if self.norm_layer.is_batchnorm:
+            return ops.bn_residual(h, self.norm_layer.norm_layer)
+        return to_cl(self.norm_layer(from_cl(h)))
+
+    def forward(self, x):
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class SpikingTransposeDecoderLayer(nn.Module):
@@ -183,20 +230,22 @@ class SpikingTransposeDecoderLayer(nn.Module):
                                                v_th=spiking_kwargs["v_th"])
         self.sn = Spiking_neuron(**spiking_kwargs)
 
-    def forward(self, x):
-        x = self.deconv(x)
+    def forward_cl(self, x, spike_input=True):
+        h = conv_cl(x, self.deconv[0], spike_input, transposed=True)
         if self.norm is not None:
-            x = self.norm_layer(x)
-        return self.sn(x)
+            return _bn_sn(h, self.norm_layer, self.sn)
+        return self.sn(h, 1)
+
+    def forward(self, x):
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class MS_SpikingTransposeDecoderLayer(SpikingTransposeDecoderLayer):
     """neuron -> deconv -> norm (reference :461-474)."""
 
-    def forward(self, x):
-        self.deconv[0].spike_input = True
-        x = self.deconv(self.sn(x))
-        return self.norm_layer(x) if self.norm is not None else x
+    def forward_cl(self, x):
+        h = conv_cl(self.sn(x, 1), self.deconv[0], True, transposed=True)
+        return ops.bn_residual(h, self.norm_layer.norm_layer) if self.norm is not None else h
 
 
 class SpikingPredLayer(nn.Module):
@@ -207,8 +256,11 @@ class SpikingPredLayer(nn.Module):
         self.norm = None
         self.conv = _conv(in_channels, out_channels, kernel_size, stride, kernel_size // 2, True)
 
+    def forward_cl(self, x, spike_input=True):
+        return conv_cl(x, self.conv[0], spike_input)
+
     def forward(self, x):
-        return self.conv(x)
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class MS_SpikingPredLayer(nn.Module):
@@ -219,10 +271,12 @@ class MS_SpikingPredLayer(nn.Module):
         self.norm = None
         self.sn = Spiking_neuron(**spiking_kwargs)
         self.conv = _conv(in_channels, out_channels, kernel_size, stride, kernel_size // 2, True)
-        self.conv[0].spike_input = True
+
+    def forward_cl(self, x):
+        return conv_cl(self.sn(x, 1), self.conv[0], True)
 
     def forward(self, x):
-        return self.conv(self.sn(x))
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class SpikingPEDLayer(nn.Module):
@@ -240,13 +294,15 @@ class SpikingPEDLayer(nn.Module):
             self.norm_layer = nn.BatchNorm2d(out_channels)
         self.sn = Spiking_neuron(**spiking_kwargs)
 
-    def forward(self, x):
-        T, B, C, H, W = x.shape
-        x_res = ops.spike_conv2d(x.flatten(0, 1), self.conv_res.weight, self.conv_res.bias, 2, 0, exact_input=False)
-        y = ops.spike_conv2d(self.sn(x).flatten(0, 1), self.conv.weight, self.conv.bias, self.conv.stride, 1)
+    def forward_cl(self, x):
+        x_res = conv_cl(x, self.conv_res, False)                 # 1x1 stride-2 shortcut on the membrane input
+        y = conv_cl(self.sn(x, 1), self.conv, True)
         if self.norm is not None:
-            y = self.norm_layer(y)
-        return (y + x_res).reshape(T, B, -1, self.patch[0], self.patch[1]).contiguous()
+            return ops.bn_residual(y, self.norm_layer, x_res)
+        return y + x_res
+
+    def forward(self, x):
+        return from_cl(self.forward_cl(to_cl(x))).contiguous()
 
 
 def _connect(out, identity, fn):
@@ -282,31 +338,32 @@ class _ResBlockBase(nn.Module):
 class SEWResBlock(_ResBlockBase):
     """conv-norm-neuron x2, spike-element-wise shortcut (reference :827-878)."""
 
+    def forward_cl(self, x):
+        h = conv_cl(x, self.conv1[0], True)                      # spikes (+ integer SEW sums): exact in TF32
+        s = _bn_sn(h, self.norm1, self.sn1) if self.norm is not None else self.sn1(h, 1)
+        h = conv_cl(s, self.conv2[0], True)
+        s = _bn_sn(h, self.norm2, self.sn2) if self.norm is not None else self.sn2(h, 1)
+        return _connect(s, x, self.connect_function)
+
     def forward(self, x):
-        self.conv1[0].spike_input = self.conv2[0].spike_input = True   # spikes (+ integer SEW sums)
-        identity = x
-        x = self.conv1(x)
-        if self.norm is not None:
-            x = self.norm1(x)
-        x = self.conv2(self.sn1(x))
-        if self.norm is not None:
-            x = self.norm2(x)
-        return _connect(self.sn2(x), identity, self.connect_function)
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class MS_ResBlock(_ResBlockBase):
     """neuron-conv-norm x2, membrane shortcut (reference :880-933)."""
 
+    def forward_cl(self, x):
+        h = conv_cl(self.sn1(x, 1), self.conv1[0], True)
+        s = _bn_sn(h, self.norm1, self.sn2) if self.norm is not None else self.sn2(h, 1)
+        h = conv_cl(s, self.conv2[0], True)
+        if self.norm is not None and self.connect_function == "ADD":
+            return ops.bn_residual(h, self.norm2.norm_layer, x)
+        if self.norm is not None:
+            h = ops.bn_residual(h, self.norm2.norm_layer)
+        return _connect(h, x, self.connect_function)
+
     def forward(self, x):
-        self.conv1[0].spike_input = self.conv2[0].spike_input = True
-        identity = x
-        x = self.conv1(self.sn1(x))
-        if self.norm is not None:
-            x = self.norm1(x)
-        x = self.conv2(self.sn2(x))
-        if self.norm is not None:
-            x = self.norm2(x)
-        return _connect(x, identity, self.connect_function)
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class spiking_residual_feature_generator(nn.Module):
@@ -319,10 +376,13 @@ class spiking_residual_feature_generator(nn.Module):
             self.res_block_type(dim, dim, stride=1, spike_norm=norm, connect_function=cnt_fun, **spiking_kwargs)
             for _ in range(num_resblocks)])
 
-    def forward(self, x):
+    def forward_cl(self, x):
         for blk in self.resblocks:
-            x = blk(x)
+            x = blk.forward_cl(x)
         return x
+
+    def forward(self, x):
+        return from_cl(self.forward_cl(to_cl(x)))
 
 
 class MS_spiking_residual_feature_generator(spiking_residual_feature_generator):
@@ -337,6 +397,15 @@ def regroup_bins_to_steps(x, num_bins, num_steps):
     B, _, _, H, W = x.shape
     g = num_bins // num_steps
     return x.reshape(B, g, num_steps, 2, H, W).permute(2, 0, 1, 3, 4, 5).reshape(num_steps, B, g * 2, H, W)
+
+
+def regroup_bins_to_steps_cl(x, num_bins, num_steps):
+    """Same regroup straight into the channels-last layout: (B, bins, 2, H, W) -> (B, steps, H, W, num_ch)."""
+    if x.size(1) > num_bins:
+        x = x[:, :num_bins]
+    B, _, _, H, W = x.shape
+    g = num_bins // num_steps
+    return x.reshape(B, g, num_steps, 2, H, W).permute(0, 2, 4, 5, 1, 3).reshape(B, num_steps, H, W, g * 2).contiguous()
 
 
 class MS_PED_Spiking_PatchEmbed_Conv_sfn(nn.Module):
@@ -364,9 +433,16 @@ class MS_PED_Spiking_PatchEmbed_Conv_sfn(nn.Module):
         self.proj = SpikingPEDLayer(embed_dim, embed_dim, kernel_size=3, stride=patch_size[2:], padding=1,
                                     norm=spike_norm, patch_resolution=self.patches_resolution, **spiking_kwargs)
 
+    def forward_cl(self, x):
+        """voxels (B, bins, 2, H, W) -> (B, T, H/4, W/4, embed_dim)."""
+        x = regroup_bins_to_steps_cl(x, self.num_bins, self.num_steps)
+        x = self.head.forward_cl(x, spike_input=False)            # real-valued voxel input: plain fp32 conv
+        x = self.conv.forward_cl(x)
+        x = self.residual_encoding.forward_cl(x)
+        return self.proj.forward_cl(x)
+
     def forward(self, x):
-        x = regroup_bins_to_steps(x, self.num_bins, self.num_steps)
-        return self.proj(self.residual_encoding(self.conv(self.head(x))))
+        return from_cl(self.forward_cl(x)).contiguous()
 
     def extra_repr(self):
         return f" num_steps={self.num_steps}, patches_resolution={self.patches_resolution}"

@@ -496,11 +496,15 @@ class Spiking_SwinTransformer3D_v2(nn.Module):
                 outs.append(pre)
         return outs
 
+    def features_cl(self, x):
+        """x: (B, bins, 2, H, W) voxels -> list of per-stage features (B, D, Hi, Wi, Ci), no layout copies."""
+        if self.pos_drop.p != 0.0:
+            raise NotImplementedError("pos_drop > 0 is not built (the reference passes drop_rate=0)")
+        return self.forward_cl(self.patch_embed.forward_cl(x))
+
     def forward(self, x):
         """x: (B, bins, 2, H, W) voxels -> tuple of (B, Ci, D, Hi, Wi) views (reference :1223-1246)."""
-        x = self.pos_drop(self.patch_embed(x))                       # (T, B, C, H, W)
-        x = x.permute(1, 0, 3, 4, 2).contiguous()                    # (B, D, H, W, C): the only layout copy
-        return tuple(o.permute(0, 4, 1, 2, 3) for o in self.forward_cl(x))
+        return tuple(o.permute(0, 4, 1, 2, 3) for o in self.features_cl(x))
 
 
 class MS_Spiking_SwinTransformer3D_v2(Spiking_SwinTransformer3D_v2):

@@ -133,3 +133,14 @@ def test_window_geometry_host_math():
     assert g.window == (2, 9, 9) and g.shift == (1, 0, 4) and g.nW == 5 * 1 * 2
     g = ops.WindowGeom(1, 5, 8, 8, (2, 8, 8), (1, 4, 4))        # MDR stage 4
     assert g.shift == (1, 0, 0) and g.Dp == 6
+
+
+@pytest.mark.parametrize("bins,steps", [(10, 10), (20, 10), (10, 5), (12, 4)])
+def test_bins_to_steps_regroup_matches_reference_loop(bins, steps):
+    """The one-permute regroup == the reference's zero-fill + per-channel copy loop (Spiking_modules.py:1775-1786)."""
+    from oracle import port
+    from sdformerflow_b200.STSwinNet_SNN import Spiking_modules as m
+    x = torch.randn(2, bins, 2, 6, 8)
+    ref = port.regroup_events(x, bins, steps)
+    assert torch.equal(ref, m.regroup_bins_to_steps(x, bins, steps))
+    assert torch.equal(m.to_cl(ref), m.regroup_bins_to_steps_cl(x, bins, steps))
