@@ -25,6 +25,7 @@ struct QkP {
   const float* grad_gate; float* grad_q; float* grad_k; float* part_q; float* part_k;
   int64_t M, P, C, nH, MP, tile_w;
   int R, k, wd;
+  FastDiv dP, dwd, dnH;
   NeuronP nrn;
 };
 
@@ -37,13 +38,12 @@ __device__ __forceinline__ float head_sum8(float v) {
 
 // destination row/col of source group j = ((t*M + m)*P + pos)*nH + ch   (Appendix B.3)
 __device__ __forceinline__ int64_t gate_dest(const QkP& p, int64_t t, int64_t nr, int64_t ch) {
-  const int64_t j = (t * p.MP + nr) * p.nH + ch;
-  const int64_t pos2 = j % p.P;
-  int64_t r = j / p.P;
-  const int64_t t2 = r % p.wd; r /= p.wd;
-  const int64_t h2 = r % p.nH;
-  const int64_t m2 = r / p.nH;
-  return ((t2 * p.M + m2) * p.P + pos2) * p.C + h2 * 32;
+  const uint32_t j = (uint32_t)((t * p.MP + nr) * p.nH + ch);   // < 2^31, checked on the host
+  uint32_t r, pos2, t2, m2, h2;
+  p.dP.divmod(j, r, pos2);
+  p.dwd.divmod(r, r, t2);
+  p.dnH.divmod(r, m2, h2);
+  return (((int64_t)t2 * p.M + m2) * p.P + pos2) * p.C + h2 * 32;
 }
 
 template <int T, int DT, bool BWD>
@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(512) qkgate_kernel(const QkP p) {
     const int64_t nr = nr0 + ry;
     const bool valid = nr < p.MP;
     const int64_t nrc = valid ? nr : 0;
-    const int64_t pcoff = (nrc % p.P) * p.C + col;   // offset inside one (wh,ww,C) slab of pos
+    uint32_t mq, posq;
+    p.dP.divmod((uint32_t)nrc, mq, posq);
+    const int64_t pcoff = (int64_t)posq * p.C + col;  // offset inside one (wh,ww,C) slab of pos
     float4 qp[TM], kp[TM];
 #pragma unroll
     for (int t = 0; t < TM; ++t)
@@ -224,7 +226,9 @@ static int qk_common(const float* q_pre, const float* k_pre, int64_t ld, const f
   int st = validate_neuron(nc);
   if (st) return st;
   p->q_pre = q_pre; p->k_pre = k_pre; p->ld = ld; p->q_scale = qs; p->q_shift = qh; p->k_scale = ks; p->k_shift = kh;
+  SDF_REQUIRE(wd * M * P * nH < (int64_t)1 << 31, "qkgate: token*head count exceeds 2^31");
   p->pos = pos; p->M = M; p->P = P; p->C = C; p->nH = nH; p->MP = M * P; p->wd = (int)wd; p->nrn = make_neuron(nc);
+  p->dP.init((uint32_t)P); p->dwd.init((uint32_t)wd); p->dnH.init((uint32_t)nH);
   return SDF_OK;
 }
 

@@ -99,33 +99,49 @@ struct FinP {
   const float* mean_in; const float* rstd_in; float* gw; float* gb; float* coef;
 };
 
+// one warp per channel: lanes stride over the per-block partials, fixed-order shuffle tree in double
+// (deterministic; the single rounding to fp32 at the end keeps mean/var within 1 ulp of exact).
+__device__ __forceinline__ void warp_sum_partials(const float* partials, int64_t nblk, int64_t C, int64_t c, double& s0, double& s1) {
+  const int lane = threadIdx.x & 31;
+  double a = 0.0, b = 0.0;
+  for (int64_t blk = lane; blk < nblk; blk += 32) {
+    a += (double)partials[(blk * 2 + 0) * C + c];
+    b += (double)partials[(blk * 2 + 1) * C + c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  s0 = a; s1 = b;
+}
+
 __global__ void bn_finalize_kernel(const FinP p) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= p.C) return;
+  const int lane = threadIdx.x & 31;
   float mean, var;
   if (p.training) {
-    // fixed-order sum over the per-block partials in double: deterministic, and the single
-    // rounding to fp32 at the end keeps mean/var within 1 ulp of an exact reduction.
-    double s = 0.0, ss = 0.0;
-    for (int64_t b = 0; b < p.nblk; ++b) {
-      s += (double)p.partials[(b * 2 + 0) * p.C + c];
-      ss += (double)p.partials[(b * 2 + 1) * p.C + c];
-    }
+    double s, ss;
+    warp_sum_partials(p.partials, p.nblk, p.C, c, s, ss);
     const double n = (double)p.count;
     const double m = s / n;
     double v = ss / n - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
-    if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
-    if (p.running_var) {
-      const float unbiased = (float)(v * (n / (n > 1.0 ? n - 1.0 : 1.0)));
-      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
+    if (lane == 0) {
+      if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+      if (p.running_var) {
+        const float unbiased = (float)(v * (n / (n > 1.0 ? n - 1.0 : 1.0)));
+        p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
+      }
     }
   } else {
     mean = p.running_mean[c];
     var = p.running_var[c];
   }
+  if (lane != 0) return;
   const float rstd = 1.f / sqrtf(var + p.eps);
   const float w = p.weight ? p.weight[c] : 1.f;
   const float b = p.bias ? p.bias[c] : 0.f;
@@ -137,13 +153,11 @@ __global__ void bn_finalize_kernel(const FinP p) {
 }
 
 __global__ void bn_bwd_finalize_kernel(const FinP p) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= p.C) return;
-  double s = 0.0, su = 0.0;
-  for (int64_t b = 0; b < p.nblk; ++b) {
-    s += (double)p.partials[(b * 2 + 0) * p.C + c];
-    su += (double)p.partials[(b * 2 + 1) * p.C + c];
-  }
+  double s, su;
+  warp_sum_partials(p.partials, p.nblk, p.C, c, s, su);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = p.mean_in[c], rstd = p.rstd_in[c];
   const double w = p.weight ? (double)p.weight[c] : 1.0;
   const double dgamma = (su - mean * s) * rstd;  // sum dy * xhat
@@ -223,8 +237,8 @@ extern "C" int sdf_bn_finalize(const sdf_bn_finalize_args* a) {
   p.weight = a->weight; p.bias = a->bias; p.running_mean = a->running_mean; p.running_var = a->running_var;
   p.momentum = (float)a->momentum; p.eps = (float)a->eps; p.training = a->training;
   p.scale = a->scale; p.shift = a->shift; p.mean = a->mean; p.rstd = a->rstd;
-  const int threads = 128;
-  bn_finalize_kernel<<<(unsigned)((a->C + threads - 1) / threads), threads, 0, (cudaStream_t)a->stream>>>(p);
+  const int threads = 256;   // 8 channels (warps) per block
+  bn_finalize_kernel<<<(unsigned)((a->C * 32 + threads - 1) / threads), threads, 0, (cudaStream_t)a->stream>>>(p);
   return finish_launch("sdf_bn_finalize");
 }
 
@@ -234,8 +248,8 @@ extern "C" int sdf_bn_bwd_finalize(const sdf_bn_bwd_finalize_args* a) {
   p.partials = a->partials; p.nblk = a->n_partial_blocks; p.count = a->count; p.C = a->C;
   p.weight = a->weight; p.mean_in = a->mean; p.rstd_in = a->rstd; p.gw = a->grad_weight; p.gb = a->grad_bias;
   p.coef = a->coef; p.training = a->training;
-  const int threads = 128;
-  bn_bwd_finalize_kernel<<<(unsigned)((a->C + threads - 1) / threads), threads, 0, (cudaStream_t)a->stream>>>(p);
+  const int threads = 256;
+  bn_bwd_finalize_kernel<<<(unsigned)((a->C * 32 + threads - 1) / threads), threads, 0, (cudaStream_t)a->stream>>>(p);
   return finish_launch("sdf_bn_bwd_finalize");
 }
 

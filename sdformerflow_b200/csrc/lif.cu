@@ -156,7 +156,7 @@ struct LifBwdP {
 };
 
 template <int T, int V>
-__global__ void __launch_bounds__(256) lif_bwd_kernel(const LifBwdP p) {
+__global__ void __launch_bounds__(256, 2) lif_bwd_kernel(const LifBwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   extern __shared__ float smem[];
   const SeqP& s = p.s;
@@ -174,13 +174,10 @@ __global__ void __launch_bounds__(256) lif_bwd_kernel(const LifBwdP p) {
     const int64_t n = row * s.row_w + col;
     if (n >= s.n_neurons) continue;
     const int64_t off = seq_base(s, n);
-    float u[TM][V], g[TM][V], h[TM][V];
+    float u[TM][V], h[TM][V];
 #pragma unroll
     for (int t = 0; t < TM; ++t)
       if (t < Tn) ldv<V>(p.u + off + t * s.stride_t, u[t]);
-#pragma unroll
-    for (int t = 0; t < TM; ++t)
-      if (t < Tn) ldv<V>(p.gs + off + t * s.stride_t, g[t]);
     if (s.chan_mode >= 2) load_affine<V>(s, p.scale, p.shift, n, sc, sh);
     float v0[V], v[V];
     if (p.v_init) {
@@ -210,10 +207,11 @@ __global__ void __launch_bounds__(256) lif_bwd_kernel(const LifBwdP p) {
 #pragma unroll
     for (int t = TM - 1; t >= 0; --t) {
       if (t < Tn) {
-        float dx[V], du[V];
+        float dx[V], du[V], g[V];
+        ldv<V>(p.gs + off + t * s.stride_t, g);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float gh = neuron_grad_h(nrn, h[t][i], g[t][i], gv[i]);
+          float gh = neuron_grad_h(nrn, h[t][i], g[i], gv[i]);
           dx[i] = gh * dh_dx;
           gv[i] = gh * dh_dv;
           du[i] = dx[i] * sc[i];

@@ -129,6 +129,22 @@ __device__ __forceinline__ float neuron_dh_dv(const NeuronP& p) {
   return p.kind == SDF_NEURON_IF ? 1.f : 1.f - p.inv_tau;
 }
 
+// ---- 32-bit division by a runtime constant (multiply-high + shift), valid for n < 2^31 ----------
+struct FastDiv {
+  uint32_t d, mul, sh;
+  __host__ void init(uint32_t div) {
+    d = div;
+    if (div <= 1) { mul = 0; sh = 0; return; }
+    uint32_t lg = 0;
+    while ((1ull << lg) < div) ++lg;                 // ceil(log2 div)
+    const uint32_t pw = 31 + lg;
+    mul = (uint32_t)(((1ull << pw) + div - 1) / div);
+    sh = pw - 32;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d <= 1 ? n : (__umulhi(n, mul) >> sh); }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 // ---- float4 helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float& f4(float4& v, int i) { return reinterpret_cast<float*>(&v)[i]; }
 __device__ __forceinline__ const float& f4(const float4& v, int i) { return reinterpret_cast<const float*>(&v)[i]; }

@@ -108,5 +108,52 @@ def main():
     report("window_scatter+residual", geom.rows * C * 4 + x.numel() * 8, ms)
 
 
+def qktv():
+    """K3/K4 sweep: algorithmic 4*N^2*32 FLOP per (window, pseudo-head) forward, 8*N^2*32 backward."""
+    dev = "cuda"
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = peaks.get("bf16_tflops", 1590.0)
+    for (wd, wh, ww, C, nH, M, masked) in [(2, 9, 9, 96, 3, 10080, True), (2, 9, 9, 96, 3, 10080, False),
+                                           (2, 9, 9, 768, 24, 240, True), (4, 12, 12, 96, 3, 3360, True)]:
+        N, P = wd * wh * ww, wh * ww
+        rows = wd * M * P
+        g = torch.Generator(device=dev).manual_seed(0)
+        q, k, v = ((torch.rand(rows, C, device=dev, generator=g) < 0.2).to(torch.uint8) for _ in range(3))
+        table = torch.randn((2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1), nH, device=dev) * 0.02
+        nW = M // 8 if M % 8 == 0 else 1
+        region = torch.randint(0, 3, (nW, N), device=dev, dtype=torch.uint8) if masked else None
+        out = torch.empty(rows, C, device=dev)
+
+        def fwd():
+            capi.call("sdf_attn_qktv_fwd", capi.struct(
+                "sdf_attn_qktv_fwd_args", q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), bias_table=table.data_ptr(),
+                region=None if region is None else region.data_ptr(), out=out.data_ptr(), M=M, nH=nH, nW=nW, wd=wd,
+                wh=wh, ww=ww, scale=0.125, stream=torch.cuda.current_stream().cuda_stream))
+        ms = timeit(fwd, iters=5)
+        flop = 4.0 * N * N * 32 * M * nH
+        nbytes = 3 * rows * C + 4 * rows * C
+        pk, how = peak_gbs()
+        print(json.dumps({"kernel": f"attn_qktv_fwd window=({wd},{wh},{ww}) C={C} M={M} mask={masked}", "ms": round(ms, 4),
+                          "algo_TFLOPs": round(flop / ms / 1e9, 1), "frac_of_bf16_peak": round(flop / ms / 1e9 / tf_peak, 4),
+                          "GBps": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / pk, 3)}), flush=True)
+        go = torch.randn(rows, C, device=dev)
+        gq, gk, gv = (torch.empty(rows, C, device=dev) for _ in range(3))
+        gtab = torch.zeros_like(table)
+
+        def bwd():
+            capi.call("sdf_attn_qktv_bwd", capi.struct(
+                "sdf_attn_qktv_bwd_args", q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), bias_table=table.data_ptr(),
+                region=None if region is None else region.data_ptr(), grad_out=go.data_ptr(), grad_q=gq.data_ptr(),
+                grad_k=gk.data_ptr(), grad_v=gv.data_ptr(), grad_bias_table=gtab.data_ptr(), M=M, nH=nH, nW=nW, wd=wd,
+                wh=wh, ww=ww, scale=0.125, stream=torch.cuda.current_stream().cuda_stream))
+        ms = timeit(bwd, iters=3)
+        print(json.dumps({"kernel": f"attn_qktv_bwd window=({wd},{wh},{ww}) C={C} M={M}", "ms": round(ms, 4),
+                          "algo_TFLOPs": round(2 * flop / ms / 1e9, 1)}), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--qktv" in sys.argv:
+        qktv()
+    else:
+        main()
+        qktv()
