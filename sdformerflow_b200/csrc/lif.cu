@@ -12,6 +12,7 @@
 // the input is saved for backward: K2 re-reads u, recomputes h_t and walks the adjoint
 // recurrence in registers, emitting the per-channel BatchNorm partial sums on the way.
 // Algorithmic traffic per neuron-timestep: fwd 4 B in + {4,1,2} B out; bwd 12 B.
+#include <cstdlib>
 #include "sdf_common.cuh"
 
 namespace sdf {
@@ -155,8 +156,10 @@ struct LifBwdP {
   SeqP s; NeuronP nrn;
 };
 
-template <int T, int V>
-__global__ void __launch_bounds__(256, 2) lif_bwd_kernel(const LifBwdP p) {
+// PRE = 1: all grad loads issued up front (max loads in flight, ~190 regs, 1 CTA/SM);
+// PRE = 0: grad loads streamed inside the adjoint loop (128 regs, 2 CTAs/SM).
+template <int T, int V, int PRE>
+__global__ void __launch_bounds__(256, PRE ? 1 : 2) lif_bwd_kernel(const LifBwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   extern __shared__ float smem[];
   const SeqP& s = p.s;
@@ -174,10 +177,15 @@ __global__ void __launch_bounds__(256, 2) lif_bwd_kernel(const LifBwdP p) {
     const int64_t n = row * s.row_w + col;
     if (n >= s.n_neurons) continue;
     const int64_t off = seq_base(s, n);
-    float u[TM][V], h[TM][V];
+    float u[TM][V], h[TM][V], gpre[PRE ? TM : 1][V];
 #pragma unroll
     for (int t = 0; t < TM; ++t)
       if (t < Tn) ldv<V>(p.u + off + t * s.stride_t, u[t]);
+    if (PRE) {
+#pragma unroll
+      for (int t = 0; t < TM; ++t)
+        if (t < Tn) ldv<V>(p.gs + off + t * s.stride_t, gpre[PRE ? t : 0]);
+    }
     if (s.chan_mode >= 2) load_affine<V>(s, p.scale, p.shift, n, sc, sh);
     float v0[V], v[V];
     if (p.v_init) {
@@ -208,7 +216,12 @@ __global__ void __launch_bounds__(256, 2) lif_bwd_kernel(const LifBwdP p) {
     for (int t = TM - 1; t >= 0; --t) {
       if (t < Tn) {
         float dx[V], du[V], g[V];
-        ldv<V>(p.gs + off + t * s.stride_t, g);
+        if (PRE) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) g[i] = gpre[PRE ? t : 0][i];
+        } else {
+          ldv<V>(p.gs + off + t * s.stride_t, g);
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           float gh = neuron_grad_h(nrn, h[t][i], g[i], gv[i]);
@@ -528,15 +541,19 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
                     sizeof(float) * (a->n_partial_blocks - L.grid.x) * 2 * a->C, stream);
   if (a->plif_partials) cudaMemsetAsync(a->plif_partials, 0, sizeof(float) * a->n_partial_blocks, stream);
   const size_t smem = sizeof(float) * 4 * (size_t)L.threads;
+  static const int pre_mode = [] { const char* e = getenv("SDF_LIF_BWD_PRELOAD"); return e ? atoi(e) : 1; }();
   if (L.V == 4) {
     switch (T) {
-      case 2: lif_bwd_kernel<2, 4><<<L.grid, L.threads, smem, stream>>>(p); break;
-      case 4: lif_bwd_kernel<4, 4><<<L.grid, L.threads, smem, stream>>>(p); break;
-      case 5: lif_bwd_kernel<5, 4><<<L.grid, L.threads, smem, stream>>>(p); break;
-      default: lif_bwd_kernel<10, 4><<<L.grid, L.threads, smem, stream>>>(p); break;
+      case 2: lif_bwd_kernel<2, 4, 1><<<L.grid, L.threads, smem, stream>>>(p); break;
+      case 4: lif_bwd_kernel<4, 4, 1><<<L.grid, L.threads, smem, stream>>>(p); break;
+      case 5: lif_bwd_kernel<5, 4, 1><<<L.grid, L.threads, smem, stream>>>(p); break;
+      default:
+        if (pre_mode) lif_bwd_kernel<10, 4, 1><<<L.grid, L.threads, smem, stream>>>(p);
+        else lif_bwd_kernel<10, 4, 0><<<L.grid, L.threads, smem, stream>>>(p);
+        break;
     }
   } else {
-    lif_bwd_kernel<0, 1><<<L.grid, L.threads, smem, stream>>>(p);
+    lif_bwd_kernel<0, 1, 0><<<L.grid, L.threads, smem, stream>>>(p);
   }
   return finish_launch("sdf_lif_bwd");
 }

@@ -102,7 +102,7 @@ __device__ __forceinline__ float surrogate_grad(const NeuronP& p, float z) {
   if (p.sg == SDF_SG_ATAN) {
     float c = 1.5707963267948966f * p.sg_alpha;
     float cz = c * z;
-    return (p.sg_alpha * 0.5f) / (1.f + cz * cz);
+    return __fdividef(p.sg_alpha * 0.5f, 1.f + cz * cz);   // gradient path: 2-ulp division is plenty
   }
   float sgax = 1.f / (1.f + __expf(-p.sg_alpha * z));
   return (1.f - sgax) * sgax * p.sg_alpha;

@@ -439,9 +439,13 @@ class _SpikeConvFn(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         stride, padding, transposed, output_padding, has_bias = ctx.cfg
         two = lambda v: [v, v] if isinstance(v, int) else list(v)  # noqa: E731
+        # keep the incoming gradient in the activation's memory format (NHWC): a plain .contiguous() here would be a
+        # full NHWC->NCHW transpose of every conv gradient
+        cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        g = g.contiguous(memory_format=torch.channels_last) if cl else g.contiguous()
         with _tf32(True):
             gx, gw, gb = torch.ops.aten.convolution_backward(
-                g.contiguous(), x, weight, [weight.shape[1] if transposed else weight.shape[0]] if has_bias else None,
+                g, x, weight, [weight.shape[1] if transposed else weight.shape[0]] if has_bias else None,
                 two(stride), two(padding), [1, 1], transposed, two(output_padding), 1,
                 [ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]])
         return gx, gw, gb, None, None, None, None
