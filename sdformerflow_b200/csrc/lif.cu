@@ -103,8 +103,8 @@ struct LifFwdP {
 };
 
 // T > 0: compile-time step count (fully unrolled).  T == 0: runtime T <= 32.
-template <int T, int V, int DT>
-__global__ void __launch_bounds__(512) lif_fwd_kernel(const LifFwdP p) {
+template <int T, int V, int DT, bool SIMPLE>
+__global__ void __launch_bounds__(512, (T > 0 && T <= 10) ? 2 : 1) lif_fwd_kernel(const LifFwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   const SeqP& s = p.s;
   const NeuronP nrn = p.nrn;
@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(512) lif_fwd_kernel(const LifFwdP p) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           float xx = fmaf(x[t][i], sc[i], sh[i]);
-          h[i] = neuron_charge(nrn, v[i], xx);
+          h[i] = neuron_charge_t<SIMPLE>(nrn, v[i], xx);
           sp[i] = neuron_fire(nrn, h[i]);
-          v[i] = neuron_reset(nrn, h[i], sp[i]);
+          v[i] = neuron_reset_t<SIMPLE>(nrn, h[i], sp[i]);
         }
         store_spikes<DT, V>(p.spike, off + t * s.stride_t, sp);
         if (p.h_seq) stv<V>(p.h_seq + off + t * s.stride_t, h);
@@ -158,8 +158,8 @@ struct LifBwdP {
 
 // PRE = 1: all grad loads issued up front (max loads in flight, ~190 regs, 1 CTA/SM);
 // PRE = 0: grad loads streamed inside the adjoint loop (128 regs, 2 CTAs/SM).
-template <int T, int V, int PRE>
-__global__ void __launch_bounds__(256, PRE ? 1 : 2) lif_bwd_kernel(const LifBwdP p) {
+template <int T, int V, int PRE, bool SIMPLE>
+__global__ void __launch_bounds__(256, (V == 2) ? 2 : (PRE ? 1 : 2)) lif_bwd_kernel(const LifBwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   extern __shared__ float smem[];
   const SeqP& s = p.s;
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(256, PRE ? 1 : 2) lif_bwd_kernel(const LifBwdP
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           float xx = fmaf(u[t][i], sc[i], sh[i]);
-          h[t][i] = neuron_charge(nrn, v[i], xx);
-          v[i] = neuron_reset(nrn, h[t][i], neuron_fire(nrn, h[t][i]));
+          h[t][i] = neuron_charge_t<SIMPLE>(nrn, v[i], xx);
+          v[i] = neuron_reset_t<SIMPLE>(nrn, h[t][i], neuron_fire(nrn, h[t][i]));
         }
       }
     }
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, PRE ? 1 : 2) lif_bwd_kernel(const LifBwdP
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float gh = neuron_grad_h(nrn, h[t][i], g[i], gv[i]);
+          float gh = neuron_grad_h_t<SIMPLE>(nrn, h[t][i], g[i], gv[i]);
           dx[i] = gh * dh_dx;
           gv[i] = gh * dh_dv;
           du[i] = dx[i] * sc[i];
@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(256, PRE ? 1 : 2) lif_bwd_kernel(const LifBwdP
       }
     }
   }
-  if (p.bn_partials && s.chan_mode == 1 && V == 4)
-    block_reduce_rows_to_partials<2>(acc, smem, p.bn_partials, s.R, s.k, s.C, (int64_t)blockIdx.y * s.tile_w);
+  if (p.bn_partials && s.chan_mode == 1 && V > 1)
+    block_reduce_rows_to_partials<2, V>(acc, smem, p.bn_partials, s.R, s.k, s.C, (int64_t)blockIdx.y * s.tile_w);
   if (p.plif_partials) {
     __syncthreads();
     float w = plif_acc;
@@ -438,7 +438,7 @@ static int build_seq(const sdf_seq_layout& lay, int64_t C, int64_t hw, bool affi
   s->C = C > 0 ? C : 1; s->hw = hw > 0 ? hw : 1; s->T = (int)lay.T;
   if (lay.stride_b == 0) s->inner = lay.n_neurons;
   RowTiling rt;
-  bool chan_fixed = affine && hw == 1 && V == 4 && (lay.stride_b == 0 || lay.inner % C == 0) &&
+  bool chan_fixed = affine && hw == 1 && V > 1 && (lay.stride_b == 0 || lay.inner % C == 0) &&
                     (lay.n_neurons % C == 0) && make_row_tiling(lay.n_neurons / C, C, V, target, (int)max_blocks, &rt);
   if (want_partials)
     SDF_REQUIRE(chan_fixed, "neuron backward: bn_partials need 16B-aligned channels-last input with C %% 4 == 0");
@@ -465,7 +465,7 @@ using namespace sdf;
 
 extern "C" int64_t sdf_partial_blocks(int64_t rows, int64_t C) {
   (void)rows; (void)C;
-  return (int64_t)kNumSMs * 2;
+  return (int64_t)kNumSMs * 4;
 }
 
 #define SDF_DISPATCH_DT(KERNEL, TT, VV, DT, ...)                                       \
@@ -473,6 +473,19 @@ extern "C" int64_t sdf_partial_blocks(int64_t rows, int64_t C) {
     if (DT == SDF_SPIKE_F32) KERNEL<TT, VV, SDF_SPIKE_F32> __VA_ARGS__;                \
     else if (DT == SDF_SPIKE_U8) KERNEL<TT, VV, SDF_SPIKE_U8> __VA_ARGS__;             \
     else KERNEL<TT, VV, SDF_SPIKE_BF16> __VA_ARGS__;                                   \
+  } while (0)
+// LIF forward: + SIMPLE fast path for the hot step counts
+#define SDF_DISPATCH_LIF(TT, VV, DT, SIMPLE, ...)                                                   \
+  do {                                                                                              \
+    if (SIMPLE) {                                                                                   \
+      if (DT == SDF_SPIKE_F32) lif_fwd_kernel<TT, VV, SDF_SPIKE_F32, true> __VA_ARGS__;             \
+      else if (DT == SDF_SPIKE_U8) lif_fwd_kernel<TT, VV, SDF_SPIKE_U8, true> __VA_ARGS__;          \
+      else lif_fwd_kernel<TT, VV, SDF_SPIKE_BF16, true> __VA_ARGS__;                                \
+    } else {                                                                                        \
+      if (DT == SDF_SPIKE_F32) lif_fwd_kernel<TT, VV, SDF_SPIKE_F32, false> __VA_ARGS__;            \
+      else if (DT == SDF_SPIKE_U8) lif_fwd_kernel<TT, VV, SDF_SPIKE_U8, false> __VA_ARGS__;         \
+      else lif_fwd_kernel<TT, VV, SDF_SPIKE_BF16, false> __VA_ARGS__;                               \
+    }                                                                                               \
   } while (0)
 
 extern "C" int sdf_lif_fwd(const sdf_lif_fwd_args* a) {
@@ -495,16 +508,17 @@ extern "C" int sdf_lif_fwd(const sdf_lif_fwd_args* a) {
   if (st) return st;
   p.s = L.s;
   cudaStream_t stream = (cudaStream_t)a->stream;
+  const bool simple = neuron_is_simple(p.nrn);
   if (L.V == 4) {
     switch (T) {
-      case 2: SDF_DISPATCH_DT(lif_fwd_kernel, 2, 4, DT, <<<L.grid, L.threads, 0, stream>>>(p)); break;
-      case 4: SDF_DISPATCH_DT(lif_fwd_kernel, 4, 4, DT, <<<L.grid, L.threads, 0, stream>>>(p)); break;
-      case 5: SDF_DISPATCH_DT(lif_fwd_kernel, 5, 4, DT, <<<L.grid, L.threads, 0, stream>>>(p)); break;
-      case 10: SDF_DISPATCH_DT(lif_fwd_kernel, 10, 4, DT, <<<L.grid, L.threads, 0, stream>>>(p)); break;
-      default: SDF_DISPATCH_DT(lif_fwd_kernel, 20, 4, DT, <<<L.grid, L.threads, 0, stream>>>(p)); break;
+      case 2: SDF_DISPATCH_LIF(2, 4, DT, simple, <<<L.grid, L.threads, 0, stream>>>(p)); break;
+      case 4: SDF_DISPATCH_LIF(4, 4, DT, false, <<<L.grid, L.threads, 0, stream>>>(p)); break;
+      case 5: SDF_DISPATCH_LIF(5, 4, DT, simple, <<<L.grid, L.threads, 0, stream>>>(p)); break;
+      case 10: SDF_DISPATCH_LIF(10, 4, DT, simple, <<<L.grid, L.threads, 0, stream>>>(p)); break;
+      default: SDF_DISPATCH_LIF(20, 4, DT, false, <<<L.grid, L.threads, 0, stream>>>(p)); break;
     }
   } else {
-    SDF_DISPATCH_DT(lif_fwd_kernel, 0, 1, DT, <<<L.grid, L.threads, 0, stream>>>(p));
+    SDF_DISPATCH_LIF(0, 1, DT, false, <<<L.grid, L.threads, 0, stream>>>(p));
   }
   return finish_launch("sdf_lif_fwd");
 }
@@ -525,14 +539,15 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   const int T = (int)a->lay.T;
   const bool fastT = (T == 2 || T == 4 || T == 5 || T == 10);
   const bool parts = a->bn_partials || a->plif_partials;
-  int64_t max_blocks = (int64_t)kNumSMs * 2;
+  int64_t max_blocks = (int64_t)kNumSMs * (T == 10 ? 3 : 2);
   if (parts) {
     SDF_REQUIRE(a->n_partial_blocks >= 1, "sdf_lif_bwd: n_partial_blocks < 1");
     if (a->n_partial_blocks < max_blocks) max_blocks = a->n_partial_blocks;
   }
   if (a->bn_partials) SDF_REQUIRE(fastT, "sdf_lif_bwd: bn_partials supported for T in {2,4,5,10}");
   SeqLaunch L;
-  st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, fastT ? 4 : 1, 256, max_blocks, &L);
+  // T = 10 keeps u, h (and the preloaded grads) in registers: 2 neurons per thread there, 4 otherwise
+  st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, fastT ? (T == 10 ? 2 : 4) : 1, 256, max_blocks, &L);
   if (st) return st;
   p.s = L.s;
   if (a->plif_partials) SDF_REQUIRE(L.grid.y == 1 || L.grid.x * L.grid.y <= a->n_partial_blocks, "sdf_lif_bwd: plif partial capacity");
@@ -541,19 +556,24 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
                     sizeof(float) * (a->n_partial_blocks - L.grid.x) * 2 * a->C, stream);
   if (a->plif_partials) cudaMemsetAsync(a->plif_partials, 0, sizeof(float) * a->n_partial_blocks, stream);
   const size_t smem = sizeof(float) * 4 * (size_t)L.threads;
-  static const int pre_mode = [] { const char* e = getenv("SDF_LIF_BWD_PRELOAD"); return e ? atoi(e) : 1; }();
+  const bool simple = neuron_is_simple(p.nrn);
   if (L.V == 4) {
     switch (T) {
-      case 2: lif_bwd_kernel<2, 4, 1><<<L.grid, L.threads, smem, stream>>>(p); break;
-      case 4: lif_bwd_kernel<4, 4, 1><<<L.grid, L.threads, smem, stream>>>(p); break;
-      case 5: lif_bwd_kernel<5, 4, 1><<<L.grid, L.threads, smem, stream>>>(p); break;
+      case 2:
+        if (simple) lif_bwd_kernel<2, 4, 1, true><<<L.grid, L.threads, smem, stream>>>(p);
+        else lif_bwd_kernel<2, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
+        break;
+      case 4: lif_bwd_kernel<4, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p); break;
       default:
-        if (pre_mode) lif_bwd_kernel<10, 4, 1><<<L.grid, L.threads, smem, stream>>>(p);
-        else lif_bwd_kernel<10, 4, 0><<<L.grid, L.threads, smem, stream>>>(p);
+        if (simple) lif_bwd_kernel<5, 4, 1, true><<<L.grid, L.threads, smem, stream>>>(p);
+        else lif_bwd_kernel<5, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
         break;
     }
+  } else if (L.V == 2) {
+    if (simple) lif_bwd_kernel<10, 2, 1, true><<<L.grid, L.threads, smem, stream>>>(p);
+    else lif_bwd_kernel<10, 2, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
   } else {
-    lif_bwd_kernel<0, 1, 0><<<L.grid, L.threads, smem, stream>>>(p);
+    lif_bwd_kernel<0, 1, 0, false><<<L.grid, L.threads, smem, stream>>>(p);
   }
   return finish_launch("sdf_lif_bwd");
 }

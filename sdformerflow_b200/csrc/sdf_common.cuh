@@ -83,6 +83,18 @@ NeuronP make_neuron(const sdf_neuron_cfg& c);
 int validate_neuron(const sdf_neuron_cfg& c);
 
 // charge: h from (v, x).  Exact op order of spikingjelly: no FMA contraction.
+// SIMPLE = LIF, soft reset (v_reset None), tau a power of two, detach_reset, ATan: the configuration of every
+// shipped/smoke config; same arithmetic as the generic path with the uniform branches compiled out.
+__host__ __device__ __forceinline__ bool neuron_is_simple(const NeuronP& p) {
+  return p.kind == SDF_NEURON_LIF && !p.hard && p.tau_pow2 && p.detach && p.sg == SDF_SG_ATAN;
+}
+template <bool SIMPLE>
+__device__ __forceinline__ float neuron_charge_t(const NeuronP& p, float v, float x);
+template <bool SIMPLE>
+__device__ __forceinline__ float neuron_reset_t(const NeuronP& p, float h, float s);
+template <bool SIMPLE>
+__device__ __forceinline__ float neuron_grad_h_t(const NeuronP& p, float h, float gs, float gv);
+
 __device__ __forceinline__ float neuron_charge(const NeuronP& p, float v, float x) {
   if (p.kind == SDF_NEURON_IF) return __fadd_rn(v, x);
   float d = (p.hard && p.v_reset != 0.f) ? __fsub_rn(x, __fsub_rn(v, p.v_reset)) : __fsub_rn(x, v);
@@ -122,6 +134,20 @@ __device__ __forceinline__ float neuron_grad_h(const NeuronP& p, float h, float 
   }
   return gs * sg + gv * dv_dh;
 }
+template <> __device__ __forceinline__ float neuron_charge_t<false>(const NeuronP& p, float v, float x) { return neuron_charge(p, v, x); }
+template <> __device__ __forceinline__ float neuron_charge_t<true>(const NeuronP& p, float v, float x) {
+  return __fadd_rn(v, __fmul_rn(__fsub_rn(x, v), p.inv_tau));
+}
+template <> __device__ __forceinline__ float neuron_reset_t<false>(const NeuronP& p, float h, float s) { return neuron_reset(p, h, s); }
+template <> __device__ __forceinline__ float neuron_reset_t<true>(const NeuronP& p, float h, float s) { return __fsub_rn(h, s * p.v_th); }
+template <> __device__ __forceinline__ float neuron_grad_h_t<false>(const NeuronP& p, float h, float gs, float gv) {
+  return neuron_grad_h(p, h, gs, gv);
+}
+template <> __device__ __forceinline__ float neuron_grad_h_t<true>(const NeuronP& p, float h, float gs, float gv) {
+  const float cz = 1.5707963267948966f * p.sg_alpha * __fsub_rn(h, p.v_th);
+  return fmaf(gs, __fdividef(p.sg_alpha * 0.5f, fmaf(cz, cz, 1.f)), gv);
+}
+
 __device__ __forceinline__ float neuron_dh_dx(const NeuronP& p) {
   return p.kind == SDF_NEURON_IF ? 1.f : p.inv_tau;
 }
@@ -167,25 +193,28 @@ bool make_row_tiling(int64_t rows, int64_t C, int V, int target_threads, int max
 
 // Block-level reduction of per-thread channel accumulators across the k rows of a block; result
 // written (not accumulated) to partials[blockIdx.x][slot][col0 + rx*4 ..].  smem: float[threads*4].
-template <int NV>
+template <int NV, int V = 4>
 __device__ __forceinline__ void block_reduce_rows_to_partials(float (*acc)[4], float* smem, float* partials,
                                                               int R, int k, int64_t C, int64_t col0) {
   const int rx = threadIdx.x % R;
   const int ry = threadIdx.x / R;
-  float4* s4 = reinterpret_cast<float4*>(smem);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     __syncthreads();
-    s4[ry * R + rx] = make_float4(acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
+#pragma unroll
+    for (int i = 0; i < V; ++i) smem[(ry * R + rx) * V + i] = acc[v][i];
     __syncthreads();
     if (ry == 0) {
-      float4 t = s4[rx];
+      float t[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) t[i] = smem[rx * V + i];
       for (int j = 1; j < k; ++j) {
-        float4 o = s4[j * R + rx];
-        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+#pragma unroll
+        for (int i = 0; i < V; ++i) t[i] += smem[(j * R + rx) * V + i];
       }
-      float* dst = partials + ((int64_t)blockIdx.x * NV + v) * C + col0 + rx * 4;
-      *reinterpret_cast<float4*>(dst) = t;
+      float* dst = partials + ((int64_t)blockIdx.x * NV + v) * C + col0 + rx * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) dst[i] = t[i];
     }
   }
 }
