@@ -222,10 +222,8 @@ def run_b200(args, rank, local_rank, world):
     model.to(dev).train()
     functional.set_step_mode(model, "m")
     functional.set_backend(model, "cupy", prod.neuron.LIFNode)   # accepted no-op, as the reference scripts call it
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], bucket_cap_mb=25,
-                                                        gradient_as_bucket_view=True)
+    from sdformerflow_b200 import distributed as sdist
+    net = sdist.wrap(model, local_rank)          # DDP: bucketed NCCL all-reduce overlapped with backward
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
 
     B = B_PER_GPU
@@ -304,7 +302,8 @@ def run_b200(args, rank, local_rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "gemm": "cuBLAS/cuDNN fp32 (TF32 off)", "l2": "activations per step >> 126 MB L2; no explicit flush",
+                       "gemm": "cuBLAS/cuDNN TF32x2 weight split on spike operands (fp32-grade), fp32 elsewhere; TF32 backward",
+                       "l2": "activations per step >> 126 MB L2; no explicit flush",
                        "weights": "random init (init_weights, seed 0)"},
             "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},

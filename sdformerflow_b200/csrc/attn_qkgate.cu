@@ -46,7 +46,7 @@ __device__ __forceinline__ int64_t gate_dest(const QkP& p, int64_t t, int64_t nr
   return (((int64_t)t2 * p.M + m2) * p.P + pos2) * p.C + h2 * 32;
 }
 
-template <int T, int DT, bool BWD>
+template <int T, int DT, bool BWD, bool SIMPLE>
 __global__ void __launch_bounds__(512) qkgate_kernel(const QkP p) {
   constexpr int TM = T > 0 ? T : 8;
   extern __shared__ float smem[];
@@ -97,19 +97,19 @@ __global__ void __launch_bounds__(512) qkgate_kernel(const QkP p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float xq = fmaf(f4(qp[t], i), f4(qsc, i), f4(qsh, i));
-          f4(hq[t], i) = neuron_charge(nrn, vq[i], xq);
+          f4(hq[t], i) = neuron_charge_t<SIMPLE>(nrn, vq[i], xq);
           const float sq = neuron_fire(nrn, f4(hq[t], i));
-          vq[i] = neuron_reset(nrn, f4(hq[t], i), sq);
+          vq[i] = neuron_reset_t<SIMPLE>(nrn, f4(hq[t], i), sq);
           cnt += sq;
           const float xk = __fadd_rn(fmaf(f4(kp[t], i), f4(ksc, i), f4(ksh, i)), f4(pe, i));
-          f4(hk[t], i) = neuron_charge(nrn, vk[i], xk);
+          f4(hk[t], i) = neuron_charge_t<SIMPLE>(nrn, vk[i], xk);
           f4(sk, i) = neuron_fire(nrn, f4(hk[t], i));
-          vk[i] = neuron_reset(nrn, f4(hk[t], i), f4(sk, i));
+          vk[i] = neuron_reset_t<SIMPLE>(nrn, f4(hk[t], i), f4(sk, i));
         }
         cnt = head_sum8(cnt);               // exact small integer in fp32
-        ha[t] = neuron_charge(nrn, va, cnt);
+        ha[t] = neuron_charge_t<SIMPLE>(nrn, va, cnt);
         av[t] = neuron_fire(nrn, ha[t]);
-        va = neuron_reset(nrn, ha[t], av[t]);
+        va = neuron_reset_t<SIMPLE>(nrn, ha[t], av[t]);
         if (!BWD && valid) {
           float4 g;
 #pragma unroll
@@ -137,16 +137,16 @@ __global__ void __launch_bounds__(512) qkgate_kernel(const QkP p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) da += f4(dg[t], i) * neuron_fire(nrn, f4(hk[t], i));
           da = head_sum8(da);
-          const float gha = neuron_grad_h(nrn, ha[t], da, gva);
+          const float gha = neuron_grad_h_t<SIMPLE>(nrn, ha[t], da, gva);
           const float dcnt = gha * dh_dx;   // d/d(sum q), broadcast to the 32 q spikes
           gva = gha * dh_dv;
           float4 dq, dk;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float ghq = neuron_grad_h(nrn, f4(hq[t], i), dcnt, gvq[i]);
+            const float ghq = neuron_grad_h_t<SIMPLE>(nrn, f4(hq[t], i), dcnt, gvq[i]);
             f4(dq, i) = ghq * dh_dx;
             gvq[i] = ghq * dh_dv;
-            const float ghk = neuron_grad_h(nrn, f4(hk[t], i), f4(dg[t], i) * av[t], gvk[i]);
+            const float ghk = neuron_grad_h_t<SIMPLE>(nrn, f4(hk[t], i), f4(dg[t], i) * av[t], gvk[i]);
             f4(dk, i) = ghk * dh_dx;
             gvk[i] = ghk * dh_dv;
             if (valid) {
@@ -247,15 +247,17 @@ extern "C" int sdf_attn_qkgate_fwd(const sdf_attn_qkgate_fwd_args* a) {
   p.tile_w = rt.tile_w; p.R = rt.R; p.k = rt.k;
   dim3 grid(rt.blocks, rt.ncol, 1);
   cudaStream_t stream = (cudaStream_t)a->stream;
-#define QK_FWD(TT)                                                                                        \
-  do {                                                                                                    \
-    if (DT == SDF_SPIKE_F32) qkgate_kernel<TT, SDF_SPIKE_F32, false><<<grid, rt.threads, 0, stream>>>(p); \
-    else if (DT == SDF_SPIKE_U8) qkgate_kernel<TT, SDF_SPIKE_U8, false><<<grid, rt.threads, 0, stream>>>(p); \
-    else qkgate_kernel<TT, SDF_SPIKE_BF16, false><<<grid, rt.threads, 0, stream>>>(p);                    \
+#define QK_FWD(TT, SM)                                                                                        \
+  do {                                                                                                        \
+    if (DT == SDF_SPIKE_F32) qkgate_kernel<TT, SDF_SPIKE_F32, false, SM><<<grid, rt.threads, 0, stream>>>(p); \
+    else if (DT == SDF_SPIKE_U8) qkgate_kernel<TT, SDF_SPIKE_U8, false, SM><<<grid, rt.threads, 0, stream>>>(p); \
+    else qkgate_kernel<TT, SDF_SPIKE_BF16, false, SM><<<grid, rt.threads, 0, stream>>>(p);                    \
   } while (0)
-  if (a->wd == 2) QK_FWD(2);
-  else if (a->wd == 4) QK_FWD(4);
-  else QK_FWD(0);
+  const bool simple = neuron_is_simple(p.nrn);
+  if (a->wd == 2 && simple) QK_FWD(2, true);
+  else if (a->wd == 2) QK_FWD(2, false);
+  else if (a->wd == 4) QK_FWD(4, false);
+  else QK_FWD(0, false);
 #undef QK_FWD
   return finish_launch("sdf_attn_qkgate_fwd");
 }
@@ -286,9 +288,10 @@ extern "C" int sdf_attn_qkgate_bwd(const sdf_attn_qkgate_bwd_args* a) {
     cudaMemsetAsync(a->bn_partials_k + off, 0, n, stream);
   }
   const size_t smem = sizeof(float) * 4 * rt.threads;
-  if (a->wd == 2) qkgate_kernel<2, SDF_SPIKE_F32, true><<<grid, rt.threads, smem, stream>>>(p);
-  else if (a->wd == 4) qkgate_kernel<4, SDF_SPIKE_F32, true><<<grid, rt.threads, smem, stream>>>(p);
-  else qkgate_kernel<0, SDF_SPIKE_F32, true><<<grid, rt.threads, smem, stream>>>(p);
+  if (a->wd == 2 && neuron_is_simple(p.nrn)) qkgate_kernel<2, SDF_SPIKE_F32, true, true><<<grid, rt.threads, smem, stream>>>(p);
+  else if (a->wd == 2) qkgate_kernel<2, SDF_SPIKE_F32, true, false><<<grid, rt.threads, smem, stream>>>(p);
+  else if (a->wd == 4) qkgate_kernel<4, SDF_SPIKE_F32, true, false><<<grid, rt.threads, smem, stream>>>(p);
+  else qkgate_kernel<0, SDF_SPIKE_F32, true, false><<<grid, rt.threads, smem, stream>>>(p);
   return finish_launch("sdf_attn_qkgate_bwd");
 }
 

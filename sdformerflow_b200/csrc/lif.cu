@@ -104,7 +104,7 @@ struct LifFwdP {
 
 // T > 0: compile-time step count (fully unrolled).  T == 0: runtime T <= 32.
 template <int T, int V, int DT, bool SIMPLE>
-__global__ void __launch_bounds__(512, (T > 0 && T <= 10) ? 2 : 1) lif_fwd_kernel(const LifFwdP p) {
+__global__ void __launch_bounds__(512, (T > 0 && T <= 10 && DT != SDF_SPIKE_F32) ? 2 : 1) lif_fwd_kernel(const LifFwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   const SeqP& s = p.s;
   const NeuronP nrn = p.nrn;
