@@ -32,9 +32,8 @@
 
 namespace sdf {
 
-constexpr int kThreads = 256;      // 8 warps: two 128-lane TMEM slots
-constexpr int kKT = 192;           // key tile (TMEM columns of S per slot)
-constexpr int kSlotCols = 256;     // TMEM columns per slot: [0,192) S/T, [192,224) O
+constexpr int kSlotThreads = 256;  // 8 warps per 128-lane TMEM slot: four lane quarters x two column halves
+constexpr int kKTmax = 192;        // largest key tile (TMEM columns of S per slot); O accumulator sits right after it
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,6 +114,25 @@ __device__ __forceinline__ float h2f(uint16_t h) {
   return __half2float(__ushort_as_half(h));
 }
 
+// two fp32 -> packed 16-bit pair (lo = a, hi = b) in one instruction, and back
+template <int BF>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  uint32_t r;
+  if (BF) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+template <int BF>
+__device__ __forceinline__ void unpack2(uint32_t r, float& a, float& b) {
+  if (BF) {
+    a = __uint_as_float(r << 16);
+    b = __uint_as_float(r & 0xFFFF0000u);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r));
+    a = f.x; b = f.y;
+  }
+}
+
 // ---- kernel parameters ----------------------------------------------------------------------------
 struct QktvP {
   const uint8_t* q; const uint8_t* k; const uint8_t* v;
@@ -122,7 +140,7 @@ struct QktvP {
   float* out; int32_t* s_dbg; float* attn_dbg;
   const float* grad_out; float* grad_q; float* grad_k; float* grad_v; float* grad_table;
   int64_t M, nH, nW, P;
-  int N, wd, wh, ww, Rpad, n_mt, n_kt, tab;
+  int N, wd, wh, ww, Rpad, n_mt, n_kt, tab, kt, slot_cols, tmem_cols;
   float scale;
   int has_mask;
 };
@@ -155,7 +173,7 @@ __device__ __forceinline__ uint32_t trans_off(int d, int n) { return (uint32_t)(
 // stage rows [0, N) of a u8 {0,1} [N, 32] block
 template <int BF>
 __device__ __forceinline__ void stage_plain_u8(uint8_t* smem, uint32_t base, int Rpad, const uint8_t* src, int N) {
-  for (int i = threadIdx.x; i < N * 2; i += kThreads) {       // one 16-byte half-row per item
+  for (int i = threadIdx.x; i < N * 2; i += blockDim.x) {       // one 16-byte half-row per item
     const int r = i >> 1, hf = i & 1;
     const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * 32 + hf * 16));
     const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
@@ -172,7 +190,7 @@ __device__ __forceinline__ void stage_plain_u8(uint8_t* smem, uint32_t base, int
 }
 template <int BF>
 __device__ __forceinline__ void stage_trans_u8(uint8_t* smem, uint32_t base, const uint8_t* src, int N) {
-  for (int i = threadIdx.x; i < N * 2; i += kThreads) {
+  for (int i = threadIdx.x; i < N * 2; i += blockDim.x) {
     const int r = i >> 1, hf = i & 1;
     const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * 32 + hf * 16));
     const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
@@ -190,7 +208,7 @@ __device__ __forceinline__ const float* go_row(const QktvP& p, int64_t mwin, int
 }
 template <int BF>
 __device__ __forceinline__ void stage_plain_f32(uint8_t* smem, uint32_t base, int Rpad, const QktvP& p, int64_t mwin, int64_t head) {
-  for (int i = threadIdx.x; i < p.N * 4; i += kThreads) {     // 8 floats -> one 16-byte chunk
+  for (int i = threadIdx.x; i < p.N * 4; i += blockDim.x) {     // 8 floats -> one 16-byte chunk
     const int r = i >> 2, c = i & 3;
     const float* src = go_row(p, mwin, head, r) + c * 8;
     const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
@@ -202,7 +220,7 @@ __device__ __forceinline__ void stage_plain_f32(uint8_t* smem, uint32_t base, in
 }
 template <int BF>
 __device__ __forceinline__ void stage_trans_f32(uint8_t* smem, uint32_t base, const QktvP& p, int64_t mwin, int64_t head) {
-  for (int i = threadIdx.x; i < p.N * 8; i += kThreads) {
+  for (int i = threadIdx.x; i < p.N * 8; i += blockDim.x) {
     const int r = i >> 3, c = i & 7;
     const float4 a = __ldg(reinterpret_cast<const float4*>(go_row(p, mwin, head, r) + c * 4));
     *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 0, r)) = f2h<BF>(a.x);
@@ -216,8 +234,12 @@ __device__ __forceinline__ void stage_trans_f32(uint8_t* smem, uint32_t base, co
 // PHASE 1: dQ = scale*(dO V^T) K     A=dO B=V  Bt=K^T   out -> grad_q, side effect d(bias table)
 // PHASE 2: dK = scale*(V dO^T) Q     A=V  B=dO Bt=Q^T   out -> grad_k
 // PHASE 3: dV = T^T dO               A=K  B=Q  Bt=dO^T  out -> grad_v      (T^T[j][i]: roles of i, j swapped)
-template <int PHASE>
-__global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
+// NSLOT = 2: one 512-thread CTA per SM working on two M-tiles at a time (large windows, smem-bound occupancy);
+// NSLOT = 1: 256-thread CTAs, two per SM, each with its own 256 TMEM columns — independent pairs overlap each
+// other's staging / MMA / epilogue latencies.
+template <int PHASE, bool MASK, bool DBG, int NSLOT>
+__global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv_kernel(const QktvP p) {
+  constexpr int kThreads = kSlotThreads * NSLOT;
   constexpr int BF = PHASE == 0 ? 0 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const SmemPlan sp = plan_smem(p.Rpad, p.tab, PHASE == 1);
@@ -250,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -259,7 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
   const uint32_t tmem_base = *tmem_slot;
   uint32_t ph_s = 0, ph_o = 0;
 
-  const int slot = warp >> 2;                                   // which M-tile of the current pair of M-tiles
+  const int slot = NSLOT == 2 ? (warp >> 2) & 1 : 0;            // which M-tile of the current group of M-tiles
+  const int half = NSLOT == 2 ? warp >> 3 : warp >> 2;          // which half of the column chunks this warp takes
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16; // this warp's TMEM lanes
   const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b), bt_base = smem_u32(smem + sp.bt);
   const uint32_t lbo_plain = (uint32_t)Rpad * 16, sbo = 128, lbo_t = 512;
@@ -275,30 +298,30 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
     if (PHASE == 1) { stage_plain_f32<BF>(smem, sp.a, Rpad, p, mwin, head); stage_plain_u8<BF>(smem, sp.b, Rpad, vp, N); stage_trans_u8<BF>(smem, sp.bt, kp, N); }
     if (PHASE == 2) { stage_plain_u8<BF>(smem, sp.a, Rpad, vp, N); stage_plain_f32<BF>(smem, sp.b, Rpad, p, mwin, head); stage_trans_u8<BF>(smem, sp.bt, qp, N); }
     if (PHASE == 3) { stage_plain_u8<BF>(smem, sp.a, Rpad, kp, N); stage_plain_u8<BF>(smem, sp.b, Rpad, qp, N); stage_trans_f32<BF>(smem, sp.bt, p, mwin, head); }
-    if (p.has_mask && (PHASE == 0 || PHASE == 3)) {
+    if (MASK && (PHASE == 0 || PHASE == 3)) {
       const uint8_t* rp = p.region + (mwin % p.nW) * N;
       for (int n = tid; n < N; n += kThreads) reg_s[n] = __ldg(rp + n);
     }
     fence_async_smem();
     __syncthreads();
 
-    for (int mt0 = 0; mt0 < p.n_mt; mt0 += 2) {
-      const int n_slots = (p.n_mt - mt0) >= 2 ? 2 : 1;
+    for (int mt0 = 0; mt0 < p.n_mt; mt0 += NSLOT) {
+      const int n_slots = (p.n_mt - mt0) >= NSLOT ? NSLOT : 1;
       const int mt = mt0 + slot;
       const int row = mt * 128 + (warp & 3) * 32 + lane;         // A-operand row handled by this thread
       const bool row_ok = slot < n_slots && row < N;
       const int lin_i = row_ok ? lin_s[row] : 0;
       const int reg_i = row_ok ? reg_s[row] : 0;
       for (int kt = 0; kt < p.n_kt; ++kt) {
-        const int key0 = kt * kKT;
+        const int key0 = kt * p.kt;
         int nk = N - key0;
-        nk = nk > kKT ? kKT : ((nk + 15) & ~15);
+        nk = nk > p.kt ? p.kt : ((nk + 15) & ~15);
         // ---- MMA 1: S[128 x nk] = A[128 x 32] * B[nk x 32]^T, both slots ----
         if (tid == 0) {
           tc_fence_after();
           const uint32_t idesc = make_idesc(BF, 128, nk);
           for (int s = 0; s < n_slots; ++s) {
-            const uint32_t d = tmem_base + s * kSlotCols;
+            const uint32_t d = tmem_base + s * p.slot_cols;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t ad = make_desc(a_base + ks * 2 * lbo_plain + (uint32_t)(mt0 + s) * 128 * 16, lbo_plain, sbo);
@@ -311,43 +334,58 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
         mbar_wait(&bars[0], ph_s);
         ph_s ^= 1;
         tc_fence_after();
-        // ---- epilogue 1: S -> T = hi + lo (in place) ----
+        // ---- epilogue 1: S -> T = hi + lo (in place); the two warp halves take alternate 16-column chunks ----
         if (slot < n_slots) {
-          const uint32_t tcol = tmem_base + lane_base + slot * kSlotCols;
-          for (int c0 = 0; c0 < nk; c0 += 16) {
+          const uint32_t tcol = tmem_base + lane_base + slot * p.slot_cols;
+          // bias index is linear in the token coordinates: tab[lin_i - lin_j + off] (PHASE 3: roles swapped).
+          // Padding rows/columns need no guard: lin = region = 0 there keeps every index in range, the values
+          // stay finite and meet all-zero V^T columns (or are never written out).
+          const float* tab_i = tab_s + (PHASE == 3 ? lin_off - lin_i : lin_off + lin_i);
+          for (int c0 = half * 16; c0 < nk; c0 += 32) {
             uint32_t r[16], o[16];
             tmem_ld16(tcol + c0, r);
-            uint16_t hi[16], lo[16];
+            const int j0 = key0 + c0;
+            int lj[16];
+            uint32_t rj[4];
+            if (PHASE == 0 || PHASE == 3) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const int4 v4 = *reinterpret_cast<const int4*>(lin_s + j0 + q4 * 4);
+                lj[q4 * 4] = v4.x; lj[q4 * 4 + 1] = v4.y; lj[q4 * 4 + 2] = v4.z; lj[q4 * 4 + 3] = v4.w;
+              }
+              if (MASK) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(reg_s + j0);
+                rj[0] = r4.x; rj[1] = r4.y; rj[2] = r4.z; rj[3] = r4.w;
+              }
+            }
+            float t[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              const int j = key0 + c0 + e;
-              const float s = __uint_as_float(r[e]);
-              float t;
+              const float sv = __uint_as_float(r[e]);
               if (PHASE == 0 || PHASE == 3) {
-                // PHASE 0: this thread is query i = row, column j is the key.  PHASE 3: thread row is the KEY j',
-                // column is the query i' (T^T): bias[i'][j'] = tab[lin_i' - lin_j' + off], mask symmetric.
-                const int lj = lin_s[j < Rpad ? j : 0];
-                const int idx = PHASE == 0 ? (lin_i - lj + lin_off) : (lj - lin_i + lin_off);
-                t = __fadd_rn(__fmul_rn(s, p.scale), tab_s[(idx >= 0 && idx < p.tab) ? idx : 0]);
-                if (p.has_mask && reg_s[j < Rpad ? j : 0] != reg_i) t = __fadd_rn(t, -100.f);
-                if (PHASE == 0 && row_ok && j < N) {
-                  const int64_t o2 = (pair * N + row) * N + j;
-                  if (p.s_dbg) p.s_dbg[o2] = (int32_t)s;
-                  if (p.attn_dbg) p.attn_dbg[o2] = t;
+                t[e] = fmaf(sv, p.scale, PHASE == 3 ? tab_i[lj[e]] : tab_i[-lj[e]]);
+                if (MASK) {
+                  const int rg = (int)((rj[e >> 2] >> ((e & 3) * 8)) & 0xFF);
+                  if (rg != reg_i) t[e] -= 100.f;
+                }
+                if (DBG && PHASE == 0 && row_ok && j0 + e < N) {
+                  const int64_t o2 = (pair * N + row) * N + j0 + e;
+                  if (p.s_dbg) p.s_dbg[o2] = (int32_t)sv;
+                  if (p.attn_dbg) p.attn_dbg[o2] = t[e];
                 }
               } else {
-                // s = dA[i][j] (PHASE 1, thread row = query i) or dA^T[j][i] (PHASE 2)
-                if (PHASE == 1 && row_ok && j < N) atomicAdd(&dtab_s[lin_i - lin_s[j] + lin_off], s);
-                t = s * p.scale;
+                // sv = dA[i][j] (PHASE 1, thread row = query i) or dA^T[j][i] (PHASE 2)
+                if (PHASE == 1 && row_ok && j0 + e < N) atomicAdd(&dtab_s[lin_i - lin_s[j0 + e] + lin_off], sv);
+                t[e] = sv * p.scale;
               }
-              if (!row_ok || j >= N) t = 0.f;
-              hi[e] = f2h<BF>(t);
-              lo[e] = f2h<BF>(t - h2f<BF>(hi[e]));
             }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              o[c] = hi[2 * c] | ((uint32_t)hi[2 * c + 1] << 16);
-              o[8 + c] = lo[2 * c] | ((uint32_t)lo[2 * c + 1] << 16);
+              const uint32_t hi = pack2<BF>(t[2 * c], t[2 * c + 1]);
+              float ha, hb;
+              unpack2<BF>(hi, ha, hb);
+              o[c] = hi;
+              o[8 + c] = pack2<BF>(t[2 * c] - ha, t[2 * c + 1] - hb);
             }
             tmem_st16(tcol + c0, o);
           }
@@ -360,10 +398,10 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
           tc_fence_after();
           const uint32_t idesc = make_idesc(BF, 128, 32);
           for (int s = 0; s < n_slots; ++s) {
-            const uint32_t d = tmem_base + s * kSlotCols + kKT;
+            const uint32_t d = tmem_base + s * p.slot_cols + p.kt;
             for (int c0 = 0; c0 < nk; c0 += 16) {
               const uint64_t bd = make_desc(bt_base + (uint32_t)((key0 + c0) >> 3) * lbo_t, lbo_t, sbo);
-              const uint32_t a_hi = tmem_base + s * kSlotCols + c0;
+              const uint32_t a_hi = tmem_base + s * p.slot_cols + c0;
               mma_ts(d, a_hi, bd, idesc, (kt > 0 || c0 > 0) ? 1u : 0u);
               mma_ts(d, a_hi + 8, bd, idesc, 1u);
             }
@@ -376,10 +414,9 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
       ph_o ^= 1;
       tc_fence_after();
       if (slot < n_slots) {
-        const uint32_t tcol = tmem_base + lane_base + slot * kSlotCols + kKT;
-        uint32_t r0[16], r1[16];
+        const uint32_t tcol = tmem_base + lane_base + slot * p.slot_cols + p.kt + half * 16;
+        uint32_t r0[16];
         tmem_ld16(tcol, r0);
-        tmem_ld16(tcol + 16, r1);
         if (row_ok) {
           float* dst;
           if (PHASE == 0) {
@@ -389,13 +426,11 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
             float* base = PHASE == 1 ? p.grad_q : (PHASE == 2 ? p.grad_k : p.grad_v);
             dst = base + (pair * N + row) * 32;
           }
+          dst += half * 16;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 4; ++c)
             st_stream4(dst + c * 4, make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
                                                 __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3])));
-            st_stream4(dst + 16 + c * 4, make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
-                                                     __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3])));
-          }
         }
       }
       tc_fence_before();
@@ -408,11 +443,11 @@ __global__ void __launch_bounds__(kThreads, 1) qktv_kernel(const QktvP p) {
       if (dtab_s[i] != 0.f) atomicAdd(p.grad_table + (int64_t)i * p.nH + head, dtab_s[i]);
   }
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
 }
 
 static int qktv_setup(int64_t M, int64_t nH, int64_t nW, int64_t wd, int64_t wh, int64_t ww, double scale, bool bwd,
-                      QktvP* p, SmemPlan* sp, int* grid) {
+                      QktvP* p, SmemPlan* sp, int* grid, int* nslot) {
   SDF_REQUIRE(M > 0 && nH > 0 && wd > 0 && wh > 0 && ww > 0, "qktv: bad dims");
   const int64_t N = wd * wh * ww;
   SDF_REQUIRE(N >= 8 && N <= 1024, "qktv: window tokens N=%lld must be in [8, 1024]", (long long)N);
@@ -420,12 +455,20 @@ static int qktv_setup(int64_t M, int64_t nH, int64_t nW, int64_t wd, int64_t wh,
   p->M = M; p->nH = nH; p->nW = nW; p->P = wh * ww; p->N = (int)N; p->wd = (int)wd; p->wh = (int)wh; p->ww = (int)ww;
   p->Rpad = (int)((N + 127) / 128 * 128);
   p->n_mt = p->Rpad / 128;
-  p->n_kt = (int)((N + kKT - 1) / kKT);
   p->tab = (int)((2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1));
   p->scale = (float)scale;
   *sp = plan_smem(p->Rpad, p->tab, bwd);
   SDF_REQUIRE(sp->total <= 227 * 1024, "qktv: window too large for shared memory (%u B)", sp->total);
-  int g = kNumSMs / (int)nH * (int)nH;
+  // small windows: 256-thread CTAs with 128 TMEM columns each (key tile 96 + 32 O columns), 3-4 per SM, so that
+  // independent pairs overlap each other's staging / MMA / epilogue latencies; large windows: one 512-thread CTA
+  // per SM working on two M-tiles (2 x (192 + 32) columns).
+  int ctas = 1;
+  if (sp->total <= 55 * 1024) { *nslot = 1; ctas = 4; p->kt = 96; p->slot_cols = 128; p->tmem_cols = 128; }
+  else if (sp->total <= 72 * 1024) { *nslot = 1; ctas = 3; p->kt = 96; p->slot_cols = 128; p->tmem_cols = 128; }
+  else if (sp->total <= 110 * 1024) { *nslot = 1; ctas = 2; p->kt = kKTmax; p->slot_cols = 256; p->tmem_cols = 256; }
+  else { *nslot = 2; p->kt = kKTmax; p->slot_cols = 256; p->tmem_cols = 512; }
+  p->n_kt = (int)((N + p->kt - 1) / p->kt);
+  int g = (kNumSMs * ctas) / (int)nH * (int)nH;
   if (g < nH) g = (int)nH;
   if ((int64_t)g > M * nH) g = (int)(M * nH);
   *grid = g;
@@ -441,13 +484,25 @@ extern "C" int sdf_attn_qktv_fwd(const sdf_attn_qktv_fwd_args* a) {
   SDF_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->out), "sdf_attn_qktv_fwd: 16-byte alignment");
   QktvP p = {};
   SmemPlan sp;
-  int grid;
-  int st = qktv_setup(a->M, a->nH, a->nW, a->wd, a->wh, a->ww, a->scale, false, &p, &sp, &grid);
+  int grid, nslot;
+  int st = qktv_setup(a->M, a->nH, a->nW, a->wd, a->wh, a->ww, a->scale, false, &p, &sp, &grid, &nslot);
   if (st) return st;
   p.q = a->q; p.k = a->k; p.v = a->v; p.bias_table = a->bias_table; p.region = a->region; p.has_mask = a->region != nullptr;
   p.out = a->out; p.s_dbg = a->s_dbg; p.attn_dbg = a->attn_dbg;
-  cudaFuncSetAttribute(qktv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-  qktv_kernel<0><<<grid, kThreads, sp.total, (cudaStream_t)a->stream>>>(p);
+  const bool dbg = a->s_dbg || a->attn_dbg;
+  cudaStream_t stream = (cudaStream_t)a->stream;
+#define QKTV_LAUNCH(PH, MK, DB)                                                                                       \
+  do {                                                                                                                \
+    if (nslot == 1) {                                                                                                 \
+      cudaFuncSetAttribute(qktv_kernel<PH, MK, DB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);   \
+      qktv_kernel<PH, MK, DB, 1><<<grid, kSlotThreads, sp.total, stream>>>(p);                                        \
+    } else {                                                                                                          \
+      cudaFuncSetAttribute(qktv_kernel<PH, MK, DB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);   \
+      qktv_kernel<PH, MK, DB, 2><<<grid, kSlotThreads * 2, sp.total, stream>>>(p);                                    \
+    }                                                                                                                 \
+  } while (0)
+  if (dbg) { if (p.has_mask) QKTV_LAUNCH(0, true, true); else QKTV_LAUNCH(0, false, true); }
+  else { if (p.has_mask) QKTV_LAUNCH(0, true, false); else QKTV_LAUNCH(0, false, false); }
   return finish_launch("sdf_attn_qktv_fwd");
 }
 
@@ -458,21 +513,18 @@ extern "C" int sdf_attn_qktv_bwd(const sdf_attn_qktv_bwd_args* a) {
                   aligned16(a->grad_k) && aligned16(a->grad_v), "sdf_attn_qktv_bwd: 16-byte alignment");
   QktvP p = {};
   SmemPlan sp;
-  int grid;
-  int st = qktv_setup(a->M, a->nH, a->nW, a->wd, a->wh, a->ww, a->scale, true, &p, &sp, &grid);
+  int grid, nslot;
+  int st = qktv_setup(a->M, a->nH, a->nW, a->wd, a->wh, a->ww, a->scale, true, &p, &sp, &grid, &nslot);
   if (st) return st;
   p.q = a->q; p.k = a->k; p.v = a->v; p.bias_table = a->bias_table; p.region = a->region; p.has_mask = a->region != nullptr;
   p.grad_out = a->grad_out; p.grad_q = a->grad_q; p.grad_k = a->grad_k; p.grad_v = a->grad_v; p.grad_table = a->grad_bias_table;
   cudaStream_t stream = (cudaStream_t)a->stream;
-  cudaFuncSetAttribute(qktv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-  cudaFuncSetAttribute(qktv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-  cudaFuncSetAttribute(qktv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-  qktv_kernel<1><<<grid, kThreads, sp.total, stream>>>(p);
+  QKTV_LAUNCH(1, false, false);
   st = finish_launch("sdf_attn_qktv_bwd(dQ)");
   if (st) return st;
-  qktv_kernel<2><<<grid, kThreads, sp.total, stream>>>(p);
+  QKTV_LAUNCH(2, false, false);
   st = finish_launch("sdf_attn_qktv_bwd(dK)");
   if (st) return st;
-  qktv_kernel<3><<<grid, kThreads, sp.total, stream>>>(p);
+  if (p.has_mask) QKTV_LAUNCH(3, true, false); else QKTV_LAUNCH(3, false, false);
   return finish_launch("sdf_attn_qktv_bwd(dV)");
 }
