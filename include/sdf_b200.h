@@ -523,6 +523,18 @@ typedef struct {
 
 int sdf_attn_qktv_bwd(const sdf_attn_qktv_bwd_args* a);
 
+/* ---- TF32 x 2 weight split (fp32-faithful spike GEMM / conv on tensor cores) -------
+ * hi = rn_tf32(w), lo = rn_tf32(w - hi): both exactly representable in TF32, |w - hi - lo| <= 2^-22 |w|. */
+typedef struct {
+  const float* w;
+  float* hi;
+  float* lo;
+  int64_t n;
+  void* stream;
+} sdf_split_tf32_args;
+
+int sdf_split_tf32(const sdf_split_tf32_args* a);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 int sdf_version(void);             /* major*100 + minor */
 const char* sdf_last_error(void);  /* thread-local, never NULL */

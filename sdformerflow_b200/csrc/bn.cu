@@ -181,6 +181,16 @@ __global__ void bn_bwd_finalize_kernel(const FinP p) {
   }
 }
 
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & ~0x1FFFu);   // round to nearest on the 13 dropped bits
+    const float l = __fsub_rn(x, h);                                              // exact
+    hi[i] = h;
+    lo[i] = __uint_as_float((__float_as_uint(l) + 0x1000u) & ~0x1FFFu);
+  }
+}
+
 static int rows_launch_setup(int64_t rows, int64_t C, int64_t max_blocks, RowsP* p, dim3* grid, int* threads) {
   RowTiling rt;
   SDF_REQUIRE(C % 4 == 0 && make_row_tiling(rows, C, 4, 512, (int)max_blocks, &rt), "bn: C=%lld must be a multiple of 4", (long long)C);
@@ -280,4 +290,13 @@ extern "C" int sdf_bn_apply(const sdf_bn_apply_args* a) {
   if (st) return st;
   bn_rows_kernel<0><<<grid, threads, 0, (cudaStream_t)a->stream>>>(p);
   return finish_launch("sdf_bn_apply");
+}
+
+extern "C" int sdf_split_tf32(const sdf_split_tf32_args* a) {
+  SDF_REQUIRE(a && a->w && a->hi && a->lo && a->n >= 0, "sdf_split_tf32: null argument");
+  if (a->n == 0) return SDF_OK;
+  const int threads = 256;
+  int64_t need = (a->n + threads - 1) / threads;
+  split_tf32_kernel<<<(unsigned)(need < kNumSMs * 8 ? need : kNumSMs * 8), threads, 0, (cudaStream_t)a->stream>>>(a->w, a->hi, a->lo, a->n);
+  return finish_launch("sdf_split_tf32");
 }

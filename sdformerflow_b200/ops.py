@@ -361,11 +361,11 @@ GEMM_MODE = "tf32x2"
 
 
 def split_tf32(w):
-    """w (fp32) -> hi, lo, both exactly representable in TF32, hi + lo == w up to 2^-22 |w|."""
-    wi = w.contiguous().view(torch.int32)
-    hi = ((wi + 0x1000) & ~0x1FFF).view(torch.float32)      # round-to-nearest on the 13 dropped bits
-    lo = w - hi                                              # exact in fp32
-    lo = ((lo.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    """w (fp32) -> hi, lo, both exactly representable in TF32, hi + lo == w up to 2^-22 |w| (one kernel)."""
+    w = w.contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    capi.call("sdf_split_tf32", capi.struct("sdf_split_tf32_args", w=_ptr(w), hi=_ptr(hi), lo=_ptr(lo), n=w.numel(),
+                                            stream=_stream()))
     return hi, lo
 
 
@@ -410,12 +410,28 @@ class _SpikeLinearFn(torch.autograd.Function):
         return gs, gw, gb
 
 
+class _PlainLinearFn(torch.autograd.Function):
+    """Real-valued operand: true fp32 forward (SIMT), single-pass TF32 backward."""
+
+    @staticmethod
+    def forward(ctx, s, weight, bias):
+        with _tf32(False):
+            y = torch.nn.functional.linear(s, weight, bias)
+        ctx.save_for_backward(s, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    backward = _SpikeLinearFn.backward
+
+
 def spike_linear(s, weight, bias=None, exact_input=True):
     """F.linear(s, weight, bias) for a spike (or small-integer) operand s with fp32-grade results on
-    tensor cores; exact_input=False (real-valued s) keeps the plain fp32 GEMM."""
-    if GEMM_MODE == "fp32" or not exact_input:
+    tensor cores; exact_input=False (real-valued s) keeps the plain fp32 forward GEMM."""
+    if GEMM_MODE == "fp32":
         with _tf32(False):
             return torch.nn.functional.linear(s, weight, bias)
+    if not exact_input:
+        return _PlainLinearFn.apply(s, weight, bias)
     return _SpikeLinearFn.apply(s, weight, bias)
 
 
@@ -451,8 +467,28 @@ class _SpikeConvFn(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None
 
 
+class _PlainConvFn(torch.autograd.Function):
+    """Real-valued operand: true fp32 forward, single-pass TF32 backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, transposed, output_padding):
+        conv = torch.nn.functional.conv_transpose2d if transposed else torch.nn.functional.conv2d
+        kw = dict(stride=stride, padding=padding)
+        if transposed:
+            kw["output_padding"] = output_padding
+        with _tf32(False):
+            y = conv(x, weight, bias, **kw)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding, transposed, output_padding, bias is not None)
+        return y
+
+    backward = _SpikeConvFn.backward
+
+
 def spike_conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_padding=0, exact_input=True):
     """conv2d / conv_transpose2d on a spike operand, fp32-grade on tensor cores (see split_tf32)."""
+    if GEMM_MODE != "fp32" and not exact_input:
+        return _PlainConvFn.apply(x, weight, bias, stride, padding, transposed, output_padding)
     if GEMM_MODE == "fp32" or not exact_input:
         with _tf32(False):
             if transposed:
