@@ -535,6 +535,20 @@ typedef struct {
 
 int sdf_split_tf32(const sdf_split_tf32_args* a);
 
+/* ---- direct 3x3 conv for a few input channels (patch-embed head) -------------------------------
+ * y[n,h,w,:] = sum_{ky,kx,c} x[n,h+ky-1,w+kx-1,c] * w[:,c,ky,kx] (+ bias), stride 1, zero pad 1, channels-last.
+ * Replaces the head conv of MS_PED_Spiking_PatchEmbed_Conv_sfn (Spiking_modules.py:1737-1745, :270-277). */
+typedef struct {
+  const float* x;      /* (N, H, W, Cin) */
+  const float* w;      /* (Cout, Cin, 3, 3) torch layout */
+  const float* bias;   /* optional [Cout] */
+  float* y;            /* (N, H, W, Cout) */
+  int64_t N, H, W, Cin, Cout;
+  void* stream;
+} sdf_conv3x3_cl_args;
+
+int sdf_conv3x3_cl_fwd(const sdf_conv3x3_cl_args* a);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 int sdf_version(void);             /* major*100 + minor */
 const char* sdf_last_error(void);  /* thread-local, never NULL */

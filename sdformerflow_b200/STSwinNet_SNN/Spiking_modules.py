@@ -138,6 +138,10 @@ def from_cl(y):
 def conv_cl(x, conv, spike_input, transposed=False):
     """x (B, T, H, W, Cin) -> (B, T, H', W', Cout); `conv` is an nn.Conv2d / nn.ConvTranspose2d parameter holder."""
     B, T, H, W, C = x.shape
+    if (not transposed and not spike_input and C <= 4 and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1)
+            and tuple(conv.padding) == (1, 1) and conv.weight.shape[0] % 4 == 0 and ops.GEMM_MODE != "fp32"):
+        y = ops.conv3x3_small_cin(x.view(B * T, H, W, C), conv.weight, conv.bias)     # patch-embed head: direct kernel
+        return y.view(B, T, H, W, y.shape[-1])
     x4 = x.view(B * T, H, W, C).permute(0, 3, 1, 2)                # logical NCHW with channels_last strides
     y4 = ops.spike_conv2d(x4, conv.weight, conv.bias, conv.stride, conv.padding, transposed,
                           conv.output_padding if transposed else 0, exact_input=spike_input)

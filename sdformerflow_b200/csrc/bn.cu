@@ -103,11 +103,18 @@ struct FinP {
 // (deterministic; the single rounding to fp32 at the end keeps mean/var within 1 ulp of exact).
 __device__ __forceinline__ void warp_sum_partials(const float* partials, int64_t nblk, int64_t C, int64_t c, double& s0, double& s1) {
   const int lane = threadIdx.x & 31;
-  double a = 0.0, b = 0.0;
-  for (int64_t blk = lane; blk < nblk; blk += 32) {
+  double a = 0.0, b = 0.0, a2 = 0.0, b2 = 0.0;
+  int64_t blk = lane;
+  for (; blk + 32 < nblk; blk += 64) {           // two independent chains per lane, fixed order
+    const float x0 = partials[(blk * 2 + 0) * C + c], y0 = partials[(blk * 2 + 1) * C + c];
+    const float x1 = partials[((blk + 32) * 2 + 0) * C + c], y1 = partials[((blk + 32) * 2 + 1) * C + c];
+    a += (double)x0; b += (double)y0; a2 += (double)x1; b2 += (double)y1;
+  }
+  for (; blk < nblk; blk += 32) {
     a += (double)partials[(blk * 2 + 0) * C + c];
     b += (double)partials[(blk * 2 + 1) * C + c];
   }
+  a += a2; b += b2;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);

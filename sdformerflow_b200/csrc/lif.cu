@@ -465,7 +465,7 @@ using namespace sdf;
 
 extern "C" int64_t sdf_partial_blocks(int64_t rows, int64_t C) {
   (void)rows; (void)C;
-  return (int64_t)kNumSMs * 4;
+  return (int64_t)kNumSMs * 2;
 }
 
 #define SDF_DISPATCH_DT(KERNEL, TT, VV, DT, ...)                                       \
@@ -539,7 +539,7 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   const int T = (int)a->lay.T;
   const bool fastT = (T == 2 || T == 4 || T == 5 || T == 10);
   const bool parts = a->bn_partials || a->plif_partials;
-  int64_t max_blocks = (int64_t)kNumSMs * (T == 10 ? 3 : 2);
+  int64_t max_blocks = (int64_t)kNumSMs * 2;
   if (parts) {
     SDF_REQUIRE(a->n_partial_blocks >= 1, "sdf_lif_bwd: n_partial_blocks < 1");
     if (a->n_partial_blocks < max_blocks) max_blocks = a->n_partial_blocks;

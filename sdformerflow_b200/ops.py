@@ -11,7 +11,7 @@ import torch
 
 from . import capi
 
-N_PARTIAL = 592  # == sdf_partial_blocks(): up to 4 CTAs per SM x 148 SMs
+N_PARTIAL = 296  # == sdf_partial_blocks(): 2 CTAs per SM x 148 SMs
 
 
 def _need_cuda(*ts):
@@ -483,6 +483,43 @@ class _PlainConvFn(torch.autograd.Function):
         return y
 
     backward = _SpikeConvFn.backward
+
+
+class _SmallCinConvFn(torch.autograd.Function):
+    """3x3 / stride 1 / pad 1 conv with Cin <= 4 on a channels-last (N, H, W, Cin) tensor: direct fp32 kernel forward
+    (patch-embed head, reference Spiking_modules.py:1737-1745), library TF32 weight/input gradients backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x, weight)
+        x = x.contiguous()
+        N, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        y = torch.empty((N, H, W, Cout), device=x.device, dtype=torch.float32)
+        w = weight.detach().contiguous()
+        capi.call("sdf_conv3x3_cl_fwd", capi.struct(
+            "sdf_conv3x3_cl_args", x=_ptr(x), w=_ptr(w), bias=_ptr(None if bias is None else bias.detach().contiguous()),
+            y=_ptr(y), N=N, H=H, W=W, Cin=Cin, Cout=Cout, stream=_stream()), algo_bytes=4 * (x.numel() + y.numel()))
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g4 = g.contiguous().permute(0, 3, 1, 2)           # logical NCHW, channels_last strides
+        x4 = x.permute(0, 3, 1, 2)
+        with _tf32(True):
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                g4, x4, weight, [weight.shape[0]] if ctx.has_bias else None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]])
+        if gx is not None:
+            gx = gx.permute(0, 2, 3, 1)
+        return gx, gw, gb
+
+
+def conv3x3_small_cin(x, weight, bias=None):
+    return _SmallCinConvFn.apply(x, weight, bias)
 
 
 def spike_conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_padding=0, exact_input=True):

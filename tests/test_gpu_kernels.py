@@ -400,3 +400,23 @@ def test_spike_linear_and_conv_are_fp32_grade(mode):
         assert ((Wp.grad.double() - gw_ref).abs().max() / gw_ref.abs().max()).item() <= tol
     finally:
         ops.GEMM_MODE = old
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W", [(2, 48, 17, 23), (1, 8, 5, 4), (4, 64, 9, 16)])
+def test_small_cin_conv_fwd_bwd(Cin, Cout, H, W):
+    """Direct 3x3 conv of the patch-embed head vs F.conv2d (fp64 reference), and its gradients."""
+    ops, capi = _ops()
+    g = torch.Generator().manual_seed(Cin * 10 + Cout)
+    x = (torch.rand(6, H, W, Cin, generator=g) * (torch.rand(6, H, W, Cin, generator=g) < 0.3)).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.3).requires_grad_(True)
+    b = torch.randn(Cout, generator=g).requires_grad_(True)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), b.double(), stride=1, padding=1).permute(0, 2, 3, 1)
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go.double())
+    xg, wg, bg = (t.detach().to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = ops.conv3x3_small_cin(xg, wg, bg)
+    y.backward(go.to(DEV))
+    assert ((y.detach().cpu().double() - ref.detach()).abs().max() / ref.abs().max()).item() <= 1e-6
+    assert ((wg.grad.cpu().double() - w.grad.double()).abs().max() / w.grad.abs().max()).item() <= 3e-3
+    assert ((xg.grad.cpu().double() - x.grad.double()).abs().max() / x.grad.abs().max()).item() <= 3e-3
+    assert ((bg.grad.cpu().double() - b.grad.double()).abs().max() / b.grad.abs().max()).item() <= 1e-4
