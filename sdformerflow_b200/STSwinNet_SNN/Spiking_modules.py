@@ -142,6 +142,12 @@ def conv_cl(x, conv, spike_input, transposed=False):
             and tuple(conv.padding) == (1, 1) and conv.weight.shape[0] % 4 == 0 and ops.GEMM_MODE != "fp32"):
         y = ops.conv3x3_small_cin(x.view(B * T, H, W, C), conv.weight, conv.bias)     # patch-embed head: direct kernel
         return y.view(B, T, H, W, y.shape[-1])
+    if (not transposed and tuple(conv.kernel_size) == (1, 1) and tuple(conv.padding) == (0, 0) and conv.groups == 1):
+        # 1x1 (strided) convolution == Linear on the (sub-sampled) channels-last rows: cuBLAS instead of cuDNN's
+        # slow SIMT path (PED shortcut conv_res, 1x1 prediction heads)
+        sh, sw = conv.stride
+        xs = x if (sh, sw) == (1, 1) else x[:, :, ::sh, ::sw, :]
+        return ops.spike_linear(xs, conv.weight.view(conv.weight.shape[0], C), conv.bias, exact_input=spike_input)
     x4 = x.view(B * T, H, W, C).permute(0, 3, 1, 2)                # logical NCHW with channels_last strides
     y4 = ops.spike_conv2d(x4, conv.weight, conv.bias, conv.stride, conv.padding, transposed,
                           conv.output_padding if transposed else 0, exact_input=spike_input)
