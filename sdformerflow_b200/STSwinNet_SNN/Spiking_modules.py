@@ -206,10 +206,12 @@ class MS_SpikingConvEncoderLayer(nn.Module):
             self.norm_layer = SpikingNormLayer(out_channels, spiking_kwargs["num_steps"], self.norm,
                                                v_th=spiking_kwargs["v_th"])
 
-    def forward_cl(self, x):
+    def forward_cl(self, x, spike_input=None):
+        """spike_input: whether x is a spike tensor (exact in TF32).  Defaults to "a neuron runs first"; the patch
+        embedding passes True for its first_layer=True conv, whose input is the head layer's spikes."""
         if not self.first_layer:
             x = self.sn(x, 1)
-        h = conv_cl(x, self.conv[0], not self.first_layer)
+        h = conv_cl(x, self.conv[0], (not self.first_layer) if spike_input is None else spike_input)
         if self.norm is None:
             return h
         if self.norm_layer.is_batchnorm:
@@ -447,7 +449,7 @@ class MS_PED_Spiking_PatchEmbed_Conv_sfn(nn.Module):
         """voxels (B, bins, 2, H, W) -> (B, T, H/4, W/4, embed_dim)."""
         x = regroup_bins_to_steps_cl(x, self.num_bins, self.num_steps)
         x = self.head.forward_cl(x, spike_input=False)            # real-valued voxel input: plain fp32 conv
-        x = self.conv.forward_cl(x)
+        x = self.conv.forward_cl(x, spike_input=True)             # input = head's spikes
         x = self.residual_encoding.forward_cl(x)
         return self.proj.forward_cl(x)
 

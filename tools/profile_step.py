@@ -38,7 +38,7 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
     for _ in range(2):
         step()
     torch.cuda.synchronize()
@@ -53,3 +53,7 @@ T = sum(tot.values())
 print(f"GPU busy {T / 2e3:.2f} ms/step")
 for k, v in tot.most_common(45):
     print(f"{v / T * 100:6.2f}%  {v / 2e3:8.3f} ms/step  n={cnt[k] // 2:5d}  {k}")
+
+if "--ops" in sys.argv:
+    print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=28, max_name_column_width=40,
+                                                             max_shapes_column_width=90))
