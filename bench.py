@@ -199,6 +199,83 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def run_infer(args, rank, local_rank, world):
+    """BASELINE.json configs[1]: MS_SpikingformerFlowNet_en4 inference, batch 8 per GPU, 10-bin 480x640, eval mode
+    (BatchNorm folded into the neuron prologues), replicas only (no collective).  Extra line, not the headline."""
+    import copy
+    import torch.distributed as dist
+    from sdformerflow_b200 import capi
+    from sdformerflow_b200.sj import functional
+    from sdformerflow_b200.STSwinNet_SNN import Spiking_STSwinNet as prod
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Hi, Wi, Bi = 480, 640, 8
+    mc, sc = model_cfg()
+    sc["input_size"] = [Hi, Wi]
+    torch.manual_seed(0)
+    model = getattr(prod, mc["name"])(copy.deepcopy(mc), copy.deepcopy(sc))
+    model.init_weights()
+    model.to(dev).eval()
+    functional.set_step_mode(model, "m")
+    g = torch.Generator().manual_seed(16146 + rank)
+    xh = (torch.rand(Bi, BINS, 2, Hi, Wi, generator=g) * (torch.rand(Bi, BINS, 2, Hi, Wi, generator=g) < 0.10)).pin_memory()
+    xd = xh.to(dev)
+
+    def step(x):
+        functional.reset_net(model)
+        with torch.no_grad():
+            return model(x)["flow"][-1]
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(xd)
+    timer = capi.KernelTimer(only={"sdf_lif_fwd"})
+    capi.set_timer(timer)
+    n0 = capi.launch_count()
+    ms_total = timed(lambda: step(xd), args.steps)
+    launches = capi.launch_count() - n0
+    capi.set_timer(None)
+    ks = timer.summary().get("sdf_lif_fwd", {"launches": 0, "ms": 0.0, "bytes": 0, "gbps": 0.0})
+    ms_e2e = timed(lambda: step(xh.to(dev, non_blocking=True)).sum().item(), args.steps)
+    if rank == 0:
+        peak, how = measured_peaks()
+        print(json.dumps({
+            "metric": "SDformerFlow inference samples/s", "value": world * Bi * args.steps / (ms_total * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MS_SpikingformerFlowNet_en4 lif(v_th=0.1) inference (eval), B=8/GPU, 480x640, T=10, window (2,9,9)",
+                       "parallelism": f"replicas x{world}"},
+            "e2e": {"value": world * Bi * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": xh.numel() * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "sdf_lif_fwd", "achieved": ks["gbps"], "peak": peak, "unit": "GB/s",
+                         "frac": ks["gbps"] / peak, "traffic": None, "peak_kind": how, "launches": ks["launches"]},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args, rank, local_rank, world):
     import copy
     import torch.distributed as dist
@@ -328,6 +405,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train (default, the headline metric: BASELINE.json configs[2]) or infer (configs[1]: eval, "
+                         "B=8/GPU, 480x640)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -340,7 +420,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
-    run_b200(args, rank, local_rank, world)
+    if args.workload == "infer":
+        run_infer(args, rank, local_rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":
