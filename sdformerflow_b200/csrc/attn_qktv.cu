@@ -8,15 +8,15 @@
 // the rows of one (window m', pseudo-head h') pair are 32 contiguous bytes each, N*32 B in all.
 //
 // One persistent CTA per SM walks pairs with a fixed pseudo-head.  Per pair:
-//   stage  Q, K (row-major -> UMMA canonical K-major, no swizzle) and V^T into shared memory,
-//          u8 {0,1} -> fp16 (exact);
+//   stage  Q, K, V (row-major bytes -> UMMA canonical no-swizzle layout [16-B chunk][row][16 B]) into
+//          shared memory, u8 {0,1} -> fp16 (exact); Q, K are read K-major, V MN-major (no transpose);
 //   MMA 1  S = Q K^T           tcgen05.mma kind::f16, M=128, N<=192, K=16 x2, fp32 accum in TMEM
 //                              (S are exact integer counts 0..32);
 //   epi 1  T = scale*S + bias[lin_i - lin_j + off] + (-100)[region_i != region_j], in registers
 //          (tcgen05.ld), split T = hi + lo in fp16 (22 significant bits) and written back IN PLACE
 //          over S (tcgen05.st) as the A operand of the second contraction — the N x N matrix never
 //          leaves the SM;
-//   MMA 2  O += T_hi V + T_lo V   tcgen05.mma kind::f16 with A from TMEM, B = V^T from smem;
+//   MMA 2  O += T_hi V + T_lo V   tcgen05.mma kind::f16 with A from TMEM, B = V (MN-major) from smem;
 //   epi 2  O rows -> global in the proj-input order of :362-363 (128 B per row).
 // The backward (K4) is three more passes of the same two-contraction structure:
 //   dA = dO V^T  -> dQ = scale*dA K        (+ d(bias table) accumulated in shared memory)
@@ -96,8 +96,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 // instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, format 0 = F16, 1 = BF16
-__device__ __forceinline__ uint32_t make_idesc(int fmt, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// b_mn = 1: B operand is MN-major (its N index is the contiguous one)
+__device__ __forceinline__ uint32_t make_idesc(int fmt, int M, int N, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- 16-bit operand helpers ---------------------------------------------------------------------
@@ -154,7 +156,7 @@ __host__ __device__ inline SmemPlan plan_smem(int Rpad, int tab, bool bwd) {
   uint32_t o = 0;
   s.a = o; o += (uint32_t)Rpad * 64;          // [4 chunks][Rpad rows][16 B]
   s.b = o; o += (uint32_t)Rpad * 64;
-  s.bt = o; o += (uint32_t)Rpad * 64;         // [Rpad/8 key chunks][32 dims][16 B]
+  s.bt = o; o += (uint32_t)Rpad * 64;         // third operand, same layout, read MN-major by MMA 2
   s.lin = o; o += (uint32_t)Rpad * 4;
   s.reg = o; o += (uint32_t)((Rpad + 15) / 16 * 16);
   s.tab = o; o += (uint32_t)((tab * 4 + 15) / 16 * 16);
@@ -167,8 +169,6 @@ __host__ __device__ inline SmemPlan plan_smem(int Rpad, int tab, bool bwd) {
 
 // plain operand: element (row r, dim d) at chunk (d/8), row r  -> [c][r][16 B]
 __device__ __forceinline__ uint32_t plain_off(int Rpad, int r, int c16) { return (uint32_t)(c16 * Rpad + r) * 16; }
-// transposed operand (rows = 32 dims, K = tokens): element (dim d, token n) -> [n/8][d][ (n%8)*2 ]
-__device__ __forceinline__ uint32_t trans_off(int d, int n) { return (uint32_t)((n >> 3) * 32 + d) * 16 + (n & 7) * 2; }
 
 // stage rows [0, N) of a u8 {0,1} [N, 32] block
 template <int BF>
@@ -188,19 +188,6 @@ __device__ __forceinline__ void stage_plain_u8(uint8_t* smem, uint32_t base, int
     *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
   }
 }
-template <int BF>
-__device__ __forceinline__ void stage_trans_u8(uint8_t* smem, uint32_t base, const uint8_t* src, int N) {
-  for (int i = threadIdx.x; i < N * 2; i += blockDim.x) {
-    const int r = i >> 1, hf = i & 1;
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * 32 + hf * 16));
-    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t b = (ws[j >> 2] >> ((j & 3) * 8)) & 0xFF;
-      *reinterpret_cast<uint16_t*>(smem + base + trans_off(hf * 16 + j, r)) = b ? one16<BF>() : (uint16_t)0;
-    }
-  }
-}
 // fp32 rows gathered from the proj-input layout: token n of pair (m', h') lives at row (t*M + m')*P + pos, col h'*32
 __device__ __forceinline__ const float* go_row(const QktvP& p, int64_t mwin, int64_t head, int n) {
   const int64_t t = n / p.P, pos = n - t * p.P;
@@ -218,18 +205,6 @@ __device__ __forceinline__ void stage_plain_f32(uint8_t* smem, uint32_t base, in
     *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, c)) = o;
   }
 }
-template <int BF>
-__device__ __forceinline__ void stage_trans_f32(uint8_t* smem, uint32_t base, const QktvP& p, int64_t mwin, int64_t head) {
-  for (int i = threadIdx.x; i < p.N * 8; i += blockDim.x) {
-    const int r = i >> 3, c = i & 7;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(go_row(p, mwin, head, r) + c * 4));
-    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 0, r)) = f2h<BF>(a.x);
-    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 1, r)) = f2h<BF>(a.y);
-    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 2, r)) = f2h<BF>(a.z);
-    *reinterpret_cast<uint16_t*>(smem + base + trans_off(c * 4 + 3, r)) = f2h<BF>(a.w);
-  }
-}
-
 // PHASE 0: forward O = T V           A=Q  B=K  Bt=V^T   out -> p.out (permuted rows)
 // PHASE 1: dQ = scale*(dO V^T) K     A=dO B=V  Bt=K^T   out -> grad_q, side effect d(bias table)
 // PHASE 2: dK = scale*(V dO^T) Q     A=V  B=dO Bt=Q^T   out -> grad_k
@@ -285,7 +260,7 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
   const int half = NSLOT == 2 ? warp >> 3 : warp >> 2;          // which half of the column chunks this warp takes
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16; // this warp's TMEM lanes
   const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b), bt_base = smem_u32(smem + sp.bt);
-  const uint32_t lbo_plain = (uint32_t)Rpad * 16, sbo = 128, lbo_t = 512;
+  const uint32_t lbo_plain = (uint32_t)Rpad * 16, sbo = 128;
 
   const int64_t n_pairs = p.M * p.nH;
   for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -294,10 +269,10 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
     const uint8_t* kp = p.k + pair * N * 32;
     const uint8_t* vp = p.v + pair * N * 32;
     // ---- stage operands ----
-    if (PHASE == 0) { stage_plain_u8<BF>(smem, sp.a, Rpad, qp, N); stage_plain_u8<BF>(smem, sp.b, Rpad, kp, N); stage_trans_u8<BF>(smem, sp.bt, vp, N); }
-    if (PHASE == 1) { stage_plain_f32<BF>(smem, sp.a, Rpad, p, mwin, head); stage_plain_u8<BF>(smem, sp.b, Rpad, vp, N); stage_trans_u8<BF>(smem, sp.bt, kp, N); }
-    if (PHASE == 2) { stage_plain_u8<BF>(smem, sp.a, Rpad, vp, N); stage_plain_f32<BF>(smem, sp.b, Rpad, p, mwin, head); stage_trans_u8<BF>(smem, sp.bt, qp, N); }
-    if (PHASE == 3) { stage_plain_u8<BF>(smem, sp.a, Rpad, kp, N); stage_plain_u8<BF>(smem, sp.b, Rpad, qp, N); stage_trans_f32<BF>(smem, sp.bt, p, mwin, head); }
+    if (PHASE == 0) { stage_plain_u8<BF>(smem, sp.a, Rpad, qp, N); stage_plain_u8<BF>(smem, sp.b, Rpad, kp, N); stage_plain_u8<BF>(smem, sp.bt, Rpad, vp, N); }
+    if (PHASE == 1) { stage_plain_f32<BF>(smem, sp.a, Rpad, p, mwin, head); stage_plain_u8<BF>(smem, sp.b, Rpad, vp, N); stage_plain_u8<BF>(smem, sp.bt, Rpad, kp, N); }
+    if (PHASE == 2) { stage_plain_u8<BF>(smem, sp.a, Rpad, vp, N); stage_plain_f32<BF>(smem, sp.b, Rpad, p, mwin, head); stage_plain_u8<BF>(smem, sp.bt, Rpad, qp, N); }
+    if (PHASE == 3) { stage_plain_u8<BF>(smem, sp.a, Rpad, kp, N); stage_plain_u8<BF>(smem, sp.b, Rpad, qp, N); stage_plain_f32<BF>(smem, sp.bt, Rpad, p, mwin, head); }
     if (MASK && (PHASE == 0 || PHASE == 3)) {
       const uint8_t* rp = p.region + (mwin % p.nW) * N;
       for (int n = tid; n < N; n += kThreads) reg_s[n] = __ldg(rp + n);
@@ -310,6 +285,7 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
       const int mt = mt0 + slot;
       const int row = mt * 128 + (warp & 3) * 32 + lane;         // A-operand row handled by this thread
       const bool row_ok = slot < n_slots && row < N;
+      const bool warp_ok = slot < n_slots && (mt * 128 + (warp & 3) * 32) < N;   // any valid row in this warp's 32 lanes
       const int lin_i = row_ok ? lin_s[row] : 0;
       const int reg_i = row_ok ? reg_s[row] : 0;
       for (int kt = 0; kt < p.n_kt; ++kt) {
@@ -335,7 +311,7 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
         ph_s ^= 1;
         tc_fence_after();
         // ---- epilogue 1: S -> T = hi + lo (in place); the two warp halves take alternate 16-column chunks ----
-        if (slot < n_slots) {
+        if (warp_ok) {
           const uint32_t tcol = tmem_base + lane_base + slot * p.slot_cols;
           // bias index is linear in the token coordinates: tab[lin_i - lin_j + off] (PHASE 3: roles swapped).
           // Padding rows/columns need no guard: lin = region = 0 there keeps every index in range, the values
@@ -396,11 +372,13 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
         // ---- MMA 2: O[128 x 32] (+)= T_hi * Bt + T_lo * Bt over the 16-key chunks of this tile ----
         if (tid == 0) {
           tc_fence_after();
-          const uint32_t idesc = make_idesc(BF, 128, 32);
+          // B = the third operand in its plain [dim chunk][token][16 B] layout read MN-major: N (=dim) chunks of 8
+          // are SBO = Rpad*16 B apart, K (=token) groups of 8 are LBO = 128 B apart.
+          const uint32_t idesc = make_idesc(BF, 128, 32, 1);
           for (int s = 0; s < n_slots; ++s) {
             const uint32_t d = tmem_base + s * p.slot_cols + p.kt;
             for (int c0 = 0; c0 < nk; c0 += 16) {
-              const uint64_t bd = make_desc(bt_base + (uint32_t)((key0 + c0) >> 3) * lbo_t, lbo_t, sbo);
+              const uint64_t bd = make_desc(bt_base + (uint32_t)(key0 + c0) * 16, 128, lbo_plain);
               const uint32_t a_hi = tmem_base + s * p.slot_cols + c0;
               mma_ts(d, a_hi, bd, idesc, (kt > 0 || c0 > 0) ? 1u : 0u);
               mma_ts(d, a_hi + 8, bd, idesc, 1u);
@@ -413,7 +391,7 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
       mbar_wait(&bars[1], ph_o);
       ph_o ^= 1;
       tc_fence_after();
-      if (slot < n_slots) {
+      if (warp_ok) {
         const uint32_t tcol = tmem_base + lane_base + slot * p.slot_cols + p.kt + half * 16;
         uint32_t r0[16];
         tmem_ld16(tcol, r0);
