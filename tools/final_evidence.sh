@@ -9,10 +9,18 @@ python bench.py --workload infer --steps 5 --warmup 3 2>/dev/null | tail -1 > gp
 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r01_bench_reference_arm.json
 python tools/microbench.py 2>/dev/null > gpurun_out/r01_microbench.jsonl
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_launches_final.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r01_ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:lif_fwd_kernel -s 126 -c 42 -o gpurun_out/r01_ncu_lif_fwd_in_bench python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:lif_bwd_kernel -s 1 -c 1 -o gpurun_out/r01_ncu_lif_bwd_final python tools/ncu_targets.py lif_bwd > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:qkgate_kernel -s 1 -c 1 -o gpurun_out/r01_ncu_qkgate_final python tools/ncu_targets.py qkgate > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:qktv_kernel -s 1 -c 1 -o gpurun_out/r01_ncu_qktv_final python tools/ncu_targets.py qktv > /dev/null 2>&1
+# full captures: keep only the raw-page CSV (the .ncu-rep files exceed the 64 MiB return limit)
+cap() {  # name, kernel regex, skip, count, command...
+  local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
+  ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -o /tmp/$name "$@" > /dev/null 2>&1
+  ncu -i /tmp/$name.ncu-rep --page raw --csv > gpurun_out/$name.raw.csv 2>/dev/null
+  rm -f /tmp/$name.ncu-rep
+}
+cap r01_ncu_lif_fwd_in_bench lif_fwd_kernel 126 42 python bench.py --steps 1 --warmup 3 --no-cpu-baseline
+cap r01_ncu_lif_fwd_final lif_fwd_kernel 2 2 python tools/ncu_targets.py lif_fwd
+cap r01_ncu_lif_bwd_final lif_bwd_kernel 1 1 python tools/ncu_targets.py lif_bwd
+cap r01_ncu_qkgate_final qkgate_kernel 1 1 python tools/ncu_targets.py qkgate
+cap r01_ncu_qktv_final qktv_kernel 1 1 python tools/ncu_targets.py qktv
 ls -la gpurun_out/ | tail -20
 cat gpurun_out/r01_pytest_gpu.txt gpurun_out/r01_smoke.txt
 cut -c1-600 gpurun_out/r01_bench_n1.json
