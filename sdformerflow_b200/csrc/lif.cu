@@ -159,7 +159,7 @@ struct LifBwdP {
 // PRE = 1: all grad loads issued up front (max loads in flight, ~190 regs, 1 CTA/SM);
 // PRE = 0: grad loads streamed inside the adjoint loop (128 regs, 2 CTAs/SM).
 template <int T, int V, int PRE, bool SIMPLE>
-__global__ void __launch_bounds__(256, (V == 2) ? 2 : (PRE ? 1 : 2)) lif_bwd_kernel(const LifBwdP p) {
+__global__ void __launch_bounds__(256, (V == 2) ? (PRE ? 2 : 3) : (PRE ? 1 : 2)) lif_bwd_kernel(const LifBwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   extern __shared__ float smem[];
   const SeqP& s = p.s;
@@ -465,7 +465,7 @@ using namespace sdf;
 
 extern "C" int64_t sdf_partial_blocks(int64_t rows, int64_t C) {
   (void)rows; (void)C;
-  return (int64_t)kNumSMs * 2;
+  return (int64_t)kNumSMs * 3;
 }
 
 #define SDF_DISPATCH_DT(KERNEL, TT, VV, DT, ...)                                       \
@@ -539,7 +539,7 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   const int T = (int)a->lay.T;
   const bool fastT = (T == 2 || T == 4 || T == 5 || T == 10);
   const bool parts = a->bn_partials || a->plif_partials;
-  int64_t max_blocks = (int64_t)kNumSMs * 2;
+  int64_t max_blocks = (int64_t)kNumSMs * (T == 10 ? 3 : 2);
   if (parts) {
     SDF_REQUIRE(a->n_partial_blocks >= 1, "sdf_lif_bwd: n_partial_blocks < 1");
     if (a->n_partial_blocks < max_blocks) max_blocks = a->n_partial_blocks;
@@ -570,7 +570,9 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
         break;
     }
   } else if (L.V == 2) {
-    if (simple) lif_bwd_kernel<10, 2, 1, true><<<L.grid, L.threads, smem, stream>>>(p);
+    static const int pre_mode = [] { const char* e = getenv("SDF_LIF_BWD_PRELOAD"); return e ? atoi(e) : 1; }();
+    if (simple && pre_mode) lif_bwd_kernel<10, 2, 1, true><<<L.grid, L.threads, smem, stream>>>(p);
+    else if (simple) lif_bwd_kernel<10, 2, 0, true><<<L.grid, L.threads, smem, stream>>>(p);
     else lif_bwd_kernel<10, 2, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
   } else {
     lif_bwd_kernel<0, 1, 0, false><<<L.grid, L.threads, smem, stream>>>(p);

@@ -11,7 +11,7 @@ import torch
 
 from . import capi
 
-N_PARTIAL = 296  # == sdf_partial_blocks(): 2 CTAs per SM x 148 SMs
+N_PARTIAL = 444  # == sdf_partial_blocks(): up to 3 CTAs per SM x 148 SMs
 
 
 def _need_cuda(*ts):

@@ -106,6 +106,31 @@ def main():
     y = torch.randn(geom.rows, C, device=dev)
     ms = timeit(lambda: ops.window_scatter(y, geom, res=x))
     report("window_scatter+residual", geom.rows * C * 4 + x.numel() * 8, ms)
+    # backward kernels of the same block
+    gg = torch.randn(geom.rows, C, device=dev)
+    gq, gk = torch.empty(geom.rows, C, device=dev), torch.empty(geom.rows, C, device=dev)
+    pq, pk = torch.empty(ops.N_PARTIAL, 2, C, device=dev), torch.empty(ops.N_PARTIAL, 2, C, device=dev)
+
+    def qkb():
+        capi.call("sdf_attn_qkgate_bwd", capi.struct(
+            "sdf_attn_qkgate_bwd_args", q_pre=qk.data_ptr(), k_pre=qk[:, C:].data_ptr(), ld=2 * C, q_scale=sc.data_ptr(),
+            q_shift=sh.data_ptr(), k_scale=sc.data_ptr(), k_shift=sh.data_ptr(), pos=pos.data_ptr(), grad_gate=gg.data_ptr(),
+            grad_q=gq.data_ptr(), grad_k=gk.data_ptr(), bn_partials_q=pq.data_ptr(), bn_partials_k=pk.data_ptr(),
+            n_partial_blocks=ops.N_PARTIAL, wd=2, M=geom.M, P=geom.P, C=C, nH=nH, neuron=cfg.c(),
+            stream=torch.cuda.current_stream().cuda_stream))
+    ms = timeit(qkb)
+    report("attn_qkgate_bwd (+BN partials)", geom.rows * C * 20, ms)
+    coef = torch.randn(3, C, device=dev)
+    du = torch.empty(geom.rows, C, device=dev)
+    ms = timeit(lambda: capi.call("sdf_bn_bwd_apply", capi.struct(
+        "sdf_bn_bwd_apply_args", dy=gg.data_ptr(), u=y.data_ptr(), ld_u=C, du=du.data_ptr(), ld_du=C, coef=coef.data_ptr(),
+        rows=geom.rows, C=C, stream=torch.cuda.current_stream().cuda_stream)))
+    report("bn_bwd_apply", geom.rows * C * 12, ms)
+    gxw = torch.empty_like(x)
+    ms = timeit(lambda: capi.call("sdf_lif_window_bwd", capi.struct(
+        "sdf_lif_window_bwd_args", x=x.data_ptr(), grad_spike=gg.data_ptr(), grad_x=gxw.data_ptr(), win2x=geom.win2x.data_ptr(),
+        wd=2, MP=geom.M * geom.P, C=C, neuron=cfg.c(), stream=torch.cuda.current_stream().cuda_stream)))
+    report("lif_window_bwd", x.numel() * 8 + geom.rows * C * 4, ms)
 
 
 def qktv():
