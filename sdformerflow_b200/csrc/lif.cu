@@ -159,7 +159,7 @@ struct LifBwdP {
 // PRE = 1: all grad loads issued up front (max loads in flight, ~190 regs, 1 CTA/SM);
 // PRE = 0: grad loads streamed inside the adjoint loop (128 regs, 2 CTAs/SM).
 template <int T, int V, int PRE, bool SIMPLE>
-__global__ void __launch_bounds__(256, (V == 2) ? (PRE ? 2 : 3) : (PRE ? 1 : 2)) lif_bwd_kernel(const LifBwdP p) {
+__global__ void __launch_bounds__(288, (V == 2) ? (PRE ? 2 : 3) : (PRE ? 1 : 2)) lif_bwd_kernel(const LifBwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   extern __shared__ float smem[];
   const SeqP& s = p.s;
@@ -547,7 +547,10 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   if (a->bn_partials) SDF_REQUIRE(fastT, "sdf_lif_bwd: bn_partials supported for T in {2,4,5,10}");
   SeqLaunch L;
   // T = 10 keeps u, h (and the preloaded grads) in registers: 2 neurons per thread there, 4 otherwise
-  st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, fastT ? (T == 10 ? 2 : 4) : 1, 256, max_blocks, &L);
+  static const int v4_t10 = [] { const char* e = getenv("SDF_LIF_BWD_V4"); return e ? atoi(e) : 1; }();
+  // T = 10 with 4 neurons/thread keeps u, h and the preloaded grads in ~220 registers: 288-thread CTAs, one per SM
+  st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, fastT ? ((T == 10 && !v4_t10) ? 2 : 4) : 1,
+                 (T == 10 && v4_t10) ? 288 : 256, max_blocks, &L);
   if (st) return st;
   p.s = L.s;
   if (a->plif_partials) SDF_REQUIRE(L.grid.y == 1 || L.grid.x * L.grid.y <= a->n_partial_blocks, "sdf_lif_bwd: plif partial capacity");
@@ -564,6 +567,10 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
         else lif_bwd_kernel<2, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
         break;
       case 4: lif_bwd_kernel<4, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p); break;
+      case 10:
+        if (simple) lif_bwd_kernel<10, 4, 1, true><<<L.grid, L.threads, smem, stream>>>(p);
+        else lif_bwd_kernel<10, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
+        break;
       default:
         if (simple) lif_bwd_kernel<5, 4, 1, true><<<L.grid, L.threads, smem, stream>>>(p);
         else lif_bwd_kernel<5, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
