@@ -372,6 +372,11 @@ def run_b200(args, rank, local_rank, world):
 
     if rank == 0:
         peak, how = measured_peaks()
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic_lif_fwd.json")
+        if os.path.exists(tp):      # dram bytes per K1 launch from the committed `ncu --set full` capture of this command
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_traffic_lif_fwd.json (ncu --set full, 42 K1 launches of one step)"
         value = world * B * args.steps / (ms_total * 1e-3)
         e2e_v = world * B * args.steps / (ms_e2e * 1e-3)
         line = {
@@ -388,9 +393,10 @@ def run_b200(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "sdf_lif_fwd (K1, all launches in the timed region)",
                          "achieved": ksum["gbps"], "peak": peak, "unit": "GB/s", "frac": ksum["gbps"] / peak,
-                         "traffic": None, "peak_kind": how, "launches": ksum["launches"],
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_kind": how, "launches": ksum["launches"],
                          "kernel_ms_per_step": ksum["ms"] / args.steps,
-                         "algo_bytes_per_step": ksum["bytes"] / args.steps},
+                         "algo_bytes_per_step": ksum["bytes"] / args.steps,
+                         "algo_bytes_per_launch": ksum["bytes"] / max(ksum["launches"], 1)},
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line), flush=True)
