@@ -26,6 +26,7 @@
 //
 // Arithmetic intensity: 4*N^2*32 algorithmic FLOP per pair against 3*N*32 B in and
 // N*128 B out — HBM-bound at N=162, tensor-bound from N~576; bench reports both.
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "sdf_common.cuh"
@@ -73,6 +74,23 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       : "memory");
 }
 
+// same, descriptors given as (lo word, shared hi word) so that per-MMA operand changes are one 32-bit add;
+// ACC is compile time (enable-input-d)
+template <bool ACC>
+__device__ __forceinline__ void mma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void mma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -94,6 +112,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // contiguous; SBO = byte distance between 8-row groups, LBO = byte distance between 16-B K chunks.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// SWIZZLE_64B canonical layout (both majors, 16-bit elements, 32 elements = 64 B per row): rows of 64 B at a
+// 64-B pitch, 8-row groups 512 B apart (SBO), and inside the 1024-B-aligned buffer the 16-B chunk index is XORed
+// with address bits [7,8] = (row / 2) % 4.  K-major: a K step of 16 elements advances the start address by 32 B;
+// MN-major (rows = K index): a K step of 16 rows advances it by 1024 B.  LBO is not used (one swizzle span).
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 // instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, format 0 = F16, 1 = BF16
 // b_mn = 1: B operand is MN-major (its N index is the contiguous one)
@@ -167,8 +192,8 @@ __host__ __device__ inline SmemPlan plan_smem(int Rpad, int tab, bool bwd) {
   return s;
 }
 
-// plain operand: element (row r, dim d) at chunk (d/8), row r  -> [c][r][16 B]
-__device__ __forceinline__ uint32_t plain_off(int Rpad, int r, int c16) { return (uint32_t)(c16 * Rpad + r) * 16; }
+// operand tile: element (row r, dim d) in 16-B chunk d/8 of the 64-B row r, SWIZZLE_64B
+__device__ __forceinline__ uint32_t plain_off(int /*Rpad*/, int r, int c16) { return (uint32_t)r * 64 + (uint32_t)((c16 ^ ((r >> 1) & 3)) << 4); }
 
 // stage rows [0, N) of a u8 {0,1} [N, 32] block
 template <int BF>
@@ -260,7 +285,7 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
   const int half = NSLOT == 2 ? warp >> 3 : warp >> 2;          // which half of the column chunks this warp takes
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16; // this warp's TMEM lanes
   const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b), bt_base = smem_u32(smem + sp.bt);
-  const uint32_t lbo_plain = (uint32_t)Rpad * 16, sbo = 128;
+
 
   const int64_t n_pairs = p.M * p.nH;
   for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -300,8 +325,8 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
             const uint32_t d = tmem_base + s * p.slot_cols;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t ad = make_desc(a_base + ks * 2 * lbo_plain + (uint32_t)(mt0 + s) * 128 * 16, lbo_plain, sbo);
-              const uint64_t bd = make_desc(b_base + ks * 2 * lbo_plain + (uint32_t)key0 * 16, lbo_plain, sbo);
+              const uint64_t ad = make_desc_sw64(a_base + ks * 32 + (uint32_t)(mt0 + s) * 128 * 64);
+              const uint64_t bd = make_desc_sw64(b_base + ks * 32 + (uint32_t)key0 * 64);
               mma_ss(d, ad, bd, idesc, ks);
             }
           }
@@ -378,7 +403,7 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
           for (int s = 0; s < n_slots; ++s) {
             const uint32_t d = tmem_base + s * p.slot_cols + p.kt;
             for (int c0 = 0; c0 < nk; c0 += 16) {
-              const uint64_t bd = make_desc(bt_base + (uint32_t)(key0 + c0) * 16, 128, lbo_plain);
+              const uint64_t bd = make_desc_sw64(bt_base + (uint32_t)(key0 + c0) * 64);
               const uint32_t a_hi = tmem_base + s * p.slot_cols + c0;
               mma_ts(d, a_hi, bd, idesc, (kt > 0 || c0 > 0) ? 1u : 0u);
               mma_ts(d, a_hi + 8, bd, idesc, 1u);
@@ -424,6 +449,503 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
 }
 
+
+// ================================================================================================
+// K3 v2 — warp-specialised forward for windows whose bias matrix fits in tensor memory
+// ================================================================================================
+// O = scale * ( S@V + (Bias_h/scale)@V ) - 100 * ( sum_j V_j - sum_{j in region(i)} V_j )
+//   * S = Q K^T are exact integers <= 32, so S converts EXACTLY to fp16: the per-element epilogue is one packed
+//     cvt per two elements (in place over S in TMEM) instead of bias lookup + mask + hi/lo split;
+//   * Bias_h is fixed per CTA (fixed pseudo-head): it is built once, split hi + lo in fp16 (22 significant
+//     bits) and stays RESIDENT in TMEM as the A operand of two more MMAs per key chunk;
+//   * the shift mask only ever adds -100 * (number of spiking keys of the other regions): 27 region sums of V.
+// Roles: warps 0-3 epilogue (one per TMEM lane quarter), warp 4 MMA issuer, warps 5-8 producers (global ->
+// fp16 canonical shared-memory layouts, double buffered).  All hand-offs are mbarriers; S is double buffered in
+// TMEM so MMA 1 of item i+1 and MMA 2 of item i overlap the conversion of item i.
+// TMEM map (columns): [0,176) Bias hi (two M-tiles x 88), [176,352) Bias lo, [352,416) S0, [416,480) S1, [480,512) O.
+constexpr int kV2Threads = 416;               // 4 S-conversion warps, 1 MMA warp, 4 producer warps, 4 output warps
+constexpr int kV2KT = 64;
+constexpr int kV2S0 = 352, kV2S1 = 416, kV2O = 480;
+constexpr int kV2Regions = 27;
+constexpr int kV2Loads = 9;                 // 16-byte loads in flight per producer thread (6 N / 128, N <= 176)
+
+// one lane of a converged warp; keeps the surrounding code warp-uniform so that descriptors stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+struct V2Plan {
+  uint32_t op[2];       // operand buffers: Q | K | V, each Rpad*64 B
+  uint32_t rsum;        // 4 output warps x (kV2Regions + 1) x 32 ints: per-warp region sums of V, last row = the warp's total
+  uint32_t reg;         // Rpad bytes: region id of every token of the current window
+  uint32_t rowoff;      // Rpad x int64: element offset of token row i inside a window's output rows
+  uint32_t ostage;      // 4 output warps x 32 rows x 144 B (128 B + 16 B pad: conflict-free both ways)
+  uint32_t lin, tab, bars, tmem_slot, total;
+};
+__host__ __device__ inline V2Plan plan_v2(int Rpad, int tab) {
+  V2Plan s;
+  uint32_t o = 0;
+  for (int b = 0; b < 2; ++b) { s.op[b] = o; o += (uint32_t)Rpad * 64 * 3; }
+  s.rsum = o; o += (4 * (kV2Regions + 1) + kV2Regions) * 32 * 4;   // + combined table: keys outside region r, per dim
+  s.reg = o; o += (uint32_t)((Rpad + 15) / 16 * 16);
+  s.rowoff = o; o += (uint32_t)Rpad * 8;
+  s.ostage = o; o += 4 * 32 * 144;
+  s.lin = o; o += (uint32_t)Rpad * 4;
+  s.tab = o; o += (uint32_t)((tab * 4 + 15) / 16 * 16);
+  s.bars = o; o += 16 * 8;
+  s.tmem_slot = o; o += 16;
+  s.total = o;
+  return s;
+}
+
+#ifdef SDF_V2_TRACE
+__device__ long long g_v2_trace[16 * 64];
+#define V2_TR(slot, it) do { if (blockIdx.x == 0 && (it) < 64) g_v2_trace[(slot) * 64 + (it)] = clock64(); } while (0)
+#else
+#define V2_TR(slot, it) do { } while (0)
+#endif
+
+template <int NPAD, bool MASK>
+__global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const V2Plan sp = plan_v2(p.Rpad, p.tab);
+  int* lin_s = reinterpret_cast<int*>(smem + sp.lin);
+  float* tab_s = reinterpret_cast<float*>(smem + sp.tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* full = bars;          // [2] producers -> MMA/epilogue: operands of buffer b are in shared memory
+  uint64_t* empty = bars + 2;     // [2] MMA commit + epilogue warps -> producers: buffer b may be overwritten
+  uint64_t* s_full = bars + 4;    // [2] MMA commit -> epilogue: S buffer holds fresh counts
+  uint64_t* s16_full = bars + 6;  // [2] epilogue -> MMA: S converted to fp16 in place
+  uint64_t* o_full = bars + 8;    //     MMA commit -> epilogue: O of the current M-tile is complete
+  uint64_t* o_free = bars + 9;    //     epilogue -> MMA: O has been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_slot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, Rpad = p.Rpad;
+  constexpr int npad = NPAD;                  // keys padded to the MMA K granularity (compile time: the MMA issue
+                                              // sequence is fully unrolled with immediate operands)
+  constexpr int w2 = npad >> 1;               // TMEM columns of one fp16 bias tile
+  constexpr int n_kt = (npad + kV2KT - 1) / kV2KT;
+  constexpr int n_mt = npad > 128 ? 2 : 1;
+  constexpr int n_items = n_mt * n_kt;
+  const int64_t head = blockIdx.x % p.nH;
+  const int A_ = (2 * p.wh - 1) * (2 * p.ww - 1), B_ = 2 * p.ww - 1;
+  const int lin_off = (p.wd - 1) * A_ + (p.wh - 1) * B_ + (p.ww - 1);
+
+  // ---- one-time setup (all threads) ----
+  for (uint32_t i = tid * 16; i < sp.rsum; i += kV2Threads * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  for (int n = tid; n < Rpad; n += kV2Threads) {
+    const int d = n / (p.wh * p.ww), rem = n - d * (p.wh * p.ww), hh = rem / p.ww, w = rem - hh * p.ww;
+    lin_s[n] = n < N ? d * A_ + hh * B_ + w : 0;
+    smem[sp.reg + n] = 0;
+    // token (t = d, pos) of window mwin lives at row (t * M + mwin) * P + pos of the [wd * M * P, C] output
+    reinterpret_cast<int64_t*>(smem + sp.rowoff)[n] = ((int64_t)d * p.M * p.P + rem) * (p.nH * 32);
+  }
+  const float inv_scale = 1.f / p.scale;
+  for (int i = tid; i < p.tab; i += kV2Threads) tab_s[i] = __ldg(p.bias_table + (int64_t)i * p.nH + head) * inv_scale;
+  if (tid == 0) {
+    mbar_init(&full[0], 4); mbar_init(&full[1], 4);
+    mbar_init(&empty[0], 5); mbar_init(&empty[1], 5);
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s16_full[0], 4); mbar_init(&s16_full[1], 4);
+    mbar_init(o_full, 1); mbar_init(o_free, 4); mbar_init(&bars[10], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // resident bias: rows of both M-tiles, hi and lo halves, written by the epilogue warps (they own the lanes)
+  if (warp < 4) {
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int mt = 0; mt < n_mt; ++mt) {
+      const int row = mt * 128 + warp * 32 + lane;
+      const float* tab_i = tab_s + lin_off + (row < N ? lin_s[row] : 0);
+      for (int c0 = 0; c0 < npad; c0 += 16) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int j0 = c0 + 2 * c;
+          const float t0 = (row < N && j0 < N) ? tab_i[-lin_s[j0]] : 0.f;
+          const float t1 = (row < N && j0 + 1 < N) ? tab_i[-lin_s[j0 + 1]] : 0.f;
+          hi[c] = pack2<0>(t0, t1);
+          float ha, hb;
+          unpack2<0>(hi[c], ha, hb);
+          lo[c] = pack2<0>(t0 - ha, t1 - hb);
+        }
+        // 16 keys = 8 TMEM columns: hi -> [mt*w2 + c0/2, +8), lo -> [(n_mt + mt)*w2 + c0/2, +8)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tmem_base + lane_base + mt * w2 + (c0 >> 1)),
+                     "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tmem_base + lane_base + (n_mt + mt) * w2 + (c0 >> 1)),
+                     "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int64_t n_pairs = p.M * p.nH;
+
+
+  if (warp >= 5 && warp < 9) {
+    // =========================== producers ===========================
+    const int pt = tid - 5 * 32;                                  // 0..127
+    int pi = 0;
+    for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
+      const int b = pi & 1;
+      if (pt == 0) V2_TR(10, pi);
+      mbar_wait(&empty[b], ((pi >> 1) & 1) ^ 1);
+      if (pt == 0) V2_TR(11, pi);
+      // all 16-byte half-rows of Q, K and V of this pair: issue every load first, then convert and store
+      const uint8_t* src = p.q + pair * N * 32;
+      const int64_t kq = (p.k - p.q), vq = (p.v - p.q);
+      const int per = 2 * N, n_it = 3 * per;
+      uint4 w[kV2Loads];
+#pragma unroll
+      for (int u = 0; u < kV2Loads; ++u) {
+        const int g = pt + u * 128;
+        if (g < n_it) {
+          const int a = g >= 2 * per ? 2 : (g >= per ? 1 : 0);
+          const int i = g - a * per;
+          w[u] = __ldg(reinterpret_cast<const uint4*>(src + (a == 0 ? 0 : (a == 1 ? kq : vq)) + (int64_t)i * 16));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kV2Loads; ++u) {
+        const int g = pt + u * 128;
+        if (g < n_it) {
+          const int a = g >= 2 * per ? 2 : (g >= per ? 1 : 0);
+          const int i = g - a * per;
+          const int r = i >> 1, hf = i & 1;
+          const uint32_t ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // bytes are 0/1: spread them to 16-bit lanes and multiply by the fp16 pattern of 1.0
+            o[2 * j] = __byte_perm(ws[j], 0, 0x4140) * 0x3C00u;
+            o[2 * j + 1] = __byte_perm(ws[j], 0, 0x4342) * 0x3C00u;
+          }
+          const uint32_t base = sp.op[b] + (uint32_t)a * Rpad * 64;
+          *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[b]);
+      if (pt == 0) V2_TR(12, pi);
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    // The whole warp runs the warp-uniform control flow; one elected lane issues.  The tile structure is compile
+    // time, so every descriptor / TMEM address below is (per-pair base + immediate): the issue stream is
+    // back-to-back UTCHMMA, which is what lets N=32 MMAs run at their 16-cycle floor (tools/ubench/mma_chain.cu).
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint32_t kDescHi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B, version 1, SWIZZLE_64B
+      constexpr uint32_t idesc2 = (1u << 4) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      int pi = 0, item = 0, tile = 0;
+      for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
+        const int b = pi & 1;
+        mbar_wait(&full[b], (pi >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_lo = ((smem_u32(smem + sp.op[b]) & 0x3FFFF) >> 4) | (1u << 16);
+        const uint32_t k_lo = q_lo + (uint32_t)((Rpad * 64) >> 4), v_lo = k_lo + (uint32_t)((Rpad * 64) >> 4);
+#pragma unroll
+        for (int li = 0; li < n_items; ++li, ++item) {
+          const int sb = item & 1;
+          const uint32_t s_cur = tm + kV2S0 + (uint32_t)sb * 64u, s_nxt = tm + kV2S0 + (uint32_t)(sb ^ 1) * 64u;
+          V2_TR(0, item);
+          // MMA 1 of this item (first item of the pair only) and of the next one
+#pragma unroll
+          for (int lj = (li == 0 ? 0 : li + 1); lj <= li + 1 && lj < n_items; ++lj) {
+            const int mt1 = lj / n_kt, kt1 = lj % n_kt;
+            const int key1 = kt1 * kV2KT;
+            const int nk1 = (npad - key1) < kV2KT ? (npad - key1) : kV2KT;
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(nk1 >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t d1 = lj == li ? s_cur : s_nxt;
+            if (elect_one()) {
+              mma_ss_lh<false>(d1, q_lo + (uint32_t)(mt1 * 128 * 64 >> 4), k_lo + (uint32_t)(key1 * 64 >> 4), kDescHi, idesc1);
+              mma_ss_lh<true>(d1, q_lo + (uint32_t)(mt1 * 128 * 64 >> 4) + 2, k_lo + (uint32_t)(key1 * 64 >> 4) + 2, kDescHi, idesc1);
+              tc_commit(&s_full[lj == li ? sb : sb ^ 1]);
+            }
+            __syncwarp();
+          }
+          const int mt = li / n_kt, kt = li % n_kt;
+          const int key0 = kt * kV2KT;
+          const int nk = (npad - key0) < kV2KT ? (npad - key0) : kV2KT;
+          V2_TR(3, item);
+          mbar_wait(&s16_full[sb], (item >> 1) & 1);
+          tc_fence_after();
+          V2_TR(1, item);
+          if (kt == 0) {
+            mbar_wait(o_free, (tile & 1) ^ 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint32_t d = tm + kV2O;
+#pragma unroll
+            for (int c0 = 0; c0 < nk; c0 += 16) {
+              // B = V read MN-major: a 16-key step advances the start address by 16 rows * 64 B
+              const uint32_t bv = v_lo + (uint32_t)((key0 + c0) * 64 >> 4);
+              const uint32_t kc = (uint32_t)((key0 + c0) >> 1);
+              if (kt == 0 && c0 == 0) mma_ts_lh<false>(d, tm + mt * w2 + kc, bv, kDescHi, idesc2);
+              else mma_ts_lh<true>(d, tm + mt * w2 + kc, bv, kDescHi, idesc2);
+              mma_ts_lh<true>(d, tm + (n_mt + mt) * w2 + kc, bv, kDescHi, idesc2);
+              mma_ts_lh<true>(d, s_cur + (uint32_t)(c0 >> 1), bv, kDescHi, idesc2);
+            }
+            if (kt == n_kt - 1) tc_commit(o_full);
+          }
+          __syncwarp();
+          if (kt == n_kt - 1) ++tile;
+          V2_TR(2, item);
+        }
+        if (elect_one()) tc_commit(&empty[b]);
+        __syncwarp();
+      }
+      // drain: every commit above has been delivered once this one has
+      if (elect_one()) tc_commit(&bars[10]);
+      __syncwarp();
+      mbar_wait(&bars[10], 0);
+    }
+  } else if (warp < 4) {
+    // =========================== S-conversion warps (one per TMEM lane quarter) ===========================
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int item = 0;
+    for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll
+      for (int li = 0; li < n_items; ++li, ++item) {
+        const int sb = item & 1;
+        const int kt = li % n_kt;
+        const int key0 = kt * kV2KT;
+        const int nk = (npad - key0) < kV2KT ? (npad - key0) : kV2KT;
+        const uint32_t scol = tmem_base + lane_base + (sb ? kV2S1 : kV2S0);
+        if (tid == 0) V2_TR(4, item);
+        mbar_wait(&s_full[sb], (item >> 1) & 1);
+        tc_fence_after();
+        if (tid == 0) V2_TR(5, item);
+        // S (fp32 exact integers) -> fp16 pairs, in place: this warp is the only one touching these lanes
+        uint32_t r0[32], o[32];
+        tmem_ld32(scol, r0);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[c] = pack2<0>(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+        if (nk > 32) {
+          tmem_ld32(scol + 32, r0);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[16 + c] = pack2<0>(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[16 + c] = 0;
+        }
+        tmem_st32(scol, o);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s16_full[sb]);
+        if (tid == 0) V2_TR(6, item);
+      }
+    }
+  } else {
+    // =========================== output warps (9..12, lane quarter = warp % 4) ===========================
+    const int qw = warp & 3;
+    const uint32_t lane_base = (uint32_t)(qw * 32) << 16;
+    const int P = (int)p.P;
+    const int64_t* rowoff_s = reinterpret_cast<const int64_t*>(smem + sp.rowoff);
+    int pi = 0, tile = 0;
+    for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
+      const int b = pi & 1;
+      const int64_t mwin = pair / p.nH;
+      uint8_t rg_next[2] = {0, 0};
+      if (MASK) {
+        const uint8_t* rp = p.region + (int64_t)((int)mwin % (int)p.nW) * N;
+        const int otid = qw * 32 + lane;
+        rg_next[0] = __ldg(rp + min(otid, N - 1));
+        rg_next[1] = __ldg(rp + min(otid + 128, N - 1));
+        mbar_wait(&full[b], (pi >> 1) & 1);
+      }
+      int* rs_all = reinterpret_cast<int*>(smem + sp.rsum);
+      int* rs_w = rs_all + qw * ((kV2Regions + 1) * 32);
+      uint8_t* rg = smem + sp.reg;
+      if (MASK) {
+        // Region sums R[r][d] = sum over the keys j of region r of V[j][d], without atomics: lane = dim d, each
+        // output warp walks a quarter of the keys; the region id is warp-uniform per key and keys of one region
+        // come in runs, so a run accumulates in a register and is flushed into this warp's private copy.
+        const int otid = qw * 32 + lane;
+        if (otid == 0) V2_TR(13, pi);
+        // region ids of this window's tokens; the tail up to the next multiple of 8 repeats the last id (those
+        // rows of V are zero), so the pass below needs no bounds checks
+        for (int n = otid; n < ((N + 7) & ~7); n += 128) rg[n] = rg_next[n >= 128];
+        for (int r = 0; r <= kV2Regions; ++r) rs_w[r * 32 + lane] = 0;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (otid == 0) V2_TR(14, pi);
+        // rows in groups of 8 (one swizzle period): the four chunk offsets are lane constants
+        const int per_w = (((N + 3) >> 2) + 7) & ~7, j0 = qw * per_w, j1 = min((N + 7) & ~7, j0 + per_w);
+        const uint8_t* vb = smem + sp.op[b] + 2u * Rpad * 64 + (lane & 7) * 2;
+        const int c = lane >> 3;
+        const uint32_t o0 = (uint32_t)(c ^ 0) << 4, o1 = (uint32_t)(c ^ 1) << 4, o2 = (uint32_t)(c ^ 2) << 4, o3 = (uint32_t)(c ^ 3) << 4;
+        int cur = j0 < j1 ? (int)rg[j0] : 0, acc = 0, tot = 0;
+        for (int jb = j0; jb < j1; jb += 8) {
+          const uint8_t* vr = vb + jb * 64;
+          const uint2 r8 = *reinterpret_cast<const uint2*>(rg + jb);
+          uint32_t vv[8];
+          vv[0] = *reinterpret_cast<const uint16_t*>(vr + 0 * 64 + o0);
+          vv[1] = *reinterpret_cast<const uint16_t*>(vr + 1 * 64 + o0);
+          vv[2] = *reinterpret_cast<const uint16_t*>(vr + 2 * 64 + o1);
+          vv[3] = *reinterpret_cast<const uint16_t*>(vr + 3 * 64 + o1);
+          vv[4] = *reinterpret_cast<const uint16_t*>(vr + 4 * 64 + o2);
+          vv[5] = *reinterpret_cast<const uint16_t*>(vr + 5 * 64 + o2);
+          vv[6] = *reinterpret_cast<const uint16_t*>(vr + 6 * 64 + o3);
+          vv[7] = *reinterpret_cast<const uint16_t*>(vr + 7 * 64 + o3);
+          const uint32_t cur4 = (uint32_t)cur * 0x01010101u;
+          if (r8.x == cur4 && r8.y == cur4) {      // the whole group continues the current run (the common case)
+            acc += (int)(((vv[0] + vv[1]) + (vv[2] + vv[3]) + (vv[4] + vv[5]) + (vv[6] + vv[7])) / 0x3C00u);   // fp16 1.0 = 0x3C00
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int rj = (int)(((u < 4 ? r8.x : r8.y) >> ((u & 3) * 8)) & 0xFF);
+              if (rj != cur) {                     // warp-uniform branch, once per run of equal region ids
+                rs_w[cur * 32 + lane] += acc;
+                tot += acc; acc = 0; cur = rj;
+              }
+              acc += (int)(vv[u] >> 13);
+            }
+          }
+        }
+        rs_w[cur * 32 + lane] += acc;
+        rs_w[kV2Regions * 32 + lane] = tot + acc;
+        if (otid == 0) V2_TR(15, pi);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        // combine the four copies: other[r][d] = (number of spiking keys, dim d) - (those inside region r)
+        int* oth = rs_all + 4 * (kV2Regions + 1) * 32;
+        for (int idx = otid; idx < kV2Regions * 32; idx += 128) {
+          const int d = idx & 31;
+          int o = 0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int* cw = rs_all + w * ((kV2Regions + 1) * 32);
+            o += cw[kV2Regions * 32 + d] - cw[idx];
+          }
+          oth[idx] = o;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (otid == 0) V2_TR(9, pi);
+      }
+      for (int mt = 0; mt < n_mt; ++mt, ++tile) {
+        // O of this M-tile is complete: out = scale * O - 100 * (Vsum - R[region(i)])
+        mbar_wait(o_full, tile & 1);
+        tc_fence_after();
+        if (lane == 0 && qw == 0) V2_TR(7, tile);
+        uint32_t ov[32];
+        tmem_ld32(tmem_base + lane_base + kV2O, ov);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+        // scale + mask term, then transpose through shared memory so that each store instruction writes four
+        // complete 128-B rows (thread-per-row stores would touch 32 lines per instruction and clog the LSU)
+        const int row0 = mt * 128 + qw * 32;
+        uint8_t* stg = smem + sp.ostage + (uint32_t)qw * (32 * 144);
+        {
+          const int row = row0 + lane;
+          const int ri = ((MASK && row < N) ? (int)rg[row] : 0) * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 v;
+            int4 other = make_int4(0, 0, 0, 0);     // spiking keys outside this row's region, per dim
+            if (MASK) other = *reinterpret_cast<const int4*>(rs_all + 4 * (kV2Regions + 1) * 32 + ri + 4 * c);
+            v.x = fmaf(__uint_as_float(ov[4 * c]), p.scale, -100.f * (float)other.x);
+            v.y = fmaf(__uint_as_float(ov[4 * c + 1]), p.scale, -100.f * (float)other.y);
+            v.z = fmaf(__uint_as_float(ov[4 * c + 2]), p.scale, -100.f * (float)other.z);
+            v.w = fmaf(__uint_as_float(ov[4 * c + 3]), p.scale, -100.f * (float)other.w);
+            *reinterpret_cast<float4*>(stg + lane * 144 + c * 16) = v;
+          }
+        }
+        __syncwarp();
+        {
+          const int sub = lane >> 3, ch = lane & 7;
+          float* obase = p.out + (mwin * P) * (p.nH * 32) + head * 32 + ch * 4;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rl = sub + 4 * k, row = row0 + rl;
+            if (row < N) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + rl * 144 + ch * 16);
+              st_stream4(obase + rowoff_s[row], v);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && qw == 0) V2_TR(8, tile);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[b]);
+      if (MASK) asm volatile("bar.sync 2, 128;" ::: "memory");   // region tables are rewritten for the next pair
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+template <int NPAD>
+static void launch_v2_npad(bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
+  if (mask) {
+    cudaFuncSetAttribute(qktv2_kernel<NPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    qktv2_kernel<NPAD, true><<<grid, kV2Threads, smem_bytes, stream>>>(p);
+  } else {
+    cudaFuncSetAttribute(qktv2_kernel<NPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    qktv2_kernel<NPAD, false><<<grid, kV2Threads, smem_bytes, stream>>>(p);
+  }
+}
+static void launch_v2(int npad, bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
+  switch (npad) {
+    case 16: launch_v2_npad<16>(mask, grid, smem_bytes, stream, p); break;
+    case 32: launch_v2_npad<32>(mask, grid, smem_bytes, stream, p); break;
+    case 48: launch_v2_npad<48>(mask, grid, smem_bytes, stream, p); break;
+    case 64: launch_v2_npad<64>(mask, grid, smem_bytes, stream, p); break;
+    case 80: launch_v2_npad<80>(mask, grid, smem_bytes, stream, p); break;
+    case 96: launch_v2_npad<96>(mask, grid, smem_bytes, stream, p); break;
+    case 112: launch_v2_npad<112>(mask, grid, smem_bytes, stream, p); break;
+    case 128: launch_v2_npad<128>(mask, grid, smem_bytes, stream, p); break;
+    case 144: launch_v2_npad<144>(mask, grid, smem_bytes, stream, p); break;
+    case 160: launch_v2_npad<160>(mask, grid, smem_bytes, stream, p); break;
+    default: launch_v2_npad<176>(mask, grid, smem_bytes, stream, p); break;
+  }
+}
+#ifdef SDF_V2_TRACE
+extern "C" int sdf_debug_v2_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, sdf::g_v2_trace, sizeof(long long) * 16 * 64);
+}
+#endif
 static int qktv_setup(int64_t M, int64_t nH, int64_t nW, int64_t wd, int64_t wh, int64_t ww, double scale, bool bwd,
                       QktvP* p, SmemPlan* sp, int* grid, int* nslot) {
   SDF_REQUIRE(M > 0 && nH > 0 && wd > 0 && wh > 0 && ww > 0, "qktv: bad dims");
@@ -469,6 +991,19 @@ extern "C" int sdf_attn_qktv_fwd(const sdf_attn_qktv_fwd_args* a) {
   p.out = a->out; p.s_dbg = a->s_dbg; p.attn_dbg = a->attn_dbg;
   const bool dbg = a->s_dbg || a->attn_dbg;
   cudaStream_t stream = (cudaStream_t)a->stream;
+  {
+    // v2 (warp-specialised, bias resident in TMEM) when both M-tiles' fp16 hi/lo bias fit in 352 columns
+    static const int use_v2 = [] { const char* e = getenv("SDF_QKTV_V2"); return e ? atoi(e) : 1; }();
+    const int npad = (p.N + 15) & ~15;
+    const V2Plan vp = plan_v2(p.Rpad, p.tab);
+    if (use_v2 && !dbg && p.n_mt * npad <= 352 && vp.total <= 200 * 1024 && a->scale != 0.0) {
+      int g = kNumSMs / (int)a->nH * (int)a->nH;
+      if (g < a->nH) g = (int)a->nH;
+      if ((int64_t)g > a->M * a->nH) g = (int)(a->M * a->nH);
+      launch_v2(npad, p.has_mask != 0, g, vp.total, stream, p);
+      return finish_launch("sdf_attn_qktv_fwd(v2)");
+    }
+  }
 #define QKTV_LAUNCH(PH, MK, DB)                                                                                       \
   do {                                                                                                                \
     if (nslot == 1) {                                                                                                 \

@@ -146,7 +146,15 @@ def qktv():
         q, k, v = ((torch.rand(rows, C, device=dev, generator=g) < 0.2).to(torch.uint8) for _ in range(3))
         table = torch.randn((2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1), nH, device=dev) * 0.02
         nW = M // 8 if M % 8 == 0 else 1
-        region = torch.randint(0, 3, (nW, N), device=dev, dtype=torch.uint8) if masked else None
+        region = None
+        if masked:
+            # shifted-window region ids as sdf_window_index produces them: one cut per axis, only in the windows on the
+            # far border of that axis (here: every 2nd window in depth, every 4th in height / width)
+            dd, hh, wc = torch.meshgrid(torch.arange(wd), torch.arange(wh), torch.arange(ww), indexing="ij")
+            idx = torch.arange(nW).view(-1, 1)
+            a, b, c = (idx % 2 == 1), ((idx // 2) % 4 == 3), ((idx // 8) % 4 == 3)
+            region = (9 * a * (dd.reshape(1, -1) >= wd // 2) + 3 * b * (hh.reshape(1, -1) > wh // 2)
+                      + c * (wc.reshape(1, -1) > ww // 2)).to(torch.uint8).to(dev).contiguous()
         out = torch.empty(rows, C, device=dev)
 
         def fwd():
