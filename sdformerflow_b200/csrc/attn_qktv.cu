@@ -59,6 +59,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp; keeps the surrounding code warp-uniform so that descriptors stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -120,6 +126,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
+// the same descriptor as two 32-bit words: per-MMA address changes are a 32-bit add on the low word
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B, version 1, SWIZZLE_64B
 // instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, format 0 = F16, 1 = BF16
 // b_mn = 1: B operand is MN-major (its N index is the contiguous one)
 __device__ __forceinline__ uint32_t make_idesc(int fmt, int M, int N, int b_mn = 0) {
@@ -279,6 +288,7 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform copy for the MMA issuer
   uint32_t ph_s = 0, ph_o = 0;
 
   const int slot = NSLOT == 2 ? (warp >> 2) & 1 : 0;            // which M-tile of the current group of M-tiles
@@ -318,19 +328,21 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
         int nk = N - key0;
         nk = nk > p.kt ? p.kt : ((nk + 15) & ~15);
         // ---- MMA 1: S[128 x nk] = A[128 x 32] * B[nk x 32]^T, both slots ----
-        if (tid == 0) {
+        // Issued by one elected lane of warp 0 while the whole warp runs the (warp-uniform) address arithmetic:
+        // descriptors then live in uniform registers and the UTCHMMA stream is not throttled by R2UR round trips.
+        if (warp == 0) {
           tc_fence_after();
           const uint32_t idesc = make_idesc(BF, 128, nk);
-          for (int s = 0; s < n_slots; ++s) {
-            const uint32_t d = tmem_base + s * p.slot_cols;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t ad = make_desc_sw64(a_base + ks * 32 + (uint32_t)(mt0 + s) * 128 * 64);
-              const uint64_t bd = make_desc_sw64(b_base + ks * 32 + (uint32_t)key0 * 64);
-              mma_ss(d, ad, bd, idesc, ks);
+          const uint32_t a_lo = desc_lo(a_base + (uint32_t)mt0 * 128 * 64), b_lo = desc_lo(b_base + (uint32_t)key0 * 64);
+          if (elect_one()) {
+            for (int s = 0; s < n_slots; ++s) {
+              const uint32_t d = tm_u + s * p.slot_cols;
+              mma_ss_lh<false>(d, a_lo + (uint32_t)s * (128 * 64 >> 4), b_lo, kDescHiSw64, idesc);
+              mma_ss_lh<true>(d, a_lo + (uint32_t)s * (128 * 64 >> 4) + 2, b_lo + 2, kDescHiSw64, idesc);
             }
+            tc_commit(&bars[0]);
           }
-          tc_commit(&bars[0]);
+          __syncwarp();
         }
         mbar_wait(&bars[0], ph_s);
         ph_s ^= 1;
@@ -395,21 +407,27 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
         tc_fence_before();
         __syncthreads();
         // ---- MMA 2: O[128 x 32] (+)= T_hi * Bt + T_lo * Bt over the 16-key chunks of this tile ----
-        if (tid == 0) {
+        if (warp == 0) {
           tc_fence_after();
-          // B = the third operand in its plain [dim chunk][token][16 B] layout read MN-major: N (=dim) chunks of 8
-          // are SBO = Rpad*16 B apart, K (=token) groups of 8 are LBO = 128 B apart.
+          // B = the third operand read MN-major (rows = keys): a 16-key step advances the start address by 1024 B
           const uint32_t idesc = make_idesc(BF, 128, 32, 1);
-          for (int s = 0; s < n_slots; ++s) {
-            const uint32_t d = tmem_base + s * p.slot_cols + p.kt;
-            for (int c0 = 0; c0 < nk; c0 += 16) {
-              const uint64_t bd = make_desc_sw64(bt_base + (uint32_t)(key0 + c0) * 64);
-              const uint32_t a_hi = tmem_base + s * p.slot_cols + c0;
-              mma_ts(d, a_hi, bd, idesc, (kt > 0 || c0 > 0) ? 1u : 0u);
-              mma_ts(d, a_hi + 8, bd, idesc, 1u);
+          const uint32_t bt_lo = desc_lo(bt_base + (uint32_t)key0 * 64);
+          if (elect_one()) {
+            for (int s = 0; s < n_slots; ++s) {
+              const uint32_t d = tm_u + s * p.slot_cols + p.kt;
+              uint32_t a_hi = tm_u + s * p.slot_cols, bd = bt_lo;
+              if (kt == 0) mma_ts_lh<false>(d, a_hi, bd, kDescHiSw64, idesc);
+              else mma_ts_lh<true>(d, a_hi, bd, kDescHiSw64, idesc);
+              mma_ts_lh<true>(d, a_hi + 8, bd, kDescHiSw64, idesc);
+              for (int c0 = 16; c0 < nk; c0 += 16) {
+                a_hi += 16; bd += 1024 >> 4;
+                mma_ts_lh<true>(d, a_hi, bd, kDescHiSw64, idesc);
+                mma_ts_lh<true>(d, a_hi + 8, bd, kDescHiSw64, idesc);
+              }
             }
+            if (kt == p.n_kt - 1) tc_commit(&bars[1]);
           }
-          if (kt == p.n_kt - 1) tc_commit(&bars[1]);
+          __syncwarp();
         }
       }
       // ---- epilogue 2: O rows -> global ----
@@ -469,12 +487,6 @@ constexpr int kV2S0 = 352, kV2S1 = 416, kV2O = 480;
 constexpr int kV2Regions = 27;
 constexpr int kV2Loads = 9;                 // 16-byte loads in flight per producer thread (6 N / 128, N <= 176)
 
-// one lane of a converged warp; keeps the surrounding code warp-uniform so that descriptors stay in uniform registers
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
