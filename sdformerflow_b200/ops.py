@@ -947,15 +947,17 @@ def qktv_attention(q_pre, k_pre, v_pre, bn_q, bn_k, bn_v, table, cfg, region, wd
                          bns[2].bias, table, bns, cfg, region, dims, scale, want_attn, *psn)
 
 
-def qktv_debug(q, k, v, table, region, M, nH, nW, window, scale):
-    """Raw forward call on uint8 spikes [M*nH*N, 32]: returns (out [wd*M*P, C], S int32 [M*nH,N,N], attn fp32)."""
+def qktv_debug(q, k, v, table, region, M, nH, nW, window, scale, debug=True):
+    """Raw forward call on uint8 spikes [M*nH*N, 32]: returns (out [wd*M*P, C], S int32 [M*nH,N,N], attn fp32).
+    debug=False leaves the two debug outputs out (returns None for them), which is what the model path does and
+    what lets the library pick its fast kernel for small windows."""
     wd, wh, ww = window
     N, P = wd * wh * ww, wh * ww
     rows, C = wd * M * P, nH * 32
     dev = q.device
     out = torch.empty((rows, C), device=dev, dtype=torch.float32)
-    s_dbg = torch.empty((M * nH, N, N), device=dev, dtype=torch.int32)
-    attn = torch.empty((M * nH, N, N), device=dev, dtype=torch.float32)
+    s_dbg = torch.empty((M * nH, N, N), device=dev, dtype=torch.int32) if debug else None
+    attn = torch.empty((M * nH, N, N), device=dev, dtype=torch.float32) if debug else None
     capi.call("sdf_attn_qktv_fwd", capi.struct(
         "sdf_attn_qktv_fwd_args", q=_ptr(q), k=_ptr(k), v=_ptr(v), bias_table=_ptr(table.contiguous()), region=_ptr(region),
         out=_ptr(out), s_dbg=_ptr(s_dbg), attn_dbg=_ptr(attn), M=M, nH=nH, nW=nW, wd=wd, wh=wh, ww=ww, scale=float(scale),

@@ -62,6 +62,67 @@ def test_qktv_forward(case):
     assert err.item() <= 2e-6, err.item()
 
 
+# window sizes that cover every key-padding template of the small-window kernel (N <= 176: bias resident in TMEM),
+# one and two M-tiles, full and partial key tiles
+FAST_CASES = [
+    # wd, wh, ww, nH, B, nWin/sample
+    (1, 4, 4, 2, 2, 3),      # N = 16
+    (2, 3, 4, 2, 2, 3),      # N = 24  -> 32
+    (3, 4, 4, 1, 1, 5),      # N = 48
+    (2, 5, 5, 3, 1, 4),      # N = 50  -> 64
+    (2, 6, 6, 2, 1, 4),      # N = 72  -> 80
+    (2, 6, 8, 2, 1, 3),      # N = 96
+    (2, 7, 7, 3, 1, 4),      # N = 98  -> 112
+    (2, 8, 8, 6, 1, 2),      # N = 128: one full M-tile, no padding rows
+    (1, 12, 12, 2, 1, 3),    # N = 144: two M-tiles
+    (2, 8, 10, 3, 1, 2),     # N = 160
+    (2, 9, 9, 3, 2, 4),      # N = 162 -> 176
+    (4, 6, 7, 2, 1, 3),      # N = 168 -> 176
+    (2, 9, 9, 24, 3, 40),    # many (window, head) pairs per CTA: exercises the pipeline wrap-around
+]
+
+
+def _shift_regions(wd, wh, ww, nW):
+    """Region ids shaped like sdf_window_index's: one cut per axis, present in some of the windows only."""
+    dd, hh, wc = torch.meshgrid(torch.arange(wd), torch.arange(wh), torch.arange(ww), indexing="ij")
+    idx = torch.arange(nW).view(-1, 1)
+    a, b, c = (idx % 2 == 1), (idx % 3 == 2), (idx % 4 >= 2)
+    return (9 * a * (dd.reshape(1, -1) >= max(wd // 2, 1)) + 3 * b * (hh.reshape(1, -1) > wh // 2)
+            + c * (wc.reshape(1, -1) > ww // 2)).to(torch.uint8).contiguous()
+
+
+@pytest.mark.parametrize("case", FAST_CASES)
+@pytest.mark.parametrize("mask", ["none", "shift", "random"])
+@pytest.mark.parametrize("scale", [0.125, 32 ** -0.5])
+def test_qktv_forward_fast_kernel(case, mask, scale):
+    """The non-debug call (what the model issues) against the reference formula; for N <= 176 this is the
+    warp-specialised kernel, which shares no epilogue code with the debug path tested above."""
+    from sdformerflow_b200 import ops
+    wd, wh, ww, nH, B, nW = case
+    q, k, v, table, region, M, N, P, C = _inputs(wd, wh, ww, nH, B, nW, mask == "random", seed=7)
+    if mask == "shift":
+        region = _shift_regions(wd, wh, ww, nW)
+    _, _, x = _reference(q, k, v, table, region, M, N, nH, (wd, wh, ww), scale)
+    out, _, _ = ops.qktv_debug(q.to(DEV), k.to(DEV), v.to(DEV), table.to(DEV),
+                               None if region is None else region.to(DEV), M, nH, nW, (wd, wh, ww), scale, debug=False)
+    torch.cuda.synchronize()
+    err = (out.cpu() - x).abs().max() / x.abs().max()
+    assert err.item() <= 2e-6, err.item()
+
+
+def test_qktv_forward_fast_kernel_is_deterministic():
+    """The four warp roles hand over through mbarriers only; a missed hand-over shows up as run-to-run noise."""
+    from sdformerflow_b200 import ops
+    wd, wh, ww, nH, B, nW = 2, 9, 9, 3, 4, 60
+    q, k, v, table, _, M, N, P, C = _inputs(wd, wh, ww, nH, B, nW, False, seed=11)
+    region = _shift_regions(wd, wh, ww, nW).to(DEV)
+    args = (q.to(DEV), k.to(DEV), v.to(DEV), table.to(DEV), region, M, nH, nW, (wd, wh, ww), 32 ** -0.5)
+    first = ops.qktv_debug(*args, debug=False)[0].clone()
+    for _ in range(20):
+        again = ops.qktv_debug(*args, debug=False)[0]
+        assert torch.equal(first, again)
+
+
 @pytest.mark.parametrize("case", CASES[:5])
 def test_qktv_backward(case):
     from sdformerflow_b200 import ops
