@@ -928,6 +928,482 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
+// ================================================================================================
+// K4 v2 — the same warp-specialised pipeline for the three backward contractions (small windows)
+// ================================================================================================
+// attn = scale S + Bias + Mask is linear in Q, K, V and the bias table, so with dA = dO V^T (per window and head):
+//   PHASE 1  dQ = scale (dA K),  dTable[m] = sum over (i, j) with rel(i, j) = m of dA[i][j]
+//   PHASE 2  dK = scale (dA^T Q)
+//   PHASE 3  dV = attn^T dO = scale (S^T dO + (Bias^T / scale) dO) - 100 (sum_i dO_i - sum_{i in region(j)} dO_i)
+// Operand slots (bf16, SWIZZLE_64B): X1 = A of MMA 1 (M-tile rows), X2 = B of MMA 1 (64-row tiles), X3 = B of MMA 2
+// (read MN-major):   PHASE 1: dO, V, K     PHASE 2: V, dO, Q     PHASE 3: K, Q, dO.     dO enters in bf16 (as in v1).
+// PHASE 1/2: the S-conversion warps turn scale * dA into bf16 hi + lo in place (two MMAs per 16-row chunk).
+// PHASE 3: S^T is exact in bf16; Bias^T / scale sits in TMEM as bf16 hi + lo like the forward's bias.
+// dTable: instead of one shared-memory atomic per (i, j) per window, dA is ALSO accumulated over all the windows of
+// this CTA (fixed head) into a persistent TMEM accumulator (the 352 columns the forward uses for the bias); the
+// scatter over relative positions then runs once per CTA.
+template <bool ACC_RT>
+__device__ __forceinline__ void mma_ss_lh_rt(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+template <int NPAD, int PHASE, bool MASK>
+__global__ void __launch_bounds__(kV2Threads, 1) qktv2_bwd_kernel(const QktvP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const V2Plan sp = plan_v2(p.Rpad, p.tab);
+  int* lin_s = reinterpret_cast<int*>(smem + sp.lin);
+  float* tab_s = reinterpret_cast<float*>(smem + sp.tab);      // PHASE 3: bias / scale;  PHASE 1: dTable accumulator
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 2;
+  uint64_t* s_full = bars + 4;
+  uint64_t* s16_full = bars + 6;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_free = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_slot);
+  const int64_t* rowoff_s = reinterpret_cast<const int64_t*>(smem + sp.rowoff);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, Rpad = p.Rpad;
+  constexpr int npad = NPAD;
+  constexpr int w2 = npad >> 1;
+  constexpr int n_kt = (npad + kV2KT - 1) / kV2KT;
+  constexpr int n_mt = npad > 128 ? 2 : 1;
+  constexpr int n_items = n_mt * n_kt;
+  // which slot holds dO, and which global spike arrays feed the other two
+  constexpr int kGoSlot = PHASE == 1 ? 0 : (PHASE == 2 ? 1 : 2);
+  const int64_t head = blockIdx.x % p.nH;
+  const int A_ = (2 * p.wh - 1) * (2 * p.ww - 1), B_ = 2 * p.ww - 1;
+  const int lin_off = (p.wd - 1) * A_ + (p.wh - 1) * B_ + (p.ww - 1);
+
+  // ---- one-time setup ----
+  for (uint32_t i = tid * 16; i < sp.rsum; i += kV2Threads * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  for (int n = tid; n < Rpad; n += kV2Threads) {
+    const int d = n / (p.wh * p.ww), rem = n - d * (p.wh * p.ww), hh = rem / p.ww, w = rem - hh * p.ww;
+    lin_s[n] = n < N ? d * A_ + hh * B_ + w : 0;
+    smem[sp.reg + n] = 0;
+    reinterpret_cast<int64_t*>(smem + sp.rowoff)[n] = ((int64_t)d * p.M * p.P + rem) * (p.nH * 32);
+  }
+  if (PHASE == 3) {
+    const float inv_scale = 1.f / p.scale;
+    for (int i = tid; i < p.tab; i += kV2Threads) tab_s[i] = __ldg(p.bias_table + (int64_t)i * p.nH + head) * inv_scale;
+  } else if (PHASE == 1) {
+    for (int i = tid; i < p.tab; i += kV2Threads) tab_s[i] = 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&full[0], 4); mbar_init(&full[1], 4);
+    mbar_init(&empty[0], 5); mbar_init(&empty[1], 5);
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s16_full[0], 4); mbar_init(&s16_full[1], 4);
+    mbar_init(o_full, 1); mbar_init(o_free, 4); mbar_init(&bars[10], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (PHASE == 3 && warp < 4) {
+    // resident Bias^T / scale: A-operand row = key j, column = query i, value tab[rel(i, j)]
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int mt = 0; mt < n_mt; ++mt) {
+      const int row = mt * 128 + warp * 32 + lane;
+      const float* tab_j = tab_s + lin_off - (row < N ? lin_s[row] : 0);
+      for (int c0 = 0; c0 < npad; c0 += 16) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int i0 = c0 + 2 * c;
+          const float t0 = (row < N && i0 < N) ? tab_j[lin_s[i0]] : 0.f;
+          const float t1 = (row < N && i0 + 1 < N) ? tab_j[lin_s[i0 + 1]] : 0.f;
+          hi[c] = pack2<1>(t0, t1);
+          float ha, hb;
+          unpack2<1>(hi[c], ha, hb);
+          lo[c] = pack2<1>(t0 - ha, t1 - hb);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tmem_base + lane_base + mt * w2 + (c0 >> 1)),
+                     "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tmem_base + lane_base + (n_mt + mt) * w2 + (c0 >> 1)),
+                     "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int64_t n_pairs = p.M * p.nH;
+
+  if (warp >= 5 && warp < 9) {
+    // =========================== producers ===========================
+    const int pt = tid - 5 * 32;
+    const uint8_t* sa = PHASE == 1 ? p.v : (PHASE == 2 ? p.v : p.k);     // first spike array (slot order)
+    const uint8_t* sb_ = PHASE == 1 ? p.k : p.q;                           // second spike array
+    constexpr int slot_a = PHASE == 1 ? 1 : 0;                             // PHASE 1: V -> X2; PHASE 2: V -> X1; PHASE 3: K -> X1
+    constexpr int slot_b = PHASE == 1 ? 2 : (PHASE == 2 ? 2 : 1);          // PHASE 1: K -> X3; PHASE 2: Q -> X3; PHASE 3: Q -> X2
+    constexpr int kGoLoads = (4 * 176 + 127) / 128, kSpLoads = (4 * 176 + 127) / 128;
+    int pi = 0;
+    for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
+      const int b = pi & 1;
+      mbar_wait(&empty[b], ((pi >> 1) & 1) ^ 1);
+      const int64_t mwin = pair / p.nH;
+      const float* go = p.grad_out + (mwin * p.P) * (p.nH * 32) + head * 32;
+      // dO: one item = 8 floats of a row -> one 16-B bf16 chunk;  spikes: one item = 16 bytes -> two chunks
+      float4 g0[kGoLoads], g1[kGoLoads];
+      uint4 w[kSpLoads];
+      const int n_go = 4 * N, per = 2 * N, n_sp = 2 * per;
+#pragma unroll
+      for (int u = 0; u < kGoLoads; ++u) {
+        const int g = pt + u * 128;
+        if (g < n_go) {
+          const float* src = go + rowoff_s[g >> 2] + (g & 3) * 8;
+          g0[u] = __ldg(reinterpret_cast<const float4*>(src));
+          g1[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSpLoads; ++u) {
+        const int g = pt + u * 128;
+        if (g < n_sp) {
+          const int a = g >= per ? 1 : 0;
+          const int i = g - a * per;
+          w[u] = __ldg(reinterpret_cast<const uint4*>((a ? sb_ : sa) + pair * N * 32 + (int64_t)i * 16));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGoLoads; ++u) {
+        const int g = pt + u * 128;
+        if (g < n_go) {
+          const uint4 o = make_uint4(pack2<1>(g0[u].x, g0[u].y), pack2<1>(g0[u].z, g0[u].w), pack2<1>(g1[u].x, g1[u].y), pack2<1>(g1[u].z, g1[u].w));
+          *reinterpret_cast<uint4*>(smem + sp.op[b] + (uint32_t)kGoSlot * Rpad * 64 + plain_off(Rpad, g >> 2, g & 3)) = o;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSpLoads; ++u) {
+        const int g = pt + u * 128;
+        if (g < n_sp) {
+          const int a = g >= per ? 1 : 0;
+          const int i = g - a * per;
+          const int r = i >> 1, hf = i & 1;
+          const uint32_t ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[2 * j] = __byte_perm(ws[j], 0, 0x4140) * 0x3F80u;       // bf16 1.0
+            o[2 * j + 1] = __byte_perm(ws[j], 0, 0x4342) * 0x3F80u;
+          }
+          const uint32_t base = sp.op[b] + (uint32_t)(a ? slot_b : slot_a) * Rpad * 64;
+          *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[b]);
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t kDescHi = kDescHiSw64;
+    constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // bf16, B MN-major
+    int pi = 0, item = 0, tile = 0;
+    for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
+      const int b = pi & 1;
+      mbar_wait(&full[b], (pi >> 1) & 1);
+      tc_fence_after();
+      const uint32_t x1_lo = desc_lo(smem_u32(smem + sp.op[b]));
+      const uint32_t x2_lo = x1_lo + (uint32_t)((Rpad * 64) >> 4), x3_lo = x2_lo + (uint32_t)((Rpad * 64) >> 4);
+      const uint32_t acc_p = pi > 0 ? 1u : 0u;
+#pragma unroll
+      for (int li = 0; li < n_items; ++li, ++item) {
+        const int sb = item & 1;
+        const uint32_t s_cur = tm + kV2S0 + (uint32_t)sb * 64u, s_nxt = tm + kV2S0 + (uint32_t)(sb ^ 1) * 64u;
+#pragma unroll
+        for (int lj = (li == 0 ? 0 : li + 1); lj <= li + 1 && lj < n_items; ++lj) {
+          const int mt1 = lj / n_kt, kt1 = lj % n_kt;
+          const int key1 = kt1 * kV2KT;
+          const int nk1 = (npad - key1) < kV2KT ? (npad - key1) : kV2KT;
+          const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nk1 >> 3) << 17) | ((128u >> 4) << 24);
+          const uint32_t d1 = lj == li ? s_cur : s_nxt;
+          const uint32_t a1 = x1_lo + (uint32_t)(mt1 * 128 * 64 >> 4), b1 = x2_lo + (uint32_t)(key1 * 64 >> 4);
+          if (elect_one()) {
+            mma_ss_lh<false>(d1, a1, b1, kDescHi, idesc1);
+            mma_ss_lh<true>(d1, a1 + 2, b1 + 2, kDescHi, idesc1);
+            if (PHASE == 1) {     // the same product once more, summed over this CTA's windows (dTable)
+              const uint32_t dp = tm + (uint32_t)(mt1 * npad + key1);
+              mma_ss_lh_rt<true>(dp, a1, b1, kDescHi, idesc1, acc_p);
+              mma_ss_lh<true>(dp, a1 + 2, b1 + 2, kDescHi, idesc1);
+            }
+            tc_commit(&s_full[lj == li ? sb : sb ^ 1]);
+          }
+          __syncwarp();
+        }
+        const int mt = li / n_kt, kt = li % n_kt;
+        const int key0 = kt * kV2KT;
+        const int nk = (npad - key0) < kV2KT ? (npad - key0) : kV2KT;
+        mbar_wait(&s16_full[sb], (item >> 1) & 1);
+        tc_fence_after();
+        if (kt == 0) {
+          mbar_wait(o_free, (tile & 1) ^ 1);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          const uint32_t d = tm + kV2O;
+#pragma unroll
+          for (int c0 = 0; c0 < nk; c0 += 16) {
+            const uint32_t bv = x3_lo + (uint32_t)((key0 + c0) * 64 >> 4);
+            if (PHASE == 3) {
+              const uint32_t kc = (uint32_t)((key0 + c0) >> 1);
+              if (kt == 0 && c0 == 0) mma_ts_lh<false>(d, tm + mt * w2 + kc, bv, kDescHi, idesc2);
+              else mma_ts_lh<true>(d, tm + mt * w2 + kc, bv, kDescHi, idesc2);
+              mma_ts_lh<true>(d, tm + (n_mt + mt) * w2 + kc, bv, kDescHi, idesc2);
+              mma_ts_lh<true>(d, s_cur + (uint32_t)(c0 >> 1), bv, kDescHi, idesc2);
+            } else {
+              if (kt == 0 && c0 == 0) mma_ts_lh<false>(d, s_cur + (uint32_t)(c0 >> 1), bv, kDescHi, idesc2);
+              else mma_ts_lh<true>(d, s_cur + (uint32_t)(c0 >> 1), bv, kDescHi, idesc2);
+              mma_ts_lh<true>(d, s_cur + 32u + (uint32_t)(c0 >> 1), bv, kDescHi, idesc2);
+            }
+          }
+          if (kt == n_kt - 1) tc_commit(o_full);
+        }
+        __syncwarp();
+        if (kt == n_kt - 1) ++tile;
+      }
+      if (elect_one()) tc_commit(&empty[b]);
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit(&bars[10]);
+    __syncwarp();
+    mbar_wait(&bars[10], 0);
+  } else if (warp < 4) {
+    // =========================== S-conversion warps ===========================
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int item = 0;
+    for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll
+      for (int li = 0; li < n_items; ++li, ++item) {
+        const int sb = item & 1;
+        const int kt = li % n_kt;
+        const int key0 = kt * kV2KT;
+        const int nk = (npad - key0) < kV2KT ? (npad - key0) : kV2KT;
+        const uint32_t scol = tmem_base + lane_base + (sb ? kV2S1 : kV2S0);
+        mbar_wait(&s_full[sb], (item >> 1) & 1);
+        tc_fence_after();
+        uint32_t r0[32], hi[32], lo[32];
+        tmem_ld32(scol, r0);
+        if (PHASE == 3) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) hi[c] = pack2<1>(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));   // exact
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float t0 = __uint_as_float(r0[2 * c]) * p.scale, t1 = __uint_as_float(r0[2 * c + 1]) * p.scale;
+            hi[c] = pack2<1>(t0, t1);
+            float ha, hb;
+            unpack2<1>(hi[c], ha, hb);
+            lo[c] = pack2<1>(t0 - ha, t1 - hb);
+          }
+        }
+        if (nk > 32) {
+          tmem_ld32(scol + 32, r0);
+          if (PHASE == 3) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) hi[16 + c] = pack2<1>(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float t0 = __uint_as_float(r0[2 * c]) * p.scale, t1 = __uint_as_float(r0[2 * c + 1]) * p.scale;
+              hi[16 + c] = pack2<1>(t0, t1);
+              float ha, hb;
+              unpack2<1>(hi[16 + c], ha, hb);
+              lo[16 + c] = pack2<1>(t0 - ha, t1 - hb);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { hi[16 + c] = 0; lo[16 + c] = 0; }
+        }
+        tmem_st32(scol, hi);                       // both loads are complete: safe to overwrite in place
+        if (PHASE != 3) tmem_st32(scol + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s16_full[sb]);
+      }
+    }
+    if (PHASE == 1) {
+      // every window of this CTA is in the persistent accumulator: scatter it over the relative positions once.
+      // Lanes are consecutive query rows at one key column -> distinct table entries within an instruction.
+      tc_fence_after();
+      for (int mt = 0; mt < n_mt; ++mt) {
+        const int row = mt * 128 + warp * 32 + lane;
+        const int lin_i = row < N ? lin_s[row] : 0;
+        for (int c0 = 0; c0 < npad; c0 += 32) {
+          uint32_t r0[32];
+          tmem_ld32(tmem_base + lane_base + (uint32_t)(mt * npad + c0), r0);
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (row < N && c0 + e < N) atomicAdd(&tab_s[lin_off + lin_i - lin_s[c0 + e]], __uint_as_float(r0[e]));
+        }
+      }
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      for (int i = tid; i < p.tab; i += 128)
+        if (tab_s[i] != 0.f) atomicAdd(p.grad_table + (int64_t)i * p.nH + head, tab_s[i]);
+    }
+  } else {
+    // =========================== output warps ===========================
+    const int qw = warp & 3;
+    const uint32_t lane_base = (uint32_t)(qw * 32) << 16;
+    float* gout = PHASE == 1 ? p.grad_q : (PHASE == 2 ? p.grad_k : p.grad_v);
+    int pi = 0, tile = 0;
+    for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
+      const int b = pi & 1;
+      const int64_t mwin = pair / p.nH;
+      float* rs_all = reinterpret_cast<float*>(smem + sp.rsum);
+      float* rs_w = rs_all + qw * ((kV2Regions + 1) * 32);
+      uint8_t* rg = smem + sp.reg;
+      if (PHASE == 3 && MASK) {
+        // float region sums of dO (bf16-rounded, as the MMAs see it): same run-based walk as the forward's
+        const int otid = qw * 32 + lane;
+        const uint8_t* rp = p.region + (int64_t)((int)mwin % (int)p.nW) * N;
+        const uint8_t rg0 = __ldg(rp + min(otid, N - 1)), rg1 = __ldg(rp + min(otid + 128, N - 1));
+        mbar_wait(&full[b], (pi >> 1) & 1);
+        for (int n = otid; n < ((N + 7) & ~7); n += 128) rg[n] = n >= 128 ? rg1 : rg0;
+        for (int r = 0; r <= kV2Regions; ++r) rs_w[r * 32 + lane] = 0.f;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int per_w = (((N + 3) >> 2) + 7) & ~7, j0 = qw * per_w, j1 = min((N + 7) & ~7, j0 + per_w);
+        const uint8_t* vb = smem + sp.op[b] + 2u * Rpad * 64 + (lane & 7) * 2;
+        const int c = lane >> 3;
+        const uint32_t o0 = (uint32_t)(c ^ 0) << 4, o1 = (uint32_t)(c ^ 1) << 4, o2 = (uint32_t)(c ^ 2) << 4, o3 = (uint32_t)(c ^ 3) << 4;
+        int cur = j0 < j1 ? (int)rg[j0] : 0;
+        float acc = 0.f, tot = 0.f;
+        for (int jb = j0; jb < j1; jb += 8) {
+          const uint8_t* vr = vb + jb * 64;
+          const uint2 r8 = *reinterpret_cast<const uint2*>(rg + jb);
+          float vv[8];
+          vv[0] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 0 * 64 + o0) << 16);
+          vv[1] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 1 * 64 + o0) << 16);
+          vv[2] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 2 * 64 + o1) << 16);
+          vv[3] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 3 * 64 + o1) << 16);
+          vv[4] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 4 * 64 + o2) << 16);
+          vv[5] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 5 * 64 + o2) << 16);
+          vv[6] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 6 * 64 + o3) << 16);
+          vv[7] = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(vr + 7 * 64 + o3) << 16);
+          const uint32_t cur4 = (uint32_t)cur * 0x01010101u;
+          if (r8.x == cur4 && r8.y == cur4) {
+            acc += ((vv[0] + vv[1]) + (vv[2] + vv[3])) + ((vv[4] + vv[5]) + (vv[6] + vv[7]));
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int rj = (int)(((u < 4 ? r8.x : r8.y) >> ((u & 3) * 8)) & 0xFF);
+              if (rj != cur) {
+                rs_w[cur * 32 + lane] += acc;
+                tot += acc; acc = 0.f; cur = rj;
+              }
+              acc += vv[u];
+            }
+          }
+        }
+        rs_w[cur * 32 + lane] += acc;
+        rs_w[kV2Regions * 32 + lane] = tot + acc;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        float* oth = rs_all + 4 * (kV2Regions + 1) * 32;
+        for (int idx = otid; idx < kV2Regions * 32; idx += 128) {
+          const int d = idx & 31;
+          float o = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float* cw = rs_all + w * ((kV2Regions + 1) * 32);
+            o += cw[kV2Regions * 32 + d] - cw[idx];
+          }
+          oth[idx] = o;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+      for (int mt = 0; mt < n_mt; ++mt, ++tile) {
+        mbar_wait(o_full, tile & 1);
+        tc_fence_after();
+        uint32_t ov[32];
+        tmem_ld32(tmem_base + lane_base + kV2O, ov);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+        const int row0 = mt * 128 + qw * 32;
+        uint8_t* stg = smem + sp.ostage + (uint32_t)qw * (32 * 144);
+        {
+          const int row = row0 + lane;
+          const int ri = ((PHASE == 3 && MASK && row < N) ? (int)rg[row] : 0) * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 v;
+            if (PHASE == 3) {
+              float4 other = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (MASK) other = *reinterpret_cast<const float4*>(rs_all + 4 * (kV2Regions + 1) * 32 + ri + 4 * c);
+              v.x = fmaf(__uint_as_float(ov[4 * c]), p.scale, -100.f * other.x);
+              v.y = fmaf(__uint_as_float(ov[4 * c + 1]), p.scale, -100.f * other.y);
+              v.z = fmaf(__uint_as_float(ov[4 * c + 2]), p.scale, -100.f * other.z);
+              v.w = fmaf(__uint_as_float(ov[4 * c + 3]), p.scale, -100.f * other.w);
+            } else {
+              v = make_float4(__uint_as_float(ov[4 * c]), __uint_as_float(ov[4 * c + 1]), __uint_as_float(ov[4 * c + 2]), __uint_as_float(ov[4 * c + 3]));
+            }
+            *reinterpret_cast<float4*>(stg + lane * 144 + c * 16) = v;
+          }
+        }
+        __syncwarp();
+        {
+          // gradient rows of one (window, head) are contiguous: [pair * N + row][32]
+          const int sub = lane >> 3, ch = lane & 7;
+          float* obase = gout + pair * N * 32 + ch * 4;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rl = sub + 4 * k, row = row0 + rl;
+            if (row < N) st_stream4(obase + (int64_t)row * 32, *reinterpret_cast<const float4*>(stg + rl * 144 + ch * 16));
+          }
+        }
+        __syncwarp();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[b]);
+      if (PHASE == 3 && MASK) asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+template <int NPAD>
+static void launch_v2_bwd_npad(bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    kern<<<grid, kV2Threads, smem_bytes, stream>>>(p);
+  };
+  if (mask) go(qktv2_bwd_kernel<NPAD, 3, true>); else go(qktv2_bwd_kernel<NPAD, 3, false>);
+  go(qktv2_bwd_kernel<NPAD, 1, false>);
+  go(qktv2_bwd_kernel<NPAD, 2, false>);
+}
+static void launch_v2_bwd(int npad, bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
+  switch (npad) {
+    case 16: launch_v2_bwd_npad<16>(mask, grid, smem_bytes, stream, p); break;
+    case 32: launch_v2_bwd_npad<32>(mask, grid, smem_bytes, stream, p); break;
+    case 48: launch_v2_bwd_npad<48>(mask, grid, smem_bytes, stream, p); break;
+    case 64: launch_v2_bwd_npad<64>(mask, grid, smem_bytes, stream, p); break;
+    case 80: launch_v2_bwd_npad<80>(mask, grid, smem_bytes, stream, p); break;
+    case 96: launch_v2_bwd_npad<96>(mask, grid, smem_bytes, stream, p); break;
+    case 112: launch_v2_bwd_npad<112>(mask, grid, smem_bytes, stream, p); break;
+    case 128: launch_v2_bwd_npad<128>(mask, grid, smem_bytes, stream, p); break;
+    case 144: launch_v2_bwd_npad<144>(mask, grid, smem_bytes, stream, p); break;
+    case 160: launch_v2_bwd_npad<160>(mask, grid, smem_bytes, stream, p); break;
+    default: launch_v2_bwd_npad<176>(mask, grid, smem_bytes, stream, p); break;
+  }
+}
+
 template <int NPAD>
 static void launch_v2_npad(bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
   if (mask) {
@@ -1044,6 +1520,20 @@ extern "C" int sdf_attn_qktv_bwd(const sdf_attn_qktv_bwd_args* a) {
   p.q = a->q; p.k = a->k; p.v = a->v; p.bias_table = a->bias_table; p.region = a->region; p.has_mask = a->region != nullptr;
   p.grad_out = a->grad_out; p.grad_q = a->grad_q; p.grad_k = a->grad_k; p.grad_v = a->grad_v; p.grad_table = a->grad_bias_table;
   cudaStream_t stream = (cudaStream_t)a->stream;
+  {
+    // small windows: the warp-specialised kernels (dV, dQ + dTable, dK), same eligibility as the forward's
+    static const int use_v2 = [] { const char* e = getenv("SDF_QKTV_V2"); return e ? atoi(e) : 1; }();
+    const int npad = (p.N + 15) & ~15;
+    const V2Plan vp = plan_v2(p.Rpad, p.tab);
+    if (use_v2 && p.n_mt * npad <= 352 && vp.total <= 200 * 1024 && a->scale != 0.0) {
+      int g = kNumSMs / (int)a->nH * (int)a->nH;
+      if (g < a->nH) g = (int)a->nH;
+      if ((int64_t)g > a->M * a->nH) g = (int)(a->M * a->nH);
+      launch_v2_bwd(npad, p.has_mask != 0, g, vp.total, stream, p);
+      count_launch(); count_launch();
+      return finish_launch("sdf_attn_qktv_bwd(v2)");
+    }
+  }
   QKTV_LAUNCH(1, false, false);
   st = finish_launch("sdf_attn_qktv_bwd(dQ)");
   if (st) return st;
