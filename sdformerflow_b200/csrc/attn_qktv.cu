@@ -481,11 +481,12 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
 // fp16 canonical shared-memory layouts, double buffered).  All hand-offs are mbarriers; S is double buffered in
 // TMEM so MMA 1 of item i+1 and MMA 2 of item i overlap the conversion of item i.
 // TMEM map (columns): [0,176) Bias hi (two M-tiles x 88), [176,352) Bias lo, [352,416) S0, [416,480) S1, [480,512) O.
-constexpr int kV2Threads = 416;               // 4 S-conversion warps, 1 MMA warp, 4 producer warps, 4 output warps
+constexpr int kV2Threads = 544;               // warps 0-3 S-conversion, 4 MMA, 5-8 + 13-16 producers, 9-12 output
+constexpr int kV2Producers = 256;
 constexpr int kV2KT = 64;
 constexpr int kV2S0 = 352, kV2S1 = 416, kV2O = 480;
 constexpr int kV2Regions = 27;
-constexpr int kV2Loads = 9;                 // 16-byte loads in flight per producer thread (6 N / 128, N <= 176)
+constexpr int kV2Loads = (6 * 176 + kV2Producers - 1) / kV2Producers;   // 16-byte loads in flight per producer thread
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
   const float inv_scale = 1.f / p.scale;
   for (int i = tid; i < p.tab; i += kV2Threads) tab_s[i] = __ldg(p.bias_table + (int64_t)i * p.nH + head) * inv_scale;
   if (tid == 0) {
-    mbar_init(&full[0], 4); mbar_init(&full[1], 4);
+    mbar_init(&full[0], kV2Producers / 32); mbar_init(&full[1], kV2Producers / 32);
     mbar_init(&empty[0], 5); mbar_init(&empty[1], 5);
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
     mbar_init(&s16_full[0], 4); mbar_init(&s16_full[1], 4);
@@ -630,9 +631,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
   const int64_t n_pairs = p.M * p.nH;
 
 
-  if (warp >= 5 && warp < 9) {
+  if ((warp >= 5 && warp < 9) || warp >= 13) {
     // =========================== producers ===========================
-    const int pt = tid - 5 * 32;                                  // 0..127
+    const int pt = (warp < 9 ? warp - 5 : warp - 9) * 32 + lane;  // 0..255
     int pi = 0;
     for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
       const int b = pi & 1;
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
       uint4 w[kV2Loads];
 #pragma unroll
       for (int u = 0; u < kV2Loads; ++u) {
-        const int g = pt + u * 128;
+        const int g = pt + u * kV2Producers;
         if (g < n_it) {
           const int a = g >= 2 * per ? 2 : (g >= per ? 1 : 0);
           const int i = g - a * per;
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
       }
 #pragma unroll
       for (int u = 0; u < kV2Loads; ++u) {
-        const int g = pt + u * 128;
+        const int g = pt + u * kV2Producers;
         if (g < n_it) {
           const int a = g >= 2 * per ? 2 : (g >= per ? 1 : 0);
           const int i = g - a * per;
@@ -883,6 +884,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_free);
+        if (lane == 0 && qw == 0) V2_TR(13, tile);
         // scale + mask term, then transpose through shared memory so that each store instruction writes four
         // complete 128-B rows (thread-per-row stores would touch 32 lines per instruction and clog the LSU)
         const int row0 = mt * 128 + qw * 32;
@@ -903,6 +905,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
           }
         }
         __syncwarp();
+        if (lane == 0 && qw == 0) V2_TR(14, tile);
         {
           const int sub = lane >> 3, ch = lane & 7;
           float* obase = p.out + (mwin * P) * (p.nH * 32) + head * 32 + ch * 4;
@@ -993,7 +996,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_bwd_kernel(const QktvP p)
     for (int i = tid; i < p.tab; i += kV2Threads) tab_s[i] = 0.f;
   }
   if (tid == 0) {
-    mbar_init(&full[0], 4); mbar_init(&full[1], 4);
+    mbar_init(&full[0], kV2Producers / 32); mbar_init(&full[1], kV2Producers / 32);
     mbar_init(&empty[0], 5); mbar_init(&empty[1], 5);
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
     mbar_init(&s16_full[0], 4); mbar_init(&s16_full[1], 4);
@@ -1040,14 +1043,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_bwd_kernel(const QktvP p)
 
   const int64_t n_pairs = p.M * p.nH;
 
-  if (warp >= 5 && warp < 9) {
+  if ((warp >= 5 && warp < 9) || warp >= 13) {
     // =========================== producers ===========================
-    const int pt = tid - 5 * 32;
+    const int pt = (warp < 9 ? warp - 5 : warp - 9) * 32 + lane;
     const uint8_t* sa = PHASE == 1 ? p.v : (PHASE == 2 ? p.v : p.k);     // first spike array (slot order)
     const uint8_t* sb_ = PHASE == 1 ? p.k : p.q;                           // second spike array
     constexpr int slot_a = PHASE == 1 ? 1 : 0;                             // PHASE 1: V -> X2; PHASE 2: V -> X1; PHASE 3: K -> X1
     constexpr int slot_b = PHASE == 1 ? 2 : (PHASE == 2 ? 2 : 1);          // PHASE 1: K -> X3; PHASE 2: Q -> X3; PHASE 3: Q -> X2
-    constexpr int kGoLoads = (4 * 176 + 127) / 128, kSpLoads = (4 * 176 + 127) / 128;
+    constexpr int kGoLoads = (4 * 176 + kV2Producers - 1) / kV2Producers, kSpLoads = (4 * 176 + kV2Producers - 1) / kV2Producers;
     int pi = 0;
     for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pi) {
       const int b = pi & 1;
@@ -1060,7 +1063,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_bwd_kernel(const QktvP p)
       const int n_go = 4 * N, per = 2 * N, n_sp = 2 * per;
 #pragma unroll
       for (int u = 0; u < kGoLoads; ++u) {
-        const int g = pt + u * 128;
+        const int g = pt + u * kV2Producers;
         if (g < n_go) {
           const float* src = go + rowoff_s[g >> 2] + (g & 3) * 8;
           g0[u] = __ldg(reinterpret_cast<const float4*>(src));
@@ -1069,7 +1072,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_bwd_kernel(const QktvP p)
       }
 #pragma unroll
       for (int u = 0; u < kSpLoads; ++u) {
-        const int g = pt + u * 128;
+        const int g = pt + u * kV2Producers;
         if (g < n_sp) {
           const int a = g >= per ? 1 : 0;
           const int i = g - a * per;
@@ -1078,7 +1081,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_bwd_kernel(const QktvP p)
       }
 #pragma unroll
       for (int u = 0; u < kGoLoads; ++u) {
-        const int g = pt + u * 128;
+        const int g = pt + u * kV2Producers;
         if (g < n_go) {
           const uint4 o = make_uint4(pack2<1>(g0[u].x, g0[u].y), pack2<1>(g0[u].z, g0[u].w), pack2<1>(g1[u].x, g1[u].y), pack2<1>(g1[u].z, g1[u].w));
           *reinterpret_cast<uint4*>(smem + sp.op[b] + (uint32_t)kGoSlot * Rpad * 64 + plain_off(Rpad, g >> 2, g & 3)) = o;
@@ -1086,7 +1089,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_bwd_kernel(const QktvP p)
       }
 #pragma unroll
       for (int u = 0; u < kSpLoads; ++u) {
-        const int g = pt + u * 128;
+        const int g = pt + u * kV2Producers;
         if (g < n_sp) {
           const int a = g >= per ? 1 : 0;
           const int i = g - a * per;

@@ -20,7 +20,10 @@ cap r01_ncu_lif_fwd_in_bench lif_fwd_kernel 126 42 python bench.py --steps 1 --w
 cap r01_ncu_lif_fwd_final lif_fwd_kernel 2 2 python tools/ncu_targets.py lif_fwd
 cap r01_ncu_lif_bwd_final lif_bwd_kernel 1 1 python tools/ncu_targets.py lif_bwd
 cap r01_ncu_qkgate_final qkgate_kernel 1 1 python tools/ncu_targets.py qkgate
-cap r01_ncu_qktv_final qktv_kernel 1 1 python tools/ncu_targets.py qktv
+cap r01_ncu_qktv2_fwd qktv2_kernel 1 2 python tools/ncu_targets.py qktv
+cap r01_ncu_qktv2_bwd qktv2_bwd_kernel 0 3 python tools/ncu_targets.py qktv
+cap r01_ncu_qktv_v1_large qktv_kernel 1 1 python tools/ncu_targets.py qktv
+./tools/ubench/mma_chain > gpurun_out/r01_ubench_mma_chain.jsonl 2>&1
 ls -la gpurun_out/ | tail -20
 cat gpurun_out/r01_pytest_gpu.txt gpurun_out/r01_smoke.txt
 cut -c1-600 gpurun_out/r01_bench_n1.json

@@ -48,12 +48,25 @@ if which in ("qktv", "all"):
         rows = wd * M * P
         q, k, v = ((torch.rand(rows, C3, device=dev) < 0.2).to(torch.uint8) for _ in range(3))
         table = torch.randn((2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1), nH, device=dev) * 0.02
-        region = torch.randint(0, 3, (M // 8, N3), device=dev, dtype=torch.uint8)
+        nW = M // 8
+        dd, hh, wc = torch.meshgrid(torch.arange(wd), torch.arange(wh), torch.arange(ww), indexing="ij")
+        idx = torch.arange(nW).view(-1, 1)
+        a_, b_, c_ = (idx % 2 == 1), ((idx // 2) % 4 == 3), ((idx // 8) % 4 == 3)
+        region = (9 * a_ * (dd.reshape(1, -1) >= wd // 2) + 3 * b_ * (hh.reshape(1, -1) > wh // 2)
+                  + c_ * (wc.reshape(1, -1) > ww // 2)).to(torch.uint8).to(dev).contiguous()
         out = torch.empty(rows, C3, device=dev)
-        for _ in range(2):
+        go = torch.randn(rows, C3, device=dev)
+        gq, gk, gv = (torch.empty(rows, C3, device=dev) for _ in range(3))
+        gtab = torch.zeros_like(table)
+        # launch order (per window size): fwd masked x2, fwd unmasked x2, bwd masked x1 (= 3 kernels)
+        for reg in (region, region, None, None):
             capi.call("sdf_attn_qktv_fwd", capi.struct(
                 "sdf_attn_qktv_fwd_args", q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), bias_table=table.data_ptr(),
-                region=region.data_ptr(), out=out.data_ptr(), M=M, nH=nH, nW=M // 8, wd=wd, wh=wh, ww=ww, scale=0.125,
-                stream=st()))
+                region=None if reg is None else reg.data_ptr(), out=out.data_ptr(), M=M, nH=nH, nW=nW, wd=wd, wh=wh, ww=ww,
+                scale=0.125, stream=st()))
+        capi.call("sdf_attn_qktv_bwd", capi.struct(
+            "sdf_attn_qktv_bwd_args", q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), bias_table=table.data_ptr(),
+            region=region.data_ptr(), grad_out=go.data_ptr(), grad_q=gq.data_ptr(), grad_k=gk.data_ptr(), grad_v=gv.data_ptr(),
+            grad_bias_table=gtab.data_ptr(), M=M, nH=nH, nW=nW, wd=wd, wh=wh, ww=ww, scale=0.125, stream=st()))
 torch.cuda.synchronize()
 print("done")
