@@ -300,8 +300,17 @@ def run_b200(args, rank, local_rank, world):
     functional.set_step_mode(model, "m")
     functional.set_backend(model, "cupy", prod.neuron.LIFNode)   # accepted no-op, as the reference scripts call it
     from sdformerflow_b200 import distributed as sdist
-    net = sdist.wrap(model, local_rank)          # DDP: bucketed NCCL all-reduce overlapped with backward
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
+    # "auto": replay the step as one CUDA graph on a single GPU; multi-GPU runs stay eager under DDP (capturing the NCCL
+    # all-reduce inside the step hung on this stack, so it is not attempted)
+    use_graph = args.graph in ("on", "auto") and world == 1
+    if use_graph:
+        # whole-step CUDA graph: the replica is not wrapped in DDP (its reducer hooks are host logic); the gradient
+        # all-reduce is issued explicitly after backward, inside the captured step
+        net = model
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True, capturable=True)
+    else:
+        net = sdist.wrap(model, local_rank)          # DDP: bucketed NCCL all-reduce overlapped with backward
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
 
     B = B_PER_GPU
     xh, gth, mh = synth_batch(B, 16146 + rank)
@@ -313,6 +322,8 @@ def run_b200(args, rank, local_rank, world):
         flows = net(x)["flow"]
         loss = flow_loss(flows, gt, mask)
         loss.backward()
+        if use_graph and world > 1:
+            sdist.allreduce_gradients(model.parameters(), world)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -335,18 +346,52 @@ def run_b200(args, rank, local_rank, world):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    eager_step = step
+    graph_launches = None
+    if use_graph:
+        # warm up on a side stream (cudnn autotune, lazily built window tables, optimizer state), then capture ONE
+        # full step (reset + forward + loss + backward [+ all-reduce] + AdamW) and replay it per step on static inputs
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(args.warmup, 3) + (8 if world > 1 else 0)):
+                eager_step(xd, gtd, md)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        sx, sgt, smk = xd.clone(), gtd.clone(), md.clone()
+        graph = torch.cuda.CUDAGraph()
+        n_cap = capi.launch_count()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            static_loss = eager_step(sx, sgt, smk)
+        graph_launches = capi.launch_count() - n_cap
+
+        def step(x, gt, mask):           # noqa: F811  (same work as eager_step, replayed)
+            if x is not sx:
+                sx.copy_(x, non_blocking=True)
+                sgt.copy_(gt, non_blocking=True)
+                smk.copy_(mask, non_blocking=True)
+            graph.replay()
+            return static_loss
+        xd, gtd, md = sx, sgt, smk
+
     for _ in range(max(args.warmup, 3)):
         step(xd, gtd, md)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     timer = capi.KernelTimer(only={"sdf_lif_fwd"})
-    capi.set_timer(timer)
+    if not use_graph:
+        capi.set_timer(timer)
     n0 = capi.launch_count()
     ms_total = timed(lambda: step(xd, gtd, md), args.steps)
-    launches = capi.launch_count() - n0
+    launches = capi.launch_count() - n0 if not use_graph else graph_launches * args.steps
     capi.set_timer(None)
     clocks = sampler.stop() if rank == 0 else None
+    if use_graph:
+        # per-kernel CUDA events cannot be recorded inside a replay: time K1 in an eager pass of the same step
+        capi.set_timer(timer)
+        timed(lambda: eager_step(xd, gtd, md), args.steps)
+        capi.set_timer(None)
     ksum = timer.summary().get("sdf_lif_fwd", {"launches": 0, "ms": 0.0, "bytes": 0, "gbps": 0.0})
 
     # end to end through the public API: pinned host inputs -> device every step, loss read back every step
@@ -386,7 +431,9 @@ def run_b200(args, rank, local_rank, world):
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
                        "gemm": "cuBLAS/cuDNN TF32x2 weight split on spike operands (fp32-grade), fp32 elsewhere; TF32 backward",
                        "l2": "activations per step >> 126 MB L2; no explicit flush",
-                       "weights": "random init (init_weights, seed 0)"},
+                       "weights": "random init (init_weights, seed 0)",
+                       "launch": ("one CUDA graph per step (reset+fwd+loss+bwd" + ("+all-reduce" if world > 1 else "") + "+AdamW), replayed; K1 roofline "
+                                  "timed in an eager pass of the same step") if use_graph else "eager (one launch per kernel)"},
             "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -411,6 +458,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the training step as one CUDA graph (auto: single-GPU runs only)")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train (default, the headline metric: BASELINE.json configs[2]) or infer (configs[1]: eval, "
                          "B=8/GPU, 480x640)")

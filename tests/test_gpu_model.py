@@ -255,3 +255,61 @@ def test_double_forward_without_reset_raises():
         model(x)
         with pytest.raises(RuntimeError):
             model(x)
+
+
+def test_train_step_as_cuda_graph_matches_eager():
+    """bench.py can replay the training step (reset + fwd + loss + bwd + AdamW) as one CUDA graph.  A replayed step
+    must be the same computation as the eager one: same loss, same updated weights, from the same state."""
+    import copy as _copy
+    mc, sc = synth.small_config("lif")
+    B = 2
+    x, (gt, mask) = synth.synth_voxels(B, 10, 96, 128).to(DEV), [t.to(DEV) for t in synth.synth_labels(B, 96, 128)]
+
+    def make():
+        model = build_product(mc, sc, DEV, train=True)
+        for lyr in model.sttmultires_unet.encoders.swin3d.layers:      # no DropPath randomness
+            for b in lyr.swin_blocks:
+                if hasattr(b.drop_path, "forced"):
+                    b.drop_path.forced = torch.ones(B)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
+
+        def step():
+            _reset(model)
+            loss = port.flow_loss(model(x)["flow"], gt, mask)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+        return model, opt, step
+
+    model_e, _, step_e = make()
+    loss_e = step_e().item()
+
+    model_g, opt_g, step_g = make()
+    state0 = _copy.deepcopy(model_g.state_dict())
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step_g()                                                   # warm-up (changes weights; restored below)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        static_loss = step_g()
+    with torch.no_grad():                                              # back to the initial state, in place
+        for k, v in model_g.state_dict().items():
+            v.copy_(state0[k])
+        for st in opt_g.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert abs(static_loss.item() - loss_e) <= 1e-4 * abs(loss_e), (static_loss.item(), loss_e)
+    pe, pg = dict(model_e.named_parameters()), dict(model_g.named_parameters())
+    # Adam's first step moves every weight by ~lr * sign(grad): identical unless a ~0 gradient changes sign between
+    # two runs (atomics order in the table / bias reductions)
+    n_bad = sum(((pe[k] - pg[k]).abs() > 2e-5).sum().item() for k in pe)
+    n_all = sum(v.numel() for v in pe.values())
+    assert n_bad <= 0.01 * n_all, (n_bad, n_all)
