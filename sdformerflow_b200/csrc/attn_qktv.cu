@@ -7,9 +7,13 @@
 // on the raw [M*nH, N, 32] reinterpretation of the (wd,M,wh,ww,C) spike buffers (Appendix B.4):
 // the rows of one (window m', pseudo-head h') pair are 32 contiguous bytes each, N*32 B in all.
 //
-// One persistent CTA per SM walks pairs with a fixed pseudo-head.  Per pair:
-//   stage  Q, K, V (row-major bytes -> UMMA canonical no-swizzle layout [16-B chunk][row][16 B]) into
-//          shared memory, u8 {0,1} -> fp16 (exact); Q, K are read K-major, V MN-major (no transpose);
+// Two kernel families live here.  v1 (qktv_kernel, below) handles every window size and the debug outputs; v2
+// (qktv2_kernel / qktv2_bwd_kernel, second half of the file) is the warp-specialised pipeline for windows of up to
+// 176 tokens, where the per-head bias fits in tensor memory — see the comment block above it.
+//
+// v1: one persistent CTA per SM walks pairs with a fixed pseudo-head.  Per pair:
+//   stage  Q, K, V (row-major bytes -> UMMA canonical SWIZZLE_64B layout: 64-B rows, 16-B chunk index XOR
+//          (row/2)%4) into shared memory, u8 {0,1} -> fp16 (exact); Q, K are read K-major, V MN-major (no transpose);
 //   MMA 1  S = Q K^T           tcgen05.mma kind::f16, M=128, N<=192, K=16 x2, fp32 accum in TMEM
 //                              (S are exact integer counts 0..32);
 //   epi 1  T = scale*S + bias[lin_i - lin_j + off] + (-100)[region_i != region_j], in registers
@@ -65,22 +69,8 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
-// same, descriptors given as (lo word, shared hi word) so that per-MMA operand changes are one 32-bit add;
+// D[tmem] (+)= A * B with A from shared memory (mma_ss_lh) or from TMEM (mma_ts_lh), B from shared memory.
+// Descriptors are given as (lo word, shared hi word) so that per-MMA operand changes are one 32-bit add;
 // ACC is compile time (enable-input-d)
 template <bool ACC>
 __device__ __forceinline__ void mma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
@@ -114,11 +104,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows x 16 B
-// contiguous; SBO = byte distance between 8-row groups, LBO = byte distance between 16-B K chunks.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
 // SWIZZLE_64B canonical layout (both majors, 16-bit elements, 32 elements = 64 B per row): rows of 64 B at a
 // 64-B pitch, 8-row groups 512 B apart (SBO), and inside the 1024-B-aligned buffer the 16-B chunk index is XORed
 // with address bits [7,8] = (row / 2) % 4.  K-major: a K step of 16 elements advances the start address by 32 B;
