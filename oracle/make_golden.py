@@ -103,6 +103,22 @@ def golden_en4(neuron_type="lif"):
     return {"neuron_type": neuron_type, "flows": [_summ(f) for f in flows]}
 
 
+def golden_cfg4():
+    """The en4 model at BASELINE.json's cfg4 shapes, eval, from the unmodified reference."""
+    from spikingjelly.activation_based import functional
+    out = {}
+    for name, kw in synth.CFG4.items():
+        mc, sc = rl.default_config("lif", **kw)
+        model = rl.build_reference_model(mc, sc, seed=0, train=False)
+        _load_synth(model)
+        x = synth.synth_voxels(1, kw["num_bins"], *kw["input_size"])
+        functional.reset_net(model)
+        with torch.no_grad():
+            flows = model(x)["flow"]
+        out[name] = {"flows": [_summ(f) for f in flows]}
+    return out
+
+
 def golden_sew_stage():
     """SEW family: one Spiking_Swin_BasicLayer (QK^T V attention, shifted + unshifted block, with
     SpikingPatchMerging) and the SDSA attention variant, eval and train."""
@@ -142,6 +158,7 @@ def main():
         "small_psn_train.pt": lambda: golden_small_model("psn", True),
         "en4_lif_eval.pt": lambda: golden_en4("lif"),
         "sew_stage.pt": golden_sew_stage,
+        "cfg4_lif_eval.pt": golden_cfg4,
     }
     only = set(sys.argv[1:])
     for name, fn in jobs.items():

@@ -115,3 +115,11 @@ def small_config(neuron_type="lif", v_th=0.1, **over):
         "mlp_ratio": 4, "input_size": list(c["input_size"]),
     }
     return model, swin
+
+
+CFG4 = {
+    # BASELINE.json configs[3]: MDR-shaped dt4 voxels (5 bins, window (2,8,8), 256x256 crops; configs of the MDR ymls)
+    # and a larger temporal window (window_size[0] = 4)
+    "t5_w288": dict(num_steps=5, num_bins=5, window_size=(2, 8, 8), input_size=(256, 256)),
+    "t10_w466": dict(num_steps=10, num_bins=10, window_size=(4, 6, 6), input_size=(192, 192)),
+}

@@ -246,6 +246,27 @@ def test_en4_shipped_config_eval(golden):
         assert torch.isfinite(a).all() and epe(sub, s["sub"]) <= mag
 
 
+@pytest.mark.parametrize("name", ["t5_w288", "t10_w466"])
+def test_cfg4_shapes_eval(golden, name):
+    """BASELINE.json configs[3] shapes (5 time bins / window (2,8,8) / 256x256, and a temporal window of 4) run through
+    the fused kernels and stay within the flow scale of the reference fixture (free-running; see the en4 test)."""
+    from oracle import reference_loader as rl
+    g = golden("cfg4_lif_eval.pt")[name]
+    kw = synth.CFG4[name]
+    mc, sc = rl.default_config("lif", **kw)
+    model = build_product(mc, sc, DEV, train=False)
+    x = synth.synth_voxels(1, kw["num_bins"], *kw["input_size"])
+    _reset(model)
+    with torch.no_grad():
+        flows = model(x.to(DEV))["flow"]
+    for a, s in zip(flows, g["flows"]):
+        assert tuple(a.shape) == s["shape"]
+        sub = a[..., ::8, ::8].cpu()
+        mag = s["sub"].pow(2).sum(1).sqrt().mean().item()
+        print(f"cfg4 {name} free-running EPE {epe(sub, s['sub']):.3f} px at |flow| {mag:.2f} px")
+        assert torch.isfinite(a).all() and epe(sub, s["sub"]) <= mag
+
+
 def test_double_forward_without_reset_raises():
     mc, sc = synth.small_config("lif")
     model = build_product(mc, sc, DEV, train=False)

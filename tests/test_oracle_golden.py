@@ -68,6 +68,23 @@ def test_en4_shipped_config_eval_matches_reference(golden):
         assert abs(a.double().abs().sum().item() - s["abs"]) <= 1e-6 * s["abs"]
 
 
+@pytest.mark.parametrize("name", ["t5_w288", "t10_w466"])
+def test_cfg4_shapes_match_reference(golden, name):
+    """BASELINE.json configs[3]: 5 time bins with window (2,8,8) at 256x256, and a temporal window of 4."""
+    from oracle import reference_loader as rl
+    g = golden("cfg4_lif_eval.pt")[name]
+    kw = synth.CFG4[name]
+    mc, sc = rl.default_config("lif", **kw)
+    P = _params(mc, sc)
+    x = synth.synth_voxels(1, kw["num_bins"], *kw["input_size"])
+    with torch.no_grad():
+        flows = port.ms_flownet_forward(x, P, port_cfg(mc, sc), port_spec(mc), port.BNMode(False))
+    for a, s in zip(flows, g["flows"]):
+        assert tuple(a.shape) == s["shape"]
+        assert torch.equal(a[..., ::8, ::8], s["sub"])
+        assert abs(a.double().sum().item() - s["sum"]) <= 1e-6 * max(1.0, abs(s["sum"]))
+
+
 @pytest.mark.parametrize("variant", ["bn", "sdsa"])
 @pytest.mark.parametrize("train", [False, True])
 def test_sew_stage_matches_reference(golden, variant, train):
