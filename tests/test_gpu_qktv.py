@@ -190,3 +190,28 @@ def test_sew_stage_against_reference_fixture(golden, variant, train):
     print(f"SEW {variant} train={train}: teacher-forced mismatch fractions {worst}")
     for name, bad in worst.items():
         assert bad <= 2e-2, (name, bad)
+
+
+@pytest.mark.parametrize("case", [c for c in FAST_CASES if c[4] * c[5] * c[3] <= 64])
+@pytest.mark.parametrize("mask", ["none", "shift"])
+def test_qktv_backward_fast_kernels(case, mask):
+    """dQ, dK, dV and d(bias table) of the small-window kernels over every key-padding template, against autograd of
+    the reference formula (dO enters the tensor cores in bf16, hence the 5e-3 relative tolerance, as for v1)."""
+    from sdformerflow_b200 import ops
+    wd, wh, ww, nH, B, nW = case
+    q, k, v, table, _, M, N, P, C = _inputs(wd, wh, ww, nH, B, nW, False, seed=13)
+    region = _shift_regions(wd, wh, ww, nW) if mask == "shift" else None
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    tb = table.clone().requires_grad_(True)
+    scale = 32 ** -0.5
+    _, _, x = _reference(qf, kf, vf, tb, region, M, N, nH, (wd, wh, ww), scale)
+    go = torch.randn(x.shape, generator=torch.Generator().manual_seed(5))
+    x.backward(go)
+    gq, gk, gv, gtab = ops.qktv_bwd_debug(q.to(DEV), k.to(DEV), v.to(DEV), table.to(DEV),
+                                          None if region is None else region.to(DEV), go.to(DEV), M, nH, nW,
+                                          (wd, wh, ww), scale)
+    for got, ref, name in ((gq, qf.grad, "dq"), (gk, kf.grad, "dk"), (gv, vf.grad, "dv")):
+        rel = (got.cpu().view_as(ref) - ref).norm() / ref.norm()
+        assert rel.item() <= 5e-3, (name, rel.item())
+    rel = (gtab.cpu() - tb.grad).norm() / tb.grad.norm()
+    assert rel.item() <= 5e-3, ("dtable", rel.item())
