@@ -291,7 +291,7 @@ def test_train_step_as_cuda_graph_matches_eager():
         for lyr in model.sttmultires_unet.encoders.swin3d.layers:      # no DropPath randomness
             for b in lyr.swin_blocks:
                 if hasattr(b.drop_path, "forced"):
-                    b.drop_path.forced = torch.ones(B)
+                    b.drop_path.forced = torch.ones(B, device=DEV)     # on the device: no host copy inside a capture
         opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
 
         def step():
