@@ -468,7 +468,6 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
 // TMEM map (columns): [0,176) Bias hi (two M-tiles x 88), [176,352) Bias lo, [352,416) S0, [416,480) S1, [480,512) O.
 constexpr int kV2Threads = 544;               // warps 0-3 S-conversion, 4 MMA, 5-8 + 13-16 producers, 9-12 output
 constexpr int kV2Producers = 256;
-constexpr int kV2ThreadsMerge = 672;          // + warps 17-20: second set of S-conversion warps (MERGE variant)
 constexpr int kV2KT = 64;
 constexpr int kV2S0 = 352, kV2S1 = 416, kV2O = 480;
 constexpr int kV2Regions = 27;
@@ -530,12 +529,8 @@ __device__ long long g_v2_trace[16 * 64];
 #define V2_TR(slot, it) do { } while (0)
 #endif
 
-// MERGE = false: S exact in fp16 + bias as two resident fp16 operands (3 MMAs per 16-key chunk, 4 S-conversion warps).
-// MERGE = true (opt-in, SDF_QKTV_V2_MERGE=1): the bias stays resident as fp32, eight S-conversion warps form
-// T = S + bias/scale and split it hi + lo per 16-key chunk in place (2 MMAs per chunk, as v1 does, but without the
-// table lookup and the mask compare).
-template <int NPAD, bool MASK, bool MERGE>
-__global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2_kernel(const QktvP p) {
+template <int NPAD, bool MASK>
+__global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const V2Plan sp = plan_v2(p.Rpad, p.tab);
   int* lin_s = reinterpret_cast<int*>(smem + sp.lin);
@@ -561,8 +556,8 @@ __global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2
   const int lin_off = (p.wd - 1) * A_ + (p.wh - 1) * B_ + (p.ww - 1);
 
   // ---- one-time setup (all threads) ----
-  for (uint32_t i = tid * 16; i < sp.rsum; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
-  for (int n = tid; n < Rpad; n += blockDim.x) {
+  for (uint32_t i = tid * 16; i < sp.rsum; i += kV2Threads * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  for (int n = tid; n < Rpad; n += kV2Threads) {
     const int d = n / (p.wh * p.ww), rem = n - d * (p.wh * p.ww), hh = rem / p.ww, w = rem - hh * p.ww;
     lin_s[n] = n < N ? d * A_ + hh * B_ + w : 0;
     smem[sp.reg + n] = 0;
@@ -570,12 +565,12 @@ __global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2
     reinterpret_cast<int64_t*>(smem + sp.rowoff)[n] = ((int64_t)d * p.M * p.P + rem) * (p.nH * 32);
   }
   const float inv_scale = 1.f / p.scale;
-  for (int i = tid; i < p.tab; i += blockDim.x) tab_s[i] = __ldg(p.bias_table + (int64_t)i * p.nH + head) * inv_scale;
+  for (int i = tid; i < p.tab; i += kV2Threads) tab_s[i] = __ldg(p.bias_table + (int64_t)i * p.nH + head) * inv_scale;
   if (tid == 0) {
     mbar_init(&full[0], kV2Producers / 32); mbar_init(&full[1], kV2Producers / 32);
     mbar_init(&empty[0], 5); mbar_init(&empty[1], 5);
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(&s16_full[0], MERGE ? 8 : 4); mbar_init(&s16_full[1], MERGE ? 8 : 4);
+    mbar_init(&s16_full[0], 4); mbar_init(&s16_full[1], 4);
     mbar_init(o_full, 1); mbar_init(o_free, 4); mbar_init(&bars[10], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -593,16 +588,6 @@ __global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2
     for (int mt = 0; mt < n_mt; ++mt) {
       const int row = mt * 128 + warp * 32 + lane;
       const float* tab_i = tab_s + lin_off + (row < N ? lin_s[row] : 0);
-      if (MERGE) {
-        // fp32, one column per key: tile mt at columns [mt * npad, +npad)
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-          uint32_t bv[16];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) bv[c] = __float_as_uint((row < N && c0 + c < N) ? tab_i[-lin_s[c0 + c]] : 0.f);
-          tmem_st16(tmem_base + lane_base + (uint32_t)(mt * npad + c0), bv);
-        }
-        continue;
-      }
       for (int c0 = 0; c0 < npad; c0 += 16) {
         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -631,7 +616,7 @@ __global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2
   const int64_t n_pairs = p.M * p.nH;
 
 
-  if ((warp >= 5 && warp < 9) || (warp >= 13 && warp < 17)) {
+  if ((warp >= 5 && warp < 9) || warp >= 13) {
     // =========================== producers ===========================
     const int pt = (warp < 9 ? warp - 5 : warp - 9) * 32 + lane;  // 0..255
     int pi = 0;
@@ -733,12 +718,6 @@ __global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2
               // B = V read MN-major: a 16-key step advances the start address by 16 rows * 64 B
               const uint32_t bv = v_lo + (uint32_t)((key0 + c0) * 64 >> 4);
               const uint32_t kc = (uint32_t)((key0 + c0) >> 1);
-              if (MERGE) {          // T hi at columns [c0, c0 + 8), lo at [c0 + 8, c0 + 16) of the S buffer
-                if (kt == 0 && c0 == 0) mma_ts_lh<false>(d, s_cur + (uint32_t)c0, bv, kDescHi, idesc2);
-                else mma_ts_lh<true>(d, s_cur + (uint32_t)c0, bv, kDescHi, idesc2);
-                mma_ts_lh<true>(d, s_cur + (uint32_t)c0 + 8u, bv, kDescHi, idesc2);
-                continue;
-              }
               if (kt == 0 && c0 == 0) mma_ts_lh<false>(d, tm + mt * w2 + kc, bv, kDescHi, idesc2);
               else mma_ts_lh<true>(d, tm + mt * w2 + kc, bv, kDescHi, idesc2);
               mma_ts_lh<true>(d, tm + (n_mt + mt) * w2 + kc, bv, kDescHi, idesc2);
@@ -758,10 +737,9 @@ __global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2
       __syncwarp();
       mbar_wait(&bars[10], 0);
     }
-  } else if (warp < 4 || warp >= 17) {
-    // =========================== S-conversion warps (one per TMEM lane quarter; MERGE: two, splitting the chunks) ======
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const int half = warp >= 17 ? 1 : 0;
+  } else if (warp < 4) {
+    // =========================== S-conversion warps (one per TMEM lane quarter) ===========================
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     int item = 0;
     for (int64_t pair = (int64_t)blockIdx.x; pair < n_pairs; pair += gridDim.x) {
 #pragma unroll
@@ -775,35 +753,6 @@ __global__ void __launch_bounds__(MERGE ? kV2ThreadsMerge : kV2Threads, 1) qktv2
         mbar_wait(&s_full[sb], (item >> 1) & 1);
         tc_fence_after();
         if (tid == 0) V2_TR(5, item);
-        if (MERGE) {
-          const int mt = li / n_kt;
-          const uint32_t bcol = tmem_base + lane_base + (uint32_t)(mt * npad + key0);
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = half * 32 + cc * 16;
-            if (c0 < nk) {
-              uint32_t sv[16], bv[16], o16[16];
-              tmem_ld16(scol + c0, sv);
-              tmem_ld16(bcol + c0, bv);
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float t0 = __uint_as_float(sv[2 * c]) + __uint_as_float(bv[2 * c]);
-                const float t1 = __uint_as_float(sv[2 * c + 1]) + __uint_as_float(bv[2 * c + 1]);
-                const uint32_t h = pack2<0>(t0, t1);
-                float ha, hb;
-                unpack2<0>(h, ha, hb);
-                o16[c] = h;
-                o16[8 + c] = pack2<0>(t0 - ha, t1 - hb);
-              }
-              tmem_st16(scol + c0, o16);       // in place, chunk by chunk: no other warp touches these 16 columns
-            }
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s16_full[sb]);
-          continue;
-        }
         // S (fp32 exact integers) -> fp16 pairs, in place: this warp is the only one touching these lanes
         uint32_t r0[32], o[32];
         tmem_ld32(scol, r0);
@@ -1445,15 +1394,12 @@ static void launch_v2_bwd(int npad, bool mask, int grid, uint32_t smem_bytes, cu
 
 template <int NPAD>
 static void launch_v2_npad(bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
-  static const int merge = [] { const char* e = getenv("SDF_QKTV_V2_MERGE"); return e ? atoi(e) : 0; }();
-  auto go = [&](auto kern, int threads) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    kern<<<grid, threads, smem_bytes, stream>>>(p);
-  };
-  if (merge) {
-    if (mask) go(qktv2_kernel<NPAD, true, true>, kV2ThreadsMerge); else go(qktv2_kernel<NPAD, false, true>, kV2ThreadsMerge);
+  if (mask) {
+    cudaFuncSetAttribute(qktv2_kernel<NPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    qktv2_kernel<NPAD, true><<<grid, kV2Threads, smem_bytes, stream>>>(p);
   } else {
-    if (mask) go(qktv2_kernel<NPAD, true, false>, kV2Threads); else go(qktv2_kernel<NPAD, false, false>, kV2Threads);
+    cudaFuncSetAttribute(qktv2_kernel<NPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    qktv2_kernel<NPAD, false><<<grid, kV2Threads, smem_bytes, stream>>>(p);
   }
 }
 static void launch_v2(int npad, bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
