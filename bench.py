@@ -300,9 +300,10 @@ def run_b200(args, rank, local_rank, world):
     functional.set_step_mode(model, "m")
     functional.set_backend(model, "cupy", prod.neuron.LIFNode)   # accepted no-op, as the reference scripts call it
     from sdformerflow_b200 import distributed as sdist
-    # "auto": replay the step as one CUDA graph on a single GPU; multi-GPU runs stay eager under DDP (capturing the NCCL
-    # all-reduce inside the step hung on this stack, so it is not attempted)
-    use_graph = args.graph in ("on", "auto") and world == 1
+    # Single GPU: the whole step (reset+fwd+loss+bwd+AdamW) is one CUDA graph.  Multi-GPU ("--graph on"): capturing the
+    # NCCL all-reduce inside the step hung on this stack, so the graph covers reset+fwd+loss+bwd and the bucketed
+    # all-reduce + fused AdamW follow eagerly (a dozen launches).  "--graph off": eager launches (DDP when N > 1).
+    use_graph = args.graph in ("on", "auto")
     if use_graph:
         # whole-step CUDA graph: the replica is not wrapped in DDP (its reducer hooks are host logic); the gradient
         # all-reduce is issued explicitly after backward, inside the captured step
@@ -317,13 +318,19 @@ def run_b200(args, rank, local_rank, world):
     xh, gth, mh = xh.pin_memory(), gth.pin_memory(), mh.pin_memory()
     xd, gtd, md = xh.to(dev), gth.to(dev), mh.to(dev)
 
-    def step(x, gt, mask):
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def fwd_bwd(x, gt, mask):
         functional.reset_net(model)
         flows = net(x)["flow"]
         loss = flow_loss(flows, gt, mask)
         loss.backward()
+        return loss
+
+    def step(x, gt, mask):
+        loss = fwd_bwd(x, gt, mask)
         if use_graph and world > 1:
-            sdist.allreduce_gradients(model.parameters(), world)
+            sdist.allreduce_gradients(params, world)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -362,9 +369,11 @@ def run_b200(args, rank, local_rank, world):
         sx, sgt, smk = xd.clone(), gtd.clone(), md.clone()
         graph = torch.cuda.CUDAGraph()
         n_cap = capi.launch_count()
+        opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            static_loss = eager_step(sx, sgt, smk)
+            static_loss = eager_step(sx, sgt, smk) if world == 1 else fwd_bwd(sx, sgt, smk)
         graph_launches = capi.launch_count() - n_cap
+        static_grads = [p.grad for p in params] if world > 1 else None
 
         def step(x, gt, mask):           # noqa: F811  (same work as eager_step, replayed)
             if x is not sx:
@@ -372,6 +381,11 @@ def run_b200(args, rank, local_rank, world):
                 sgt.copy_(gt, non_blocking=True)
                 smk.copy_(mask, non_blocking=True)
             graph.replay()
+            if world > 1:                # gradients live in the graph's static buffers; reduce and apply them eagerly
+                for p_, g_ in zip(params, static_grads):
+                    p_.grad = g_
+                sdist.allreduce_gradients(params, world)
+                opt.step()
             return static_loss
         xd, gtd, md = sx, sgt, smk
 
@@ -435,8 +449,9 @@ def run_b200(args, rank, local_rank, world):
                        "gemm": "cuBLAS/cuDNN TF32x2 weight split on spike operands (fp32-grade), fp32 elsewhere; TF32 backward",
                        "l2": "activations per step >> 126 MB L2; no explicit flush",
                        "weights": "random init (init_weights, seed 0)",
-                       "launch": ("one CUDA graph per step (reset+fwd+loss+bwd" + ("+all-reduce" if world > 1 else "") + "+AdamW), replayed; K1 roofline "
-                                  "timed in an eager pass of the same step") if use_graph else "eager (one launch per kernel)"},
+                       "launch": (("one CUDA graph per step (reset+fwd+loss+bwd+AdamW), replayed" if world == 1 else
+                                   "one CUDA graph per step for reset+fwd+loss+bwd, then eager bucketed all-reduce + fused AdamW")
+                                  + "; K1 roofline timed in an eager pass of the same step") if use_graph else "eager (one launch per kernel)"},
             "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
@@ -465,7 +480,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the training step as one CUDA graph (auto: single-GPU runs only)")
+                    help="replay the training step as a CUDA graph (auto = on); off = eager launches, DDP for N > 1")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train (default, the headline metric: BASELINE.json configs[2]) or infer (configs[1]: eval, "
                          "B=8/GPU, 480x640)")
