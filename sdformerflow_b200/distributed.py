@@ -52,18 +52,15 @@ def allreduce_gradients(params, world=None, bucket_bytes=25 * 1024 * 1024, avera
         return 0
     n = 0
     for bucket in make_buckets(list(params), bucket_bytes):
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        for p in bucket:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in bucket]
+        flat = torch.cat([g.reshape(-1) for g in grads])          # one launch in, one multi-tensor launch out
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         if average:
             flat.div_(world)
-        off = 0
-        for p in bucket:
-            k = p.numel()
-            if p.grad is None:
-                p.grad = flat[off:off + k].view_as(p).clone()
-            else:
-                p.grad.copy_(flat[off:off + k].view_as(p))
-            off += k
+        torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
         n += 1
     return n
 
