@@ -549,6 +549,116 @@ typedef struct {
 
 int sdf_conv3x3_cl_fwd(const sdf_conv3x3_cl_args* a);
 
+/* ---- G1/G2: spike GEMM / implicit-GEMM convolution on tcgen05 + TMA (csrc/spike_gemm.cu) -----------
+ * Replaces the cuBLAS / cuDNN calls behind sj_layer.Linear / sj_layer.Conv2d on spike operands:
+ * Spiking_swin_transformer3D.py:126-131 (fc1/fc2), :267-290 and :632-652 (linear_q/k/v, proj), :909 (reduction);
+ * Spiking_modules.py:268,318,803,845-846 (3x3 convolutions).
+ *
+ * Weights are pre-quantised once per optimizer step into three signed 8-bit digit planes of a 23-bit fixed-point value per
+ * output channel (power-of-two scale in wscale):  w ~= wscale[co] * (hi*65536 + mid*256 + lo).  The forward is then an exact
+ * integer contraction (tcgen05.mma kind::i8, u8 spikes x s8 digits -> s32) recombined and rounded ONCE to fp32, so the
+ * result does not depend on tiling or summation order.  |w - w_q| <= 2^-23 * 2^ceil(log2 max_k|w[co,k]|).
+ * Element (co, ci, tap) of the fp32 weight is read at w[co*s_co + ci*s_ci + tap_map[t]*s_tap]:
+ *   Linear (Cout, K):            taps 1, s_co = K, s_ci = 1
+ *   Conv2d (Cout, Cin, kh, kw):  taps kh*kw, s_co = Cin*taps, s_ci = taps, s_tap = 1, tap_map[t] = t */
+typedef struct {
+  const float* w;
+  int8_t* wq;          /* out: sdf_spike_gemm_wq_bytes(Cout, Cin, taps) bytes, 16-byte aligned */
+  float* wscale;       /* out: [Cout] */
+  int64_t wq_bytes;    /* capacity of wq */
+  int64_t Cout, Cin, taps;
+  int64_t s_co, s_ci, s_tap;
+  int64_t tap_map[9];
+  void* stream;
+} sdf_spike_gemm_pack_args;
+
+int sdf_spike_gemm_pack(const sdf_spike_gemm_pack_args* a);
+int64_t sdf_spike_gemm_wq_bytes(int64_t Cout, int64_t Cin, int64_t taps);
+int64_t sdf_spike_gemm_nt(int64_t Cout);   /* output channels per N tile (layout parameter of wq) */
+
+/* out[r, :] = a[r, :] @ W^T + bias, a = u8 spikes (or integers <= 255) [rows, K], out fp32 [rows, ld_out].
+ * bn_partials (optional): per-CTA-group sum(out), sum(out^2) per channel, [n_partial_blocks, 2, Cout]; the library writes
+ * min(capacity, its groups) rows and zero-fills the rest (same convention as sdf_bn_stats). */
+typedef struct {
+  const uint8_t* a;
+  const int8_t* wq;
+  const float* wscale;
+  const float* bias;        /* optional [Cout] */
+  float* out;
+  float* bn_partials;       /* optional */
+  int64_t n_partial_blocks;
+  int64_t rows, K, Cout, ld_out;
+  void* stream;
+} sdf_spike_gemm_fwd_args;
+
+int sdf_spike_gemm_fwd(const sdf_spike_gemm_fwd_args* a);
+
+/* NHWC convolution of u8 spikes x (Nimg, H, W, Cin) -> fp32 out (Nimg, Ho, Wo, Cout), kernel kh x kw, stride 1 or 2,
+ * zero padding `pad`; Ho = (H + 2*pad - kh)/stride + 1.  wq from sdf_spike_gemm_pack with taps = kh*kw.  Cin % 16 == 0. */
+typedef struct {
+  const uint8_t* x;
+  const int8_t* wq;
+  const float* wscale;
+  const float* bias;
+  float* out;
+  float* bn_partials;
+  int64_t n_partial_blocks;
+  int64_t Nimg, H, W, Cin, Cout, Ho, Wo;
+  int64_t kh, kw, stride, pad;
+  void* stream;
+} sdf_spike_conv_fwd_args;
+
+int sdf_spike_conv_fwd(const sdf_spike_conv_fwd_args* a);
+
+/* out[rows, N] = a[rows, K] @ b[N, K]^T (+ bias[N]) with fp32 operands read as TF32 (tcgen05.mma kind::tf32), fp32
+ * accumulate: the data-gradient GEMM dS = G @ W of every Linear above (b = W^T stored [Cin, Cout]).  lda / ldb / ld_out in
+ * elements, multiples of 4. */
+typedef struct {
+  const float* a;
+  const float* b;
+  const float* bias;   /* optional [N] */
+  float* out;
+  int64_t rows, K, N, lda, ldb, ld_out;
+  void* stream;
+} sdf_gemm_tf32_args;
+
+int sdf_gemm_tf32(const sdf_gemm_tf32_args* a);
+
+/* ---- G3: weight gradient dW = G^T S of a Linear / convolution on a spike operand (csrc/spike_wgrad.cu) -------------
+ * G fp32 [rows, Cout] (read as TF32), S u8 spikes [rows, K]; contraction over the rows on tcgen05 (both operands MN-major),
+ * split over row slabs into `workspace`, reduced in slab order (deterministic).  accumulate != 0: dw += result.
+ * workspace_bytes >= sdf_spike_wgrad_workspace_bytes(rows (conv: Nimg*Ho*Wo + partial-patch slack), Cout, Cin, taps). */
+typedef struct {
+  const float* g;
+  const uint8_t* s;
+  float* dw;               /* [Cout, K] */
+  float* workspace;
+  int64_t workspace_bytes;
+  int64_t rows, Cout, K, ldg;
+  int32_t accumulate;
+  int32_t _pad;
+  void* stream;
+} sdf_spike_wgrad_args;
+
+int sdf_spike_wgrad(const sdf_spike_wgrad_args* a);
+int64_t sdf_spike_wgrad_workspace_bytes(int64_t rows_or_pixels, int64_t Cout, int64_t Cin, int64_t taps);
+
+/* convolution: g fp32 NHWC (Nimg, Ho, Wo, Cout), x u8 NHWC (Nimg, H, W, Cin), dw OIHW (Cout, Cin, kh, kw) */
+typedef struct {
+  const float* g;
+  const uint8_t* x;
+  float* dw;
+  float* workspace;
+  int64_t workspace_bytes;
+  int64_t Nimg, H, W, Cin, Cout, Ho, Wo;
+  int64_t kh, kw, stride, pad;
+  int32_t accumulate;
+  int32_t _pad;
+  void* stream;
+} sdf_spike_conv_wgrad_args;
+
+int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 int sdf_version(void);             /* major*100 + minor */
 const char* sdf_last_error(void);  /* thread-local, never NULL */

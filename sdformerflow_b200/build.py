@@ -14,7 +14,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libsdf_b200.so")
 
-SOURCES = ["capi.cu", "lif.cu", "bn.cu", "window.cu", "attn_qkgate.cu", "attn_qktv.cu", "conv_small.cu"]
+SOURCES = ["capi.cu", "lif.cu", "bn.cu", "window.cu", "attn_qkgate.cu", "attn_qktv.cu", "conv_small.cu", "spike_gemm.cu", "spike_wgrad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -76,6 +76,18 @@ def build_library(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB_PATH
+
+
+def build_library_locked(force=False, verbose=False):
+    """build_library() under an exclusive file lock, so N ranks starting together compile once."""
+    import fcntl
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            return build_library(force=force, verbose=verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

@@ -19,7 +19,7 @@ SDF_SPIKE_F32, SDF_SPIKE_U8, SDF_SPIKE_BF16 = 0, 1, 2
 SDF_SG_ATAN, SDF_SG_SIGMOID = 0, 1
 
 _SCALARS = {"int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "double": ctypes.c_double,
-            "uint8_t": ctypes.c_uint8, "float": ctypes.c_float}
+            "uint8_t": ctypes.c_uint8, "int8_t": ctypes.c_int8, "float": ctypes.c_float}
 
 
 def _strip_comments(text):
@@ -43,6 +43,9 @@ def parse_header(path=HEADER):
                 nm = nm.strip()
                 is_ptr = bool(ptr) or nm.startswith("*")
                 nm = nm.lstrip("* ").strip()
+                arr = re.match(r"(\w+)\s*\[(\d+)\]$", nm)
+                if arr:
+                    nm = arr.group(1)
                 if is_ptr:
                     ct = ctypes.c_void_p
                 elif base in _SCALARS:
@@ -51,6 +54,8 @@ def parse_header(path=HEADER):
                     ct = structs[base]["ctype"]
                 else:
                     raise ValueError(f"unknown type {base!r} in struct {name}")
+                if arr:
+                    ct = ct * int(arr.group(2))
                 fields.append((nm, ct))
         cls = type(name, (ctypes.Structure,), {"_fields_": fields})
         structs[name] = {"ctype": cls, "fields": fields}
@@ -87,9 +92,11 @@ def lib():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from . import build
-            build.build_library()
+        # Always go through the incremental, digest-checked build: a stale .so next to an edited header / source would be
+        # a silent ABI mismatch (the struct layouts below are parsed from the header at run time).  The build is
+        # serialised across processes (torchrun ranks) with a file lock.
+        from . import build
+        build.build_library_locked()
         L = ctypes.CDLL(LIB_PATH)
         st = structs()
         for name, (ret, args) in declared_functions().items():
@@ -122,6 +129,8 @@ def struct(name, **kw):
             v = struct(ft.__name__, **v)
         elif ft is ctypes.c_void_p:
             v = None if v is None else ctypes.c_void_p(int(v))
+        elif isinstance(v, (list, tuple)):
+            v = ft(*v)
         setattr(obj, k, v)
     return obj
 

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include "sdf_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace sdf {
 
@@ -71,6 +72,67 @@ bool make_row_tiling(int64_t rows, int64_t C, int V, int target_threads, int max
   if (cap < 1) cap = 1;
   rt->blocks = (int)(need < cap ? (need > 0 ? need : 1) : cap);
   return true;
+}
+
+// ---- TMA tensor maps -----------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint), so the library does not link libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("TMA: cuTensorMapEncodeTiled is not available from this driver");
+    return SDF_ERR_CUDA;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = elem_strides ? elem_strides[i] : 1;
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 12832 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = fn(out, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                        const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("TMA: cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] stride0 %llu", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0));
+    return SDF_ERR_CUDA;
+  }
+  return SDF_OK;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+      v = kNumSMs;
+    return v;
+  }();
+  return n;
 }
 
 }  // namespace sdf

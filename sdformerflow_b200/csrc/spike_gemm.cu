@@ -1,0 +1,560 @@
+// spike_gemm.cu — G1/G2: Linear / convolution as (implicit) GEMM on the 5th-gen tensor cores, operands moved by TMA.
+//
+// Replaces the sj_layer.Linear / sj_layer.Conv2d calls on spike operands of the reference
+// (models/STSwinNet_SNN/Spiking_swin_transformer3D.py:126-131 fc1/fc2, :267-290 / :632-652 linear_q/k/v + proj,
+//  :909 reduction; models/STSwinNet_SNN/Spiking_modules.py:268,318,803,845-846 3x3 convolutions), which the reference runs
+// as cuBLAS / cuDNN fp32 (fp16 under autocast) GEMMs on fp32 {0,1} tensors.
+//
+// G1 forward (KIND_I8): the A operand is the spike tensor itself — 1 byte per spike, loaded by TMA straight into the
+// UMMA SWIZZLE_128B layout, no conversion warps.  The fp32 weights are pre-quantised once per optimizer step
+// (sdf_spike_gemm_pack) to 23-bit fixed point per output channel (power-of-two scale) and split into three signed 8-bit
+// digit planes stacked along N, so ONE tcgen05.mma kind::i8 (u8 x s8 -> s32, exact) per 32-deep K step produces the three
+// partial accumulators side by side in TMEM; the epilogue recombines them in 64-bit integers, converts once to fp32
+// (single rounding: the result is the correctly rounded dot product of the quantised weights, independent of tiling and
+// summation order), adds the bias, writes fp32 rows through shared memory with a TMA store, and accumulates the per-channel
+// sum / sum of squares that BatchNorm needs (the separate sdf_bn_stats pass over the output disappears).
+// G2 (KIND_TF32): the same pipeline with fp32 operands read as TF32 (dgrad: dS = G W, both real-valued).
+//
+// Convolutions are the same GEMM with K = taps x Cin: an M tile is an 8 x 16 patch of output pixels, and each tap's A tile is
+// a 4-D TMA box of the NHWC input shifted by the tap offset — zero padding is the TMA out-of-bounds fill, stride 2 is the
+// tensor map's element stride; no im2col buffer and no padded copy (cuDNN's nhwcAddPaddingKernel) exist.
+//
+// Kernel anatomy (192 threads, one persistent CTA per SM, fixed N tile per CTA):
+//   warp 4      TMA producer: A (and B unless the weights stay resident in shared memory) chunks into a ring of stages
+//   warp 5      MMA issuer (one elected lane): 4 x tcgen05.mma per 128-byte K chunk, tcgen05.commit frees the stage;
+//               accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 0-3   epilogue: tcgen05.ld (lane quarter = warp id) -> combine/scale/bias -> swizzled smem -> TMA store; BN sums
+#include "sdf_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace sdf {
+using namespace tc;
+
+constexpr int kGemmThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kChunkBytes = 128;                 // K bytes per operand row per chunk: one SWIZZLE_128B span
+constexpr int kAChunk = kTileM * kChunkBytes;    // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kPatchH = 8, kPatchW = 16;         // conv M tile = 8 x 16 output pixels
+constexpr int kMaxTaps = 9;
+
+struct GemmP {
+  int64_t rows;                 // linear: valid rows; conv: unused
+  int n_mtiles, n_ntiles, n_kchunks, n_groups;
+  int nt, ncols, Cout, stages, b_resident, kc_elems;
+  int out_bufs;                 // staging buffers of the epilogue (1 or 2)
+  int stat_splits;              // row splits of the per-tile column sums (threads = nt * stat_splits <= 128)
+  const float* wscale;
+  const float* bias;
+  float* bn_partials;
+  int n_partial_cap;
+  // convolution geometry (conv = 1): output (Nimg, Ho, Wo), tiles_h x tiles_w patches per image
+  int conv, tiles_h, tiles_w, Ho, Wo, stride, taps, cpt;   // cpt = K chunks per tap
+  int dh[kMaxTaps], dw[kMaxTaps];                          // input offset of tap t (already includes -padding)
+  int out_sh, out_sw, out_oh, out_ow;                      // transposed conv: output pixel = patch pixel * out_s + out_o
+};
+
+struct GemmSmem {
+  uint32_t a, b, out, sc, bars, tmem_slot, total;
+};
+__host__ __device__ inline GemmSmem gemm_smem_plan(const GemmP& p) {
+  GemmSmem s;
+  uint32_t o = 0;
+  s.a = o; o += (uint32_t)p.stages * kAChunk;
+  s.b = o; o += (uint32_t)(p.b_resident ? p.n_kchunks : p.stages) * (uint32_t)p.ncols * kChunkBytes;
+  s.out = o; o += (uint32_t)p.out_bufs * kTileM * p.nt * 4;   // epilogue staging (double buffered when it fits)
+  s.sc = o; o += (uint32_t)p.nt * 8;
+  s.bars = o; o += (2 * kMaxStages + 5) * 8;
+  s.tmem_slot = o; o += 16;
+  s.total = o;
+  return s;
+}
+
+// tile -> coordinates
+struct TileCoord {
+  int c1, c2, c3;     // A / out coordinates beyond the innermost (row | w, h, img)
+};
+__device__ __forceinline__ TileCoord tile_coord(const GemmP& p, int m_tile) {
+  TileCoord t;
+  if (!p.conv) { t.c1 = m_tile * kTileM; t.c2 = 0; t.c3 = 0; return t; }
+  const int per_img = p.tiles_h * p.tiles_w;
+  const int img = m_tile / per_img, rem = m_tile - img * per_img;
+  const int ph = rem / p.tiles_w, pw = rem - ph * p.tiles_w;
+  t.c1 = pw * kPatchW; t.c2 = ph * kPatchH; t.c3 = img;
+  return t;
+}
+// number of valid rows mask: is tile row r inside the output?
+__device__ __forceinline__ bool row_valid(const GemmP& p, const TileCoord& t, int r) {
+  if (!p.conv) return (int64_t)t.c1 + r < p.rows;
+  return (t.c2 + r / kPatchW) < p.Ho && (t.c1 + r % kPatchW) < p.Wo;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO, const GemmP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const GemmSmem sp = gemm_smem_plan(p);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;       // [2]
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
+  uint64_t* bres = bars + 2 * kMaxStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_slot);
+  float* sc_s = reinterpret_cast<float*>(smem + sp.sc);   // [nt] scale, [nt] bias
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tile = blockIdx.x % p.n_ntiles;             // fixed per CTA (gridDim.x = n_groups * n_ntiles)
+  const int group = blockIdx.x / p.n_ntiles;
+  const int n0 = n_tile * p.nt;
+  const uint32_t bchunk = (uint32_t)p.ncols * kChunkBytes;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(bres, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmO); }
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  for (int i = tid; i < p.nt; i += kGemmThreads) {
+    const int c = n0 + i;
+    sc_s[i] = (KIND == KIND_I8 && c < p.Cout) ? __ldg(p.wscale + c) : 1.f;
+    sc_s[p.nt + i] = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b);
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      if (p.b_resident) {
+        mbar_expect_tx(bres, (uint32_t)p.n_kchunks * bchunk);
+        for (int kc = 0; kc < p.n_kchunks; ++kc) tma_load_2d(&tmB, bres, b_base + kc * bchunk, kc * p.kc_elems, n_tile * p.ncols);
+      }
+      uint32_t it = 0;
+      for (int m = group; m < p.n_mtiles; m += p.n_groups) {
+        const TileCoord t = tile_coord(p, m);
+        for (int kc = 0; kc < p.n_kchunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], kAChunk + (p.b_resident ? 0u : bchunk));
+          if (!p.conv) {
+            tma_load_2d(&tmA, &full[s], a_base + s * kAChunk, kc * p.kc_elems, t.c1);
+          } else {
+            const int tap = kc / p.cpt, cc = kc - tap * p.cpt;
+            tma_load_4d(&tmA, &full[s], a_base + s * kAChunk, cc * p.kc_elems, t.c1 * p.stride + p.dw[tap],
+                        t.c2 * p.stride + p.dh[tap], t.c3);
+          }
+          if (!p.b_resident) tma_load_2d(&tmB, &full[s], b_base + s * bchunk, kc * p.kc_elems, n_tile * p.ncols);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint32_t idesc = KIND == KIND_I8 ? idesc_i8_u8s8(kTileM, p.ncols) : idesc_tf32(kTileM, p.ncols);
+      constexpr uint32_t hi = desc_hi_sw128(1024);
+      if (p.b_resident) { mbar_wait(bres, 0); }
+      uint32_t it = 0, tile_i = 0;
+      for (int m = group; m < p.n_mtiles; m += p.n_groups, ++tile_i) {
+        const uint32_t as = tile_i & 1, aph = (tile_i >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + as * (uint32_t)p.ncols;
+        for (int kc = 0; kc < p.n_kchunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo(a_base + s * kAChunk);
+          const uint32_t b_lo = desc_lo(b_base + (p.b_resident ? kc : s) * bchunk);
+#pragma unroll
+          for (int ks = 0; ks < kChunkBytes / 32; ++ks)
+            mma_ss<KIND>(d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc, (kc | ks) != 0 ? 1u : 0u);
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&tfull[as]);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====
+    const int r = tid;                                   // tile row = TMEM lane
+    const int n_sub = p.nt / 16;
+    const uint32_t out_bytes = (uint32_t)kTileM * p.nt * 4;
+    // column-sum role of this thread: column scol, rows [srow0, srow1) of every tile
+    const int scol = tid % p.nt, ssplit = tid / p.nt;
+    const bool stat_thread = p.bn_partials != nullptr && ssplit < p.stat_splits;
+    const int rows_per_split = (kTileM + p.stat_splits - 1) / p.stat_splits;
+    const int srow0 = ssplit * rows_per_split, srow1 = min(kTileM, srow0 + rows_per_split);
+    const uint32_t scol_off = (uint32_t)(scol >> 4) * (kTileM * 64) + (scol & 3) * 4;
+    const int scol_j = (scol & 15) >> 2;
+    float sum = 0.f, sq = 0.f;
+    uint32_t tile_i = 0;
+    for (int m = group; m < p.n_mtiles; m += p.n_groups, ++tile_i) {
+      const TileCoord t = tile_coord(p, m);
+      const uint32_t as = tile_i & 1, aph = (tile_i >> 1) & 1;
+      uint8_t* out_s = smem + sp.out + (p.out_bufs == 2 ? as : 0u) * out_bytes;
+      const uint32_t out_base = smem_u32(out_s);
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      // the TMA stores issued from this staging buffer two tiles ago must have finished reading it
+      if (tid == 0) { if (p.out_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+      named_bar_sync(1, 128);
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + as * (uint32_t)p.ncols;
+      for (int cc = 0; cc < n_sub; ++cc) {
+        float y[16];
+        if (KIND == KIND_I8) {
+          uint32_t lo[16], mid[16], hi3[16];
+          tmem_ld16_nowait(trow + cc * 16, lo);
+          tmem_ld16_nowait(trow + p.nt + cc * 16, mid);
+          tmem_ld16_nowait(trow + 2 * p.nt + cc * 16, hi3);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const long long q = ((long long)(int)hi3[i] << 16) + ((long long)(int)mid[i] << 8) + (long long)(int)lo[i];
+            y[i] = __fadd_rn(__fmul_rn(__ll2float_rn(q), sc_s[cc * 16 + i]), sc_s[p.nt + cc * 16 + i]);
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16_nowait(trow + cc * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]) + sc_s[p.nt + cc * 16 + i];
+        }
+        uint8_t* row = out_s + cc * (kTileM * 64) + r * 64;
+        const int x = (r >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(row + ((j ^ x) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      }
+      // accumulator stage free for the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&tempty[as]);
+      fence_async_smem();
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+        for (int cc = 0; cc < n_sub; ++cc) {
+          if (n0 + cc * 16 >= p.Cout) break;
+          if (!p.conv) tma_store_2d(&tmO, out_base + cc * (kTileM * 64), n0 + cc * 16, t.c1);
+          else tma_store_4d(&tmO, out_base + cc * (kTileM * 64), n0 + cc * 16, t.c1, t.c2, t.c3);
+        }
+        tma_store_commit();
+      }
+      if (stat_thread) {
+        const uint8_t* col = out_s + scol_off;
+        const bool full_tile = p.conv ? (t.c2 + kPatchH <= p.Ho && t.c1 + kPatchW <= p.Wo) : ((int64_t)t.c1 + kTileM <= p.rows);
+        if (full_tile) {
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 4
+          for (int rr = srow0; rr < srow1; rr += 2) {    // rows_per_split is even whenever stat_splits divides 128
+            const float v0 = *reinterpret_cast<const float*>(col + rr * 64 + ((scol_j ^ ((rr >> 1) & 3)) << 4));
+            const float v1 = *reinterpret_cast<const float*>(col + (rr + 1) * 64 + ((scol_j ^ ((rr >> 1) & 3)) << 4));
+            s0 += v0; q0 = fmaf(v0, v0, q0);
+            s1 += v1; q1 = fmaf(v1, v1, q1);
+          }
+          sum += s0 + s1;
+          sq += q0 + q1;
+        } else {
+          for (int rr = srow0; rr < srow1; ++rr) {
+            if (!row_valid(p, t, rr)) continue;
+            const float v = *reinterpret_cast<const float*>(col + rr * 64 + ((scol_j ^ ((rr >> 1) & 3)) << 4));
+            sum += v;
+            sq = fmaf(v, v, sq);
+          }
+        }
+      }
+    }
+    if (tid == 0) tma_store_wait_all();
+    if (stat_thread && n0 + scol < p.Cout) {
+      const int prow = group * p.stat_splits + ssplit;
+      p.bn_partials[((int64_t)prow * 2 + 0) * p.Cout + n0 + scol] = sum;
+      p.bn_partials[((int64_t)prow * 2 + 1) * p.Cout + n0 + scol] = sq;
+      // zero-fill the unused partial rows (the caller's finalize reduces all n_partial_cap rows)
+      if (group == 0)
+        for (int g = p.n_groups * p.stat_splits + ssplit; g < p.n_partial_cap; g += p.stat_splits) {
+          p.bn_partials[((int64_t)g * 2 + 0) * p.Cout + n0 + scol] = 0.f;
+          p.bn_partials[((int64_t)g * 2 + 1) * p.Cout + n0 + scol] = 0.f;
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+// ---- weight packing --------------------------------------------------------------------------------------------
+// w element (co, ci, tap) at co*s_co + ci*s_ci + tap*s_tap (Linear: taps = 1, s_co = K, s_ci = 1; Conv2d OIHW: s_co = Cin*taps,
+// s_ci = taps, s_tap = 1; ConvTranspose2d IOHW: s_ci = Cout*taps, s_co = taps).  tap_map[t] = source tap of GEMM tap t.
+struct PackP {
+  const float* w;
+  int8_t* wq;
+  float* wscale;
+  int Cout, Cin, taps, nt, n_ntiles, Kpad, cpt;
+  int64_t s_co, s_ci, s_tap;
+  int tap_map[kMaxTaps];
+};
+__global__ void pack_kernel(const PackP p) {
+  const int co = blockIdx.x;                      // one block per (padded) output channel
+  __shared__ float red[32];
+  float mx = 0.f;
+  if (co < p.Cout)
+    for (int i = threadIdx.x; i < p.Cin * p.taps; i += blockDim.x) {
+      const int ci = i / p.taps, tp = i - ci * p.taps;
+      mx = fmaxf(mx, fabsf(__ldg(p.w + co * p.s_co + ci * p.s_ci + p.tap_map[tp] * p.s_tap)));
+    }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  int e = 0;
+  if (mx > 0.f) frexpf(mx, &e);                   // mx = m * 2^e, m in [0.5, 1)  ->  |w| * 2^(22-e) < 2^22
+  const float qs = ldexpf(1.f, 22 - e);
+  if (threadIdx.x == 0 && co < p.Cout) p.wscale[co] = ldexpf(1.f, e - 22);
+  const int n_tile = co / p.nt, j = co - n_tile * p.nt;
+  int8_t* base = p.wq + ((int64_t)n_tile * 3 * p.nt + j) * p.Kpad;   // plane s at + s*nt*Kpad
+  const int kpt = p.cpt * kChunkBytes;            // padded K per tap
+  for (int k = threadIdx.x; k < p.Kpad; k += blockDim.x) {
+    const int tp = k / kpt, ci = k - tp * kpt;
+    int q = 0;
+    if (co < p.Cout && ci < p.Cin && tp < p.taps)
+      q = __float2int_rn(__ldg(p.w + co * p.s_co + ci * p.s_ci + p.tap_map[tp] * p.s_tap) * qs);
+    const int lo = ((q + 128) & 255) - 128;
+    const int q1 = (q - lo) >> 8;
+    const int mid = ((q1 + 128) & 255) - 128;
+    const int hi = (q1 - mid) >> 8;
+    base[k] = (int8_t)lo;
+    base[(int64_t)p.nt * p.Kpad + k] = (int8_t)mid;
+    base[(int64_t)2 * p.nt * p.Kpad + k] = (int8_t)hi;
+  }
+}
+
+// N tile width: multiple of 16, minimal padding then as wide as possible
+static int pick_nt(int C, int max_nt) {
+  int best = 16, best_pad = 1 << 30;
+  for (int nt = max_nt; nt >= 16; nt -= 16) {
+    const int pad = (C + nt - 1) / nt * nt - C;
+    if (pad < best_pad) { best_pad = pad; best = nt; }
+  }
+  return best;
+}
+
+}  // namespace sdf
+
+using namespace sdf;
+
+extern "C" int64_t sdf_spike_gemm_nt(int64_t Cout) { return pick_nt((int)Cout, 64); }
+
+extern "C" int sdf_spike_gemm_pack(const sdf_spike_gemm_pack_args* a) {
+  SDF_REQUIRE(a->w && a->wq && a->wscale, "spike_gemm_pack: null pointer");
+  SDF_REQUIRE(a->taps >= 1 && a->taps <= kMaxTaps, "spike_gemm_pack: taps=%lld", (long long)a->taps);
+  PackP p;
+  p.w = a->w; p.wq = a->wq; p.wscale = a->wscale;
+  p.Cout = (int)a->Cout; p.Cin = (int)a->Cin; p.taps = (int)a->taps;
+  p.nt = pick_nt(p.Cout, 64);
+  p.n_ntiles = (p.Cout + p.nt - 1) / p.nt;
+  p.cpt = (p.Cin + kChunkBytes - 1) / kChunkBytes;
+  p.Kpad = p.taps * p.cpt * kChunkBytes;
+  SDF_REQUIRE(a->wq_bytes >= (int64_t)p.n_ntiles * 3 * p.nt * p.Kpad, "spike_gemm_pack: wq buffer too small (%lld < %lld)",
+              (long long)a->wq_bytes, (long long)p.n_ntiles * 3 * p.nt * p.Kpad);
+  p.s_co = a->s_co; p.s_ci = a->s_ci; p.s_tap = a->s_tap;
+  for (int t = 0; t < kMaxTaps; ++t) p.tap_map[t] = t < p.taps ? (int)a->tap_map[t] : 0;
+  pack_kernel<<<p.n_ntiles * p.nt, 128, 0, (cudaStream_t)a->stream>>>(p);
+  return finish_launch("sdf_spike_gemm_pack");
+}
+
+extern "C" int64_t sdf_spike_gemm_wq_bytes(int64_t Cout, int64_t Cin, int64_t taps) {
+  const int nt = pick_nt((int)Cout, 64);
+  const int64_t n_ntiles = (Cout + nt - 1) / nt;
+  const int64_t cpt = (Cin + kChunkBytes - 1) / kChunkBytes;
+  return n_ntiles * 3 * nt * taps * cpt * kChunkBytes;
+}
+
+namespace sdf {
+// common launch: fills the stage count / residency policy and launches
+template <int KIND>
+static int launch_gemm(GemmP& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t st,
+                       const char* what) {
+  const int sms = num_sms();
+  SDF_REQUIRE(p.n_ntiles <= sms, "%s: Cout too large (%d N tiles)", what, p.n_ntiles);
+  p.n_groups = sms / p.n_ntiles;
+  if (p.n_groups > p.n_mtiles) p.n_groups = p.n_mtiles;
+  if (p.n_groups < 1) p.n_groups = 1;
+  p.stat_splits = 1;
+  if (p.bn_partials) {
+    SDF_REQUIRE(p.n_partial_cap >= 1, "%s: n_partial_blocks must be >= 1", what);
+    if (p.n_groups > p.n_partial_cap) p.n_groups = p.n_partial_cap;
+    // per-tile column sums: split the 128 rows over the idle epilogue threads (power of two so that halves stay even)
+    while (p.stat_splits * 2 * p.nt <= kTileM && p.n_groups * p.stat_splits * 2 <= p.n_partial_cap) p.stat_splits *= 2;
+  }
+  const uint32_t budget = 220 * 1024;
+  const uint32_t bchunk = (uint32_t)p.ncols * kChunkBytes;
+  // policy: double-buffer the staging tile and keep the weights resident whenever >= 4 (resp. 3) ring stages still fit
+  p.b_resident = 0;
+  p.out_bufs = 1;
+  p.stages = 2;
+  {
+    GemmP q = p; q.out_bufs = 2; q.stages = 4;
+    if (gemm_smem_plan(q).total <= budget) p.out_bufs = 2;
+    q = p; q.b_resident = 1; q.stages = 3;
+    if (gemm_smem_plan(q).total <= budget && p.n_mtiles / p.n_groups >= 2) p.b_resident = 1;
+  }
+  for (int s = kMaxStages; s >= 2; --s) {
+    GemmP q = p; q.stages = s;
+    if (gemm_smem_plan(q).total <= budget) { p.stages = s; break; }
+    if (s == 2) { set_error("%s: tile does not fit shared memory (ncols %d, K chunks %d)", what, p.ncols, p.n_kchunks); return SDF_ERR_UNSUPPORTED; }
+  }
+  (void)bchunk;
+  const GemmSmem sp = gemm_smem_plan(p);
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[KIND]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return SDF_ERR_CUDA; }
+    attr_done[KIND] = true;
+  }
+  gemm_kernel<KIND><<<p.n_groups * p.n_ntiles, kGemmThreads, sp.total, st>>>(tmA, tmB, tmO, p);
+  return finish_launch(what);
+}
+}  // namespace sdf
+
+extern "C" int sdf_spike_gemm_fwd(const sdf_spike_gemm_fwd_args* a) {
+  SDF_REQUIRE(a->a && a->wq && a->wscale && a->out, "spike_gemm_fwd: null pointer");
+  SDF_REQUIRE(a->rows > 0 && a->K > 0 && a->Cout > 0, "spike_gemm_fwd: empty problem");
+  SDF_REQUIRE(a->K % 16 == 0, "spike_gemm_fwd: K=%lld must be a multiple of 16 (TMA row pitch)", (long long)a->K);
+  SDF_REQUIRE(a->Cout % 4 == 0 && a->ld_out % 4 == 0, "spike_gemm_fwd: Cout / ld_out must be multiples of 4");
+  SDF_REQUIRE(aligned16(a->a) && aligned16(a->out) && aligned16(a->wq), "spike_gemm_fwd: pointers must be 16-byte aligned");
+  GemmP p{};
+  p.rows = a->rows;
+  p.nt = pick_nt((int)a->Cout, 64);
+  p.n_ntiles = ((int)a->Cout + p.nt - 1) / p.nt;
+  p.ncols = 3 * p.nt;
+  p.Cout = (int)a->Cout;
+  p.n_mtiles = (int)((a->rows + kTileM - 1) / kTileM);
+  p.n_kchunks = (int)((a->K + kChunkBytes - 1) / kChunkBytes);
+  p.kc_elems = kChunkBytes;
+  p.wscale = a->wscale; p.bias = a->bias; p.bn_partials = a->bn_partials; p.n_partial_cap = (int)a->n_partial_blocks;
+  const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->rows};
+    const uint64_t str[1] = {(uint64_t)a->K};
+    const uint32_t box[2] = {(uint32_t)kChunkBytes, (uint32_t)kTileM};
+    int st = make_tmap(&tmA, 0, 2, a->a, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)Kpad, (uint64_t)p.n_ntiles * p.ncols};
+    const uint64_t str[1] = {(uint64_t)Kpad};
+    const uint32_t box[2] = {(uint32_t)kChunkBytes, (uint32_t)p.ncols};
+    int st = make_tmap(&tmB, 0, 2, a->wq, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->Cout, (uint64_t)a->rows};
+    const uint64_t str[1] = {(uint64_t)a->ld_out * 4};
+    const uint32_t box[2] = {16, (uint32_t)kTileM};
+    int st = make_tmap(&tmO, 1, 2, a->out, dims, str, box, nullptr, 64);
+    if (st) return st;
+  }
+  return launch_gemm<KIND_I8>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_spike_gemm_fwd");
+}
+
+extern "C" int sdf_gemm_tf32(const sdf_gemm_tf32_args* a) {
+  SDF_REQUIRE(a->a && a->b && a->out, "gemm_tf32: null pointer");
+  SDF_REQUIRE(a->rows > 0 && a->K > 0 && a->N > 0, "gemm_tf32: empty problem");
+  SDF_REQUIRE(a->K % 4 == 0 && a->N % 4 == 0 && a->ld_out % 4 == 0, "gemm_tf32: K, N, ld_out must be multiples of 4");
+  SDF_REQUIRE(aligned16(a->a) && aligned16(a->b) && aligned16(a->out), "gemm_tf32: pointers must be 16-byte aligned");
+  GemmP p{};
+  p.rows = a->rows;
+  p.nt = pick_nt((int)a->N, 128);
+  p.n_ntiles = ((int)a->N + p.nt - 1) / p.nt;
+  p.ncols = p.nt;
+  p.Cout = (int)a->N;
+  p.n_mtiles = (int)((a->rows + kTileM - 1) / kTileM);
+  p.n_kchunks = (int)((a->K + 31) / 32);
+  p.kc_elems = 32;
+  p.bias = a->bias;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->rows};
+    const uint64_t str[1] = {(uint64_t)a->lda * 4};
+    const uint32_t box[2] = {32, (uint32_t)kTileM};
+    int st = make_tmap(&tmA, 1, 2, a->a, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    const uint64_t str[1] = {(uint64_t)a->ldb * 4};
+    const uint32_t box[2] = {32, (uint32_t)p.nt};
+    int st = make_tmap(&tmB, 1, 2, a->b, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->rows};
+    const uint64_t str[1] = {(uint64_t)a->ld_out * 4};
+    const uint32_t box[2] = {16, (uint32_t)kTileM};
+    int st = make_tmap(&tmO, 1, 2, a->out, dims, str, box, nullptr, 64);
+    if (st) return st;
+  }
+  return launch_gemm<KIND_TF32>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_gemm_tf32");
+}
+
+extern "C" int sdf_spike_conv_fwd(const sdf_spike_conv_fwd_args* a) {
+  SDF_REQUIRE(a->x && a->wq && a->wscale && a->out, "spike_conv_fwd: null pointer");
+  SDF_REQUIRE(a->Nimg > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "spike_conv_fwd: empty problem");
+  SDF_REQUIRE(a->Cin % 16 == 0, "spike_conv_fwd: Cin=%lld must be a multiple of 16 (TMA pixel pitch)", (long long)a->Cin);
+  SDF_REQUIRE(a->Cout % 4 == 0, "spike_conv_fwd: Cout must be a multiple of 4");
+  SDF_REQUIRE(a->stride == 1 || a->stride == 2, "spike_conv_fwd: stride must be 1 or 2");
+  SDF_REQUIRE(a->kh * a->kw >= 1 && a->kh * a->kw <= kMaxTaps, "spike_conv_fwd: kernel %lldx%lld unsupported", (long long)a->kh, (long long)a->kw);
+  SDF_REQUIRE(a->Ho == (a->H + 2 * a->pad - a->kh) / a->stride + 1 && a->Wo == (a->W + 2 * a->pad - a->kw) / a->stride + 1,
+              "spike_conv_fwd: output size does not match the geometry");
+  SDF_REQUIRE(aligned16(a->x) && aligned16(a->out) && aligned16(a->wq), "spike_conv_fwd: pointers must be 16-byte aligned");
+  GemmP p{};
+  p.conv = 1;
+  p.nt = pick_nt((int)a->Cout, 64);
+  p.n_ntiles = ((int)a->Cout + p.nt - 1) / p.nt;
+  p.ncols = 3 * p.nt;
+  p.Cout = (int)a->Cout;
+  p.Ho = (int)a->Ho; p.Wo = (int)a->Wo;
+  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
+  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
+  p.n_mtiles = (int)a->Nimg * p.tiles_h * p.tiles_w;
+  p.stride = (int)a->stride;
+  p.taps = (int)(a->kh * a->kw);
+  p.cpt = (int)((a->Cin + kChunkBytes - 1) / kChunkBytes);
+  p.n_kchunks = p.taps * p.cpt;
+  p.kc_elems = kChunkBytes;
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = i / (int)a->kw - (int)a->pad; p.dw[i] = i % (int)a->kw - (int)a->pad; }
+  p.wscale = a->wscale; p.bias = a->bias; p.bn_partials = a->bn_partials; p.n_partial_cap = (int)a->n_partial_blocks;
+  const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
+    const uint32_t box[4] = {(uint32_t)kChunkBytes, (uint32_t)(kPatchW * a->stride), (uint32_t)(kPatchH * a->stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)a->stride, (uint32_t)a->stride, 1};
+    int st = make_tmap(&tmA, 0, 4, a->x, dims, str, box, es, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)Kpad, (uint64_t)p.n_ntiles * p.ncols};
+    const uint64_t str[1] = {(uint64_t)Kpad};
+    const uint32_t box[2] = {(uint32_t)kChunkBytes, (uint32_t)p.ncols};
+    int st = make_tmap(&tmB, 0, 2, a->wq, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->Wo * a->Cout * 4, (uint64_t)a->Ho * a->Wo * a->Cout * 4};
+    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    int st = make_tmap(&tmO, 1, 4, a->out, dims, str, box, nullptr, 64);
+    if (st) return st;
+  }
+  return launch_gemm<KIND_I8>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_spike_conv_fwd");
+}

@@ -1,0 +1,354 @@
+// spike_wgrad.cu — G3: weight gradient of a Linear / convolution on a spike operand, dW = G^T S, on tcgen05 + TMA.
+//
+// Replaces the autograd weight-gradient GEMMs of the reference's sj_layer.Linear / sj_layer.Conv2d on spike tensors
+// (Spiking_swin_transformer3D.py:126-131,267-290,632-652,909; Spiking_modules.py:268,318,803,845-846), which cuBLAS / cuDNN
+// run as [Cout, rows] x [rows, K] contractions over the (huge) row / pixel axis with fp32 spikes.
+//
+//   dW[co, tap, ci] = sum_p G[p, co] * S[p*stride + off(tap), ci]          p = output pixel (Linear: row, one tap)
+//
+// D[M = co, N = (tap, ci)] accumulates in TMEM over a slab of pixels; both operands are "MN-major" for the MMA (the
+// contraction index is the slow one in memory), which tcgen05 takes directly through the descriptor major bits — no transposes.
+//   A = G, fp32, read as TF32: TMA boxes of [32 pixels][32 channels] land in the MN-major layout as they are.  MN-major TF32
+//       operands exist in one shared-memory layout only, SWIZZLE_128B with 32-byte atoms (UMMA layout type 1 = TMA
+//       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunk index XOR (row & 3), K groups of 4 rows (SBO = 512 B).
+//   B = S, 1-byte spikes: TMA brings the raw bytes (4-D box shifted by the tap offset, zero fill outside the image = the
+//       convolution padding); four converter warps expand them to fp32 {0,1} in the same MN-major layout (exact in TF32).
+// One CTA = one (128-channel M tile, <= 256-column N tile, pixel slab); partial tiles go to a workspace and a second kernel
+// reduces the slabs in a fixed order (deterministic) into the parameter's own layout (Linear [Cout,K], Conv OIHW).
+#include "sdf_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace sdf {
+using namespace tc;
+
+constexpr int kWgThreads = 192;      // warps 0-3: converters, then epilogue; warp 4: TMA producer; warp 5: MMA issuer
+constexpr int kWgRB = 32;            // pixels (GEMM K) per pipeline stage
+constexpr int kWgM = 128;            // output channels per tile
+constexpr int kWgMaxN = 256;         // columns per tile
+constexpr int kWgStages = 3;
+constexpr int kWgPatchW = 16, kWgPatchH = 2;
+
+struct WgradP {
+  int n_chunks;            // pixel chunks (of 32) in the whole problem
+  int chunks_per_slab, n_slabs;
+  int n_mtiles, n_ntiles;
+  int Cout, Cin;
+  int taps_per_tile;       // Cin <= 256: taps grouped per tile (all Cin channels each)
+  int ci_tiles;            // Cin > 256: 256-wide channel slices per tap (taps_per_tile = 1)
+  int taps;
+  int ncols_total;         // taps * Cin: row length of the partial tiles
+  int box_w;               // channels per spike TMA box = row pitch of the raw staging tile (min(Cin, 256))
+  int conv, tiles_h, tiles_w, stride;
+  int dh[9], dw[9];
+  float* partial;          // [n_slabs][Cout][ncols_total]
+};
+
+struct WgSmem { uint32_t a, stg, b, bars, tmem_slot, total; };
+__host__ __device__ inline WgSmem wg_smem_plan() {
+  WgSmem s;
+  uint32_t o = 0;
+  s.a = o; o += kWgStages * (kWgM * kWgRB * 4);            // 16 KB per stage
+  s.b = o; o += kWgStages * (kWgMaxN * kWgRB * 4);         // 32 KB per stage
+  s.stg = o; o += kWgStages * (kWgMaxN * kWgRB);           // 8 KB per stage
+  s.bars = o; o += (3 * kWgStages + 1) * 8;
+  s.tmem_slot = o; o += 16;
+  s.total = o;
+  return s;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS, const WgradP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const WgSmem sp = wg_smem_plan();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* full_tma = bars;                    // TMA landed (A + raw spike bytes)
+  uint64_t* full_b = bars + kWgStages;          // converters finished B
+  uint64_t* empty = bars + 2 * kWgStages;       // MMAs of the stage retired
+  uint64_t* done = bars + 3 * kWgStages;        // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_slot);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // tile decode: blockIdx.x = (slab * n_mtiles + m_tile) * n_ntiles + n_tile  (N tiles of one slab adjacent: they share G in L2)
+  const int n_tile = blockIdx.x % p.n_ntiles;
+  const int m_tile = (blockIdx.x / p.n_ntiles) % p.n_mtiles;
+  const int slab = blockIdx.x / (p.n_ntiles * p.n_mtiles);
+  int tap0, ntap, ci0, width;                   // this tile's columns: taps [tap0, tap0+ntap) x channels [ci0, ci0+width)
+  if (p.ci_tiles > 1) {
+    tap0 = n_tile / p.ci_tiles; ntap = 1;
+    ci0 = (n_tile % p.ci_tiles) * kWgMaxN;
+    width = min(kWgMaxN, p.Cin - ci0);
+  } else {
+    tap0 = n_tile * p.taps_per_tile; ntap = min(p.taps_per_tile, p.taps - tap0);
+    ci0 = 0; width = p.Cin;
+  }
+  const int ncols = ntap * width;               // multiple of 16 (host-checked)
+  const int c_begin = slab * p.chunks_per_slab;
+  const int c_end = min(p.n_chunks, c_begin + p.chunks_per_slab);
+  const int n_iter = c_end - c_begin;
+
+  if (tid == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_tma[i], 1); mbar_init(&full_b[i], 4); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4 && elect_one()) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmS); }
+  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b), stg_base = smem_u32(smem + sp.stg);
+  constexpr uint32_t kAStage = kWgM * kWgRB * 4, kBStage = kWgMaxN * kWgRB * 4, kStgStage = kWgMaxN * kWgRB;
+  constexpr uint32_t kBlk = kWgRB * 128;        // one 32-column MN block: 32 pixel rows x 128 B
+
+  if (warp == 4) {
+    if (elect_one()) {
+      const int per_img = p.tiles_h * p.tiles_w;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kWgStages;
+        const uint32_t ph = (it / kWgStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full_tma[s], kAStage + (uint32_t)(ntap * p.box_w * kWgRB));
+        const int chunk = c_begin + it;
+        if (!p.conv) {
+          for (int mb = 0; mb < 4; ++mb) tma_load_2d(&tmG, &full_tma[s], a_base + s * kAStage + mb * kBlk, m_tile * kWgM + mb * 32, chunk * kWgRB);
+          tma_load_2d(&tmS, &full_tma[s], stg_base + s * kStgStage, ci0, chunk * kWgRB);
+        } else {
+          const int img = chunk / per_img, rem = chunk - img * per_img;
+          const int py = rem / p.tiles_w, px = rem - py * p.tiles_w;
+          const int w0 = px * kWgPatchW, h0 = py * kWgPatchH;
+          for (int mb = 0; mb < 4; ++mb)
+            tma_load_4d(&tmG, &full_tma[s], a_base + s * kAStage + mb * kBlk, m_tile * kWgM + mb * 32, w0, h0, img);
+          for (int t = 0; t < ntap; ++t)
+            tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage + t * (p.box_w * kWgRB), ci0, w0 * p.stride + p.dw[tap0 + t],
+                        h0 * p.stride + p.dh[tap0 + t], img);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t idesc = idesc_tf32(kWgM, ncols, 1, 1);
+      constexpr uint32_t hi = desc_hi_sw128_base32(512);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kWgStages;
+        const uint32_t ph = (it / kWgStages) & 1;
+        mbar_wait(&full_tma[s], ph);
+        mbar_wait(&full_b[s], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < kWgRB / 8; ++g) {   // one MMA per 8 pixels (K = 8 for TF32): the 8-row group is 1024 B further
+          const uint32_t a_lo = desc_lo(a_base + s * kAStage + g * 1024, kBlk);
+          const uint32_t b_lo = desc_lo(b_base + s * kBStage + g * 1024, kBlk);
+          mma_ss<KIND_TF32>(tmem_base, a_lo, b_lo, hi, idesc, (it | g) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);
+      }
+      tc_commit(done);
+    }
+  } else {
+    // ===== converters: raw spike bytes -> fp32 {0,1} in the MN-major SWIZZLE_128B (32-byte atom) layout =====
+    // Thread -> (fixed 4-spike word q of the tile row, row sub-phase): no divisions inside the loop.
+    const int q_per_row = ncols >> 2;           // u32 words (4 spikes) per pixel row, <= 64
+    const int rows_par = 128 / q_per_row;       // pixel rows converted in parallel (>= 2)
+    const int q = tid % q_per_row, rsub = tid / q_per_row;
+    const int wq4 = width >> 2;
+    const int tq = q / wq4, qc = q - tq * wq4;  // tap-local index, word within the tap's channels
+    const uint32_t src_off = (uint32_t)(tq * (p.box_w * kWgRB) + qc * 4);
+    const int nb = q >> 3, c = q & 7;
+    const uint32_t dst_blk = (uint32_t)nb * kBlk;
+    const bool conv_thread = rsub < rows_par;
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kWgStages;
+      const uint32_t ph = (it / kWgStages) & 1;
+      mbar_wait(&full_tma[s], ph);
+      const uint8_t* stg = smem + sp.stg + s * kStgStage + src_off;
+      uint8_t* bdst = smem + sp.b + s * kBStage + dst_blk;
+      if (conv_thread) {
+#pragma unroll 4
+        for (int r = rsub; r < kWgRB; r += rows_par) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + r * p.box_w);
+          // byte b -> float(b) without I2F: 0x4B000000 | b is 2^23 + b
+          const float4 v = make_float4(__uint_as_float(0x4B000000u | (w & 0xFF)) - 8388608.f,
+                                       __uint_as_float(0x4B000000u | ((w >> 8) & 0xFF)) - 8388608.f,
+                                       __uint_as_float(0x4B000000u | ((w >> 16) & 0xFF)) - 8388608.f,
+                                       __uint_as_float(0x4B000000u | (w >> 24)) - 8388608.f);
+          *reinterpret_cast<float4*>(bdst + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))) = v;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&full_b[s]);
+    }
+    // ===== epilogue: TMEM -> this slab's partial tile =====
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int co = m_tile * kWgM + tid;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float* dst = p.partial + ((int64_t)slab * p.Cout + co) * p.ncols_total + (int64_t)tap0 * p.Cin + ci0;
+    for (int cc = 0; cc < ncols; cc += 16) {
+      uint32_t v[16];
+      tmem_ld16_nowait(trow + cc, v);
+      tmem_ld_wait();
+      if (co < p.Cout) {
+        // columns of a tile are (tap-local, channel) pairs: tap t's channels sit Cin apart in the partial row
+        const int t = cc / width, c = cc - t * width;
+        float* d = dst + (int64_t)t * p.Cin + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(d + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
+}
+
+// dW[co*s_co + ci*s_ci + tap*s_tap] (+)= sum_s partial[s][co][tap*Cin + ci], slabs added in index order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n_slabs, int Cout, int Cin,
+                                    int taps, int64_t s_co, int64_t s_ci, int64_t s_tap, int accumulate) {
+  const int64_t total = (int64_t)Cout * taps * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < n_slabs; ++s) acc += __ldg(partial + (int64_t)s * total + i);
+    const int64_t co = i / ((int64_t)taps * Cin);
+    const int64_t rem = i - co * taps * Cin;
+    const int64_t tap = rem / Cin, ci = rem - tap * Cin;
+    float* d = dw + co * s_co + ci * s_ci + tap * s_tap;
+    *d = accumulate ? *d + acc : acc;
+  }
+}
+
+}  // namespace sdf
+
+using namespace sdf;
+
+static int wgrad_tiles(int Cin, int taps, int* taps_per_tile, int* ci_tiles, int* n_ntiles) {
+  if (Cin <= kWgMaxN) {
+    *taps_per_tile = kWgMaxN / Cin;
+    if (*taps_per_tile > taps) *taps_per_tile = taps;
+    *ci_tiles = 1;
+    *n_ntiles = (taps + *taps_per_tile - 1) / *taps_per_tile;
+  } else {
+    *taps_per_tile = 1;
+    *ci_tiles = (Cin + kWgMaxN - 1) / kWgMaxN;
+    *n_ntiles = taps * *ci_tiles;
+  }
+  return 0;
+}
+
+// slabs so that the grid is about two waves of SMs at most, at least 4 chunks per slab
+static void wgrad_slabs(WgradP& p) {
+  const int tiles = p.n_mtiles * p.n_ntiles;
+  int slabs = (num_sms() + tiles - 1) / tiles;
+  if (slabs < 1) slabs = 1;
+  int max_slabs = (p.n_chunks + 3) / 4;
+  if (max_slabs < 1) max_slabs = 1;
+  if (slabs > max_slabs) slabs = max_slabs;
+  p.chunks_per_slab = (p.n_chunks + slabs - 1) / slabs;
+  p.n_slabs = (p.n_chunks + p.chunks_per_slab - 1) / p.chunks_per_slab;
+}
+
+extern "C" int64_t sdf_spike_wgrad_workspace_bytes(int64_t rows_or_pixels, int64_t Cout, int64_t Cin, int64_t taps) {
+  WgradP p{};
+  p.n_mtiles = (int)((Cout + kWgM - 1) / kWgM);
+  wgrad_tiles((int)Cin, (int)taps, &p.taps_per_tile, &p.ci_tiles, &p.n_ntiles);
+  p.n_chunks = (int)((rows_or_pixels + kWgRB - 1) / kWgRB);   // conv callers pass whole 2 x 16 patches
+  wgrad_slabs(p);
+  const int64_t slabs = p.n_slabs;
+  return slabs * Cout * taps * Cin * 4;
+}
+
+static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tmS, float* dw, int64_t s_co, int64_t s_ci,
+                        int64_t s_tap, int accumulate, int64_t ws_bytes, cudaStream_t st, const char* what) {
+  wgrad_slabs(p);
+  SDF_REQUIRE((int64_t)p.n_slabs * p.Cout * p.ncols_total * 4 <= ws_bytes, "%s: workspace too small (%lld needed)", what,
+              (long long)p.n_slabs * p.Cout * p.ncols_total * 4);
+  static bool attr_done = false;
+  const WgSmem sp = wg_smem_plan();
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return SDF_ERR_CUDA; }
+    attr_done = true;
+  }
+  wgrad_kernel<<<p.n_slabs * p.n_mtiles * p.n_ntiles, kWgThreads, sp.total, st>>>(tmG, tmS, p);
+  int r = finish_launch(what);
+  if (r) return r;
+  const int64_t total = (int64_t)p.Cout * p.ncols_total;
+  const int blocks = (int)((total + 255) / 256 < 4 * num_sms() ? (total + 255) / 256 : 4 * num_sms());
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, p.n_slabs, p.Cout, p.Cin, p.taps, s_co, s_ci, s_tap, accumulate);
+  return finish_launch(what);
+}
+
+extern "C" int sdf_spike_wgrad(const sdf_spike_wgrad_args* a) {
+  SDF_REQUIRE(a->g && a->s && a->dw && a->workspace, "spike_wgrad: null pointer");
+  SDF_REQUIRE(a->rows > 0 && a->Cout > 0 && a->K > 0, "spike_wgrad: empty problem");
+  SDF_REQUIRE(a->Cout % 4 == 0 && a->K % 16 == 0, "spike_wgrad: Cout %% 4 and K %% 16 must be 0");
+  SDF_REQUIRE(aligned16(a->g) && aligned16(a->s) && aligned16(a->workspace), "spike_wgrad: pointers must be 16-byte aligned");
+  WgradP p{};
+  p.Cout = (int)a->Cout; p.Cin = (int)a->K; p.taps = 1; p.ncols_total = (int)a->K;
+  p.n_mtiles = (p.Cout + kWgM - 1) / kWgM;
+  wgrad_tiles(p.Cin, 1, &p.taps_per_tile, &p.ci_tiles, &p.n_ntiles);
+  p.n_chunks = (int)((a->rows + kWgRB - 1) / kWgRB);
+  p.partial = a->workspace;
+  p.box_w = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+  CUtensorMap tmG, tmS;
+  {
+    const uint64_t dims[2] = {(uint64_t)a->Cout, (uint64_t)a->rows};
+    const uint64_t str[1] = {(uint64_t)a->ldg * 4};
+    const uint32_t box[2] = {32, (uint32_t)kWgRB};
+    int st = make_tmap(&tmG, 1, 2, a->g, dims, str, box, nullptr, 12832);
+    if (st) return st;
+  }
+  {
+    const int width = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->rows};
+    const uint64_t str[1] = {(uint64_t)a->K};
+    const uint32_t box[2] = {(uint32_t)width, (uint32_t)kWgRB};
+    int st = make_tmap(&tmS, 0, 2, a->s, dims, str, box, nullptr, 0);
+    if (st) return st;
+  }
+  return wgrad_launch(p, tmG, tmS, a->dw, a->K, 1, 0, a->accumulate, a->workspace_bytes, (cudaStream_t)a->stream, "sdf_spike_wgrad");
+}
+
+extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
+  SDF_REQUIRE(a->g && a->x && a->dw && a->workspace, "spike_conv_wgrad: null pointer");
+  SDF_REQUIRE(a->Cin % 16 == 0 && a->Cout % 4 == 0, "spike_conv_wgrad: Cin %% 16 and Cout %% 4 must be 0");
+  SDF_REQUIRE(a->stride == 1 || a->stride == 2, "spike_conv_wgrad: stride must be 1 or 2");
+  SDF_REQUIRE(a->kh * a->kw >= 1 && a->kh * a->kw <= 9, "spike_conv_wgrad: kernel size unsupported");
+  SDF_REQUIRE(a->Cin <= kWgMaxN || a->Cin % kWgMaxN == 0, "spike_conv_wgrad: Cin > 256 must be a multiple of 256");
+  SDF_REQUIRE(aligned16(a->g) && aligned16(a->x) && aligned16(a->workspace), "spike_conv_wgrad: pointers must be 16-byte aligned");
+  WgradP p{};
+  p.conv = 1;
+  p.Cout = (int)a->Cout; p.Cin = (int)a->Cin; p.taps = (int)(a->kh * a->kw); p.ncols_total = p.taps * p.Cin;
+  p.n_mtiles = (p.Cout + kWgM - 1) / kWgM;
+  wgrad_tiles(p.Cin, p.taps, &p.taps_per_tile, &p.ci_tiles, &p.n_ntiles);
+  p.tiles_h = (int)((a->Ho + kWgPatchH - 1) / kWgPatchH);
+  p.tiles_w = (int)((a->Wo + kWgPatchW - 1) / kWgPatchW);
+  p.n_chunks = (int)a->Nimg * p.tiles_h * p.tiles_w;
+  p.stride = (int)a->stride;
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = i / (int)a->kw - (int)a->pad; p.dw[i] = i % (int)a->kw - (int)a->pad; }
+  p.partial = a->workspace;
+  p.box_w = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+  CUtensorMap tmG, tmS;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->Wo * a->Cout * 4, (uint64_t)a->Ho * a->Wo * a->Cout * 4};
+    const uint32_t box[4] = {32, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
+    int st = make_tmap(&tmG, 1, 4, a->g, dims, str, box, nullptr, 12832);
+    if (st) return st;
+  }
+  {
+    const int width = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
+    const uint32_t box[4] = {(uint32_t)width, (uint32_t)(kWgPatchW * a->stride), (uint32_t)(kWgPatchH * a->stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)a->stride, (uint32_t)a->stride, 1};
+    int st = make_tmap(&tmS, 0, 4, a->x, dims, str, box, es, 0);
+    if (st) return st;
+  }
+  // parameter layout OIHW: (co, ci, tap) at co*Cin*taps + ci*taps + tap
+  return wgrad_launch(p, tmG, tmS, a->dw, (int64_t)p.Cin * p.taps, p.taps, 1, a->accumulate, a->workspace_bytes,
+                      (cudaStream_t)a->stream, "sdf_spike_conv_wgrad");
+}

@@ -1,0 +1,152 @@
+"""Raw host bindings of the tcgen05 + TMA GEMM engine (csrc/spike_gemm.cu, csrc/spike_wgrad.cu).
+
+Forward: u8 spikes x 3 signed 8-bit weight digit planes (tcgen05.mma kind::i8, exact integer accumulate, one fp32 rounding).
+Data gradient: fp32 x fp32 read as TF32.  Weight gradient: G^T S with a split over the row (pixel) axis.
+Autograd wrappers live in ops.py; this module only allocates outputs and calls the C-ABI.
+"""
+import torch
+
+from . import capi
+
+N_PARTIAL = 444  # capacity of every BN partial-sum workspace ([N_PARTIAL, 2, C]); == ops.N_PARTIAL
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class PackedWeight:
+    """Digit planes + scales of one Linear / Conv weight, valid for one (data_ptr, _version) of the fp32 parameter."""
+    __slots__ = ("wq", "wscale", "Cout", "Cin", "taps", "key")
+
+    def __init__(self, wq, wscale, Cout, Cin, taps, key):
+        self.wq, self.wscale, self.Cout, self.Cin, self.taps, self.key = wq, wscale, Cout, Cin, taps, key
+
+
+_pack_cache = {}
+
+
+def pack_weight(w, layout="linear"):
+    """fp32 weight -> PackedWeight.  layout: 'linear' (Cout, K), 'conv' (Cout, Cin, kh, kw) OIHW.
+    Cached per parameter version (optimizer steps bump ``_version``); never cached while a CUDA graph is being
+    captured, so a captured training step re-packs inside the graph on every replay."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (w.data_ptr(), w._version, tuple(w.shape), layout)
+    if not capturing:
+        hit = _pack_cache.get(id(w))
+        if hit is not None and hit.key == key:
+            return hit
+    wd = w.detach()
+    if not wd.is_contiguous():
+        wd = wd.contiguous()
+    if layout == "linear":
+        Cout, Cin = wd.shape
+        taps, s_co, s_ci, s_tap = 1, Cin, 1, 0
+    elif layout == "conv":
+        Cout, Cin, kh, kw = wd.shape
+        taps = kh * kw
+        s_co, s_ci, s_tap = Cin * taps, taps, 1
+    else:
+        raise ValueError(layout)
+    L = capi.lib()
+    nbytes = int(L.sdf_spike_gemm_wq_bytes(Cout, Cin, taps))
+    wq = torch.empty(nbytes, device=w.device, dtype=torch.int8)
+    wscale = torch.empty(Cout, device=w.device, dtype=torch.float32)
+    capi.call("sdf_spike_gemm_pack", capi.struct(
+        "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(wq), wscale=_ptr(wscale), wq_bytes=nbytes, Cout=Cout, Cin=Cin,
+        taps=taps, s_co=s_co, s_ci=s_ci, s_tap=s_tap, tap_map=list(range(9)), stream=_stream()))
+    pw = PackedWeight(wq, wscale, Cout, Cin, taps, key)
+    if not capturing:
+        _pack_cache[id(w)] = pw
+    return pw
+
+
+def spike_gemm_fwd(a_u8, pw, bias=None, want_stats=False):
+    """a_u8 [rows, K] uint8 -> (out fp32 [rows, Cout], bn partials [N_PARTIAL, 2, Cout] or None)."""
+    rows, K = a_u8.shape
+    assert a_u8.dtype == torch.uint8 and a_u8.is_contiguous() and K == pw.Cin and pw.taps == 1
+    out = torch.empty((rows, pw.Cout), device=a_u8.device, dtype=torch.float32)
+    part = torch.empty((N_PARTIAL, 2, pw.Cout), device=a_u8.device, dtype=torch.float32) if want_stats else None
+    capi.call("sdf_spike_gemm_fwd", capi.struct(
+        "sdf_spike_gemm_fwd_args", a=_ptr(a_u8), wq=_ptr(pw.wq), wscale=_ptr(pw.wscale), bias=_ptr(bias), out=_ptr(out),
+        bn_partials=_ptr(part), n_partial_blocks=N_PARTIAL, rows=rows, K=K, Cout=pw.Cout, ld_out=pw.Cout, stream=_stream()),
+        algo_bytes=rows * K + 4 * rows * pw.Cout)
+    return out, part
+
+
+def spike_conv_fwd(x_u8, pw, bias, kh, kw, stride, pad, want_stats=False):
+    """x_u8 (Nimg, H, W, Cin) uint8 NHWC -> (out fp32 (Nimg, Ho, Wo, Cout), partials)."""
+    Nimg, H, W, Cin = x_u8.shape
+    assert x_u8.dtype == torch.uint8 and x_u8.is_contiguous() and Cin == pw.Cin and pw.taps == kh * kw
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    out = torch.empty((Nimg, Ho, Wo, pw.Cout), device=x_u8.device, dtype=torch.float32)
+    part = torch.empty((N_PARTIAL, 2, pw.Cout), device=x_u8.device, dtype=torch.float32) if want_stats else None
+    capi.call("sdf_spike_conv_fwd", capi.struct(
+        "sdf_spike_conv_fwd_args", x=_ptr(x_u8), wq=_ptr(pw.wq), wscale=_ptr(pw.wscale), bias=_ptr(bias), out=_ptr(out),
+        bn_partials=_ptr(part), n_partial_blocks=N_PARTIAL, Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=pw.Cout, Ho=Ho, Wo=Wo,
+        kh=kh, kw=kw, stride=stride, pad=pad, stream=_stream()),
+        algo_bytes=x_u8.numel() + 4 * out.numel())
+    return out, part
+
+
+def gemm_tf32(a, b, bias=None):
+    """a [rows, K] fp32 @ b [N, K]^T -> [rows, N] fp32, operands read as TF32."""
+    rows, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and a.stride(1) == 1 and b.stride(1) == 1
+    out = torch.empty((rows, N), device=a.device, dtype=torch.float32)
+    capi.call("sdf_gemm_tf32", capi.struct(
+        "sdf_gemm_tf32_args", a=_ptr(a), b=_ptr(b), bias=_ptr(bias), out=_ptr(out), rows=rows, K=K, N=N, lda=a.stride(0),
+        ldb=b.stride(0), ld_out=N, stream=_stream()), algo_bytes=4 * (rows * K + rows * N))
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """One grow-only fp32 workspace per device for the split-row partial tiles (consumed within the same launch pair).
+    Not shared across a CUDA-graph capture boundary: captured launches get their own buffer from the graph's pool."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes // 4, device=device, dtype=torch.float32)
+    ws = _ws_cache.get(device)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty(nbytes // 4, device=device, dtype=torch.float32)
+        _ws_cache[device] = ws
+    return ws
+
+
+def spike_wgrad(g, s_u8, out=None):
+    """dW [Cout, K] = g[rows, Cout]^T @ s_u8[rows, K]; g fp32 (TF32 operand), s uint8."""
+    rows, Cout = g.shape
+    K = s_u8.shape[1]
+    assert s_u8.shape[0] == rows and s_u8.dtype == torch.uint8 and s_u8.is_contiguous() and g.stride(1) == 1
+    nbytes = int(capi.lib().sdf_spike_wgrad_workspace_bytes(rows, Cout, K, 1))
+    ws = _workspace(nbytes, g.device)
+    acc = out is not None
+    dw = out if acc else torch.empty((Cout, K), device=g.device, dtype=torch.float32)
+    capi.call("sdf_spike_wgrad", capi.struct(
+        "sdf_spike_wgrad_args", g=_ptr(g), s=_ptr(s_u8), dw=_ptr(dw), workspace=_ptr(ws), workspace_bytes=ws.numel() * 4,
+        rows=rows, Cout=Cout, K=K, ldg=g.stride(0), accumulate=1 if acc else 0, stream=_stream()),
+        algo_bytes=rows * (4 * Cout + K))
+    return dw
+
+
+def spike_conv_wgrad(g, x_u8, kh, kw, stride, pad):
+    """dW (Cout, Cin, kh, kw) of a convolution: g fp32 NHWC (Nimg, Ho, Wo, Cout), x_u8 NHWC (Nimg, H, W, Cin)."""
+    Nimg, Ho, Wo, Cout = g.shape
+    _, H, W, Cin = x_u8.shape
+    assert g.is_contiguous() and x_u8.is_contiguous() and x_u8.dtype == torch.uint8
+    pixels = Nimg * (-(-Ho // 2) * 2) * (-(-Wo // 16) * 16)       # whole 2 x 16 patches
+    nbytes = int(capi.lib().sdf_spike_wgrad_workspace_bytes(pixels, Cout, Cin, kh * kw))
+    ws = _workspace(nbytes, g.device)
+    dw = torch.empty((Cout, Cin, kh, kw), device=g.device, dtype=torch.float32)
+    capi.call("sdf_spike_conv_wgrad", capi.struct(
+        "sdf_spike_conv_wgrad_args", g=_ptr(g), x=_ptr(x_u8), dw=_ptr(dw), workspace=_ptr(ws), workspace_bytes=ws.numel() * 4,
+        Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo, kh=kh, kw=kw, stride=stride, pad=pad, accumulate=0,
+        stream=_stream()), algo_bytes=4 * g.numel() + x_u8.numel())
+    return dw

@@ -1,0 +1,152 @@
+"""GPU parity of the tcgen05 + TMA GEMM engine (csrc/spike_gemm.cu, csrc/spike_wgrad.cu) against fp64 references.
+
+Forward (kind::i8 on u8 spikes x 3 weight digit planes): the result must be fp32-grade — the bar of the reference's fp32
+Linear / Conv2d on spike tensors (Spiking_swin_transformer3D.py:126-131,267-290,909; Spiking_modules.py:268,318,803):
+max |y - y64| <= 2e-6 * max|y64|.  It is also bit-reproducible: integer accumulation has no summation order.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _gemm():
+    from sdformerflow_b200 import gemm
+    return gemm
+
+
+def _spikes(shape, rate, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.rand(shape, generator=g) < rate).to(torch.uint8).to(DEV)
+
+
+# rows deliberately not multiples of 128; (K, Cout) = every Linear shape of the en4 model + odd ones
+LINEAR_CASES = [
+    (1000, 96, 192), (4096 + 77, 96, 96), (3000, 96, 384), (2500, 384, 96), (700, 384, 192), (1300, 192, 768),
+    (900, 768, 192), (517, 768, 3072), (300, 3072, 768), (260, 1536, 768), (129, 768, 768), (5000, 96, 4), (640, 48, 48),
+    (128, 16, 16),
+]
+
+
+@pytest.mark.parametrize("rows,K,Cout", LINEAR_CASES)
+def test_spike_gemm_fwd_fp32_grade(rows, K, Cout):
+    gemm = _gemm()
+    torch.manual_seed(rows + K + Cout)
+    a = _spikes((rows, K), 0.3, rows)
+    w = (torch.randn(Cout, K) * 0.05).to(DEV)
+    w[0, 0] = 0.37            # a large entry: the per-channel scale must cover the row maximum
+    bias = torch.randn(Cout, device=DEV)
+    pw = gemm.pack_weight(w)
+    y, part = gemm.spike_gemm_fwd(a, pw, bias, want_stats=True)
+    ref = a.double() @ w.double().t() + bias.double()
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 2e-6, err
+    # BatchNorm partial sums emitted by the epilogue
+    s = part[:, 0].double().sum(0)
+    q = part[:, 1].double().sum(0)
+    assert torch.allclose(s, y.double().sum(0), rtol=1e-5, atol=1e-3 * rows ** 0.5)
+    assert torch.allclose(q, (y.double() ** 2).sum(0), rtol=1e-5, atol=1e-3)
+    # bit-reproducible and independent of the bias-free path
+    y2, _ = gemm.spike_gemm_fwd(a, pw, bias)
+    assert torch.equal(y, y2)
+
+
+def test_spike_gemm_integer_operand_and_exactness():
+    """SEW residual sums are small integers: any u8 value is an exact operand; with weights that are exactly representable
+    in 23-bit fixed point the GEMM is exact."""
+    gemm = _gemm()
+    g = torch.Generator().manual_seed(5)
+    a = torch.randint(0, 200, (777, 192), generator=g, dtype=torch.uint8).to(DEV)
+    w = (torch.randint(-2 ** 15, 2 ** 15, (96, 192), generator=g).float() / 2 ** 17).to(DEV)
+    y, _ = gemm.spike_gemm_fwd(a, gemm.pack_weight(w))
+    ref = a.double() @ w.double().t()
+    assert torch.equal(y.double(), ref.float().double())
+
+
+@pytest.mark.parametrize("rows,K,N", [(1000, 192, 96), (4099, 96, 96), (700, 768, 384), (513, 3072, 768), (300, 768, 3072),
+                                     (2000, 384, 96), (200, 96, 48), (333, 4, 96), (260, 100, 20)])
+def test_gemm_tf32(rows, K, N):
+    gemm = _gemm()
+    torch.manual_seed(rows + K)
+    a = torch.randn(rows, K, device=DEV)
+    b = torch.randn(N, K, device=DEV) * 0.05
+    y = gemm.gemm_tf32(a, b)
+    ref = a.double() @ b.double().t()
+    # TF32 operands (10-bit mantissa, truncated) with fp32 accumulation
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 4e-3, err
+    # fp32-grade when the operands are TF32-representable
+    a2 = (torch.randint(-512, 512, (rows, K)).float() / 64).to(DEV)
+    b2 = (torch.randint(-512, 512, (N, K)).float() / 1024).to(DEV)
+    y2 = gemm.gemm_tf32(a2, b2)
+    ref2 = a2.double() @ b2.double().t()
+    # (fp32 accumulation of exact products: error ~ sqrt(K) * 2^-24)
+    assert (y2.double() - ref2).abs().max().item() <= 2e-5 * ref2.abs().max().item()
+
+
+CONV_CASES = [
+    # Nimg, H, W, Cin, Cout, k, stride, pad
+    (3, 24, 32, 96, 96, 3, 1, 1),
+    (2, 20, 27, 96, 96, 3, 1, 1),       # partial patches in both directions
+    (2, 48, 64, 48, 96, 3, 2, 1),       # patch-embed conv (stride 2)
+    (2, 18, 24, 96, 96, 3, 2, 1),       # PED conv (stride 2, odd patch count)
+    (5, 9, 12, 768, 768, 3, 1, 1),      # bottleneck res blocks
+    (2, 16, 16, 96, 32, 1, 1, 0),       # 1x1
+]
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,stride,pad", CONV_CASES)
+def test_spike_conv_fwd_fp32_grade(Nimg, H, W, Cin, Cout, k, stride, pad):
+    gemm = _gemm()
+    torch.manual_seed(H * W + Cin)
+    x = _spikes((Nimg, H, W, Cin), 0.25, H)
+    w = (torch.randn(Cout, Cin, k, k) * 0.03).to(DEV)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    pw = gemm.pack_weight(w, "conv")
+    y, part = gemm.spike_conv_fwd(x, pw, bias, k, k, stride, pad, want_stats=True)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 2e-6, err
+    s = part[:, 0].double().sum(0)
+    q = part[:, 1].double().sum(0)
+    yy = y.double().reshape(-1, Cout)
+    assert torch.allclose(s, yy.sum(0), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(q, (yy ** 2).sum(0), rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("rows,K,Cout", [(4099, 96, 384), (3000, 384, 96), (5000, 96, 192), (1300, 192, 768), (517, 768, 3072),
+                                          (300, 3072, 768), (6480, 768, 768), (40, 96, 96), (2000, 1536, 768), (999, 48, 4)])
+def test_spike_wgrad(rows, K, Cout):
+    gemm = _gemm()
+    torch.manual_seed(rows + K)
+    s = _spikes((rows, K), 0.3, rows + 1)
+    g = torch.randn(rows, Cout, device=DEV)
+    dw = gemm.spike_wgrad(g, s)
+    ref = g.double().t() @ s.double()
+    err = (dw.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 2e-3, err          # G enters as TF32 (truncated 10-bit mantissa); spikes are exact
+    # exact-operand case: fp32-grade
+    g2 = (torch.randint(-512, 512, (rows, Cout)).float() / 256).to(DEV)
+    dw2 = gemm.spike_wgrad(g2, s)
+    ref2 = g2.double().t() @ s.double()
+    assert (dw2.double() - ref2).abs().max().item() <= 2e-5 * ref2.abs().max().item()
+    assert torch.equal(dw2, gemm.spike_wgrad(g2, s))            # fixed reduction order
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,stride,pad", CONV_CASES)
+def test_spike_conv_wgrad(Nimg, H, W, Cin, Cout, k, stride, pad):
+    gemm = _gemm()
+    torch.manual_seed(H * W + Cin + 1)
+    x = _spikes((Nimg, H, W, Cin), 0.25, H + 3)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = (torch.randint(-512, 512, (Nimg, Ho, Wo, Cout)).float() / 256).to(DEV)
+    dw = gemm.spike_conv_wgrad(g, x, k, k, stride, pad)
+    xr = x.permute(0, 3, 1, 2).double().requires_grad_(False)
+    wr = torch.zeros(Cout, Cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xr, wr, None, stride=stride, padding=pad)
+    (ref,) = torch.autograd.grad(y, wr, g.permute(0, 3, 1, 2).double())
+    assert dw.shape == ref.shape
+    assert (dw.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
