@@ -73,13 +73,27 @@ class Spiking_neuron(nn.Module):
                                "scripts reset before every sample (train_flow_parallel_supervised_SNN.py:238)")
         self._dirty = True
 
-    def forward(self, x, time_dim=0):
+    @property
+    def is_plif(self):
+        return self.neuron_type == "plif"
+
+    @property
+    def fusable(self):
+        """Can run inside the window / merge / QK-gate kernels (which take tau by value and have no gradient path for
+        the PLIF parameter w)."""
+        return self.neuron_type in ("lif", "if")
+
+    def forward(self, x, time_dim=0, u8=False):
+        """u8=True: return ops.Spikes (1 byte per spike) for a consumer that runs on the tcgen05 spike GEMM."""
+        u8 = u8 and ops.spike_gemm_on()
         if self.is_psn:
-            return ops.psn(x, self.spiking_neuron.weight, self.spiking_neuron.bias, self.cfg(), time_dim)
+            return ops.psn(x, self.spiking_neuron.weight, self.spiking_neuron.bias, self.cfg(), time_dim, u8=u8)
         if self.persist_state and time_dim == 0:
+            if u8:
+                raise RuntimeError("persist_state neurons return fp32 spikes")
             return self.spiking_neuron(x)
         self.mark()
-        return ops.neuron(x, self.cfg(), time_dim, self.plif_w())
+        return ops.neuron(x, self.cfg(), time_dim, self.plif_w(), u8=u8)
 
 
 class SpikingNormLayer(nn.Module):
@@ -135,8 +149,32 @@ def from_cl(y):
     return y.permute(1, 0, 4, 2, 3)
 
 
-def conv_cl(x, conv, spike_input, transposed=False):
-    """x (B, T, H, W, Cin) -> (B, T, H', W', Cout); `conv` is an nn.Conv2d / nn.ConvTranspose2d parameter holder."""
+def u8_ok(conv, transposed=False):
+    """Does this convolution run on the tcgen05 spike GEMM engine when fed 1-byte spikes?"""
+    return (ops.spike_gemm_on() and not transposed and isinstance(conv, nn.Conv2d)
+            and conv.groups == 1 and tuple(conv.dilation) == (1, 1)
+            and ops.spike_conv_supported(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding))
+
+
+def bn_training(norm_layer):
+    """Does the BatchNorm inside this SpikingNormLayer / nn.BatchNorm2d use batch statistics now?"""
+    bn = getattr(norm_layer, "norm_layer", norm_layer)
+    return isinstance(bn, nn.modules.batchnorm._BatchNorm) and (bn.training or bn.running_mean is None)
+
+
+def conv_cl(x, conv, spike_input, transposed=False, stats=None):
+    """x (B, T, H, W, Cin) fp32 or ops.Spikes -> (B, T, H', W', Cout); `conv` is an nn.Conv2d / nn.ConvTranspose2d parameter
+    holder.  stats (bool, optional): when given, returns (y, BN partial sums of y or None) as ops.spike_linear does."""
+    if isinstance(x, ops.Spikes):
+        sh = conv.stride[0]
+        if tuple(conv.kernel_size) == (1, 1) and sh == 1:
+            return ops.spike_linear(x, conv.weight.view(conv.weight.shape[0], -1), conv.bias, stats=stats)
+        return ops.spike_conv_gemm(x, conv.weight, conv.bias, sh, conv.padding[0], stats=stats)
+    y = _conv_cl_lib(x, conv, spike_input, transposed)
+    return y if stats is None else (y, None)
+
+
+def _conv_cl_lib(x, conv, spike_input, transposed=False):
     B, T, H, W, C = x.shape
     if (not transposed and not spike_input and C <= 4 and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1)
             and tuple(conv.padding) == (1, 1) and conv.weight.shape[0] % 4 == 0 and ops.GEMM_MODE != "fp32"):
@@ -155,10 +193,11 @@ def conv_cl(x, conv, spike_input, transposed=False):
     return y.view(B, T, y.shape[1], y.shape[2], y.shape[3])
 
 
-def _bn_sn(h, norm_layer, sn):
+def _bn_sn(h, norm_layer, sn, partials=None, u8=False):
     """neuron(BN(h)) on channels-last rows, time axis = dim 1."""
     sn.mark()
-    return ops.bn_neuron(h, norm_layer.norm_layer, sn.cfg(), 1, psn=sn.spiking_neuron if sn.is_psn else None)
+    return ops.bn_neuron(h, norm_layer.norm_layer, sn.cfg(), 1, psn=sn.spiking_neuron if sn.is_psn else None,
+                         plif_w=sn.plif_w(), partials=partials, u8=u8 and ops.spike_gemm_on())
 
 
 def _conv(cin, cout, k, stride, padding, bias):
@@ -179,13 +218,15 @@ class SpikingConvEncoderLayer(nn.Module):
                                                v_th=spiking_kwargs["v_th"])
         self.sn = Spiking_neuron(**spiking_kwargs)
 
-    def forward_cl(self, x, spike_input=False):
-        h = conv_cl(x, self.conv[0], spike_input)
+    def forward_cl(self, x, spike_input=False, u8_out=False):
+        """u8_out: emit the output spikes as ops.Spikes for a consumer on the tcgen05 spike GEMM."""
         if self.norm is not None and self.norm_layer.is_batchnorm:
-            return _bn_sn(h, self.norm_layer, self.sn)
+            h, part = conv_cl(x, self.conv[0], spike_input, stats=bn_training(self.norm_layer))
+            return _bn_sn(h, self.norm_layer, self.sn, part, u8_out)
+        h = conv_cl(x, self.conv[0], spike_input)
         if self.norm is not None:
             h = to_cl(self.norm_layer(from_cl(h)))
-        return self.sn(h, 1)
+        return self.sn(h, 1, u8=u8_out)
 
     def forward(self, x):
         return from_cl(self.forward_cl(to_cl(x)))
@@ -210,13 +251,14 @@ class MS_SpikingConvEncoderLayer(nn.Module):
         """spike_input: whether x is a spike tensor (exact in TF32).  Defaults to "a neuron runs first"; the patch
         embedding passes True for its first_layer=True conv, whose input is the head layer's spikes."""
         if not self.first_layer:
-            x = self.sn(x, 1)
-        h = conv_cl(x, self.conv[0], (not self.first_layer) if spike_input is None else spike_input)
+            x = self.sn(x, 1, u8=u8_ok(self.conv[0]))
+        si = (not self.first_layer) if spike_input is None else spike_input
         if self.norm is None:
-            return h
+            return conv_cl(x, self.conv[0], si)
         if self.norm_layer.is_batchnorm:
-            return ops.bn_residual(h, self.norm_layer.norm_layer)
-        return to_cl(self.norm_layer(from_cl(h)))
+            h, part = conv_cl(x, self.conv[0], si, stats=bn_training(self.norm_layer))
+            return ops.bn_residual(h, self.norm_layer.norm_layer, partials=part)
+        return to_cl(self.norm_layer(from_cl(conv_cl(x, self.conv[0], si))))
 
     def forward(self, x):
         return from_cl(self.forward_cl(to_cl(x)))
@@ -308,10 +350,11 @@ class SpikingPEDLayer(nn.Module):
 
     def forward_cl(self, x):
         x_res = conv_cl(x, self.conv_res, False)                 # 1x1 stride-2 shortcut on the membrane input
-        y = conv_cl(self.sn(x, 1), self.conv, True)
+        s = self.sn(x, 1, u8=u8_ok(self.conv))
         if self.norm is not None:
-            return ops.bn_residual(y, self.norm_layer, x_res)
-        return y + x_res
+            y, part = conv_cl(s, self.conv, True, stats=bn_training(self.norm_layer))
+            return ops.bn_residual(y, self.norm_layer, x_res, partials=part)
+        return conv_cl(s, self.conv, True) + x_res
 
     def forward(self, x):
         return from_cl(self.forward_cl(to_cl(x))).contiguous()
@@ -351,10 +394,14 @@ class SEWResBlock(_ResBlockBase):
     """conv-norm-neuron x2, spike-element-wise shortcut (reference :827-878)."""
 
     def forward_cl(self, x):
+        ok2 = u8_ok(self.conv2[0])
+        if self.norm is None:
+            s = self.sn1(conv_cl(x, self.conv1[0], True), 1, u8=ok2)
+            return _connect(self.sn2(conv_cl(s, self.conv2[0], True), 1), x, self.connect_function)
         h = conv_cl(x, self.conv1[0], True)                      # spikes (+ integer SEW sums): exact in TF32
-        s = _bn_sn(h, self.norm1, self.sn1) if self.norm is not None else self.sn1(h, 1)
-        h = conv_cl(s, self.conv2[0], True)
-        s = _bn_sn(h, self.norm2, self.sn2) if self.norm is not None else self.sn2(h, 1)
+        s = _bn_sn(h, self.norm1, self.sn1, u8=ok2)
+        h, part = conv_cl(s, self.conv2[0], True, stats=bn_training(self.norm2))
+        s = _bn_sn(h, self.norm2, self.sn2, part)
         return _connect(s, x, self.connect_function)
 
     def forward(self, x):
@@ -365,13 +412,16 @@ class MS_ResBlock(_ResBlockBase):
     """neuron-conv-norm x2, membrane shortcut (reference :880-933)."""
 
     def forward_cl(self, x):
-        h = conv_cl(self.sn1(x, 1), self.conv1[0], True)
-        s = _bn_sn(h, self.norm1, self.sn2) if self.norm is not None else self.sn2(h, 1)
-        h = conv_cl(s, self.conv2[0], True)
-        if self.norm is not None and self.connect_function == "ADD":
-            return ops.bn_residual(h, self.norm2.norm_layer, x)
-        if self.norm is not None:
-            h = ops.bn_residual(h, self.norm2.norm_layer)
+        ok1, ok2 = u8_ok(self.conv1[0]), u8_ok(self.conv2[0])
+        if self.norm is None:
+            h = conv_cl(self.sn1(x, 1, u8=ok1), self.conv1[0], True)
+            return _connect(conv_cl(self.sn2(h, 1, u8=ok2), self.conv2[0], True), x, self.connect_function)
+        h, part = conv_cl(self.sn1(x, 1, u8=ok1), self.conv1[0], True, stats=bn_training(self.norm1))
+        s = _bn_sn(h, self.norm1, self.sn2, part, ok2)
+        h, part = conv_cl(s, self.conv2[0], True, stats=bn_training(self.norm2))
+        if self.connect_function == "ADD":
+            return ops.bn_residual(h, self.norm2.norm_layer, x, partials=part)
+        h = ops.bn_residual(h, self.norm2.norm_layer, partials=part)
         return _connect(h, x, self.connect_function)
 
     def forward(self, x):
@@ -448,7 +498,8 @@ class MS_PED_Spiking_PatchEmbed_Conv_sfn(nn.Module):
     def forward_cl(self, x):
         """voxels (B, bins, 2, H, W) -> (B, T, H/4, W/4, embed_dim)."""
         x = regroup_bins_to_steps_cl(x, self.num_bins, self.num_steps)
-        x = self.head.forward_cl(x, spike_input=False)            # real-valued voxel input: plain fp32 conv
+        # real-valued voxel input: plain fp32 conv; its spikes feed `conv` as 1-byte Spikes when that runs on the spike GEMM
+        x = self.head.forward_cl(x, spike_input=False, u8_out=u8_ok(self.conv.conv[0]))
         x = self.conv.forward_cl(x, spike_input=True)             # input = head's spikes
         x = self.residual_encoding.forward_cl(x)
         return self.proj.forward_cl(x)

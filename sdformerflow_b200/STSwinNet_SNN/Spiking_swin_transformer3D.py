@@ -7,7 +7,9 @@ window_reverse copies are all folded into kernel indexing:
   * neurons over real time read (B, D, ...) with a time stride (no x.permute(1,0,2,3,4) copy),
   * BatchNorm on "permuted views" is BN over channels-last rows (statistics are order-free),
   * the window machinery is one cached int32 table per (shape, shift) (ops.WindowGeom).
-GEMMs (Linear) are library calls (cuBLAS) in round 1; everything else is libsdf_b200.
+Linear layers on spike operands run on the library's own tcgen05 + TMA GEMM engine (ops.spike_linear on ops.Spikes:
+1-byte spikes, kind::i8 forward with the BatchNorm statistics from the epilogue, TF32 gradients); real-valued operands
+(SEW proj input) still go through cuBLAS.
 """
 import numpy as np
 import torch
@@ -18,7 +20,7 @@ from ..sj import layer as sj_layer
 from ..sj import surrogate, neuron  # noqa: F401
 from .. import ops
 from .Spiking_modules import *  # noqa: F401,F403
-from .Spiking_modules import Spiking_neuron, SpikingNormLayer, MS_PED_Spiking_PatchEmbed_Conv_sfn  # noqa: F401
+from .Spiking_modules import Spiking_neuron, SpikingNormLayer, MS_PED_Spiking_PatchEmbed_Conv_sfn, bn_training  # noqa: F401
 
 
 def get_window_size(x_size, window_size, shift_size=None):
@@ -102,16 +104,17 @@ class Spiking_Mlp(nn.Module):
         if drop != 0.0:
             raise NotImplementedError("MLP dropout > 0 is not built (reference passes drop_rate=0, Spiking_STSwinNet.py:63)")
 
-    def _bn_sn(self, h, bn, sn, time_dim):
+    def _bn_sn(self, h, bn, sn, time_dim, partials=None, u8=False):
         sn.mark()
-        return ops.bn_neuron(h, _bn_of(bn), sn.cfg(), time_dim, psn=sn.spiking_neuron if sn.is_psn else None)
+        return ops.bn_neuron(h, _bn_of(bn), sn.cfg(), time_dim, psn=sn.spiking_neuron if sn.is_psn else None,
+                             plif_w=sn.plif_w(), partials=partials, u8=u8 and ops.spike_gemm_on())
 
     def forward(self, x, time_dim=0):
         """x: [T, B, H, W, C] (time_dim 0, the reference's call) or (B, D, H, W, C) (time_dim 1)."""
-        h = ops.spike_linear(x, self.fc1.weight)           # SEW stream: spikes + residual adds = small integers
-        s = self._bn_sn(h, self.bn1, self.sn1, time_dim)
-        h = ops.spike_linear(s, self.fc2.weight)
-        return self._bn_sn(h, self.bn2, self.sn2, time_dim)
+        h = ops.spike_linear(x, self.fc1.weight)           # SEW stream: spikes + residual adds = small integers (fp32)
+        s = self._bn_sn(h, self.bn1, self.sn1, time_dim, u8=True)
+        h, part = ops.spike_linear(s, self.fc2.weight, stats=bn_training(self.bn2))
+        return self._bn_sn(h, self.bn2, self.sn2, time_dim, part)
 
     def fused(self, x):
         """block tail on the (B, D, H, W, C) stream: mlp(x) + x (reference :845, cnf ADD)."""
@@ -122,11 +125,11 @@ class MS_Spiking_Mlp(Spiking_Mlp):
     """MS MLP: sn1 -> fc1 -> bn1 -> sn2 -> fc2 -> bn2 (reference :164-181)."""
 
     def forward(self, x, time_dim=0, res=None):
-        s = self.sn1(x, time_dim)
-        h = ops.spike_linear(s, self.fc1.weight)
-        s = self._bn_sn(h, self.bn1, self.sn2, time_dim)
-        h = ops.spike_linear(s, self.fc2.weight)
-        return ops.bn_residual(h, _bn_of(self.bn2), res)
+        s = self.sn1(x, time_dim, u8=True)
+        h, part = ops.spike_linear(s, self.fc1.weight, stats=bn_training(self.bn1))
+        s = self._bn_sn(h, self.bn1, self.sn2, time_dim, part, u8=True)
+        h, part = ops.spike_linear(s, self.fc2.weight, stats=bn_training(self.bn2))
+        return ops.bn_residual(h, _bn_of(self.bn2), res, partials=part)
 
     def fused(self, x):
         return self.forward(x, time_dim=1, res=x)
@@ -179,39 +182,62 @@ class Spiking_QK_WindowAttention3D(_WindowAttentionBase):
         self.proj_sn = Spiking_neuron(**spiking_kwargs)
         self.proj_drop = sj_layer.Dropout(proj_drop)
 
+    def _wqk(self):
+        """[W_q; W_k] so that q_pre | k_pre come from ONE GEMM.  In eval the concatenation (and its packed digit planes)
+        is cached per parameter version; in training autograd needs the cat node every step."""
+        wq, wk = self.linear_q.weight, self.linear_k.weight
+        if torch.is_grad_enabled() and (wq.requires_grad or wk.requires_grad):
+            return torch.cat([wq, wk], 0)
+        key = (wq.data_ptr(), wq._version, wk.data_ptr(), wk._version)
+        hit = self.__dict__.get("_wqk_cache")
+        if hit is None or hit[0] != key or torch.cuda.is_current_stream_capturing():
+            w = torch.cat([wq.detach(), wk.detach()], 0)
+            w._sdf_cacheable = True
+            hit = self.__dict__["_wqk_cache"] = (key, w)
+        return hit[1]
+
     def _core(self, s, wd, M, P):
-        """s: input spikes [wd*M*P, C] (after proj_sn) -> proj output rows [wd*M*P, C] (before proj_bn)."""
+        """s: input spikes (after proj_sn), ops.Spikes or fp32 [wd*M*P, C] -> (gate, proj output rows [wd*M*P, C]
+        before proj_bn, BN partial sums of those rows or None)."""
         C, nH = self.dim, self.num_heads
-        if self.sn_q.is_psn:
-            return self._core_psn(s, wd, M, P)
+        if not self.sn_q.fusable:
+            return self._core_generic(s, wd, M, P)
         for sn in (self.sn_q, self.sn_k, self.sn2_q):
             sn.mark()
-        wqk = torch.cat([self.linear_q.weight, self.linear_k.weight], 0)
-        qk_pre = ops.spike_linear(s, wqk)                                       # [rows, 2C], one GEMM
-        g = ops.qkgate(qk_pre, _bn_of(self.bn_q), _bn_of(self.bn_k), self.positional_encoding, self.sn_q.cfg(),
-                       wd, M, P, nH)
-        return g, ops.spike_linear(g, self.proj.weight, self.proj.bias)
+        u8 = isinstance(s, ops.Spikes)
+        if not u8:
+            s = s.view(wd * M * P, C)
+        train_stats = bn_training(self.bn_q)
+        qk_pre, part = ops.spike_linear(s, self._wqk(), stats=train_stats)         # [rows, 2C], one GEMM
+        g = ops.qkgate(qk_pre.view(wd * M * P, 2 * C), _bn_of(self.bn_q), _bn_of(self.bn_k), self.positional_encoding,
+                       self.sn_q.cfg(), wd, M, P, nH, partials=part, u8=u8)
+        y, py = ops.spike_linear(g, self.proj.weight, self.proj.bias, stats=bn_training(self.proj_bn))
+        return g, y, py
 
-    def _core_psn(self, s, wd, M, P):
-        """PSN variant: the generic K1p kernel per neuron site + library elementwise glue."""
+    def _core_generic(self, s, wd, M, P):
+        """PSN / PLIF variant: the generic neuron kernels per site + library elementwise glue (fp32 spikes)."""
         C, nH = self.dim, self.num_heads
-        s5 = s.view(wd, M, P, C)
-        q = ops.bn_neuron(ops.spike_linear(s5, self.linear_q.weight), _bn_of(self.bn_q), self.sn_q.cfg(), 0,
-                          psn=self.sn_q.spiking_neuron)
-        k = ops.bn_residual(ops.spike_linear(s5, self.linear_k.weight), _bn_of(self.bn_k),
-                            self.positional_encoding.reshape(wd, 1, P, C).expand(wd, M, P, C))
+        if not isinstance(s, ops.Spikes):
+            s = s.view(wd, M, P, C)
+        self.sn_q.mark()
+        q_pre, pq = ops.spike_linear(s, self.linear_q.weight, stats=bn_training(self.bn_q))
+        k_pre, pk = ops.spike_linear(s, self.linear_k.weight, stats=bn_training(self.bn_k))
+        q = ops.bn_neuron(q_pre.view(wd, M, P, C), _bn_of(self.bn_q), self.sn_q.cfg(), 0,
+                          psn=self.sn_q.spiking_neuron if self.sn_q.is_psn else None, plif_w=self.sn_q.plif_w(), partials=pq)
+        k = ops.bn_residual(k_pre.view(wd, M, P, C), _bn_of(self.bn_k),
+                            self.positional_encoding.reshape(wd, 1, P, C).expand(wd, M, P, C), partials=pk)
         k = self.sn_k(k)
         att = self.sn2_q(q.reshape(wd, M, nH, -1, 32).sum(dim=-1, keepdim=True))
         g = k.reshape(M, nH, -1, 32) * att.reshape(M, nH, -1, 1)
         g = g.reshape(M, nH, wd, P, 32).permute(2, 0, 3, 1, 4).reshape(wd * M * P, C)
-        return g, ops.spike_linear(g, self.proj.weight, self.proj.bias)
+        return g, ops.spike_linear(g, self.proj.weight, self.proj.bias), None
 
     def forward(self, x, mask=None):
         """Reference call: x = x_windows (wd, B_, wh, ww, C) -> (x (B_, N, C), attention-score spikes)."""
         T, B_, P, C = self._geom_args(x)
         s = self.proj_sn(x.float().contiguous())
-        g, y = self._core(s.view(T * B_ * P, C), T, B_, P)
-        y = ops.bn_residual(y, _bn_of(self.proj_bn))
+        g, y, py = self._core(s.view(T * B_ * P, C), T, B_, P)
+        y = ops.bn_residual(y, _bn_of(self.proj_bn), partials=py)
         attn = self.attn_sn(g.view(T, B_, x.shape[2], x.shape[3], C))
         return y.view(B_, T * P, C), attn
 
@@ -219,13 +245,13 @@ class Spiking_QK_WindowAttention3D(_WindowAttentionBase):
         """(B,D,H,W,C) -> (B,D,H,W,C): shortcut + DropPath(SSA(x)) with every index op folded in (:781-840)."""
         wd, C = geom.window[0], self.dim
         rows = geom.rows
-        if self.proj_sn.is_psn:
-            s = self.proj_sn(ops.window_gather(x, geom))
+        if not self.proj_sn.fusable:
+            s = self.proj_sn(ops.window_gather(x, geom), u8=True)
         else:
             self.proj_sn.mark()
-            s = ops.lif_window(x, geom, self.proj_sn.cfg())
-        _, y = self._core(s.view(rows, C), wd, geom.M, geom.P)
-        return ops.window_scatter(y, geom, res=x, bn_module=_bn_of(self.proj_bn), alpha=alpha)
+            s = ops.lif_window(x, geom, self.proj_sn.cfg(), u8=ops.spike_gemm_on())
+        _, y, py = self._core(s, wd, geom.M, geom.P)
+        return ops.window_scatter(y.view(rows, C), geom, res=x, bn_module=_bn_of(self.proj_bn), alpha=alpha, partials=py)
 
 
 class Spiking_BN_WindowAttention3D(_WindowAttentionBase):
@@ -269,6 +295,9 @@ class Spiking_BN_WindowAttention3D(_WindowAttentionBase):
         if (wd, P) != (ws[0], ws[1] * ws[2]):
             raise NotImplementedError("relative position bias needs an unclamped window (stage >= window size)")
         sns = (self.sn_q, self.sn_k, self.sn_v)
+        if self.sn_q.is_plif:
+            raise NotImplementedError("Q K^T V window attention with ParametricLIF neurons is not built: the fused "
+                                      "attention operator has no gradient path for the PLIF parameter")
         for sn in sns:
             sn.mark()
         pres = [ops.spike_linear(xin, getattr(self, f"linear_{n}").weight) for n in ("q", "k", "v")]
@@ -300,7 +329,7 @@ class Spiking_BN_WindowAttention3D(_WindowAttentionBase):
         wd, C = geom.window[0], self.dim
         region = geom.region if geom.shifted else None
         if self.sdsa:
-            if self.proj_sn.is_psn:
+            if not self.proj_sn.fusable:
                 xin = self.proj_sn(ops.window_gather(x, geom))
             else:
                 self.proj_sn.mark()
@@ -386,16 +415,17 @@ class SpikingPatchMerging(nn.Module):
     def forward(self, x):
         """x: (B, D, H, W, C) -> (B, D, ceil(H/2), ceil(W/2), 2C)."""
         if self.ms:
-            if self.sn.is_psn:
-                s = self.sn(ops.lif_merge(x, self.sn.cfg(), apply_neuron=False), time_dim=1)
+            if not self.sn.fusable:
+                s = self.sn(ops.lif_merge(x, self.sn.cfg(), apply_neuron=False), time_dim=1, u8=True)
             else:
                 self.sn.mark()
-                s = ops.lif_merge(x, self.sn.cfg())
-            return ops.bn_residual(ops.spike_linear(s, self.reduction.weight), _bn_of(self.norm))
+                s = ops.lif_merge(x, self.sn.cfg(), u8=ops.spike_gemm_on())
+            h, part = ops.spike_linear(s, self.reduction.weight, stats=bn_training(self.norm))
+            return ops.bn_residual(h, _bn_of(self.norm), partials=part)
         g = ops.lif_merge(x, self.sn.cfg(), apply_neuron=False)
         self.sn.mark()
         return ops.bn_neuron(ops.spike_linear(g, self.reduction.weight), _bn_of(self.norm), self.sn.cfg(), 1,
-                             psn=self.sn.spiking_neuron if self.sn.is_psn else None)
+                             psn=self.sn.spiking_neuron if self.sn.is_psn else None, plif_w=self.sn.plif_w())
 
 
 class MS_SpikingPatchMerging(SpikingPatchMerging):

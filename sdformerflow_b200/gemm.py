@@ -30,11 +30,16 @@ class PackedWeight:
 _pack_cache = {}
 
 
-def pack_weight(w, layout="linear"):
+def pack_weight(w, layout="linear", cache=None):
     """fp32 weight -> PackedWeight.  layout: 'linear' (Cout, K), 'conv' (Cout, Cin, kh, kw) OIHW.
-    Cached per parameter version (optimizer steps bump ``_version``); never cached while a CUDA graph is being
-    captured, so a captured training step re-packs inside the graph on every replay."""
+    Cached per parameter version (optimizer steps bump ``_version``) for nn.Parameters (or when cache=True: the caller
+    keeps `w` alive and unchanged); never cached while a CUDA graph is being captured, so a captured training step
+    re-packs inside the graph on every replay."""
     capturing = torch.cuda.is_current_stream_capturing()
+    if cache is None:
+        cache = isinstance(w, torch.nn.Parameter)
+    if not cache:
+        capturing = True            # same effect: neither look up nor store
     key = (w.data_ptr(), w._version, tuple(w.shape), layout)
     if not capturing:
         hit = _pack_cache.get(id(w))

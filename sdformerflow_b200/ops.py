@@ -9,9 +9,46 @@ from dataclasses import dataclass
 import math
 import torch
 
-from . import capi
+from . import capi, gemm
 
 N_PARTIAL = 444  # == sdf_partial_blocks(): up to 3 CTAs per SM x 148 SMs
+
+
+class Spikes:
+    """A 1-byte spike tensor on its way from the kernel that fires it to the GEMMs that consume it (the operand format of
+    the tcgen05 kind::i8 spike GEMM: 1 B per spike in HBM instead of the reference's fp32 {0,1}).
+
+    Autograd cannot carry an integer tensor, so the pair (token, grad) stands in for it: ``token`` is an fp32 scalar that
+    the producing autograd node returns and every consuming node takes as an input — it only fixes the execution order of
+    the backward pass — and the consumers' backward deposits dL/d(spikes) in ``grad`` (summed over consumers), which the
+    producer's backward picks up.  Double backward through a Spikes edge is not supported."""
+    __slots__ = ("data", "token", "grad")
+
+    def __init__(self):
+        self.data, self.token, self.grad = None, None, None
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def add_grad(self, g):
+        self.grad = g if self.grad is None else self.grad + g
+
+    def take_grad(self):
+        g, self.grad = self.grad, None
+        if g is None:       # no consumer produced a gradient (e.g. frozen weights downstream): zero
+            g = torch.zeros(self.data.shape, device=self.data.device, dtype=torch.float32)
+        return g.contiguous()
+
+
+_zero_tokens = {}
+
+
+def _zero_token(device):
+    z = _zero_tokens.get(device)
+    if z is None:
+        z = _zero_tokens[device] = torch.zeros((), device=device, dtype=torch.float32)
+    return z
 
 
 def _need_cuda(*ts):
@@ -86,19 +123,25 @@ class BNParams:
         self.training = bn.training or bn.running_mean is None
 
 
-def _bn_forward_affine(u2d, rows, C, ld, bn: BNParams):
-    """-> scale, shift, mean, rstd (all [C]).  Train: batch stats + running update like torch."""
+def _bn_forward_affine(u2d, rows, C, ld, bn: BNParams, partials=None):
+    """-> scale, shift, mean, rstd (all [C]).  Train: batch stats + running update like torch.
+    partials: per-block (sum, sum of squares) [N_PARTIAL, 2, C] already produced by the epilogue of the GEMM that wrote
+    u2d (ops.spike_linear(..., stats=True)); without them a statistics pass over u2d runs here."""
     dev = u2d.device
     scale = torch.empty(C, device=dev, dtype=torch.float32)
     shift = torch.empty_like(scale)
     mean = torch.empty_like(scale)
     rstd = torch.empty_like(scale)
-    partials = None
+    if not bn.training:
+        partials = None
     if bn.training:
-        partials = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
-        capi.call("sdf_bn_stats", capi.struct("sdf_bn_stats_args", x=_ptr(u2d), rows=rows, C=C, ld=ld,
-                                              partials=_ptr(partials), n_partial_blocks=N_PARTIAL, stream=_stream()),
-                  algo_bytes=4 * rows * C)
+        if partials is None:
+            partials = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
+            capi.call("sdf_bn_stats", capi.struct("sdf_bn_stats_args", x=_ptr(u2d), rows=rows, C=C, ld=ld,
+                                                  partials=_ptr(partials), n_partial_blocks=N_PARTIAL, stream=_stream()),
+                      algo_bytes=4 * rows * C)
+        else:
+            assert partials.shape == (N_PARTIAL, 2, C) and partials.is_contiguous()
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
     with torch.no_grad():
@@ -150,17 +193,18 @@ class _NeuronFn(torch.autograd.Function):
     (reference Spiking_modules.py:98-99)."""
 
     @staticmethod
-    def forward(ctx, u, plif_w, cfg, time_dim, v_init, want_state):
+    def forward(ctx, u, plif_w, cfg, time_dim, v_init, want_state, holder=None):
         _need_cuda(u)
         u = u.contiguous()
         lay = seq_layout(u.shape, time_dim)
-        tau = None
-        if cfg.kind == capi.SDF_NEURON_PLIF:
-            tau = 1.0 / torch.sigmoid(plif_w.detach()).item()
-        cc = cfg.c(tau)
-        spike, _, v_final = _lif_fwd_raw(u, lay, cc, capi.SDF_SPIKE_F32, v_init=v_init, want_v=want_state)
+        cc = cfg.c(plif_tau(plif_w) if cfg.kind == capi.SDF_NEURON_PLIF else None)
+        dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
+        spike, _, v_final = _lif_fwd_raw(u, lay, cc, dt, v_init=v_init, want_v=want_state)
         ctx.save_for_backward(u, plif_w, v_init)
-        ctx.lay, ctx.cc, ctx.cfg = lay, cc, cfg
+        ctx.lay, ctx.cc, ctx.cfg, ctx.holder = lay, cc, cfg, holder
+        if holder is not None:
+            holder.data = spike
+            spike = u.new_empty(())          # the token (see Spikes)
         if want_state:
             ctx.mark_non_differentiable(v_final)
             return spike, v_final
@@ -169,7 +213,7 @@ class _NeuronFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gs, _gv):
         u, plif_w, v_init = ctx.saved_tensors
-        gs = gs.contiguous()
+        gs = gs.contiguous() if ctx.holder is None else ctx.holder.take_grad()
         gu = torch.empty_like(u)
         plif_part = None
         if ctx.cfg.kind == capi.SDF_NEURON_PLIF:
@@ -182,12 +226,32 @@ class _NeuronFn(torch.autograd.Function):
         if plif_part is not None:
             s = torch.sigmoid(plif_w.detach())
             gw = (plif_part.sum() * s * (1 - s)).reshape(plif_w.shape)
-        return gu, gw, None, None, None, None
+        return gu, gw, None, None, None, None, None
 
 
-def neuron(u, cfg: NeuronCfg, time_dim=0, plif_w=None, v_init=None, want_state=False):
-    """spikes (fp32 {0,1}) of a multi-step neuron over dim `time_dim`; optionally the final membrane."""
-    spike, v = _NeuronFn.apply(u, plif_w, cfg, time_dim, v_init, want_state)
+_plif_tau_cache = {}
+
+
+def plif_tau(plif_w):
+    """1 / sigmoid(w) of a ParametricLIFNode as a host float (the kernels take tau by value).  One device->host read per
+    parameter version, so PLIF models are not CUDA-graph capturable; lif / if / psn never come here."""
+    key = (plif_w.data_ptr(), plif_w._version)
+    hit = _plif_tau_cache.get(id(plif_w))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    tau = 1.0 / torch.sigmoid(plif_w.detach()).item()
+    _plif_tau_cache[id(plif_w)] = (key, tau)
+    return tau
+
+
+def neuron(u, cfg: NeuronCfg, time_dim=0, plif_w=None, v_init=None, want_state=False, u8=False):
+    """spikes of a multi-step neuron over dim `time_dim` — fp32 {0,1}, or a Spikes (1 byte each) with u8=True;
+    optionally the final membrane."""
+    holder = Spikes() if u8 else None
+    spike, v = _NeuronFn.apply(u, plif_w, cfg, time_dim, v_init, want_state, holder)
+    if u8:
+        holder.token = spike
+        spike = holder
     return (spike, v) if want_state else spike
 
 
@@ -204,25 +268,28 @@ class _PSNFn(torch.autograd.Function):
     (reference Spiking_submodules.py:207-211: addmm + surrogate)."""
 
     @staticmethod
-    def forward(ctx, u, weight, bias, cfg, time_dim):
+    def forward(ctx, u, weight, bias, cfg, time_dim, holder=None):
         _need_cuda(u, weight, bias)
         u = u.contiguous()
         lay = seq_layout(u.shape, time_dim)
-        if weight.shape[0] != lay["T"]:
-            raise RuntimeError(f"PSN: weight is {tuple(weight.shape)} but the input has T={lay['T']}")
-        spike = torch.empty_like(u)
+        _check_psn(weight, bias, lay)
+        dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
+        spike = torch.empty(u.shape, device=u.device, dtype=_SPIKE_TORCH[dt])
         w, b = weight.detach().contiguous(), bias.detach().contiguous()
         capi.call("sdf_psn_fwd", capi.struct(
             "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), weight=_ptr(w), bias=_ptr(b), C=0, hw=1, lay=lay,
-            spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()))
+            spike_dtype=dt, stream=_stream()), algo_bytes=u.numel() * (4 + spike.element_size()))
         ctx.save_for_backward(u, w, b)
-        ctx.lay, ctx.cfg = lay, cfg
+        ctx.lay, ctx.cfg, ctx.holder = lay, cfg, holder
+        if holder is not None:
+            holder.data = spike
+            return u.new_empty(())
         return spike
 
     @staticmethod
     def backward(ctx, gs):
         u, w, b = ctx.saved_tensors
-        gs = gs.contiguous()
+        gs = gs.contiguous() if ctx.holder is None else ctx.holder.take_grad()
         T, n = ctx.lay["T"], ctx.lay["n_neurons"]
         gu = torch.empty_like(u)
         gh = torch.empty((T, n), device=u.device, dtype=torch.float32)
@@ -231,11 +298,23 @@ class _PSNFn(torch.autograd.Function):
             "sdf_psn_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=_ptr(gu), grad_h=_ptr(gh),
             x_out=None if ctx.lay["stride_b"] == 0 else _ptr(xo), weight=_ptr(w), bias=_ptr(b), C=0, hw=1,
             lay=ctx.lay, surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
-        return gu, gh @ xo.t(), gh.sum(1, keepdim=True), None, None
+        return gu, gh @ xo.t(), gh.sum(1, keepdim=True), None, None, None
 
 
-def psn(u, weight, bias, cfg: NeuronCfg, time_dim=0):
-    return _PSNFn.apply(u, weight, bias, cfg, time_dim)
+def _check_psn(weight, bias, lay):
+    """The kernels index the [T, T] matrix with the layout's T: a PSN built for another number of steps (window depth
+    clamped, num_steps != tensor's time extent) must fail like the reference's addmm shape error, not read out of bounds."""
+    T = lay["T"]
+    if tuple(weight.shape) != (T, T) or bias.numel() != T:
+        raise RuntimeError(f"PSN: weight {tuple(weight.shape)} / bias {tuple(bias.shape)} do not match the input's T={T}")
+
+
+def psn(u, weight, bias, cfg: NeuronCfg, time_dim=0, u8=False):
+    if not u8:
+        return _PSNFn.apply(u, weight, bias, cfg, time_dim, None)
+    holder = Spikes()
+    holder.token = _PSNFn.apply(u, weight, bias, cfg, time_dim, holder)
+    return holder
 
 
 class _BNNeuronFn(torch.autograd.Function):
@@ -243,41 +322,53 @@ class _BNNeuronFn(torch.autograd.Function):
     Spiking_swin_transformer3D.py:171-174 (bn1 -> sn2), :310-311, :933-934."""
 
     @staticmethod
-    def forward(ctx, u, weight, bias, bn, cfg, time_dim, psn_w, psn_b):
+    def forward(ctx, u, weight, bias, bn, cfg, time_dim, psn_w, psn_b, plif_w, partials, holder):
         _need_cuda(u)
         u = u.contiguous()
         C = u.shape[-1]
         rows = u.numel() // C
-        scale, shift, mean, rstd = _bn_forward_affine(u, rows, C, C, bn)
+        scale, shift, mean, rstd = _bn_forward_affine(u, rows, C, C, bn, partials)
         lay = seq_layout(u.shape, time_dim)
+        dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
         if psn_w is None:
-            cc = cfg.c()
-            spike, _, _ = _lif_fwd_raw(u, lay, cc, capi.SDF_SPIKE_F32, scale, shift, C, 1)
+            cc = cfg.c(plif_tau(plif_w) if cfg.kind == capi.SDF_NEURON_PLIF else None)
+            spike, _, _ = _lif_fwd_raw(u, lay, cc, dt, scale, shift, C, 1)
         else:
             cc = None
-            spike = torch.empty_like(u)
+            _check_psn(psn_w, psn_b, lay)
+            spike = torch.empty(u.shape, device=u.device, dtype=_SPIKE_TORCH[dt])
             capi.call("sdf_psn_fwd", capi.struct(
                 "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), weight=_ptr(psn_w), bias=_ptr(psn_b),
-                scale=_ptr(scale), shift=_ptr(shift), C=C, hw=1, lay=lay, spike_dtype=capi.SDF_SPIKE_F32,
-                stream=_stream()))
-        ctx.save_for_backward(u, weight, scale, shift, mean, rstd, psn_w, psn_b)
+                scale=_ptr(scale), shift=_ptr(shift), C=C, hw=1, lay=lay, spike_dtype=dt,
+                stream=_stream()), algo_bytes=u.numel() * (4 + spike.element_size()))
+        ctx.save_for_backward(u, weight, scale, shift, mean, rstd, psn_w, psn_b, plif_w)
         ctx.lay, ctx.cc, ctx.cfg, ctx.training, ctx.rows, ctx.C = lay, cc, cfg, bn.training, rows, C
+        ctx.holder = holder
+        if holder is not None:
+            holder.data = spike
+            return u.new_empty(())
         return spike
 
     @staticmethod
     def backward(ctx, gs):
-        u, weight, scale, shift, mean, rstd, psn_w, psn_b = ctx.saved_tensors
-        gs = gs.contiguous()
+        u, weight, scale, shift, mean, rstd, psn_w, psn_b, plif_w = ctx.saved_tensors
+        gs = gs.contiguous() if ctx.holder is None else ctx.holder.take_grad()
         rows, C = ctx.rows, ctx.C
         dev = u.device
         partials = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
         dx = torch.empty_like(u)
-        g_psn_w = g_psn_b = None
+        g_psn_w = g_psn_b = g_plif = None
         if psn_w is None:
+            plif_part = None
+            if ctx.cfg.kind == capi.SDF_NEURON_PLIF:
+                plif_part = torch.empty(N_PARTIAL, device=dev, dtype=torch.float32)
             capi.call("sdf_lif_bwd", capi.struct(
                 "sdf_lif_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=None, grad_x=_ptr(dx), scale=_ptr(scale),
-                shift=_ptr(shift), bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=ctx.lay,
-                neuron=ctx.cc, stream=_stream()), algo_bytes=12 * u.numel())
+                shift=_ptr(shift), bn_partials=_ptr(partials), plif_partials=_ptr(plif_part), n_partial_blocks=N_PARTIAL,
+                C=C, hw=1, lay=ctx.lay, neuron=ctx.cc, stream=_stream()), algo_bytes=12 * u.numel())
+            if plif_part is not None:
+                sg = torch.sigmoid(plif_w.detach())
+                g_plif = (plif_part.sum() * sg * (1 - sg)).reshape(plif_w.shape)
         else:
             T, n = ctx.lay["T"], ctx.lay["n_neurons"]
             gh = torch.empty((T, n), device=dev, dtype=torch.float32)
@@ -290,7 +381,7 @@ class _BNNeuronFn(torch.autograd.Function):
             g_psn_w = gh @ xo.t()
             g_psn_b = gh.sum(1, keepdim=True)
         du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, weight, mean, rstd, ctx.training)
-        return du.view(u.shape), gw, gb, None, None, None, g_psn_w, g_psn_b
+        return du.view(u.shape), gw, gb, None, None, None, g_psn_w, g_psn_b, g_plif, None, None
 
 
 def _seq_to_layout(seq, shape, lay):
@@ -302,24 +393,32 @@ def _seq_to_layout(seq, shape, lay):
     return seq.view(T, B, lay["inner"]).permute(1, 0, 2).contiguous().view(shape)
 
 
-def bn_neuron(u, bn_module, cfg: NeuronCfg, time_dim=0, psn=None):
+def bn_neuron(u, bn_module, cfg: NeuronCfg, time_dim=0, psn=None, plif_w=None, partials=None, u8=False):
     """neuron(BN(u)); u is channels-last [..., C]; BN statistics over all leading dims (the
-    spikingjelly multi-step BN flattens (T,B): SURVEY.md Appendix A)."""
+    spikingjelly multi-step BN flattens (T,B): SURVEY.md Appendix A).  partials: BN partial sums from the GEMM that
+    produced u (skips the statistics pass); u8: return a Spikes (1 byte per spike) for the spike GEMM."""
     bn = BNParams(bn_module)
     pw, pb = (psn.weight, psn.bias) if psn is not None else (None, None)
-    return _BNNeuronFn.apply(u, bn.weight, bn.bias, bn, cfg, time_dim, pw, pb)
+    if cfg.kind == capi.SDF_NEURON_PLIF and plif_w is None:
+        raise RuntimeError("bn_neuron: a ParametricLIFNode needs its parameter w (plif_w)")
+    holder = Spikes() if u8 else None
+    out = _BNNeuronFn.apply(u, bn.weight, bn.bias, bn, cfg, time_dim, pw, pb, plif_w, partials, holder)
+    if u8:
+        holder.token = out
+        return holder
+    return out
 
 
 class _BNResidualFn(torch.autograd.Function):
     """out = res + BN(u) on channels-last rows (MS MLP tail: Spiking_swin_transformer3D.py:176-178 + :845)."""
 
     @staticmethod
-    def forward(ctx, u, res, weight, bias, bn):
+    def forward(ctx, u, res, weight, bias, bn, partials=None):
         _need_cuda(u, res)
         u = u.contiguous()
         C = u.shape[-1]
         rows = u.numel() // C
-        scale, shift, mean, rstd = _bn_forward_affine(u, rows, C, C, bn)
+        scale, shift, mean, rstd = _bn_forward_affine(u, rows, C, C, bn, partials)
         out = torch.empty_like(u)
         if res is not None:
             res = res.contiguous()
@@ -340,12 +439,12 @@ class _BNResidualFn(torch.autograd.Function):
             "sdf_bn_bwd_reduce_args", dy=_ptr(go), u=_ptr(u), ld_u=C, rows=rows, C=C, partials=_ptr(partials),
             n_partial_blocks=N_PARTIAL, stream=_stream()))
         du, gw, gb = _bn_backward(partials, go, u, C, rows, C, weight, mean, rstd, ctx.training)
-        return du.view(u.shape), (go if ctx.has_res else None), gw, gb, None
+        return du.view(u.shape), (go if ctx.has_res else None), gw, gb, None, None
 
 
-def bn_residual(u, bn_module, res=None):
+def bn_residual(u, bn_module, res=None, partials=None):
     bn = BNParams(bn_module)
-    return _BNResidualFn.apply(u, res, bn.weight, bn.bias, bn)
+    return _BNResidualFn.apply(u, res, bn.weight, bn.bias, bn, partials)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -358,6 +457,13 @@ def bn_residual(u, bn_module, res=None):
 # reference trains under fp16 autocast, train_flow_parallel_supervised_SNN.py:248, so this is at
 # least as precise).  GEMM_MODE = "fp32" restores plain SIMT fp32 everywhere.
 GEMM_MODE = "tf32x2"
+# True: spike tensors between kernels are 1-byte Spikes and Linear / Conv on them run on the library's own tcgen05 + TMA
+# GEMM engine (csrc/spike_gemm.cu, csrc/spike_wgrad.cu); False: fp32 spikes through the cuBLAS / cuDNN TF32 x 2 path above.
+USE_SPIKE_GEMM = True
+
+
+def spike_gemm_on():
+    return USE_SPIKE_GEMM and GEMM_MODE != "fp32"
 
 
 def split_tf32(w):
@@ -424,9 +530,56 @@ class _PlainLinearFn(torch.autograd.Function):
     backward = _SpikeLinearFn.backward
 
 
-def spike_linear(s, weight, bias=None, exact_input=True):
+class _SpikeGemmFn(torch.autograd.Function):
+    """y = spikes @ W^T (+ b) on the tcgen05 engine: kind::i8 forward on the 1-byte spikes (gemm.spike_gemm_fwd, exact
+    integer accumulation of three weight digit planes, BN partial sums from the epilogue), TF32 data gradient
+    (gemm.gemm_tf32) and MN-major TF32 weight gradient (gemm.spike_wgrad).  Reference: sj_layer.Linear on spike tensors,
+    Spiking_swin_transformer3D.py:126-131,267-290,632-652,909."""
+
+    @staticmethod
+    def forward(ctx, token, weight, bias, holder, want_stats):
+        a = holder.data
+        K = a.shape[-1]
+        pw = gemm.pack_weight(weight, cache=getattr(weight, "_sdf_cacheable", None))
+        y, part = gemm.spike_gemm_fwd(a.view(-1, K), pw, None if bias is None else bias.detach(), want_stats)
+        ctx.save_for_backward(weight)
+        ctx.holder, ctx.has_bias = holder, bias is not None
+        y = y.view(*a.shape[:-1], weight.shape[0])
+        if part is not None:
+            ctx.mark_non_differentiable(part)
+        return y, part
+
+    @staticmethod
+    def backward(ctx, gy, _gp):
+        (weight,) = ctx.saved_tensors
+        holder = ctx.holder
+        a = holder.data
+        K = a.shape[-1]
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if g2.stride(1) != 1 or g2.stride(0) % 4 != 0 or g2.data_ptr() % 16 != 0:
+            g2 = g2.contiguous()
+        gtok = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            holder.add_grad(gemm.gemm_tf32(g2, weight.detach().t().contiguous()).view(a.shape))
+            gtok = _zero_token(gy.device)
+        if ctx.needs_input_grad[1]:
+            gw = gemm.spike_wgrad(g2, a.view(-1, K))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gtok, gw, gb, None, None
+
+
+def spike_linear(s, weight, bias=None, exact_input=True, stats=None):
     """F.linear(s, weight, bias) for a spike (or small-integer) operand s with fp32-grade results on
-    tensor cores; exact_input=False (real-valued s) keeps the plain fp32 forward GEMM."""
+    tensor cores; exact_input=False (real-valued s) keeps the plain fp32 forward GEMM.
+    s: a Spikes (1-byte spikes) runs on the library's own tcgen05 GEMM; an fp32 tensor goes through the TF32 x 2 library
+    path.  stats (bool, optional): when given the result is (y, partials) — the BN partial sums of y from the GEMM
+    epilogue if stats is True and the tcgen05 path ran, else None."""
+    if isinstance(s, Spikes):
+        y, part = _SpikeGemmFn.apply(s.token, weight, bias, s, bool(stats))
+        return y if stats is None else (y, part)
+    if stats is not None:
+        return spike_linear(s, weight, bias, exact_input), None
     if GEMM_MODE == "fp32":
         with _tf32(False):
             return torch.nn.functional.linear(s, weight, bias)
@@ -520,6 +673,66 @@ class _SmallCinConvFn(torch.autograd.Function):
 
 def conv3x3_small_cin(x, weight, bias=None):
     return _SmallCinConvFn.apply(x, weight, bias)
+
+
+class _SpikeConvGemmFn(torch.autograd.Function):
+    """NHWC convolution of 1-byte spikes as an implicit GEMM on the tcgen05 engine (gemm.spike_conv_fwd: per-tap TMA boxes,
+    zero padding = TMA out-of-bounds fill), weight gradient on the same engine (gemm.spike_conv_wgrad); the data gradient
+    is the library's (cuDNN, TF32).  Reference: sj_layer.Conv2d on spike tensors, Spiking_modules.py:268,318,803,845-846."""
+
+    @staticmethod
+    def forward(ctx, token, weight, bias, holder, stride, padding, want_stats):
+        x = holder.data                                   # (..., H, W, Cin) u8, leading dims = images
+        H, W, Cin = x.shape[-3:]
+        kh, kw = weight.shape[2], weight.shape[3]
+        pw = gemm.pack_weight(weight, "conv")
+        y, part = gemm.spike_conv_fwd(x.view(-1, H, W, Cin), pw, None if bias is None else bias.detach(), kh, kw, stride,
+                                      padding, want_stats)
+        ctx.save_for_backward(weight)
+        ctx.holder, ctx.cfg = holder, (stride, padding, bias is not None)
+        y = y.view(*x.shape[:-3], *y.shape[1:])
+        if part is not None:
+            ctx.mark_non_differentiable(part)
+        return y, part
+
+    @staticmethod
+    def backward(ctx, gy, _gp):
+        (weight,) = ctx.saved_tensors
+        stride, padding, has_bias = ctx.cfg
+        holder = ctx.holder
+        x = holder.data
+        H, W, Cin = x.shape[-3:]
+        kh, kw = weight.shape[2], weight.shape[3]
+        g4 = gy.contiguous().view(-1, *gy.shape[-3:])      # (Nimg, Ho, Wo, Cout) NHWC
+        gtok = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # input size only: the values of the input are irrelevant for the data gradient
+            fake = g4.new_empty(1).expand(g4.shape[0], Cin, H, W)
+            with _tf32(True):
+                gx = torch.ops.aten.convolution_backward(
+                    g4.permute(0, 3, 1, 2), fake, weight, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0], 1,
+                    [True, False, False])[0]
+            holder.add_grad(gx.permute(0, 2, 3, 1).contiguous().view(x.shape))
+            gtok = _zero_token(gy.device)
+        if ctx.needs_input_grad[1]:
+            gw = gemm.spike_conv_wgrad(g4, x.view(-1, H, W, Cin), kh, kw, stride, padding)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = g4.sum((0, 1, 2))
+        return gtok, gw, gb, None, None, None, None
+
+
+def spike_conv_supported(Cin, Cout, kernel_size, stride, padding):
+    """Geometries the tcgen05 implicit-GEMM convolution takes (everything the SNN conv stack uses except transposed
+    convolutions and the 2-channel heads)."""
+    kh, kw = kernel_size
+    return (Cin % 16 == 0 and Cout % 4 == 0 and kh * kw <= 9 and tuple(stride) in ((1, 1), (2, 2))
+            and padding[0] == padding[1] and (Cin <= 256 or Cin % 256 == 0))
+
+
+def spike_conv_gemm(s: "Spikes", weight, bias=None, stride=1, padding=0, stats=None):
+    """conv2d on a Spikes tensor (..., H, W, Cin) -> fp32 (..., Ho, Wo, Cout) channels-last; `stats` as in spike_linear."""
+    y, part = _SpikeConvGemmFn.apply(s.token, weight, bias, s, stride, padding, bool(stats))
+    return y if stats is None else (y, part)
 
 
 def spike_conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_padding=0, exact_input=True):
@@ -621,35 +834,45 @@ class _LifWindowFn(torch.autograd.Function):
     """proj_sn(x_windows) with the pad/roll/partition gather folded in (reference :670 / :425)."""
 
     @staticmethod
-    def forward(ctx, x, geom, cfg):
+    def forward(ctx, x, geom, cfg, holder=None):
         _need_cuda(x)
         x = x.contiguous()
         C = x.shape[-1]
         wd, wh, ww = geom.window
-        spike = torch.empty((wd, geom.M, wh, ww, C), device=x.device, dtype=torch.float32)
+        dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
+        spike = torch.empty((wd, geom.M, wh, ww, C), device=x.device, dtype=_SPIKE_TORCH[dt])
         cc = cfg.c()
         capi.call("sdf_lif_window_fwd", capi.struct(
             "sdf_lif_window_fwd_args", x=_ptr(x), spike=_ptr(spike), win2x=_ptr(geom.win2x), wd=wd,
-            MP=geom.M * geom.P, C=C, neuron=cc, spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()),
-            algo_bytes=4 * x.numel() + 4 * spike.numel())
+            MP=geom.M * geom.P, C=C, neuron=cc, spike_dtype=dt, stream=_stream()),
+            algo_bytes=4 * x.numel() + spike.element_size() * spike.numel())
         ctx.save_for_backward(x)
-        ctx.geom, ctx.cc = geom, cc
+        ctx.geom, ctx.cc, ctx.holder = geom, cc, holder
+        if holder is not None:
+            holder.data = spike
+            return x.new_empty(())
         return spike
 
     @staticmethod
     def backward(ctx, gs):
         (x,) = ctx.saved_tensors
-        gs = gs.contiguous()
+        gs = gs.contiguous() if ctx.holder is None else ctx.holder.take_grad()
         geom = ctx.geom
         gx = torch.empty_like(x)
         capi.call("sdf_lif_window_bwd", capi.struct(
             "sdf_lif_window_bwd_args", x=_ptr(x), grad_spike=_ptr(gs), grad_x=_ptr(gx), win2x=_ptr(geom.win2x),
             wd=geom.window[0], MP=geom.M * geom.P, C=x.shape[-1], neuron=ctx.cc, stream=_stream()))
-        return gx, None, None
+        return gx, None, None, None
 
 
-def lif_window(x, geom, cfg: NeuronCfg):
-    return _LifWindowFn.apply(x, geom, cfg)
+def lif_window(x, geom, cfg: NeuronCfg, u8=False):
+    if cfg.kind == capi.SDF_NEURON_PLIF:
+        raise NotImplementedError("lif_window: ParametricLIFNode is not fused here (use window_gather + neuron)")
+    if not u8:
+        return _LifWindowFn.apply(x, geom, cfg, None)
+    holder = Spikes()
+    holder.token = _LifWindowFn.apply(x, geom, cfg, holder)
+    return holder
 
 
 def lif_window_debug(x, geom, cfg: NeuronCfg):
@@ -669,7 +892,7 @@ class _WindowScatterFn(torch.autograd.Function):
     DropPath + residual (reference Spiking_swin_transformer3D.py:713-715, :810-820, :840)."""
 
     @staticmethod
-    def forward(ctx, y, res, weight, bias, bn, geom, alpha):
+    def forward(ctx, y, res, weight, bias, bn, geom, alpha, partials=None):
         _need_cuda(y, res)
         y = y.contiguous()
         C = y.shape[-1]
@@ -677,7 +900,7 @@ class _WindowScatterFn(torch.autograd.Function):
         assert y.numel() == rows * C
         scale = shift = mean = rstd = None
         if bn is not None:
-            scale, shift, mean, rstd = _bn_forward_affine(y, rows, C, C, bn)
+            scale, shift, mean, rstd = _bn_forward_affine(y, rows, C, C, bn, partials)
         out = torch.empty((geom.B, geom.D, geom.H, geom.W, C), device=y.device, dtype=torch.float32)
         if res is not None:
             res = res.contiguous()
@@ -705,14 +928,14 @@ class _WindowScatterFn(torch.autograd.Function):
         gw = gb = None
         if ctx.has_bn:
             dy, gw, gb = _bn_backward(partials, dy, y, C, rows, C, weight, mean, rstd, ctx.training)
-        return dy.view(y.shape), (go if ctx.has_res else None), gw, gb, None, None, None
+        return dy.view(y.shape), (go if ctx.has_res else None), gw, gb, None, None, None, None
 
 
-def window_scatter(y, geom, res=None, bn_module=None, alpha=None):
+def window_scatter(y, geom, res=None, bn_module=None, alpha=None, partials=None):
     bn = BNParams(bn_module) if bn_module is not None else None
     w = bn.weight if bn is not None else None
     b = bn.bias if bn is not None else None
-    return _WindowScatterFn.apply(y, res, w, b, bn, geom, alpha)
+    return _WindowScatterFn.apply(y, res, w, b, bn, geom, alpha, partials)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -723,34 +946,46 @@ class _LifMergeFn(torch.autograd.Function):
     plain 2x2 gather of SpikingPatchMerging (:919-930)."""
 
     @staticmethod
-    def forward(ctx, x, cfg, apply_neuron):
+    def forward(ctx, x, cfg, apply_neuron, holder=None):
         _need_cuda(x)
         x = x.contiguous()
         B, D, H, W, C = x.shape
         H2, W2 = (H + 1) // 2, (W + 1) // 2
-        out = torch.empty((B, D, H2, W2, 4 * C), device=x.device, dtype=torch.float32)
+        dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
+        out = torch.empty((B, D, H2, W2, 4 * C), device=x.device, dtype=_SPIKE_TORCH[dt])
         cc = cfg.c() if apply_neuron else NeuronCfg().c()
         capi.call("sdf_lif_merge_fwd", capi.struct(
             "sdf_lif_merge_fwd_args", x=_ptr(x), spike=_ptr(out), B=B, D=D, H=H, W=W, C=C, neuron=cc,
-            spike_dtype=capi.SDF_SPIKE_F32, apply_neuron=1 if apply_neuron else 0, stream=_stream()))
+            spike_dtype=dt, apply_neuron=1 if apply_neuron else 0, stream=_stream()))
         ctx.save_for_backward(x)
-        ctx.cc, ctx.apply_neuron = cc, apply_neuron
+        ctx.cc, ctx.apply_neuron, ctx.holder = cc, apply_neuron, holder
+        if holder is not None:
+            holder.data = out
+            return x.new_empty(())
         return out
 
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        g = g.contiguous()
+        g = g.contiguous() if ctx.holder is None else ctx.holder.take_grad()
         B, D, H, W, C = x.shape
         gx = torch.empty_like(x)
         capi.call("sdf_lif_merge_bwd", capi.struct(
             "sdf_lif_merge_bwd_args", x=_ptr(x), grad_spike=_ptr(g), grad_x=_ptr(gx), B=B, D=D, H=H, W=W, C=C,
             neuron=ctx.cc, apply_neuron=1 if ctx.apply_neuron else 0, stream=_stream()))
-        return gx, None, None
+        return gx, None, None, None
 
 
-def lif_merge(x, cfg: NeuronCfg, apply_neuron=True):
-    return _LifMergeFn.apply(x, cfg, apply_neuron)
+def lif_merge(x, cfg: NeuronCfg, apply_neuron=True, u8=False):
+    if apply_neuron and cfg.kind == capi.SDF_NEURON_PLIF:
+        raise NotImplementedError("lif_merge: ParametricLIFNode is not fused here (gather with apply_neuron=False + neuron)")
+    if not u8:
+        return _LifMergeFn.apply(x, cfg, apply_neuron, None)
+    if not apply_neuron:
+        raise ValueError("lif_merge(u8=True) needs apply_neuron=True (a plain gather of membranes is not a spike tensor)")
+    holder = Spikes()
+    holder.token = _LifMergeFn.apply(x, cfg, apply_neuron, holder)
+    return holder
 
 
 # ---------------------------------------------------------------------------------------------
@@ -761,24 +996,28 @@ class _QKGateFn(torch.autograd.Function):
     (reference Spiking_swin_transformer3D.py:671-710).  qk_pre: [wd*M*P, 2C] = [q_pre | k_pre]."""
 
     @staticmethod
-    def forward(ctx, qk_pre, wq, bq, wk, bk, pos, bn_q, bn_k, cfg, wd, M, P, nH):
+    def forward(ctx, qk_pre, wq, bq, wk, bk, pos, bn_q, bn_k, cfg, wd, M, P, nH, part_q=None, part_k=None, holder=None):
         _need_cuda(qk_pre, pos)
         qk_pre = qk_pre.contiguous()
         rows = wd * M * P
         C = nH * 32
         assert qk_pre.shape == (rows, 2 * C)
         q_pre, k_pre = qk_pre[:, :C], qk_pre[:, C:]
-        qs, qh, qm, qr = _bn_forward_affine(q_pre, rows, C, 2 * C, bn_q)
-        ks, kh, km, kr = _bn_forward_affine(k_pre, rows, C, 2 * C, bn_k)
+        qs, qh, qm, qr = _bn_forward_affine(q_pre, rows, C, 2 * C, bn_q, part_q)
+        ks, kh, km, kr = _bn_forward_affine(k_pre, rows, C, 2 * C, bn_k, part_k)
         posc = pos.detach().contiguous()
-        gate = torch.empty((rows, C), device=qk_pre.device, dtype=torch.float32)
+        dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
+        gate = torch.empty((rows, C), device=qk_pre.device, dtype=_SPIKE_TORCH[dt])
         cc = cfg.c()
         capi.call("sdf_attn_qkgate_fwd", capi.struct(
             "sdf_attn_qkgate_fwd_args", q_pre=_ptr(q_pre), k_pre=_ptr(k_pre), ld=2 * C, q_scale=_ptr(qs), q_shift=_ptr(qh),
             k_scale=_ptr(ks), k_shift=_ptr(kh), pos=_ptr(posc), gate=_ptr(gate), wd=wd, M=M, P=P, C=C, nH=nH,
-            neuron=cc, spike_dtype=capi.SDF_SPIKE_F32, stream=_stream()), algo_bytes=12 * rows * C)
+            neuron=cc, spike_dtype=dt, stream=_stream()), algo_bytes=(8 + gate.element_size()) * rows * C)
         ctx.save_for_backward(qk_pre, wq, wk, pos, qs, qh, qm, qr, ks, kh, km, kr)
-        ctx.dims, ctx.cc, ctx.tq, ctx.tk = (wd, M, P, C, nH), cc, bn_q.training, bn_k.training
+        ctx.dims, ctx.cc, ctx.tq, ctx.tk, ctx.holder = (wd, M, P, C, nH), cc, bn_q.training, bn_k.training, holder
+        if holder is not None:
+            holder.data = gate
+            return qk_pre.new_empty(())
         return gate
 
     @staticmethod
@@ -786,8 +1025,8 @@ class _QKGateFn(torch.autograd.Function):
         qk_pre, wq, wk, pos, qs, qh, qm, qr, ks, kh, km, kr = ctx.saved_tensors
         wd, M, P, C, nH = ctx.dims
         rows = wd * M * P
+        gg = gg.contiguous() if ctx.holder is None else ctx.holder.take_grad()
         dev = gg.device
-        gg = gg.contiguous()
         q_pre, k_pre = qk_pre[:, :C], qk_pre[:, C:]
         gq = torch.empty((rows, C), device=dev, dtype=torch.float32)
         gk = torch.empty_like(gq)
@@ -816,12 +1055,26 @@ class _QKGateFn(torch.autograd.Function):
                 "sdf_bn_bwd_apply_args", dy=_ptr(g), u=_ptr(u), ld_u=2 * C, du=_ptr(dqk[:, half * C:]), ld_du=2 * C,
                 coef=_ptr(coef), rows=rows, C=C, stream=_stream()))
             outs += [gw, gb]
-        return (dqk, outs[0], outs[1], outs[2], outs[3], gpos.view(pos.shape), None, None, None, None, None, None, None)
+        return (dqk, outs[0], outs[1], outs[2], outs[3], gpos.view(pos.shape), None, None, None, None, None, None, None,
+                None, None, None)
 
 
-def qkgate(qk_pre, bn_q_module, bn_k_module, pos, cfg: NeuronCfg, wd, M, P, nH):
+def qkgate(qk_pre, bn_q_module, bn_k_module, pos, cfg: NeuronCfg, wd, M, P, nH, partials=None, u8=False):
+    """partials: BN partial sums [N_PARTIAL, 2, 2C] of qk_pre = [q_pre | k_pre] from the GEMM epilogue; u8: gate spikes as
+    a Spikes for the proj GEMM."""
+    if cfg.kind == capi.SDF_NEURON_PLIF:
+        raise NotImplementedError("qkgate: ParametricLIFNode is not fused here (the module falls back to the generic path)")
     bq, bk = BNParams(bn_q_module), BNParams(bn_k_module)
-    return _QKGateFn.apply(qk_pre, bq.weight, bq.bias, bk.weight, bk.bias, pos, bq, bk, cfg, wd, M, P, nH)
+    C = nH * 32
+    pq = pk = None
+    if partials is not None:
+        pq, pk = partials[:, :, :C].contiguous(), partials[:, :, C:].contiguous()
+    holder = Spikes() if u8 else None
+    out = _QKGateFn.apply(qk_pre, bq.weight, bq.bias, bk.weight, bk.bias, pos, bq, bk, cfg, wd, M, P, nH, pq, pk, holder)
+    if u8:
+        holder.token = out
+        return holder
+    return out
 
 
 def qkgate_debug(q_pre, k_pre, q_scale, q_shift, k_scale, k_shift, pos, cfg, wd, M, P, nH):

@@ -101,3 +101,7 @@ class ParametricLIFNode(BaseNode):
 
     def _plif_w(self):
         return self.w
+
+    def _tau(self):
+        # the kernels take 1/k = 1/sigmoid(w) by value (one host read per parameter version)
+        return ops.plif_tau(self.w) if self.w.is_cuda else 1.0 / torch.sigmoid(self.w.detach()).item()
