@@ -565,6 +565,8 @@ typedef struct {
   const float* w;
   int8_t* wq;          /* out: sdf_spike_gemm_wq_bytes(Cout, Cin, taps) bytes, 16-byte aligned */
   float* wscale;       /* out: [Cout] */
+  float* wt;           /* optional out: fp32 transposed copy [Cin][taps*Cout], wt[ci][tap*Cout + co] = w(co, ci, tap): the B
+                          operand of sdf_gemm_tf32 / sdf_conv_dgrad_tf32 in the backward pass */
   int64_t wq_bytes;    /* capacity of wq */
   int64_t Cout, Cin, taps;
   int64_t s_co, s_ci, s_tap;
@@ -588,6 +590,8 @@ typedef struct {
   float* bn_partials;       /* optional */
   int64_t n_partial_blocks;
   int64_t rows, K, Cout, ld_out;
+  int64_t a_max;            /* largest operand value: 1 for spikes (enables the conversion-free epilogue when K*a_max < 32768);
+                               0 = unknown (any u8) */
   void* stream;
 } sdf_spike_gemm_fwd_args;
 
@@ -605,6 +609,7 @@ typedef struct {
   int64_t n_partial_blocks;
   int64_t Nimg, H, W, Cin, Cout, Ho, Wo;
   int64_t kh, kw, stride, pad;
+  int64_t a_max;            /* as in sdf_spike_gemm_fwd_args */
   void* stream;
 } sdf_spike_conv_fwd_args;
 
@@ -623,6 +628,20 @@ typedef struct {
 } sdf_gemm_tf32_args;
 
 int sdf_gemm_tf32(const sdf_gemm_tf32_args* a);
+
+/* Data gradient of a stride-1 NHWC convolution on tcgen05 (TF32): g fp32 (Nimg, Ho, Wo, Cout) -> out fp32 (Nimg, H, W, Cin).
+ * wd = the weight re-laid as [Cin][kh*kw*Cout] with wd[ci][(kh*KW+kw)*Cout + co] = W[co][ci][kh][kw].  Cout % 32 == 0.
+ * Replaces cuDNN's dgrad behind the autograd of sj_layer.Conv2d (Spiking_modules.py:845-846, the 3x3 res-block convs). */
+typedef struct {
+  const float* g;
+  const float* wd;
+  float* out;
+  int64_t Nimg, H, W, Cin, Cout, Ho, Wo;
+  int64_t kh, kw, pad;
+  void* stream;
+} sdf_conv_dgrad_tf32_args;
+
+int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a);
 
 /* ---- G3: weight gradient dW = G^T S of a Linear / convolution on a spike operand (csrc/spike_wgrad.cu) -------------
  * G fp32 [rows, Cout] (read as TF32), S u8 spikes [rows, K]; contraction over the rows on tcgen05 (both operands MN-major),

@@ -68,6 +68,7 @@ class Spiking_neuron(nn.Module):
 
     def mark(self):
         """Called by fused operators that run this neuron inside a kernel."""
+        ops.tap_site(self.__dict__.get("_tap_name"))
         if self._dirty and not self.is_psn:
             raise RuntimeError("Spiking_neuron called twice without functional.reset_net(model); the reference "
                                "scripts reset before every sample (train_flow_parallel_supervised_SNN.py:238)")
@@ -87,6 +88,7 @@ class Spiking_neuron(nn.Module):
         """u8=True: return ops.Spikes (1 byte per spike) for a consumer that runs on the tcgen05 spike GEMM."""
         u8 = u8 and ops.spike_gemm_on()
         if self.is_psn:
+            ops.tap_site(self.__dict__.get("_tap_name"))
             return ops.psn(x, self.spiking_neuron.weight, self.spiking_neuron.bias, self.cfg(), time_dim, u8=u8)
         if self.persist_state and time_dim == 0:
             if u8:

@@ -19,18 +19,21 @@
 // a 4-D TMA box of the NHWC input shifted by the tap offset — zero padding is the TMA out-of-bounds fill, stride 2 is the
 // tensor map's element stride; no im2col buffer and no padded copy (cuDNN's nhwcAddPaddingKernel) exist.
 //
-// Kernel anatomy (192 threads, one persistent CTA per SM, fixed N tile per CTA):
-//   warp 4      TMA producer: A (and B unless the weights stay resident in shared memory) chunks into a ring of stages
-//   warp 5      MMA issuer (one elected lane): 4 x tcgen05.mma per 128-byte K chunk, tcgen05.commit frees the stage;
+// Kernel anatomy (320 threads, one persistent CTA per SM, fixed N tile per CTA):
+//   warp 8      TMA producer: A (and B unless the weights stay resident in shared memory) chunks into a ring of stages
+//   warp 9      MMA issuer (one elected lane): 4 x tcgen05.mma per 128-byte K chunk, tcgen05.commit frees the stage;
 //               accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 0-3   epilogue: tcgen05.ld (lane quarter = warp id) -> combine/scale/bias -> swizzled smem -> TMA store; BN sums
+//   warps 0-7   epilogue: tcgen05.ld (lane quarter = warp % 4, 16-column chunks interleaved between the two warps of a
+//               quarter) -> combine/scale/bias -> swizzled smem -> TMA store.  BatchNorm sums stay in registers per
+//               (row, column) across all the tiles of the CTA and are reduced over the 128 rows once at the end.
 #include "sdf_common.cuh"
 #include "tc_ptx.cuh"
 
 namespace sdf {
 using namespace tc;
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;               // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kChunkBytes = 128;                 // K bytes per operand row per chunk: one SWIZZLE_128B span
 constexpr int kAChunk = kTileM * kChunkBytes;    // 16 KB
@@ -43,7 +46,7 @@ struct GemmP {
   int n_mtiles, n_ntiles, n_kchunks, n_groups;
   int nt, ncols, Cout, stages, b_resident, kc_elems;
   int out_bufs;                 // staging buffers of the epilogue (1 or 2)
-  int stat_splits;              // row splits of the per-tile column sums (threads = nt * stat_splits <= 128)
+  int fast_cvt;                 // i8: accumulators < 2^22 in magnitude (spike operands): int -> float by magic-number add
   const float* wscale;
   const float* bias;
   float* bn_partials;
@@ -111,12 +114,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (tid == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads / 32); }
     mbar_init(bres, 1);
     mbar_fence_init();
   }
-  if (warp == 4 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmO); }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == 8 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmO); }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   for (int i = tid; i < p.nt; i += kGemmThreads) {
     const int c = n0 + i;
     sc_s[i] = (KIND == KIND_I8 && c < p.Cout) ? __ldg(p.wscale + c) : 1.f;
@@ -128,7 +131,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===== TMA producer =====
     if (elect_one()) {
       if (p.b_resident) {
@@ -154,7 +157,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===== MMA issuer =====
     if (elect_one()) {
       const uint32_t idesc = KIND == KIND_I8 ? idesc_i8_u8s8(kTileM, p.ncols) : idesc_tf32(kTileM, p.ncols);
@@ -182,18 +185,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ===== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====
-    const int r = tid;                                   // tile row = TMEM lane
+    // ===== epilogue (warps 0-7: TMEM lanes 32*(warp%4) .., chunks cc with cc % 2 == warp / 4) =====
+    const int r = tid & 127;                             // tile row = TMEM lane
+    const int half = tid >> 7;                           // which of the two warps of this lane quarter
     const int n_sub = p.nt / 16;
     const uint32_t out_bytes = (uint32_t)kTileM * p.nt * 4;
-    // column-sum role of this thread: column scol, rows [srow0, srow1) of every tile
-    const int scol = tid % p.nt, ssplit = tid / p.nt;
-    const bool stat_thread = p.bn_partials != nullptr && ssplit < p.stat_splits;
-    const int rows_per_split = (kTileM + p.stat_splits - 1) / p.stat_splits;
-    const int srow0 = ssplit * rows_per_split, srow1 = min(kTileM, srow0 + rows_per_split);
-    const uint32_t scol_off = (uint32_t)(scol >> 4) * (kTileM * 64) + (scol & 3) * 4;
-    const int scol_j = (scol & 15) >> 2;
-    float sum = 0.f, sq = 0.f;
+    constexpr int kStatChunks = 2;                       // i8: nt <= 64 -> at most 2 chunks per thread
+    float ssum[kStatChunks][16], ssq[kStatChunks][16];   // BN sums of this thread's (row, column)s over all tiles
+#pragma unroll
+    for (int a = 0; a < kStatChunks; ++a)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { ssum[a][i] = 0.f; ssq[a][i] = 0.f; }
+    const bool want_stats = KIND == KIND_I8 && p.bn_partials != nullptr;
     uint32_t tile_i = 0;
     for (int m = group; m < p.n_mtiles; m += p.n_groups, ++tile_i) {
       const TileCoord t = tile_coord(p, m);
@@ -202,42 +205,72 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t out_base = smem_u32(out_s);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      // the TMA stores issued from this staging buffer two tiles ago must have finished reading it
+      // the TMA stores issued from this staging buffer (two tiles ago when double buffered) must have finished reading it
       if (tid == 0) { if (p.out_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
-      named_bar_sync(1, 128);
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + as * (uint32_t)p.ncols;
-      for (int cc = 0; cc < n_sub; ++cc) {
-        float y[16];
-        if (KIND == KIND_I8) {
-          uint32_t lo[16], mid[16], hi3[16];
-          tmem_ld16_nowait(trow + cc * 16, lo);
-          tmem_ld16_nowait(trow + p.nt + cc * 16, mid);
-          tmem_ld16_nowait(trow + 2 * p.nt + cc * 16, hi3);
-          tmem_ld_wait();
+      named_bar_sync(1, kEpiThreads);
+      const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + as * (uint32_t)p.ncols;
+      const bool valid = want_stats && row_valid(p, t, r);
+      const int x = (r >> 1) & 3;
+      auto store_chunk = [&](int cc, const float (&y)[16]) {
+        uint8_t* row = out_s + cc * (kTileM * 64) + r * 64;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const long long q = ((long long)(int)hi3[i] << 16) + ((long long)(int)mid[i] << 8) + (long long)(int)lo[i];
-            y[i] = __fadd_rn(__fmul_rn(__ll2float_rn(q), sc_s[cc * 16 + i]), sc_s[p.nt + cc * 16 + i]);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(row + ((j ^ x) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      };
+      if (KIND == KIND_I8) {
+#pragma unroll
+        for (int a = 0; a < kStatChunks; ++a) {
+          const int cc = half + 2 * a;
+          if (cc < n_sub) {
+            uint32_t lo[16], mid[16], hi3[16];
+            float y[16];
+            tmem_ld16_nowait(trow + cc * 16, lo);
+            tmem_ld16_nowait(trow + p.nt + cc * 16, mid);
+            tmem_ld16_nowait(trow + 2 * p.nt + cc * 16, hi3);
+            tmem_ld_wait();
+            if (p.fast_cvt) {
+              // |accumulator| < 2^22: float(x) = as_float(x + 0x4B400000) - 1.5*2^23, exact; then the three digit sums are
+              // combined hi*65536 + (mid*256 + lo): the inner sum is < 2^31 and rounds once, the outer fma once more
+              // (<= 1 ulp from the exact quantised dot product, a pure function of the integer triple: order independent)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float fl = __int_as_float((int)lo[i] + 0x4B400000) - 12582912.f;
+                const float fm = __int_as_float((int)mid[i] + 0x4B400000) - 12582912.f;
+                const float fh = __int_as_float((int)hi3[i] + 0x4B400000) - 12582912.f;
+                const float q = fmaf(fh, 65536.f, fmaf(fm, 256.f, fl));
+                y[i] = __fadd_rn(__fmul_rn(q, sc_s[cc * 16 + i]), sc_s[p.nt + cc * 16 + i]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const long long q = ((long long)(int)hi3[i] << 16) + ((long long)(int)mid[i] << 8) + (long long)(int)lo[i];
+                y[i] = __fadd_rn(__fmul_rn(__ll2float_rn(q), sc_s[cc * 16 + i]), sc_s[p.nt + cc * 16 + i]);
+              }
+            }
+            store_chunk(cc, y);
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { ssum[a][i] += y[i]; ssq[a][i] = fmaf(y[i], y[i], ssq[a][i]); }
+            }
           }
-        } else {
+        }
+      } else {
+        for (int cc = half; cc < n_sub; cc += 2) {
           uint32_t v[16];
+          float y[16];
           tmem_ld16_nowait(trow + cc * 16, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]) + sc_s[p.nt + cc * 16 + i];
+          store_chunk(cc, y);
         }
-        uint8_t* row = out_s + cc * (kTileM * 64) + r * 64;
-        const int x = (r >> 1) & 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(row + ((j ^ x) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
       }
       // accumulator stage free for the MMA warp
       tc_fence_before();
       __syncwarp();
       if (elect_one()) mbar_arrive(&tempty[as]);
       fence_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (tid == 0) {
         for (int cc = 0; cc < n_sub; ++cc) {
           if (n0 + cc * 16 >= p.Cout) break;
@@ -246,46 +279,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tma_store_commit();
       }
-      if (stat_thread) {
-        const uint8_t* col = out_s + scol_off;
-        const bool full_tile = p.conv ? (t.c2 + kPatchH <= p.Ho && t.c1 + kPatchW <= p.Wo) : ((int64_t)t.c1 + kTileM <= p.rows);
-        if (full_tile) {
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 4
-          for (int rr = srow0; rr < srow1; rr += 2) {    // rows_per_split is even whenever stat_splits divides 128
-            const float v0 = *reinterpret_cast<const float*>(col + rr * 64 + ((scol_j ^ ((rr >> 1) & 3)) << 4));
-            const float v1 = *reinterpret_cast<const float*>(col + (rr + 1) * 64 + ((scol_j ^ ((rr >> 1) & 3)) << 4));
-            s0 += v0; q0 = fmaf(v0, v0, q0);
-            s1 += v1; q1 = fmaf(v1, v1, q1);
-          }
-          sum += s0 + s1;
-          sq += q0 + q1;
-        } else {
-          for (int rr = srow0; rr < srow1; ++rr) {
-            if (!row_valid(p, t, rr)) continue;
-            const float v = *reinterpret_cast<const float*>(col + rr * 64 + ((scol_j ^ ((rr >> 1) & 3)) << 4));
-            sum += v;
-            sq = fmaf(v, v, sq);
-          }
-        }
-      }
     }
     if (tid == 0) tma_store_wait_all();
-    if (stat_thread && n0 + scol < p.Cout) {
-      const int prow = group * p.stat_splits + ssplit;
-      p.bn_partials[((int64_t)prow * 2 + 0) * p.Cout + n0 + scol] = sum;
-      p.bn_partials[((int64_t)prow * 2 + 1) * p.Cout + n0 + scol] = sq;
-      // zero-fill the unused partial rows (the caller's finalize reduces all n_partial_cap rows)
-      if (group == 0)
-        for (int g = p.n_groups * p.stat_splits + ssplit; g < p.n_partial_cap; g += p.stat_splits) {
-          p.bn_partials[((int64_t)g * 2 + 0) * p.Cout + n0 + scol] = 0.f;
-          p.bn_partials[((int64_t)g * 2 + 1) * p.Cout + n0 + scol] = 0.f;
+    if (want_stats) {
+      // reduce the per-(row, column) sums over the 128 rows: [column][row ^ (column & 31)] in the staging buffer, one
+      // statistic at a time (nt * 128 floats = one staging buffer)
+      float* st = reinterpret_cast<float*>(smem + sp.out);
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        named_bar_sync(1, kEpiThreads);
+#pragma unroll
+        for (int a = 0; a < kStatChunks; ++a) {
+          const int cc = half + 2 * a;
+          if (cc < n_sub) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = cc * 16 + i;
+              st[col * kTileM + (r ^ (col & 31))] = which == 0 ? ssum[a][i] : ssq[a][i];
+            }
+          }
         }
+        named_bar_sync(1, kEpiThreads);
+        if (tid < p.nt && n0 + tid < p.Cout) {
+          float acc = 0.f;
+          for (int rr = 0; rr < kTileM; ++rr) acc += st[tid * kTileM + (rr ^ (tid & 31))];
+          p.bn_partials[((int64_t)group * 2 + which) * p.Cout + n0 + tid] = acc;
+          // zero-fill the unused partial rows (the caller's finalize reduces all n_partial_cap rows)
+          if (group == 0)
+            for (int g = p.n_groups; g < p.n_partial_cap; ++g) p.bn_partials[((int64_t)g * 2 + which) * p.Cout + n0 + tid] = 0.f;
+        }
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+  if (warp == 9) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
 // ---- weight packing --------------------------------------------------------------------------------------------
@@ -295,6 +323,7 @@ struct PackP {
   const float* w;
   int8_t* wq;
   float* wscale;
+  float* wt;      // optional: fp32 transposed copy wt[ci][tap*Cout + co] (B operand of the data-gradient GEMMs)
   int Cout, Cin, taps, nt, n_ntiles, Kpad, cpt;
   int64_t s_co, s_ci, s_tap;
   int tap_map[kMaxTaps];
@@ -323,8 +352,11 @@ __global__ void pack_kernel(const PackP p) {
   for (int k = threadIdx.x; k < p.Kpad; k += blockDim.x) {
     const int tp = k / kpt, ci = k - tp * kpt;
     int q = 0;
-    if (co < p.Cout && ci < p.Cin && tp < p.taps)
-      q = __float2int_rn(__ldg(p.w + co * p.s_co + ci * p.s_ci + p.tap_map[tp] * p.s_tap) * qs);
+    if (co < p.Cout && ci < p.Cin && tp < p.taps) {
+      const float wv = __ldg(p.w + co * p.s_co + ci * p.s_ci + p.tap_map[tp] * p.s_tap);
+      q = __float2int_rn(wv * qs);
+      if (p.wt) p.wt[((int64_t)ci * p.taps + tp) * p.Cout + co] = wv;
+    }
     const int lo = ((q + 128) & 255) - 128;
     const int q1 = (q - lo) >> 8;
     const int mid = ((q1 + 128) & 255) - 128;
@@ -355,7 +387,7 @@ extern "C" int sdf_spike_gemm_pack(const sdf_spike_gemm_pack_args* a) {
   SDF_REQUIRE(a->w && a->wq && a->wscale, "spike_gemm_pack: null pointer");
   SDF_REQUIRE(a->taps >= 1 && a->taps <= kMaxTaps, "spike_gemm_pack: taps=%lld", (long long)a->taps);
   PackP p;
-  p.w = a->w; p.wq = a->wq; p.wscale = a->wscale;
+  p.w = a->w; p.wq = a->wq; p.wscale = a->wscale; p.wt = a->wt;
   p.Cout = (int)a->Cout; p.Cin = (int)a->Cin; p.taps = (int)a->taps;
   p.nt = pick_nt(p.Cout, 64);
   p.n_ntiles = (p.Cout + p.nt - 1) / p.nt;
@@ -386,12 +418,9 @@ static int launch_gemm(GemmP& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
   p.n_groups = sms / p.n_ntiles;
   if (p.n_groups > p.n_mtiles) p.n_groups = p.n_mtiles;
   if (p.n_groups < 1) p.n_groups = 1;
-  p.stat_splits = 1;
   if (p.bn_partials) {
     SDF_REQUIRE(p.n_partial_cap >= 1, "%s: n_partial_blocks must be >= 1", what);
     if (p.n_groups > p.n_partial_cap) p.n_groups = p.n_partial_cap;
-    // per-tile column sums: split the 128 rows over the idle epilogue threads (power of two so that halves stay even)
-    while (p.stat_splits * 2 * p.nt <= kTileM && p.n_groups * p.stat_splits * 2 <= p.n_partial_cap) p.stat_splits *= 2;
   }
   const uint32_t budget = 220 * 1024;
   const uint32_t bchunk = (uint32_t)p.ncols * kChunkBytes;
@@ -439,6 +468,7 @@ extern "C" int sdf_spike_gemm_fwd(const sdf_spike_gemm_fwd_args* a) {
   p.n_kchunks = (int)((a->K + kChunkBytes - 1) / kChunkBytes);
   p.kc_elems = kChunkBytes;
   p.wscale = a->wscale; p.bias = a->bias; p.bn_partials = a->bn_partials; p.n_partial_cap = (int)a->n_partial_blocks;
+  p.fast_cvt = (a->a_max > 0 && a->K * a->a_max < 32768) ? 1 : 0;
   const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
   CUtensorMap tmA, tmB, tmO;
   {
@@ -532,6 +562,7 @@ extern "C" int sdf_spike_conv_fwd(const sdf_spike_conv_fwd_args* a) {
   p.kc_elems = kChunkBytes;
   for (int i = 0; i < p.taps; ++i) { p.dh[i] = i / (int)a->kw - (int)a->pad; p.dw[i] = i % (int)a->kw - (int)a->pad; }
   p.wscale = a->wscale; p.bias = a->bias; p.bn_partials = a->bn_partials; p.n_partial_cap = (int)a->n_partial_blocks;
+  p.fast_cvt = (a->a_max > 0 && a->Cin * a->kh * a->kw * a->a_max < 32768) ? 1 : 0;
   const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
   CUtensorMap tmA, tmB, tmO;
   {
@@ -557,4 +588,57 @@ extern "C" int sdf_spike_conv_fwd(const sdf_spike_conv_fwd_args* a) {
     if (st) return st;
   }
   return launch_gemm<KIND_I8>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_spike_conv_fwd");
+}
+
+// Data gradient of a stride-1 NHWC convolution: dX[n,h,w,ci] = sum_{kh,kw,co} G[n, h+pad-kh, w+pad-kw, co] * W[co,ci,kh,kw],
+// the same implicit GEMM with G (fp32, read as TF32) as the tapped operand and the weights re-laid as
+// wd[ci][tap*Cout + co] (K-major rows; the caller permutes the parameter once per step).
+extern "C" int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a) {
+  SDF_REQUIRE(a->g && a->wd && a->out, "conv_dgrad_tf32: null pointer");
+  SDF_REQUIRE(a->Nimg > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "conv_dgrad_tf32: empty problem");
+  SDF_REQUIRE(a->Cout % 32 == 0, "conv_dgrad_tf32: Cout=%lld must be a multiple of 32 (one 128-byte K chunk)", (long long)a->Cout);
+  SDF_REQUIRE(a->Cin % 4 == 0, "conv_dgrad_tf32: Cin must be a multiple of 4");
+  SDF_REQUIRE(a->kh * a->kw >= 1 && a->kh * a->kw <= kMaxTaps, "conv_dgrad_tf32: kernel size unsupported");
+  SDF_REQUIRE(a->Ho == a->H + 2 * a->pad - a->kh + 1 && a->Wo == a->W + 2 * a->pad - a->kw + 1, "conv_dgrad_tf32: stride-1 geometry expected");
+  SDF_REQUIRE(aligned16(a->g) && aligned16(a->wd) && aligned16(a->out), "conv_dgrad_tf32: pointers must be 16-byte aligned");
+  GemmP p{};
+  p.conv = 1;
+  p.nt = pick_nt((int)a->Cin, 128);
+  p.n_ntiles = ((int)a->Cin + p.nt - 1) / p.nt;
+  p.ncols = p.nt;
+  p.Cout = (int)a->Cin;                         // GEMM N = input channels
+  p.Ho = (int)a->H; p.Wo = (int)a->W;           // the output of this GEMM is the input image
+  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
+  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
+  p.n_mtiles = (int)a->Nimg * p.tiles_h * p.tiles_w;
+  p.stride = 1;
+  p.taps = (int)(a->kh * a->kw);
+  p.cpt = (int)(a->Cout / 32);
+  p.n_kchunks = p.taps * p.cpt;
+  p.kc_elems = 32;
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = (int)a->pad - i / (int)a->kw; p.dw[i] = (int)a->pad - i % (int)a->kw; }
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->Wo * a->Cout * 4, (uint64_t)a->Ho * a->Wo * a->Cout * 4};
+    const uint32_t box[4] = {32, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    int st = make_tmap(&tmA, 1, 4, a->g, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t K = (uint64_t)p.taps * a->Cout;
+    const uint64_t dims[2] = {K, (uint64_t)a->Cin};
+    const uint64_t str[1] = {K * 4};
+    const uint32_t box[2] = {32, (uint32_t)p.nt};
+    int st = make_tmap(&tmB, 1, 2, a->wd, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)a->Cin * 4, (uint64_t)a->W * a->Cin * 4, (uint64_t)a->H * a->W * a->Cin * 4};
+    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    int st = make_tmap(&tmO, 1, 4, a->out, dims, str, box, nullptr, 64);
+    if (st) return st;
+  }
+  return launch_gemm<KIND_TF32>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_conv_dgrad_tf32");
 }

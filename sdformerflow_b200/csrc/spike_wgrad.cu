@@ -15,17 +15,20 @@
 //       convolution padding); four converter warps expand them to fp32 {0,1} in the same MN-major layout (exact in TF32).
 // One CTA = one (128-channel M tile, <= 256-column N tile, pixel slab); partial tiles go to a workspace and a second kernel
 // reduces the slabs in a fixed order (deterministic) into the parameter's own layout (Linear [Cout,K], Conv OIHW).
+#include <cstdlib>
 #include "sdf_common.cuh"
 #include "tc_ptx.cuh"
 
 namespace sdf {
 using namespace tc;
 
-constexpr int kWgThreads = 192;      // warps 0-3: converters, then epilogue; warp 4: TMA producer; warp 5: MMA issuer
+constexpr int kWgThreads = 320;      // warps 0-7: converters, then epilogue (warps 0-3); warp 8: TMA producer; warp 9: MMA issuer
+constexpr int kWgConv = 256;         // converter threads
 constexpr int kWgRB = 32;            // pixels (GEMM K) per pipeline stage
 constexpr int kWgM = 128;            // output channels per tile
-constexpr int kWgMaxN = 256;         // columns per tile
-constexpr int kWgStages = 3;
+constexpr int kWgMaxN = 384;         // columns per tile (TMEM columns of the accumulator; issued as <= 2 MMAs of N <= 256)
+constexpr int kWgMaxStages = 8;      // TMA ring (G tile + raw spike bytes): deep, the L2/HBM round trip is ~2 us under load
+constexpr int kWgBSlots = 2;         // converted-B ring
 constexpr int kWgPatchW = 16, kWgPatchH = 2;
 
 struct WgradP {
@@ -33,24 +36,31 @@ struct WgradP {
   int chunks_per_slab, n_slabs;
   int n_mtiles, n_ntiles;
   int Cout, Cin;
-  int taps_per_tile;       // Cin <= 256: taps grouped per tile (all Cin channels each)
-  int ci_tiles;            // Cin > 256: 256-wide channel slices per tap (taps_per_tile = 1)
+  int taps_per_tile;       // Cin <= kWgMaxN: taps grouped per tile (all Cin channels each)
+  int ci_tiles;            // Cin > kWgMaxN: channel slices per tap (taps_per_tile = 1)
+  int ci_width;            // width of a channel slice (multiple of 32)
   int taps;
   int ncols_total;         // taps * Cin: row length of the partial tiles
-  int box_w;               // channels per spike TMA box = row pitch of the raw staging tile (min(Cin, 256))
+  int box_w, nbox;         // spike TMA boxes: nbox boxes of box_w (<= 256) channels per tap slice; box_w = staging row pitch
+  int max_cols;            // widest tile of this launch (sizes the shared-memory plan)
+  int stages;              // TMA ring depth
   int conv, tiles_h, tiles_w, stride;
   int dh[9], dw[9];
   float* partial;          // [n_slabs][Cout][ncols_total]
+  int debug;               // timing experiments (SDF_WGRAD_DEBUG): 1 skip conversion, 2 also skip MMA, 3 MMA only (no TMA)
 };
 
-struct WgSmem { uint32_t a, stg, b, bars, tmem_slot, total; };
-__host__ __device__ inline WgSmem wg_smem_plan() {
+struct WgSmem { uint32_t a, stg, b, bars, tmem_slot, a_stage, b_slot, stg_stage, total; };
+__host__ __device__ inline WgSmem wg_smem_plan(int max_cols, int stages) {
   WgSmem s;
   uint32_t o = 0;
-  s.a = o; o += kWgStages * (kWgM * kWgRB * 4);            // 16 KB per stage
-  s.b = o; o += kWgStages * (kWgMaxN * kWgRB * 4);         // 32 KB per stage
-  s.stg = o; o += kWgStages * (kWgMaxN * kWgRB);           // 8 KB per stage
-  s.bars = o; o += (3 * kWgStages + 1) * 8;
+  s.a_stage = kWgM * kWgRB * 4;                            // 16 KB
+  s.b_slot = (uint32_t)((max_cols + 31) / 32) * (kWgRB * 128);   // fp32 B in whole 32-column MN blocks, <= 48 KB
+  s.stg_stage = ((uint32_t)max_cols * kWgRB + 1023) / 1024 * 1024;
+  s.a = o; o += stages * s.a_stage;
+  s.b = o; o += kWgBSlots * s.b_slot;
+  s.stg = o; o += stages * s.stg_stage;
+  s.bars = o; o += (2 * kWgMaxStages + 2 * kWgBSlots + 1) * 8;
   s.tmem_slot = o; o += 16;
   s.total = o;
   return s;
@@ -59,12 +69,14 @@ __host__ __device__ inline WgSmem wg_smem_plan() {
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS, const WgradP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const WgSmem sp = wg_smem_plan();
+  const WgSmem sp = wg_smem_plan(p.max_cols, p.stages);
+  const int kWgStages = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
-  uint64_t* full_tma = bars;                    // TMA landed (A + raw spike bytes)
-  uint64_t* full_b = bars + kWgStages;          // converters finished B
-  uint64_t* empty = bars + 2 * kWgStages;       // MMAs of the stage retired
-  uint64_t* done = bars + 3 * kWgStages;        // accumulator complete
+  uint64_t* full_tma = bars;                                   // TMA landed (A + raw spike bytes)            [stages]
+  uint64_t* empty = bars + kWgMaxStages;                       // MMAs reading A of the stage retired         [stages]
+  uint64_t* full_b = bars + 2 * kWgMaxStages;                  // converters finished a B slot                [kWgBSlots]
+  uint64_t* empty_b = bars + 2 * kWgMaxStages + kWgBSlots;     // MMAs reading the B slot retired             [kWgBSlots]
+  uint64_t* done = bars + 2 * kWgMaxStages + 2 * kWgBSlots;    // accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_slot);
   const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -75,44 +87,50 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   int tap0, ntap, ci0, width;                   // this tile's columns: taps [tap0, tap0+ntap) x channels [ci0, ci0+width)
   if (p.ci_tiles > 1) {
     tap0 = n_tile / p.ci_tiles; ntap = 1;
-    ci0 = (n_tile % p.ci_tiles) * kWgMaxN;
-    width = min(kWgMaxN, p.Cin - ci0);
+    ci0 = (n_tile % p.ci_tiles) * p.ci_width;
+    width = min(p.ci_width, p.Cin - ci0);
   } else {
     tap0 = n_tile * p.taps_per_tile; ntap = min(p.taps_per_tile, p.taps - tap0);
     ci0 = 0; width = p.Cin;
   }
-  const int ncols = ntap * width;               // multiple of 16 (host-checked)
+  const int ncols = ntap * width;               // multiple of 16 (host-checked), <= kWgMaxN
+  // <= 2 MMAs per K step: N0 + N1 = ncols, both multiples of 16 and <= 256, N0 a multiple of 32 (whole MN blocks)
+  const int N0 = ncols <= 256 ? ncols : ((ncols / 2 + 31) / 32) * 32;
+  const int N1 = ncols - N0;
   const int c_begin = slab * p.chunks_per_slab;
   const int c_end = min(p.n_chunks, c_begin + p.chunks_per_slab);
   const int n_iter = c_end - c_begin;
 
   if (tid == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_tma[i], 1); mbar_init(&full_b[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_tma[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWgBSlots; ++i) { mbar_init(&full_b[i], kWgConv / 32); mbar_init(&empty_b[i], 1); }
     mbar_init(done, 1);
     mbar_fence_init();
   }
-  if (warp == 4 && elect_one()) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmS); }
-  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  if (warp == 8 && elect_one()) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmS); }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b), stg_base = smem_u32(smem + sp.stg);
-  constexpr uint32_t kAStage = kWgM * kWgRB * 4, kBStage = kWgMaxN * kWgRB * 4, kStgStage = kWgMaxN * kWgRB;
+  const uint32_t kAStage = sp.a_stage, kBSlot = sp.b_slot, kStgStage = sp.stg_stage;
   constexpr uint32_t kBlk = kWgRB * 128;        // one 32-column MN block: 32 pixel rows x 128 B
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       const int per_img = p.tiles_h * p.tiles_w;
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kWgStages;
         const uint32_t ph = (it / kWgStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full_tma[s], kAStage + (uint32_t)(ntap * p.box_w * kWgRB));
+        if (p.debug == 3) { mbar_arrive(&full_tma[s]); continue; }
+        mbar_expect_tx(&full_tma[s], kAStage + (uint32_t)(ntap * p.nbox * p.box_w * kWgRB));
         const int chunk = c_begin + it;
         if (!p.conv) {
           for (int mb = 0; mb < 4; ++mb) tma_load_2d(&tmG, &full_tma[s], a_base + s * kAStage + mb * kBlk, m_tile * kWgM + mb * 32, chunk * kWgRB);
-          tma_load_2d(&tmS, &full_tma[s], stg_base + s * kStgStage, ci0, chunk * kWgRB);
+          for (int j = 0; j < p.nbox; ++j)
+            tma_load_2d(&tmS, &full_tma[s], stg_base + s * kStgStage + j * (p.box_w * kWgRB), ci0 + j * p.box_w, chunk * kWgRB);
         } else {
           const int img = chunk / per_img, rem = chunk - img * per_img;
           const int py = rem / p.tiles_w, px = rem - py * p.tiles_w;
@@ -120,50 +138,58 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
           for (int mb = 0; mb < 4; ++mb)
             tma_load_4d(&tmG, &full_tma[s], a_base + s * kAStage + mb * kBlk, m_tile * kWgM + mb * 32, w0, h0, img);
           for (int t = 0; t < ntap; ++t)
-            tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage + t * (p.box_w * kWgRB), ci0, w0 * p.stride + p.dw[tap0 + t],
-                        h0 * p.stride + p.dh[tap0 + t], img);
+            for (int j = 0; j < p.nbox; ++j)
+              tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage + (t * p.nbox + j) * (p.box_w * kWgRB), ci0 + j * p.box_w,
+                          w0 * p.stride + p.dw[tap0 + t], h0 * p.stride + p.dh[tap0 + t], img);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
-      const uint32_t idesc = idesc_tf32(kWgM, ncols, 1, 1);
+      const uint32_t idesc0 = idesc_tf32(kWgM, N0, 1, 1);
+      const uint32_t idesc1 = idesc_tf32(kWgM, N1 > 0 ? N1 : 16, 1, 1);
       constexpr uint32_t hi = desc_hi_sw128_base32(512);
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kWgStages;
-        const uint32_t ph = (it / kWgStages) & 1;
+        const int s = it % kWgStages, bs = it % kWgBSlots;
+        const uint32_t ph = (it / kWgStages) & 1, bph = (it / kWgBSlots) & 1;
         mbar_wait(&full_tma[s], ph);
-        mbar_wait(&full_b[s], ph);
+        mbar_wait(&full_b[bs], bph);
         tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < kWgRB / 8; ++g) {   // one MMA per 8 pixels (K = 8 for TF32): the 8-row group is 1024 B further
+        for (int g = 0; g < kWgRB / 8; ++g) {   // one MMA (pair) per 8 pixels (K = 8 for TF32): the 8-row group is 1024 B further
           const uint32_t a_lo = desc_lo(a_base + s * kAStage + g * 1024, kBlk);
-          const uint32_t b_lo = desc_lo(b_base + s * kBStage + g * 1024, kBlk);
-          mma_ss<KIND_TF32>(tmem_base, a_lo, b_lo, hi, idesc, (it | g) != 0 ? 1u : 0u);
+          const uint32_t b_lo = desc_lo(b_base + bs * kBSlot + g * 1024, kBlk);
+          if (p.debug != 2) {
+            mma_ss<KIND_TF32>(tmem_base, a_lo, b_lo, hi, idesc0, (it | g) != 0 ? 1u : 0u);
+            if (N1 > 0) mma_ss<KIND_TF32>(tmem_base + N0, a_lo, b_lo + (uint32_t)(N0 / 32) * (kBlk >> 4), hi, idesc1, (it | g) != 0 ? 1u : 0u);
+          }
         }
         tc_commit(&empty[s]);
+        tc_commit(&empty_b[bs]);
       }
       tc_commit(done);
     }
   } else {
     // ===== converters: raw spike bytes -> fp32 {0,1} in the MN-major SWIZZLE_128B (32-byte atom) layout =====
     // Thread -> (fixed 4-spike word q of the tile row, row sub-phase): no divisions inside the loop.
-    const int q_per_row = ncols >> 2;           // u32 words (4 spikes) per pixel row, <= 64
-    const int rows_par = 128 / q_per_row;       // pixel rows converted in parallel (>= 2)
+    const int q_per_row = ncols >> 2;           // u32 words (4 spikes) per pixel row, <= 96
+    const int rows_par = kWgConv / q_per_row;   // pixel rows converted in parallel (>= 2)
     const int q = tid % q_per_row, rsub = tid / q_per_row;
     const int wq4 = width >> 2;
     const int tq = q / wq4, qc = q - tq * wq4;  // tap-local index, word within the tap's channels
-    const uint32_t src_off = (uint32_t)(tq * (p.box_w * kWgRB) + qc * 4);
+    const int ch = qc * 4, bj = ch / p.box_w;   // channel within the tap slice -> (spike box, offset in the box row)
+    const uint32_t src_off = (uint32_t)((tq * p.nbox + bj) * (p.box_w * kWgRB) + (ch - bj * p.box_w));
     const int nb = q >> 3, c = q & 7;
     const uint32_t dst_blk = (uint32_t)nb * kBlk;
     const bool conv_thread = rsub < rows_par;
     for (int it = 0; it < n_iter; ++it) {
-      const int s = it % kWgStages;
-      const uint32_t ph = (it / kWgStages) & 1;
+      const int s = it % kWgStages, bs = it % kWgBSlots;
+      const uint32_t ph = (it / kWgStages) & 1, bph = (it / kWgBSlots) & 1;
+      mbar_wait(&empty_b[bs], bph ^ 1);         // the MMAs that read this B slot two iterations ago have retired
       mbar_wait(&full_tma[s], ph);
       const uint8_t* stg = smem + sp.stg + s * kStgStage + src_off;
-      uint8_t* bdst = smem + sp.b + s * kBStage + dst_blk;
-      if (conv_thread) {
+      uint8_t* bdst = smem + sp.b + bs * kBSlot + dst_blk;
+      if (conv_thread && p.debug == 0) {
 #pragma unroll 4
         for (int r = rsub; r < kWgRB; r += rows_par) {
           const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + r * p.box_w);
@@ -177,32 +203,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       }
       fence_async_smem();
       __syncwarp();
-      if (elect_one()) mbar_arrive(&full_b[s]);
+      if (elect_one()) mbar_arrive(&full_b[bs]);
     }
-    // ===== epilogue: TMEM -> this slab's partial tile =====
-    mbar_wait(done, 0);
-    tc_fence_after();
-    const int co = m_tile * kWgM + tid;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float* dst = p.partial + ((int64_t)slab * p.Cout + co) * p.ncols_total + (int64_t)tap0 * p.Cin + ci0;
-    for (int cc = 0; cc < ncols; cc += 16) {
-      uint32_t v[16];
-      tmem_ld16_nowait(trow + cc, v);
-      tmem_ld_wait();
-      if (co < p.Cout) {
-        // columns of a tile are (tap-local, channel) pairs: tap t's channels sit Cin apart in the partial row
-        const int t = cc / width, c = cc - t * width;
-        float* d = dst + (int64_t)t * p.Cin + c;
+    // ===== epilogue (warps 0-3): TMEM -> this slab's partial tile =====
+    if (warp < 4) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int co = m_tile * kWgM + tid;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      float* dst = p.partial + ((int64_t)slab * p.Cout + co) * p.ncols_total + (int64_t)tap0 * p.Cin + ci0;
+      for (int cc = 0; cc < ncols; cc += 16) {
+        uint32_t v[16];
+        tmem_ld16_nowait(trow + cc, v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          // columns of a tile are (tap-local, channel) pairs: tap t's channels sit Cin apart in the partial row
+          const int t = cc / width, cch = cc - t * width;
+          float* d = dst + (int64_t)t * p.Cin + cch;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(d + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(d + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
+  if (warp == 9) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
 // dW[co*s_co + ci*s_ci + tap*s_tap] (+)= sum_s partial[s][co][tap*Cin + ci], slabs added in index order
@@ -224,15 +252,20 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 using namespace sdf;
 
-static int wgrad_tiles(int Cin, int taps, int* taps_per_tile, int* ci_tiles, int* n_ntiles) {
+// N tiling: whole taps grouped up to kWgMaxN columns (balanced), or — for wide layers — channel slices of a tap
+static int wgrad_tiles(int Cin, int taps, int* taps_per_tile, int* ci_tiles, int* ci_width, int* n_ntiles) {
   if (Cin <= kWgMaxN) {
-    *taps_per_tile = kWgMaxN / Cin;
-    if (*taps_per_tile > taps) *taps_per_tile = taps;
+    const int max_tpt = kWgMaxN / Cin;
+    const int tiles = (taps + max_tpt - 1) / max_tpt;
+    *taps_per_tile = (taps + tiles - 1) / tiles;
     *ci_tiles = 1;
+    *ci_width = Cin;
     *n_ntiles = (taps + *taps_per_tile - 1) / *taps_per_tile;
   } else {
     *taps_per_tile = 1;
     *ci_tiles = (Cin + kWgMaxN - 1) / kWgMaxN;
+    *ci_width = ((Cin + *ci_tiles - 1) / *ci_tiles + 31) / 32 * 32;    // balanced slices, whole 32-column blocks
+    *ci_tiles = (Cin + *ci_width - 1) / *ci_width;
     *n_ntiles = taps * *ci_tiles;
   }
   return 0;
@@ -253,22 +286,33 @@ static void wgrad_slabs(WgradP& p) {
 extern "C" int64_t sdf_spike_wgrad_workspace_bytes(int64_t rows_or_pixels, int64_t Cout, int64_t Cin, int64_t taps) {
   WgradP p{};
   p.n_mtiles = (int)((Cout + kWgM - 1) / kWgM);
-  wgrad_tiles((int)Cin, (int)taps, &p.taps_per_tile, &p.ci_tiles, &p.n_ntiles);
+  wgrad_tiles((int)Cin, (int)taps, &p.taps_per_tile, &p.ci_tiles, &p.ci_width, &p.n_ntiles);
   p.n_chunks = (int)((rows_or_pixels + kWgRB - 1) / kWgRB);   // conv callers pass whole 2 x 16 patches
   wgrad_slabs(p);
   const int64_t slabs = p.n_slabs;
   return slabs * Cout * taps * Cin * 4;
 }
 
+static int wgrad_debug_mode() {
+  static int m = [] { const char* e = getenv("SDF_WGRAD_DEBUG"); return e ? atoi(e) : 0; }();
+  return m;
+}
+
 static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tmS, float* dw, int64_t s_co, int64_t s_ci,
                         int64_t s_tap, int accumulate, int64_t ws_bytes, cudaStream_t st, const char* what) {
   wgrad_slabs(p);
+  p.debug = wgrad_debug_mode();
   SDF_REQUIRE((int64_t)p.n_slabs * p.Cout * p.ncols_total * 4 <= ws_bytes, "%s: workspace too small (%lld needed)", what,
               (long long)p.n_slabs * p.Cout * p.ncols_total * 4);
+  p.max_cols = p.ci_tiles > 1 ? p.ci_width : p.taps_per_tile * p.Cin;
+  SDF_REQUIRE(p.max_cols % 16 == 0 && p.max_cols <= kWgMaxN && p.box_w % 16 == 0, "%s: unsupported column tiling (%d columns, box %d)", what, p.max_cols, p.box_w);
+  p.stages = 2;
+  for (int st_ = kWgMaxStages; st_ >= 2; --st_)
+    if (wg_smem_plan(p.max_cols, st_).total <= 220 * 1024) { p.stages = st_; break; }
   static bool attr_done = false;
-  const WgSmem sp = wg_smem_plan();
+  const WgSmem sp = wg_smem_plan(p.max_cols, p.stages);
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return SDF_ERR_CUDA; }
     attr_done = true;
   }
@@ -289,10 +333,11 @@ extern "C" int sdf_spike_wgrad(const sdf_spike_wgrad_args* a) {
   WgradP p{};
   p.Cout = (int)a->Cout; p.Cin = (int)a->K; p.taps = 1; p.ncols_total = (int)a->K;
   p.n_mtiles = (p.Cout + kWgM - 1) / kWgM;
-  wgrad_tiles(p.Cin, 1, &p.taps_per_tile, &p.ci_tiles, &p.n_ntiles);
+  wgrad_tiles(p.Cin, 1, &p.taps_per_tile, &p.ci_tiles, &p.ci_width, &p.n_ntiles);
   p.n_chunks = (int)((a->rows + kWgRB - 1) / kWgRB);
   p.partial = a->workspace;
-  p.box_w = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+  p.nbox = p.ci_width > 256 ? 2 : 1;
+  p.box_w = p.ci_width / p.nbox;
   CUtensorMap tmG, tmS;
   {
     const uint64_t dims[2] = {(uint64_t)a->Cout, (uint64_t)a->rows};
@@ -302,7 +347,7 @@ extern "C" int sdf_spike_wgrad(const sdf_spike_wgrad_args* a) {
     if (st) return st;
   }
   {
-    const int width = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+    const int width = p.box_w;
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->rows};
     const uint64_t str[1] = {(uint64_t)a->K};
     const uint32_t box[2] = {(uint32_t)width, (uint32_t)kWgRB};
@@ -317,20 +362,20 @@ extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
   SDF_REQUIRE(a->Cin % 16 == 0 && a->Cout % 4 == 0, "spike_conv_wgrad: Cin %% 16 and Cout %% 4 must be 0");
   SDF_REQUIRE(a->stride == 1 || a->stride == 2, "spike_conv_wgrad: stride must be 1 or 2");
   SDF_REQUIRE(a->kh * a->kw >= 1 && a->kh * a->kw <= 9, "spike_conv_wgrad: kernel size unsupported");
-  SDF_REQUIRE(a->Cin <= kWgMaxN || a->Cin % kWgMaxN == 0, "spike_conv_wgrad: Cin > 256 must be a multiple of 256");
   SDF_REQUIRE(aligned16(a->g) && aligned16(a->x) && aligned16(a->workspace), "spike_conv_wgrad: pointers must be 16-byte aligned");
   WgradP p{};
   p.conv = 1;
   p.Cout = (int)a->Cout; p.Cin = (int)a->Cin; p.taps = (int)(a->kh * a->kw); p.ncols_total = p.taps * p.Cin;
   p.n_mtiles = (p.Cout + kWgM - 1) / kWgM;
-  wgrad_tiles(p.Cin, p.taps, &p.taps_per_tile, &p.ci_tiles, &p.n_ntiles);
+  wgrad_tiles(p.Cin, p.taps, &p.taps_per_tile, &p.ci_tiles, &p.ci_width, &p.n_ntiles);
   p.tiles_h = (int)((a->Ho + kWgPatchH - 1) / kWgPatchH);
   p.tiles_w = (int)((a->Wo + kWgPatchW - 1) / kWgPatchW);
   p.n_chunks = (int)a->Nimg * p.tiles_h * p.tiles_w;
   p.stride = (int)a->stride;
   for (int i = 0; i < p.taps; ++i) { p.dh[i] = i / (int)a->kw - (int)a->pad; p.dw[i] = i % (int)a->kw - (int)a->pad; }
   p.partial = a->workspace;
-  p.box_w = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+  p.nbox = p.ci_width > 256 ? 2 : 1;
+  p.box_w = p.ci_width / p.nbox;
   CUtensorMap tmG, tmS;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
@@ -340,7 +385,7 @@ extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
     if (st) return st;
   }
   {
-    const int width = p.Cin <= kWgMaxN ? p.Cin : kWgMaxN;
+    const int width = p.box_w;
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
     const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
     const uint32_t box[4] = {(uint32_t)width, (uint32_t)(kWgPatchW * a->stride), (uint32_t)(kWgPatchH * a->stride), 1};

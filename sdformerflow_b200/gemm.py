@@ -21,16 +21,16 @@ def _stream():
 
 class PackedWeight:
     """Digit planes + scales of one Linear / Conv weight, valid for one (data_ptr, _version) of the fp32 parameter."""
-    __slots__ = ("wq", "wscale", "Cout", "Cin", "taps", "key")
+    __slots__ = ("wq", "wscale", "wt", "Cout", "Cin", "taps", "key")
 
-    def __init__(self, wq, wscale, Cout, Cin, taps, key):
-        self.wq, self.wscale, self.Cout, self.Cin, self.taps, self.key = wq, wscale, Cout, Cin, taps, key
+    def __init__(self, wq, wscale, wt, Cout, Cin, taps, key):
+        self.wq, self.wscale, self.wt, self.Cout, self.Cin, self.taps, self.key = wq, wscale, wt, Cout, Cin, taps, key
 
 
 _pack_cache = {}
 
 
-def pack_weight(w, layout="linear", cache=None):
+def pack_weight(w, layout="linear", cache=None, need_wt=False):
     """fp32 weight -> PackedWeight.  layout: 'linear' (Cout, K), 'conv' (Cout, Cin, kh, kw) OIHW.
     Cached per parameter version (optimizer steps bump ``_version``) for nn.Parameters (or when cache=True: the caller
     keeps `w` alive and unchanged); never cached while a CUDA graph is being captured, so a captured training step
@@ -40,7 +40,7 @@ def pack_weight(w, layout="linear", cache=None):
         cache = isinstance(w, torch.nn.Parameter)
     if not cache:
         capturing = True            # same effect: neither look up nor store
-    key = (w.data_ptr(), w._version, tuple(w.shape), layout)
+    key = (w.data_ptr(), w._version, tuple(w.shape), layout, bool(w.requires_grad or need_wt))
     if not capturing:
         hit = _pack_cache.get(id(w))
         if hit is not None and hit.key == key:
@@ -61,29 +61,32 @@ def pack_weight(w, layout="linear", cache=None):
     nbytes = int(L.sdf_spike_gemm_wq_bytes(Cout, Cin, taps))
     wq = torch.empty(nbytes, device=w.device, dtype=torch.int8)
     wscale = torch.empty(Cout, device=w.device, dtype=torch.float32)
+    # transposed fp32 copy for the data-gradient GEMM, only when a backward pass can follow
+    wt = torch.empty((Cin, taps * Cout), device=w.device, dtype=torch.float32) if (w.requires_grad or need_wt) else None
     capi.call("sdf_spike_gemm_pack", capi.struct(
-        "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(wq), wscale=_ptr(wscale), wq_bytes=nbytes, Cout=Cout, Cin=Cin,
+        "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(wq), wscale=_ptr(wscale), wt=_ptr(wt), wq_bytes=nbytes, Cout=Cout, Cin=Cin,
         taps=taps, s_co=s_co, s_ci=s_ci, s_tap=s_tap, tap_map=list(range(9)), stream=_stream()))
-    pw = PackedWeight(wq, wscale, Cout, Cin, taps, key)
+    pw = PackedWeight(wq, wscale, wt, Cout, Cin, taps, key)
     if not capturing:
         _pack_cache[id(w)] = pw
     return pw
 
 
-def spike_gemm_fwd(a_u8, pw, bias=None, want_stats=False):
-    """a_u8 [rows, K] uint8 -> (out fp32 [rows, Cout], bn partials [N_PARTIAL, 2, Cout] or None)."""
+def spike_gemm_fwd(a_u8, pw, bias=None, want_stats=False, a_max=0):
+    """a_u8 [rows, K] uint8 -> (out fp32 [rows, Cout], bn partials [N_PARTIAL, 2, Cout] or None).
+    a_max: largest operand value (1 for spikes; 0 = any u8)."""
     rows, K = a_u8.shape
     assert a_u8.dtype == torch.uint8 and a_u8.is_contiguous() and K == pw.Cin and pw.taps == 1
     out = torch.empty((rows, pw.Cout), device=a_u8.device, dtype=torch.float32)
     part = torch.empty((N_PARTIAL, 2, pw.Cout), device=a_u8.device, dtype=torch.float32) if want_stats else None
     capi.call("sdf_spike_gemm_fwd", capi.struct(
         "sdf_spike_gemm_fwd_args", a=_ptr(a_u8), wq=_ptr(pw.wq), wscale=_ptr(pw.wscale), bias=_ptr(bias), out=_ptr(out),
-        bn_partials=_ptr(part), n_partial_blocks=N_PARTIAL, rows=rows, K=K, Cout=pw.Cout, ld_out=pw.Cout, stream=_stream()),
+        bn_partials=_ptr(part), n_partial_blocks=N_PARTIAL, rows=rows, K=K, Cout=pw.Cout, ld_out=pw.Cout, a_max=a_max, stream=_stream()),
         algo_bytes=rows * K + 4 * rows * pw.Cout)
     return out, part
 
 
-def spike_conv_fwd(x_u8, pw, bias, kh, kw, stride, pad, want_stats=False):
+def spike_conv_fwd(x_u8, pw, bias, kh, kw, stride, pad, want_stats=False, a_max=0):
     """x_u8 (Nimg, H, W, Cin) uint8 NHWC -> (out fp32 (Nimg, Ho, Wo, Cout), partials)."""
     Nimg, H, W, Cin = x_u8.shape
     assert x_u8.dtype == torch.uint8 and x_u8.is_contiguous() and Cin == pw.Cin and pw.taps == kh * kw
@@ -93,7 +96,7 @@ def spike_conv_fwd(x_u8, pw, bias, kh, kw, stride, pad, want_stats=False):
     capi.call("sdf_spike_conv_fwd", capi.struct(
         "sdf_spike_conv_fwd_args", x=_ptr(x_u8), wq=_ptr(pw.wq), wscale=_ptr(pw.wscale), bias=_ptr(bias), out=_ptr(out),
         bn_partials=_ptr(part), n_partial_blocks=N_PARTIAL, Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=pw.Cout, Ho=Ho, Wo=Wo,
-        kh=kh, kw=kw, stride=stride, pad=pad, stream=_stream()),
+        kh=kh, kw=kw, stride=stride, pad=pad, a_max=a_max, stream=_stream()),
         algo_bytes=x_u8.numel() + 4 * out.numel())
     return out, part
 
@@ -155,3 +158,18 @@ def spike_conv_wgrad(g, x_u8, kh, kw, stride, pad):
         Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo, kh=kh, kw=kw, stride=stride, pad=pad, accumulate=0,
         stream=_stream()), algo_bytes=4 * g.numel() + x_u8.numel())
     return dw
+
+
+def conv_dgrad_tf32(g, weight, H, W, pad, wd=None):
+    """dX (Nimg, H, W, Cin) of a stride-1 convolution: g fp32 NHWC (Nimg, Ho, Wo, Cout), weight (Cout, Cin, kh, kw).
+    wd: the [Cin][kh*kw*Cout] re-layout of the weight (PackedWeight.wt) if already at hand."""
+    Nimg, Ho, Wo, Cout = g.shape
+    _, Cin, kh, kw = weight.shape
+    assert g.is_contiguous()
+    if wd is None:
+        wd = weight.detach().permute(1, 2, 3, 0).reshape(Cin, kh * kw * Cout).contiguous()
+    out = torch.empty((Nimg, H, W, Cin), device=g.device, dtype=torch.float32)
+    capi.call("sdf_conv_dgrad_tf32", capi.struct(
+        "sdf_conv_dgrad_tf32_args", g=_ptr(g), wd=_ptr(wd), out=_ptr(out), Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=Cout, Ho=Ho,
+        Wo=Wo, kh=kh, kw=kw, pad=pad, stream=_stream()), algo_bytes=4 * (g.numel() + out.numel()))
+    return out

@@ -41,6 +41,33 @@ class Spikes:
         return g.contiguous()
 
 
+# ---- membrane taps (tests / monitors) ----------------------------------------------------------------------------------
+# With ``TAP`` set to a dict, every neuron site that runs records its membrane potential after charge (fp32, the h of
+# spikingjelly's neuronal_charge; the spikes are exactly h - v_th >= 0) under the name its Spiking_neuron module announced
+# through ``tap_site`` just before the operator ran.  Production code never sets it.
+TAP = None
+_tap_pending = []
+
+
+def tap_site(name):
+    if TAP is not None:
+        _tap_pending.append(name)
+
+
+def _tap_take(n, *hs):
+    """Record n membranes (or drop the pending names when this operator has no membrane output)."""
+    if TAP is None:
+        return
+    names = [_tap_pending.pop(0) if _tap_pending else None for _ in range(n)]
+    for nm, h in zip(names, hs):
+        if nm is not None and h is not None:
+            TAP[nm] = h
+
+
+def _tapping():
+    return TAP is not None
+
+
 _zero_tokens = {}
 
 
@@ -199,7 +226,8 @@ class _NeuronFn(torch.autograd.Function):
         lay = seq_layout(u.shape, time_dim)
         cc = cfg.c(plif_tau(plif_w) if cfg.kind == capi.SDF_NEURON_PLIF else None)
         dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
-        spike, _, v_final = _lif_fwd_raw(u, lay, cc, dt, v_init=v_init, want_v=want_state)
+        spike, h_tap, v_final = _lif_fwd_raw(u, lay, cc, dt, v_init=v_init, want_v=want_state, want_h=_tapping())
+        _tap_take(1, h_tap)
         ctx.save_for_backward(u, plif_w, v_init)
         ctx.lay, ctx.cc, ctx.cfg, ctx.holder = lay, cc, cfg, holder
         if holder is not None:
@@ -276,9 +304,11 @@ class _PSNFn(torch.autograd.Function):
         dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
         spike = torch.empty(u.shape, device=u.device, dtype=_SPIKE_TORCH[dt])
         w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        h_tap = torch.empty_like(u) if _tapping() else None
         capi.call("sdf_psn_fwd", capi.struct(
-            "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), weight=_ptr(w), bias=_ptr(b), C=0, hw=1, lay=lay,
+            "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), h_seq=_ptr(h_tap), weight=_ptr(w), bias=_ptr(b), C=0, hw=1, lay=lay,
             spike_dtype=dt, stream=_stream()), algo_bytes=u.numel() * (4 + spike.element_size()))
+        _tap_take(1, h_tap)
         ctx.save_for_backward(u, w, b)
         ctx.lay, ctx.cfg, ctx.holder = lay, cfg, holder
         if holder is not None:
@@ -332,15 +362,17 @@ class _BNNeuronFn(torch.autograd.Function):
         dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
         if psn_w is None:
             cc = cfg.c(plif_tau(plif_w) if cfg.kind == capi.SDF_NEURON_PLIF else None)
-            spike, _, _ = _lif_fwd_raw(u, lay, cc, dt, scale, shift, C, 1)
+            spike, h_tap, _ = _lif_fwd_raw(u, lay, cc, dt, scale, shift, C, 1, want_h=_tapping())
         else:
             cc = None
             _check_psn(psn_w, psn_b, lay)
             spike = torch.empty(u.shape, device=u.device, dtype=_SPIKE_TORCH[dt])
+            h_tap = torch.empty_like(u) if _tapping() else None
             capi.call("sdf_psn_fwd", capi.struct(
-                "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), weight=_ptr(psn_w), bias=_ptr(psn_b),
+                "sdf_psn_fwd_args", u=_ptr(u), spike=_ptr(spike), h_seq=_ptr(h_tap), weight=_ptr(psn_w), bias=_ptr(psn_b),
                 scale=_ptr(scale), shift=_ptr(shift), C=C, hw=1, lay=lay, spike_dtype=dt,
                 stream=_stream()), algo_bytes=u.numel() * (4 + spike.element_size()))
+        _tap_take(1, h_tap)
         ctx.save_for_backward(u, weight, scale, shift, mean, rstd, psn_w, psn_b, plif_w)
         ctx.lay, ctx.cc, ctx.cfg, ctx.training, ctx.rows, ctx.C = lay, cc, cfg, bn.training, rows, C
         ctx.holder = holder
@@ -541,9 +573,9 @@ class _SpikeGemmFn(torch.autograd.Function):
         a = holder.data
         K = a.shape[-1]
         pw = gemm.pack_weight(weight, cache=getattr(weight, "_sdf_cacheable", None))
-        y, part = gemm.spike_gemm_fwd(a.view(-1, K), pw, None if bias is None else bias.detach(), want_stats)
+        y, part = gemm.spike_gemm_fwd(a.view(-1, K), pw, None if bias is None else bias.detach(), want_stats, a_max=1)
         ctx.save_for_backward(weight)
-        ctx.holder, ctx.has_bias = holder, bias is not None
+        ctx.holder, ctx.has_bias, ctx.wt = holder, bias is not None, pw.wt
         y = y.view(*a.shape[:-1], weight.shape[0])
         if part is not None:
             ctx.mark_non_differentiable(part)
@@ -560,7 +592,8 @@ class _SpikeGemmFn(torch.autograd.Function):
             g2 = g2.contiguous()
         gtok = gw = gb = None
         if ctx.needs_input_grad[0]:
-            holder.add_grad(gemm.gemm_tf32(g2, weight.detach().t().contiguous()).view(a.shape))
+            wt = ctx.wt if ctx.wt is not None else weight.detach().t().contiguous()
+            holder.add_grad(gemm.gemm_tf32(g2, wt).view(a.shape))
             gtok = _zero_token(gy.device)
         if ctx.needs_input_grad[1]:
             gw = gemm.spike_wgrad(g2, a.view(-1, K))
@@ -677,8 +710,8 @@ def conv3x3_small_cin(x, weight, bias=None):
 
 class _SpikeConvGemmFn(torch.autograd.Function):
     """NHWC convolution of 1-byte spikes as an implicit GEMM on the tcgen05 engine (gemm.spike_conv_fwd: per-tap TMA boxes,
-    zero padding = TMA out-of-bounds fill), weight gradient on the same engine (gemm.spike_conv_wgrad); the data gradient
-    is the library's (cuDNN, TF32).  Reference: sj_layer.Conv2d on spike tensors, Spiking_modules.py:268,318,803,845-846."""
+    zero padding = TMA out-of-bounds fill), weight gradient (gemm.spike_conv_wgrad) and stride-1 data gradient
+    (gemm.conv_dgrad_tf32) on the same engine; the strided data gradient is the library's (cuDNN, TF32).  Reference: sj_layer.Conv2d on spike tensors, Spiking_modules.py:268,318,803,845-846."""
 
     @staticmethod
     def forward(ctx, token, weight, bias, holder, stride, padding, want_stats):
@@ -687,9 +720,9 @@ class _SpikeConvGemmFn(torch.autograd.Function):
         kh, kw = weight.shape[2], weight.shape[3]
         pw = gemm.pack_weight(weight, "conv")
         y, part = gemm.spike_conv_fwd(x.view(-1, H, W, Cin), pw, None if bias is None else bias.detach(), kh, kw, stride,
-                                      padding, want_stats)
+                                      padding, want_stats, a_max=1)
         ctx.save_for_backward(weight)
-        ctx.holder, ctx.cfg = holder, (stride, padding, bias is not None)
+        ctx.holder, ctx.cfg, ctx.wt = holder, (stride, padding, bias is not None), pw.wt
         y = y.view(*x.shape[:-3], *y.shape[1:])
         if part is not None:
             ctx.mark_non_differentiable(part)
@@ -706,13 +739,18 @@ class _SpikeConvGemmFn(torch.autograd.Function):
         g4 = gy.contiguous().view(-1, *gy.shape[-3:])      # (Nimg, Ho, Wo, Cout) NHWC
         gtok = gw = gb = None
         if ctx.needs_input_grad[0]:
-            # input size only: the values of the input are irrelevant for the data gradient
-            fake = g4.new_empty(1).expand(g4.shape[0], Cin, H, W)
-            with _tf32(True):
-                gx = torch.ops.aten.convolution_backward(
-                    g4.permute(0, 3, 1, 2), fake, weight, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0], 1,
-                    [True, False, False])[0]
-            holder.add_grad(gx.permute(0, 2, 3, 1).contiguous().view(x.shape))
+            if stride == 1 and weight.shape[0] % 32 == 0:
+                gx = gemm.conv_dgrad_tf32(g4, weight, H, W, padding, ctx.wt)      # own implicit GEMM (TF32)
+            else:
+                # strided dgrad stays cuDNN's; only the input SIZE and layout matter for a data gradient (channels-last,
+                # so that cuDNN neither transposes g nor returns an NCHW result)
+                fake = g4.new_empty((g4.shape[0], H, W, Cin)).permute(0, 3, 1, 2)
+                with _tf32(True):
+                    gx = torch.ops.aten.convolution_backward(
+                        g4.permute(0, 3, 1, 2), fake, weight, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0],
+                        1, [True, False, False])[0]
+                gx = gx.permute(0, 2, 3, 1).contiguous()      # no-op when cuDNN returned NHWC
+            holder.add_grad(gx.view(x.shape))
             gtok = _zero_token(gy.device)
         if ctx.needs_input_grad[1]:
             gw = gemm.spike_conv_wgrad(g4, x.view(-1, H, W, Cin), kh, kw, stride, padding)
@@ -842,10 +880,12 @@ class _LifWindowFn(torch.autograd.Function):
         dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
         spike = torch.empty((wd, geom.M, wh, ww, C), device=x.device, dtype=_SPIKE_TORCH[dt])
         cc = cfg.c()
+        h_tap = torch.empty(spike.shape, device=x.device, dtype=torch.float32) if _tapping() else None
         capi.call("sdf_lif_window_fwd", capi.struct(
-            "sdf_lif_window_fwd_args", x=_ptr(x), spike=_ptr(spike), win2x=_ptr(geom.win2x), wd=wd,
+            "sdf_lif_window_fwd_args", x=_ptr(x), spike=_ptr(spike), h_seq=_ptr(h_tap), win2x=_ptr(geom.win2x), wd=wd,
             MP=geom.M * geom.P, C=C, neuron=cc, spike_dtype=dt, stream=_stream()),
             algo_bytes=4 * x.numel() + spike.element_size() * spike.numel())
+        _tap_take(1, h_tap)
         ctx.save_for_backward(x)
         ctx.geom, ctx.cc, ctx.holder = geom, cc, holder
         if holder is not None:
@@ -954,9 +994,12 @@ class _LifMergeFn(torch.autograd.Function):
         dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
         out = torch.empty((B, D, H2, W2, 4 * C), device=x.device, dtype=_SPIKE_TORCH[dt])
         cc = cfg.c() if apply_neuron else NeuronCfg().c()
+        h_tap = torch.empty(out.shape, device=x.device, dtype=torch.float32) if (_tapping() and apply_neuron) else None
         capi.call("sdf_lif_merge_fwd", capi.struct(
-            "sdf_lif_merge_fwd_args", x=_ptr(x), spike=_ptr(out), B=B, D=D, H=H, W=W, C=C, neuron=cc,
+            "sdf_lif_merge_fwd_args", x=_ptr(x), spike=_ptr(out), h_seq=_ptr(h_tap), B=B, D=D, H=H, W=W, C=C, neuron=cc,
             spike_dtype=dt, apply_neuron=1 if apply_neuron else 0, stream=_stream()))
+        if apply_neuron:
+            _tap_take(1, h_tap)
         ctx.save_for_backward(x)
         ctx.cc, ctx.apply_neuron, ctx.holder = cc, apply_neuron, holder
         if holder is not None:
@@ -1009,10 +1052,17 @@ class _QKGateFn(torch.autograd.Function):
         dt = capi.SDF_SPIKE_F32 if holder is None else capi.SDF_SPIKE_U8
         gate = torch.empty((rows, C), device=qk_pre.device, dtype=_SPIKE_TORCH[dt])
         cc = cfg.c()
+        tq = tk = ta = None
+        if _tapping():          # membranes of sn_q, sn_k, sn2_q (the order the module announces them in)
+            tq = torch.empty((rows, C), device=qk_pre.device, dtype=torch.float32)
+            tk = torch.empty_like(tq)
+            ta = torch.empty((rows, nH), device=qk_pre.device, dtype=torch.float32)
         capi.call("sdf_attn_qkgate_fwd", capi.struct(
             "sdf_attn_qkgate_fwd_args", q_pre=_ptr(q_pre), k_pre=_ptr(k_pre), ld=2 * C, q_scale=_ptr(qs), q_shift=_ptr(qh),
-            k_scale=_ptr(ks), k_shift=_ptr(kh), pos=_ptr(posc), gate=_ptr(gate), wd=wd, M=M, P=P, C=C, nH=nH,
-            neuron=cc, spike_dtype=dt, stream=_stream()), algo_bytes=(8 + gate.element_size()) * rows * C)
+            k_scale=_ptr(ks), k_shift=_ptr(kh), pos=_ptr(posc), gate=_ptr(gate), q_h=_ptr(tq), k_h=_ptr(tk), a_h=_ptr(ta),
+            wd=wd, M=M, P=P, C=C, nH=nH, neuron=cc, spike_dtype=dt, stream=_stream()),
+            algo_bytes=(8 + gate.element_size()) * rows * C)
+        _tap_take(3, tq, tk, ta)
         ctx.save_for_backward(qk_pre, wq, wk, pos, qs, qh, qm, qr, ks, kh, km, kr)
         ctx.dims, ctx.cc, ctx.tq, ctx.tk, ctx.holder = (wd, M, P, C, nH), cc, bn_q.training, bn_k.training, holder
         if holder is not None:

@@ -48,9 +48,16 @@ def test_spike_gemm_fwd_fp32_grade(rows, K, Cout):
     q = part[:, 1].double().sum(0)
     assert torch.allclose(s, y.double().sum(0), rtol=1e-5, atol=1e-3 * rows ** 0.5)
     assert torch.allclose(q, (y.double() ** 2).sum(0), rtol=1e-5, atol=1e-3)
-    # bit-reproducible and independent of the bias-free path
+    # bit-reproducible, with or without the statistics
     y2, _ = gemm.spike_gemm_fwd(a, pw, bias)
     assert torch.equal(y, y2)
+    # spike operands (a_max = 1): conversion-free epilogue, at most 1 ulp (of the pre-bias value) from the exact path
+    y3, part3 = gemm.spike_gemm_fwd(a, pw, bias, want_stats=True, a_max=1)
+    err3 = (y3.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err3 <= 2e-6, err3
+    assert (y3 - y).abs().max().item() <= 2.5e-7 * ref.abs().max().item()
+    assert torch.equal(y3, gemm.spike_gemm_fwd(a, pw, bias, a_max=1)[0])
+    assert torch.allclose(part3[:, 0].double().sum(0), y3.double().sum(0), rtol=1e-5, atol=1e-3 * rows ** 0.5)
 
 
 def test_spike_gemm_integer_operand_and_exactness():
@@ -105,7 +112,7 @@ def test_spike_conv_fwd_fp32_grade(Nimg, H, W, Cin, Cout, k, stride, pad):
     w = (torch.randn(Cout, Cin, k, k) * 0.03).to(DEV)
     bias = torch.randn(Cout, device=DEV) * 0.1
     pw = gemm.pack_weight(w, "conv")
-    y, part = gemm.spike_conv_fwd(x, pw, bias, k, k, stride, pad, want_stats=True)
+    y, part = gemm.spike_conv_fwd(x, pw, bias, k, k, stride, pad, want_stats=True, a_max=1)
     ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), stride=stride, padding=pad).permute(0, 2, 3, 1)
     assert y.shape == ref.shape
     err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
@@ -150,3 +157,20 @@ def test_spike_conv_wgrad(Nimg, H, W, Cin, Cout, k, stride, pad):
     (ref,) = torch.autograd.grad(y, wr, g.permute(0, 3, 1, 2).double())
     assert dw.shape == ref.shape
     assert (dw.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,pad", [(3, 24, 32, 96, 96, 3, 1), (2, 20, 27, 96, 96, 3, 1), (5, 9, 12, 768, 768, 3, 1),
+                                                    (2, 16, 16, 48, 96, 1, 0)])
+def test_conv_dgrad_tf32(Nimg, H, W, Cin, Cout, k, pad):
+    gemm = _gemm()
+    torch.manual_seed(H + W)
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    g = (torch.randint(-512, 512, (Nimg, Ho, Wo, Cout)).float() / 256).to(DEV)
+    w = (torch.randint(-512, 512, (Cout, Cin, k, k)).float() / 4096).to(DEV)
+    dx = gemm.conv_dgrad_tf32(g, w, H, W, pad)
+    xr = torch.zeros(Nimg, Cin, H, W, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xr, w.double(), None, stride=1, padding=pad)
+    (ref,) = torch.autograd.grad(y, xr, g.permute(0, 3, 1, 2).double())
+    ref = ref.permute(0, 2, 3, 1)
+    assert dx.shape == ref.shape
+    assert (dx.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()

@@ -334,3 +334,82 @@ def test_train_step_as_cuda_graph_matches_eager():
     n_bad = sum(((pe[k] - pg[k]).abs() > 2e-5).sum().item() for k in pe)
     n_all = sum(v.numel() for v in pe.values())
     assert n_bad <= 0.01 * n_all, (n_bad, n_all)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-neuron-layer parity (north_star: membranes <= 1e-4 relative, spike-flip rate <= 1e-4 PER LAYER)
+# ---------------------------------------------------------------------------------------------
+def _canon(h, ref_shape):
+    """Product membrane tensor -> the oracle's layout for the same site."""
+    cands = [h]
+    if h.ndim == 5:
+        cands += [h.permute(1, 0, 2, 3, 4), h.permute(1, 0, 4, 2, 3)]
+    for c in cands:
+        if tuple(c.shape) == tuple(ref_shape):
+            return c
+    assert h.numel() == int(torch.tensor(ref_shape).prod()), (tuple(h.shape), tuple(ref_shape))
+    return h.reshape(ref_shape)          # same flat order (window-ordered attention sites, Appendix B.3)
+
+
+@pytest.mark.parametrize("nt,train", [("lif", False), ("lif", True), ("psn", False), ("psn", True)])
+def test_every_neuron_layer_membrane_and_flip_rate(nt, train):
+    """Hooks EVERY neuron layer of the model (product: ops.TAP membranes from the kernels' h_seq outputs; oracle: the
+    record lists of port.spiking_neuron) while each top-level module is fed the oracle's input, and asserts per layer:
+      * spike-flip rate <= 1e-4   (spikes are exactly h - v_th >= 0 on both sides),
+      * membrane potential within 1e-4 relative (of the layer's max |h|) — everywhere for layers with no flipped spike
+        upstream inside their module, and for all but the (<= 1e-3) positions reached by such a flip otherwise."""
+    from sdformerflow_b200 import ops
+    mc, sc = synth.small_config(nt)
+    model = build_product(mc, sc, DEV, train=train)
+    x = synth.synth_voxels(2, 10, 96, 128)
+    for lyr in model.sttmultires_unet.encoders.swin3d.layers:
+        for b in lyr.swin_blocks:
+            if hasattr(b.drop_path, "forced"):
+                b.drop_path.forced = torch.ones(2)
+    n_sites = 0
+    for name, m in model.named_modules():
+        if type(m).__name__ == "Spiking_neuron":
+            m._tap_name = name
+            n_sites += 1
+    oracle_h = {}
+    orig = port.spiking_neuron
+
+    def wrapped(x_seq, P, prefix, spec, record=None):
+        rec = []
+        out = orig(x_seq, P, prefix, spec, rec)
+        oracle_h[prefix] = rec[0].detach()
+        if record is not None:
+            record.extend(rec)
+        return out
+
+    port.spiking_neuron = wrapped
+    ops.TAP = {}
+    try:
+        for _name, _got, _ref in _teacher_forced(model, mc, sc, x, train):
+            pass
+        taps = {k: v.float().cpu() for k, v in ops.TAP.items()}
+    finally:
+        port.spiking_neuron = orig
+        ops.TAP = None
+        ops._tap_pending.clear()
+    v_th = 0.0 if nt == "psn" else mc["spiking_neuron"]["v_th"]
+    assert set(taps) == set(oracle_h), (sorted(set(oracle_h) - set(taps))[:5], sorted(set(taps) - set(oracle_h))[:5])
+    # every neuron module that runs in a forward pass was hooked (attn_sn feeds only the discarded attention score)
+    assert len(taps) == n_sites - sum(1 for n, _ in model.named_modules() if n.endswith(".attn_sn"))
+    worst_flip, worst_mem = ("", 0.0), ("", 0.0)
+    for site, ho in oracle_h.items():
+        hp = _canon(taps[site], ho.shape)
+        flips = ((hp - v_th >= 0) != (ho - v_th >= 0)).float().mean().item()
+        scale = ho.abs().max().clamp_min(1e-12)
+        rel = (hp - ho).abs() / scale
+        frac_bad = (rel > 1e-4).float().mean().item()
+        assert flips <= 1e-4, (site, flips)
+        assert frac_bad <= 1e-3, (site, frac_bad)
+        if frac_bad == 0.0:
+            assert rel.max().item() <= 1e-4
+        if flips > worst_flip[1]:
+            worst_flip = (site, flips)
+        if frac_bad > worst_mem[1]:
+            worst_mem = (site, frac_bad)
+    print(f"[{nt} train={train}] {len(taps)} neuron layers hooked; worst flip rate {worst_flip}; "
+          f"worst fraction of membranes off by > 1e-4 rel {worst_mem}")

@@ -35,8 +35,8 @@ def main():
         g = torch.randn(rows, Cout, device=dev)
         pw = gemm.pack_weight(w)
         wt = w.t().contiguous()
-        t_fwd = timeit(lambda: gemm.spike_gemm_fwd(a8, pw, None, want_stats=True))
-        t_fwd_ns = timeit(lambda: gemm.spike_gemm_fwd(a8, pw, None, want_stats=False))
+        t_fwd = timeit(lambda: gemm.spike_gemm_fwd(a8, pw, None, want_stats=True, a_max=1))
+        t_fwd_ns = timeit(lambda: gemm.spike_gemm_fwd(a8, pw, None, want_stats=False, a_max=1))
         t_lib = timeit(lambda: ops._SpikeLinearFn.apply(af, w, None))
         t_dg = timeit(lambda: gemm.gemm_tf32(g, wt))
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -60,15 +60,17 @@ def main():
         xf = x8.float().permute(0, 3, 1, 2)          # logical NCHW, channels_last strides
         w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.03
         pw = gemm.pack_weight(w, "conv")
-        t_fwd = timeit(lambda: gemm.spike_conv_fwd(x8, pw, None, 3, 3, stride, 1, want_stats=True))
+        t_fwd = timeit(lambda: gemm.spike_conv_fwd(x8, pw, None, 3, 3, stride, 1, want_stats=True, a_max=1))
         t_lib = timeit(lambda: ops._SpikeConvFn.apply(xf, w, None, stride, 1, False, 0))
         y, _ = gemm.spike_conv_fwd(x8, pw, None, 3, 3, stride, 1)
         g = torch.randn_like(y)
         t_wg = timeit(lambda: gemm.spike_conv_wgrad(g, x8, 3, 3, stride, 1))
+        t_dg = timeit(lambda: gemm.conv_dgrad_tf32(g, w, H, W, 1)) if stride == 1 else float("nan")
         flop = 2 * y.numel() * Cin * 9
         print(json.dumps({"case": name, "fwd_ms": round(t_fwd, 4), "fwd_lib_tf32x2_ms": round(t_lib, 4),
                           "fwd_TFLOPs": round(flop / t_fwd / 1e9, 1), "wgrad_ms": round(t_wg, 4),
-                          "wgrad_TFLOPs": round(flop / t_wg / 1e9, 1)}), flush=True)
+                          "wgrad_TFLOPs": round(flop / t_wg / 1e9, 1),
+                          "dgrad_ms": round(t_dg, 4)}), flush=True)
 
 
 if __name__ == "__main__":
