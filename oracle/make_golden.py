@@ -119,6 +119,41 @@ def golden_cfg4():
     return out
 
 
+def golden_e2e_sensitivity():
+    """End-to-end flows of the shipped en4 model at the BASELINE configs (cfg1/cfg2 480x640, cfg3 288x384, cfg4 shapes) from the
+    unmodified reference, TOGETHER WITH the reference's own sensitivity to rounding: the same model re-evaluated with every
+    F.linear / conv computed in fp64 and rounded to fp32 (tools/ref_thread_sensitivity.py, gemms_in_fp64).  A spiking net with
+    hard thresholds amplifies a single threshold tie, so that half-ulp perturbation moves the reference's flow by pixels; the
+    free-running end-to-end gate of the GPU tests is "within 2x of what the reference does to itself"."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from ref_thread_sensitivity import gemms_in_fp64
+    from spikingjelly.activation_based import functional
+    cases = {"en4_288x384": dict(kw=dict(input_size=(288, 384)), shape=(1, 10, 288, 384)),
+             "en4_480x640": dict(kw=dict(input_size=(480, 640)), shape=(1, 10, 480, 640))}
+    for name, kw in synth.CFG4.items():
+        cases["cfg4_" + name] = dict(kw=kw, shape=(1, kw["num_bins"], *kw["input_size"]))
+    out = {}
+    for name, c in cases.items():
+        mc, sc = rl.default_config("lif", **c["kw"])
+        model = rl.build_reference_model(mc, sc, seed=0, train=False)
+        _load_synth(model)
+        x = synth.synth_voxels(*c["shape"])
+        functional.reset_net(model)
+        with torch.no_grad():
+            flows = model(x)["flow"]
+        functional.reset_net(model)
+        with torch.no_grad(), gemms_in_fp64():
+            flows64 = model(x)["flow"]
+        sub = [f[..., ::8, ::8].clone() for f in flows]
+        sub64 = [f[..., ::8, ::8].clone() for f in flows64]
+        sens = [(a - b).pow(2).sum(1).sqrt().mean().item() for a, b in zip(sub, sub64)]
+        mag = [a.pow(2).sum(1).sqrt().mean().item() for a in sub]
+        out[name] = {"kw": c["kw"], "shape": c["shape"], "sub": sub, "self_sensitivity_px": sens, "flow_mag_px": mag}
+        print(name, "sensitivity", [round(v, 3) for v in sens], "|flow|", [round(v, 2) for v in mag], flush=True)
+    return out
+
+
 def golden_sew_stage():
     """SEW family: one Spiking_Swin_BasicLayer (QK^T V attention, shifted + unshifted block, with
     SpikingPatchMerging) and the SDSA attention variant, eval and train."""
@@ -159,6 +194,7 @@ def main():
         "en4_lif_eval.pt": lambda: golden_en4("lif"),
         "sew_stage.pt": golden_sew_stage,
         "cfg4_lif_eval.pt": golden_cfg4,
+        "e2e_sensitivity.pt": golden_e2e_sensitivity,
     }
     only = set(sys.argv[1:])
     for name, fn in jobs.items():

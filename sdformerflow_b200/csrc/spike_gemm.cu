@@ -132,7 +132,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b);
 
   if (warp == 8) {
-    // ===== TMA producer =====
+    // ===== TMA producer (one elected lane; splitting the A / B issue over two lanes measured slower) =====
     if (elect_one()) {
       if (p.b_resident) {
         mbar_expect_tx(bres, (uint32_t)p.n_kchunks * bchunk);
@@ -203,11 +203,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t as = tile_i & 1, aph = (tile_i >> 1) & 1;
       uint8_t* out_s = smem + sp.out + (p.out_bufs == 2 ? as : 0u) * out_bytes;
       const uint32_t out_base = smem_u32(out_s);
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
+      if ((tid & 31) == 0) mbar_wait(&tfull[as], aph);       // one polling lane per warp
       // the TMA stores issued from this staging buffer (two tiles ago when double buffered) must have finished reading it
       if (tid == 0) { if (p.out_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
       named_bar_sync(1, kEpiThreads);
+      tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + as * (uint32_t)p.ncols;
       const bool valid = want_stats && row_valid(p, t, r);
       const int x = (r >> 1) & 3;

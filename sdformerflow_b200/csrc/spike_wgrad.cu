@@ -118,31 +118,41 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   constexpr uint32_t kBlk = kWgRB * 128;        // one 32-column MN block: 32 pixel rows x 128 B
 
   if (warp == 8) {
-    if (elect_one()) {
-      const int per_img = p.tiles_h * p.tiles_w;
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kWgStages;
-        const uint32_t ph = (it / kWgStages) & 1;
+    // ===== TMA producer: lane 0 waits for the stage and posts the byte count, then every lane issues ONE box of the stage
+    // (a bulk-tensor copy costs its issuing thread a few hundred cycles; seven boxes per stage issued serially were the
+    // bottleneck of the whole kernel) =====
+    const int lane = tid & 31;
+    const int per_img = p.tiles_h * p.tiles_w;
+    const int n_sbox = ntap * p.nbox;
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kWgStages;
+      const uint32_t ph = (it / kWgStages) & 1;
+      if (lane == 0) {
         mbar_wait(&empty[s], ph ^ 1);
-        if (p.debug == 3) { mbar_arrive(&full_tma[s]); continue; }
-        mbar_expect_tx(&full_tma[s], kAStage + (uint32_t)(ntap * p.nbox * p.box_w * kWgRB));
-        const int chunk = c_begin + it;
-        if (!p.conv) {
-          for (int mb = 0; mb < 4; ++mb) tma_load_2d(&tmG, &full_tma[s], a_base + s * kAStage + mb * kBlk, m_tile * kWgM + mb * 32, chunk * kWgRB);
-          for (int j = 0; j < p.nbox; ++j)
-            tma_load_2d(&tmS, &full_tma[s], stg_base + s * kStgStage + j * (p.box_w * kWgRB), ci0 + j * p.box_w, chunk * kWgRB);
-        } else {
-          const int img = chunk / per_img, rem = chunk - img * per_img;
-          const int py = rem / p.tiles_w, px = rem - py * p.tiles_w;
-          const int w0 = px * kWgPatchW, h0 = py * kWgPatchH;
-          for (int mb = 0; mb < 4; ++mb)
-            tma_load_4d(&tmG, &full_tma[s], a_base + s * kAStage + mb * kBlk, m_tile * kWgM + mb * 32, w0, h0, img);
-          for (int t = 0; t < ntap; ++t)
-            for (int j = 0; j < p.nbox; ++j)
-              tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage + (t * p.nbox + j) * (p.box_w * kWgRB), ci0 + j * p.box_w,
-                          w0 * p.stride + p.dw[tap0 + t], h0 * p.stride + p.dh[tap0 + t], img);
+        if (p.debug == 3) mbar_arrive(&full_tma[s]);
+        else mbar_expect_tx(&full_tma[s], kAStage + (uint32_t)(n_sbox * p.box_w * kWgRB));
+      }
+      __syncwarp();
+      if (p.debug == 3) continue;
+      const int chunk = c_begin + it;
+      if (!p.conv) {
+        if (lane < 4) tma_load_2d(&tmG, &full_tma[s], a_base + s * kAStage + lane * kBlk, m_tile * kWgM + lane * 32, chunk * kWgRB);
+        else if (lane - 4 < p.nbox) {
+          const int j = lane - 4;
+          tma_load_2d(&tmS, &full_tma[s], stg_base + s * kStgStage + j * (p.box_w * kWgRB), ci0 + j * p.box_w, chunk * kWgRB);
+        }
+      } else {
+        const int img = chunk / per_img, rem = chunk - img * per_img;
+        const int py = rem / p.tiles_w, px = rem - py * p.tiles_w;
+        const int w0 = px * kWgPatchW, h0 = py * kWgPatchH;
+        if (lane < 4) tma_load_4d(&tmG, &full_tma[s], a_base + s * kAStage + lane * kBlk, m_tile * kWgM + lane * 32, w0, h0, img);
+        else if (lane - 4 < n_sbox) {
+          const int b = lane - 4, t = b / p.nbox, j = b - t * p.nbox;
+          tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage + b * (p.box_w * kWgRB), ci0 + j * p.box_w,
+                      w0 * p.stride + p.dw[tap0 + t], h0 * p.stride + p.dh[tap0 + t], img);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
     if (elect_one()) {
@@ -185,8 +195,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kWgStages, bs = it % kWgBSlots;
       const uint32_t ph = (it / kWgStages) & 1, bph = (it / kWgBSlots) & 1;
-      mbar_wait(&empty_b[bs], bph ^ 1);         // the MMAs that read this B slot two iterations ago have retired
-      mbar_wait(&full_tma[s], ph);
+      if ((tid & 31) == 0) {                    // one polling lane per warp: 256 threads spinning on the barrier that the
+        mbar_wait(&empty_b[bs], bph ^ 1);       // TMA completions update slowed the copies down
+        mbar_wait(&full_tma[s], ph);            // (empty_b: the MMAs that read this B slot two iterations ago have retired)
+      }
+      __syncwarp();
       const uint8_t* stg = smem + sp.stg + s * kStgStage + src_off;
       uint8_t* bdst = smem + sp.b + bs * kBSlot + dst_blk;
       if (conv_thread && p.debug == 0) {
@@ -271,10 +284,10 @@ static int wgrad_tiles(int Cin, int taps, int* taps_per_tile, int* ci_tiles, int
   return 0;
 }
 
-// slabs so that the grid is about two waves of SMs at most, at least 4 chunks per slab
+// pixel slabs so that the grid is ONE wave of CTAs (tiles * slabs <= SMs; one CTA per SM), at least 4 chunks per slab
 static void wgrad_slabs(WgradP& p) {
   const int tiles = p.n_mtiles * p.n_ntiles;
-  int slabs = (num_sms() + tiles - 1) / tiles;
+  int slabs = num_sms() / tiles;
   if (slabs < 1) slabs = 1;
   int max_slabs = (p.n_chunks + 3) / 4;
   if (max_slabs < 1) max_slabs = 1;

@@ -228,43 +228,32 @@ def test_small_model_train_step(golden):
     assert n_with_grad == sum(1 for _ in model.parameters())   # lif: every parameter gets a gradient
 
 
-def test_en4_shipped_config_eval(golden):
-    """The shipped model (MS en4, window (2,9,9)) at 288x384 runs and stays within the flow scale of the fixture."""
+@pytest.mark.parametrize("case", ["en4_288x384", "en4_480x640", "cfg4_t5_w288", "cfg4_t10_w466"])
+def test_shipped_model_end_to_end_within_reference_sensitivity(golden, case):
+    """Free-running end-to-end flow of the shipped model (MS en4) at the BASELINE shapes — cfg3 (288x384), cfg1/cfg2
+    (480x640), cfg4 (5 bins / window (2,8,8) / 256x256 and a temporal window of 4) — against the unmodified reference.
+
+    The gate is the reference's OWN sensitivity to rounding, measured in the build container and stored next to the
+    reference flows (oracle/make_golden.py::golden_e2e_sensitivity): the same reference model re-run with every GEMM / conv
+    computed in fp64 and rounded to fp32 — a half-ulp perturbation — moves its flow by 1.1 ... 3.3 px, because one
+    flipped threshold tie is amplified layer by layer (profiles/r02_ref_thread_sensitivity.jsonl: first flip = 1 neuron in
+    5.9 M, last layers 9-26 % flipped).  A re-implementation cannot be closer to the reference than the reference is to
+    itself; it must not be further than 2x that."""
     from oracle import reference_loader as rl
-    g = golden("en4_lif_eval.pt")
-    mc, sc = rl.default_config("lif", input_size=(288, 384))
+    g = golden("e2e_sensitivity.pt")[case]
+    mc, sc = rl.default_config("lif", **g["kw"])
     model = build_product(mc, sc, DEV, train=False)
-    x = synth.synth_voxels(1, 10, 288, 384)
+    x = synth.synth_voxels(*g["shape"])
     _reset(model)
     with torch.no_grad():
         flows = model(x.to(DEV))["flow"]
-    for a, s in zip(flows, g["flows"]):
-        assert tuple(a.shape) == s["shape"]
-        sub = a[..., ::8, ::8].cpu()
-        mag = s["sub"].pow(2).sum(1).sqrt().mean().item()
-        print(f"en4 free-running EPE {epe(sub, s['sub']):.3f} px at |flow| {mag:.2f} px")
-        assert torch.isfinite(a).all() and epe(sub, s["sub"]) <= mag
-
-
-@pytest.mark.parametrize("name", ["t5_w288", "t10_w466"])
-def test_cfg4_shapes_eval(golden, name):
-    """BASELINE.json configs[3] shapes (5 time bins / window (2,8,8) / 256x256, and a temporal window of 4) run through
-    the fused kernels and stay within the flow scale of the reference fixture (free-running; see the en4 test)."""
-    from oracle import reference_loader as rl
-    g = golden("cfg4_lif_eval.pt")[name]
-    kw = synth.CFG4[name]
-    mc, sc = rl.default_config("lif", **kw)
-    model = build_product(mc, sc, DEV, train=False)
-    x = synth.synth_voxels(1, kw["num_bins"], *kw["input_size"])
-    _reset(model)
-    with torch.no_grad():
-        flows = model(x.to(DEV))["flow"]
-    for a, s in zip(flows, g["flows"]):
-        assert tuple(a.shape) == s["shape"]
-        sub = a[..., ::8, ::8].cpu()
-        mag = s["sub"].pow(2).sum(1).sqrt().mean().item()
-        print(f"cfg4 {name} free-running EPE {epe(sub, s['sub']):.3f} px at |flow| {mag:.2f} px")
-        assert torch.isfinite(a).all() and epe(sub, s["sub"]) <= mag
+    assert len(flows) == len(g["sub"])
+    for i, (a, ref_sub, sens, mag) in enumerate(zip(flows, g["sub"], g["self_sensitivity_px"], g["flow_mag_px"])):
+        assert tuple(a.shape[-2:]) == tuple(g["shape"][-2:]) and torch.isfinite(a).all()
+        ours = epe(a[..., ::8, ::8].cpu(), ref_sub)
+        print(f"{case} scale {i}: EPE product-vs-reference {ours:.3f} px; reference-vs-itself (fp64 GEMMs) {sens:.3f} px; "
+              f"|flow| {mag:.2f} px")
+        assert ours <= 2.0 * sens, (case, i, ours, sens)
 
 
 def test_double_forward_without_reset_raises():
@@ -354,7 +343,8 @@ def _canon(h, ref_shape):
 @pytest.mark.parametrize("nt,train", [("lif", False), ("lif", True), ("psn", False), ("psn", True)])
 def test_every_neuron_layer_membrane_and_flip_rate(nt, train):
     """Hooks EVERY neuron layer of the model (product: ops.TAP membranes from the kernels' h_seq outputs; oracle: the
-    record lists of port.spiking_neuron) while each top-level module is fed the oracle's input, and asserts per layer:
+    record lists of port.spiking_neuron) while each module (patch-embed layers, attention half and MLP half of every Swin
+    block, mergings, res blocks, decoders, heads) is fed the oracle's input, and asserts per layer:
       * spike-flip rate <= 1e-4   (spikes are exactly h - v_th >= 0 on both sides),
       * membrane potential within 1e-4 relative (of the layer's max |h|) — everywhere for layers with no flipped spike
         upstream inside their module, and for all but the (<= 1e-3) positions reached by such a flip otherwise."""
@@ -382,34 +372,60 @@ def test_every_neuron_layer_membrane_and_flip_rate(nt, train):
             record.extend(rec)
         return out
 
+    mlp_inputs = {}
+    orig_mlp = port.ms_mlp
+
+    def wrapped_mlp(xm, P, pre, spec, mode, rec=None):
+        mlp_inputs[pre] = xm.detach().clone()            # (D, B, H, W, C): the oracle's residual stream after attention
+        return orig_mlp(xm, P, pre, spec, mode, rec)
+
     port.spiking_neuron = wrapped
+    port.ms_mlp = wrapped_mlp
     ops.TAP = {}
     try:
         for _name, _got, _ref in _teacher_forced(model, mc, sc, x, train):
             pass
+        # the MLP half of every Swin block once more, fed the ORACLE's post-attention stream: its two neuron layers are
+        # then one Linear + BatchNorm away from identical inputs, like every other layer hooked here
+        for pre, xm in mlp_inputs.items():
+            mod = model.get_submodule(pre)
+            _reset(model)
+            with torch.no_grad():
+                mod.fused(xm.permute(1, 0, 2, 3, 4).contiguous().to(DEV))
         taps = {k: v.float().cpu() for k, v in ops.TAP.items()}
     finally:
         port.spiking_neuron = orig
+        port.ms_mlp = orig_mlp
         ops.TAP = None
         ops._tap_pending.clear()
     v_th = 0.0 if nt == "psn" else mc["spiking_neuron"]["v_th"]
     assert set(taps) == set(oracle_h), (sorted(set(oracle_h) - set(taps))[:5], sorted(set(taps) - set(oracle_h))[:5])
     # every neuron module that runs in a forward pass was hooked (attn_sn feeds only the discarded attention score)
     assert len(taps) == n_sites - sum(1 for n, _ in model.named_modules() if n.endswith(".attn_sn"))
-    worst_flip, worst_mem = ("", 0.0), ("", 0.0)
+    stats = []
     for site, ho in oracle_h.items():
         hp = _canon(taps[site], ho.shape)
         flips = ((hp - v_th >= 0) != (ho - v_th >= 0)).float().mean().item()
         scale = ho.abs().max().clamp_min(1e-12)
         rel = (hp - ho).abs() / scale
-        frac_bad = (rel > 1e-4).float().mean().item()
+        bad = rel > 1e-4
+        frac_bad = bad.float().mean().item()
+        # positions (all leading dims; last dim = channels) with at least one membrane off by > 1e-4
+        rows_bad = bad.reshape(-1, bad.shape[-1]).any(1).float().mean().item() if bad.ndim > 1 else frac_bad
+        stats.append((site, flips, frac_bad, rows_bad, rel.max().item()))
+    for site, flips, frac_bad, rows_bad, mx in sorted(stats, key=lambda t: -t[2])[:8]:
+        print(f"   {site}: flip rate {flips:.2e}, membranes off > 1e-4 rel: {frac_bad:.2e} of elements, {rows_bad:.2e} of rows, max {mx:.2e}")
+    print(f"[{nt} train={train}] {len(taps)} neuron layers hooked; worst flip rate {max(t[1] for t in stats):.2e}; "
+          f"layers with bit-identical spikes: {sum(t[1] == 0 for t in stats)}; layers with every membrane within 1e-4: "
+          f"{sum(t[2] == 0 for t in stats)}")
+    for site, flips, frac_bad, rows_bad, mx in stats:
         assert flips <= 1e-4, (site, flips)
-        assert frac_bad <= 1e-3, (site, frac_bad)
-        if frac_bad == 0.0:
-            assert rel.max().item() <= 1e-4
-        if flips > worst_flip[1]:
-            worst_flip = (site, flips)
-        if frac_bad > worst_mem[1]:
-            worst_mem = (site, frac_bad)
-    print(f"[{nt} train={train}] {len(taps)} neuron layers hooked; worst flip rate {worst_flip}; "
-          f"worst fraction of membranes off by > 1e-4 rel {worst_mem}")
+        assert frac_bad <= MEMBRANE_PROPAGATION_BOUND, (site, frac_bad)
+
+
+# A flipped spike (allowed rate 1e-4) feeds a Linear / conv whose whole output row (C channels; x T time steps through the
+# neuron's recurrence, x 9 pixels through a 3x3 conv) then differs, so inside a multi-layer module the membranes of LATER
+# layers differ at exactly those positions.  Bound on the fraction of membranes off by > 1e-4 relative (measured: 48-54 of
+# the 54 layers have every membrane within 1e-4, the worst layer 4.3e-5 of its elements off; the per-layer spike-flip rate
+# itself is asserted at the 1e-4 bar, measured worst 2.7e-6).
+MEMBRANE_PROPAGATION_BOUND = 2e-4
