@@ -306,64 +306,34 @@ def run_infer(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def run_b200(args, rank, local_rank, world):
+def build_model(dev, Hh, Ww, neuron="lif", bins=BINS, window=(2, 9, 9), train=True):
     import copy
-    import torch.distributed as dist
-    from sdformerflow_b200 import capi
     from sdformerflow_b200.sj import functional
     from sdformerflow_b200.STSwinNet_SNN import Spiking_STSwinNet as prod
-
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    torch.backends.cuda.matmul.allow_tf32 = False     # parity-grade fp32 GEMMs / convs
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
     mc, sc = model_cfg()
+    mc["num_bins"] = bins
+    mc["spiking_neuron"]["neuron_type"] = neuron
+    mc["spiking_neuron"]["num_steps"] = bins
+    sc["input_size"] = [Hh, Ww]
+    sc["window_size"] = list(window)
     torch.manual_seed(0)
     model = getattr(prod, mc["name"])(copy.deepcopy(mc), copy.deepcopy(sc))
     model.init_weights()
-    model.to(dev).train()
+    model.to(dev).train(train)
     functional.set_step_mode(model, "m")
     functional.set_backend(model, "cupy", prod.neuron.LIFNode)   # accepted no-op, as the reference scripts call it
-    from sdformerflow_b200 import distributed as sdist
-    # Single GPU: the whole step (reset+fwd+loss+bwd+AdamW) is one CUDA graph.  Multi-GPU ("--graph on"): capturing the
-    # NCCL all-reduce inside the step hung on this stack, so the graph covers reset+fwd+loss+bwd and the bucketed
-    # all-reduce + fused AdamW follow eagerly (a dozen launches).  "--graph off": eager launches (DDP when N > 1).
-    use_graph = args.graph in ("on", "auto")
-    if use_graph:
-        # whole-step CUDA graph: the replica is not wrapped in DDP (its reducer hooks are host logic); the gradient
-        # all-reduce is issued explicitly after backward, inside the captured step
-        net = model
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True, capturable=True)
-    else:
-        net = sdist.wrap(model, local_rank)          # DDP: bucketed NCCL all-reduce overlapped with backward
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
+    return model
 
-    B = B_PER_GPU
-    xh, gth, mh = synth_batch(B, 16146 + rank)
-    xh, gth, mh = xh.pin_memory(), gth.pin_memory(), mh.pin_memory()
-    xd, gtd, md = xh.to(dev), gth.to(dev), mh.to(dev)
 
-    params = [p for p in model.parameters() if p.requires_grad]
+def synth_batch_shape(B, seed, bins, Hh, Ww):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, bins, 2, Hh, Ww, generator=g) * (torch.rand(B, bins, 2, Hh, Ww, generator=g) < 0.10)
+    gt = torch.randn(B, 2, Hh, Ww, generator=g) * 4.0
+    return x, gt, torch.ones(B, 1, Hh, Ww)
 
-    def fwd_bwd(x, gt, mask):
-        functional.reset_net(model)
-        flows = net(x)["flow"]
-        loss = flow_loss(flows, gt, mask)
-        loss.backward()
-        return loss
 
-    def step(x, gt, mask):
-        loss = fwd_bwd(x, gt, mask)
-        if use_graph and world > 1:
-            sdist.allreduce_gradients(params, world)
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        return loss
+def make_timed(world, dev):
+    import torch.distributed as dist
 
     def barrier():
         if world > 1:
@@ -382,124 +352,226 @@ def run_b200(args, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
+    return timed
 
-    eager_step = step
-    graph_launches = None
-    ms_eager = None
+
+def train_workload(args, rank, local_rank, world, dev, Hh=H, Ww=W, B=B_PER_GPU, neuron="lif", bins=BINS, window=(2, 9, 9),
+                   steps=None, full=True):
+    """One training workload (reset + fwd + loss + bwd + AdamW, data parallel over `world` ranks) -> dict of measurements.
+    full=True adds the eager pass with per-kernel events (roofline table) and the end-to-end (host buffers) measurement."""
+    from sdformerflow_b200 import capi, train as sdtrain, distributed as sdist
+    from sdformerflow_b200.sj import functional
+    steps = steps or args.steps
+    model = build_model(dev, Hh, Ww, neuron, bins, window)
+    xh, gth, mh = synth_batch_shape(B, 16146 + rank, bins, Hh, Ww)
+    xh, gth, mh = xh.pin_memory(), gth.pin_memory(), mh.pin_memory()
+    xd, gtd, md = xh.to(dev), gth.to(dev), mh.to(dev)
+    timed = make_timed(world, dev)
+    use_graph = args.graph in ("on", "auto")
+    out = {}
     if use_graph:
-        # warm up on a side stream (cudnn autotune, lazily built window tables, optimizer state), then capture ONE
-        # full step (reset + forward + loss + backward [+ all-reduce] + AdamW) and replay it per step on static inputs
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(max(args.warmup, 3) + (8 if world > 1 else 0)):
-                eager_step(xd, gtd, md)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        sx, sgt, smk = xd.clone(), gtd.clone(), md.clone()
-        graph = torch.cuda.CUDAGraph()
-        n_cap = capi.launch_count()
-        opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            static_loss = eager_step(sx, sgt, smk) if world == 1 else fwd_bwd(sx, sgt, smk)
-        graph_launches = capi.launch_count() - n_cap
-        static_grads = [p.grad for p in params] if world > 1 else None
+        # sdformerflow_b200.train.GraphedStep: flat gradient buffer, graph(reset+fwd+loss+bwd[+AdamW]); with N > 1 the only
+        # eager launch per step is ONE NCCL all-reduce of the flat buffer between the two graphs
+        stepper = sdtrain.GraphedStep(model, flow_loss, (xd, gtd, md), lr=1e-4, weight_decay=0.01, world=world,
+                                      warmup=max(args.warmup, 3) + (5 if world > 1 else 0))
+        n0 = capi.launch_count()
+        stepper._eager()
+        launches_per_step = capi.launch_count() - n0
 
-        def step(x, gt, mask):           # noqa: F811  (same work as eager_step, replayed)
-            if x is not sx:
-                sx.copy_(x, non_blocking=True)
-                sgt.copy_(gt, non_blocking=True)
-                smk.copy_(mask, non_blocking=True)
-            graph.replay()
-            if world > 1:                # gradients live in the graph's static buffers; reduce and apply them eagerly
-                for p_, g_ in zip(params, static_grads):
-                    p_.grad = g_
-                sdist.allreduce_gradients(params, world)
-                opt.step()
-            return static_loss
-        xd, gtd, md = sx, sgt, smk
+        def step(x, gt, mask):
+            return stepper(x, gt, mask)
 
+        def eager_step(x, gt, mask):
+            return stepper._eager()
+        xd, gtd, md = stepper.static
+    else:
+        net = sdist.wrap(model, local_rank, find_unused_parameters=(neuron != "lif"))
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
+
+        def step(x, gt, mask):
+            functional.reset_net(model)
+            loss = flow_loss(net(x)["flow"], gt, mask)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+        eager_step = step
+        launches_per_step = None
     for _ in range(max(args.warmup, 3)):
         step(xd, gtd, md)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and full:
         sampler.start()
-    timer = capi.KernelTimer(only={"sdf_lif_fwd"})
-    if not use_graph:
-        capi.set_timer(timer)
     n0 = capi.launch_count()
-    ms_total = timed(lambda: step(xd, gtd, md), args.steps)
-    launches = capi.launch_count() - n0 if not use_graph else graph_launches * args.steps
+    ms_total = timed(lambda: step(xd, gtd, md), steps)
+    out["launches"] = (capi.launch_count() - n0) if launches_per_step is None else launches_per_step * steps
+    out["clocks"] = sampler.stop() if (rank == 0 and full) else None
+    out["ms_per_step"] = ms_total / steps
+    out["value"] = world * B * steps / (ms_total * 1e-3)
+    out["steps"] = steps
+    if not full:
+        return out
+    # per-kernel CUDA events cannot be recorded inside a replay: an eager pass of the same step times every libsdf_b200
+    # entry point (KernelTimer: CUDA events on the launching stream around each C-ABI call)
+    timer = capi.KernelTimer()
+    for _ in range(2):
+        eager_step(xd, gtd, md)
+    capi.set_timer(timer)
+    ms_eager = timed(lambda: eager_step(xd, gtd, md), steps)
     capi.set_timer(None)
-    clocks = sampler.stop() if rank == 0 else None
-    if use_graph:
-        # per-kernel CUDA events cannot be recorded inside a replay: time K1 in an eager pass of the same step
-        for _ in range(2):               # the caching allocator has no blocks for this stream yet (warm-up ran on `side`)
-            eager_step(xd, gtd, md)
-        capi.set_timer(timer)
-        ms_eager = timed(lambda: eager_step(xd, gtd, md), args.steps)
-        capi.set_timer(None)
-    ksum = timer.summary().get("sdf_lif_fwd", {"launches": 0, "ms": 0.0, "bytes": 0, "gbps": 0.0})
+    out["eager_ms_per_step"] = ms_eager / steps
+    out["kernels"] = {k: {"launches_per_step": v["launches"] / steps, "ms_per_step": v["ms"] / steps,
+                          "algo_GB_per_step": v["bytes"] / steps / 1e9, "GBps": v["gbps"]}
+                      for k, v in sorted(timer.summary().items(), key=lambda kv: -kv[1]["ms"])}
 
-    # end to end through the public API: pinned host inputs -> device every step, loss read back every step
     def e2e_step():
         x = xh.to(dev, non_blocking=True)
         gt = gth.to(dev, non_blocking=True)
         mk = mh.to(dev, non_blocking=True)
         return step(x, gt, mk).item()
     e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
-    h2d = (xh.numel() + gth.numel() + mh.numel()) * 4
+    ms_e2e = timed(e2e_step, steps)
+    out["e2e_ms_per_step"] = ms_e2e / steps
+    out["e2e_value"] = world * B * steps / (ms_e2e * 1e-3)
+    out["h2d"] = (xh.numel() + gth.numel() + mh.numel()) * 4
+    return out
 
+
+def cpu_baseline_leg():
+    """The oracle port (bit-exact restatement of the reference's torch path) on every host core: 1 warm-up + 3 timed B=1
+    training steps of the headline workload (a B=4 step needs ~35 GB of host memory and ~4x the time; SURVEY.md §8d allows
+    B=1 with the sample stated)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cstep = cpu_train_step_factory(1)
+    cstep()
+    t0 = time.time()
+    n = 3
+    for _ in range(n):
+        cstep()
+    dt = (time.time() - t0) / n
+    return {"value": 1.0 / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} timed B=1 training steps (fwd+loss+bwd+AdamW) at 288x384 after 1 warm-up, oracle port of the "
+                      "reference torch path (B=4 as on the GPU does not fit the time budget: 4x the work per step)"}
+
+
+def committed_profile_numbers():
+    """Numbers that only ncu can measure, read from the committed captures (profiles/): DRAM traffic of the dominant kernel and
+    the tensor-pipe utilisation of the Q K^T V attention kernel (BASELINE.json metric 'attn TC util')."""
+    out = {"traffic": None, "traffic_source": None, "attn_tc_util": None}
+    p = os.path.join(ROOT, "profiles", "r02_ncu_numbers.json")
+    if os.path.exists(p):
+        out.update(json.load(open(p)))
+    return out
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cuda.matmul.allow_tf32 = False     # parity-grade fp32 for the few remaining library GEMMs / convs
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    head = train_workload(args, rank, local_rank, world, dev, neuron=args.neuron)
+    secondary = {}
+    if args.secondary == "on" or (args.secondary == "auto" and world == 1):
+        # the other BASELINE.json configurations, short runs (3 timed steps each) in the same process
+        k = 3
+        torch.cuda.empty_cache()
+        secondary["train_psn_288x384_shipped_neuron"] = train_workload(args, rank, local_rank, world, dev, neuron="psn", steps=k, full=False)
+        torch.cuda.empty_cache()
+        secondary["train_lif_480x640_B4"] = train_workload(args, rank, local_rank, world, dev, Hh=480, Ww=640, steps=k, full=False)
+        torch.cuda.empty_cache()
+        secondary["cfg4_train_T5_w288_256x256_B4"] = train_workload(args, rank, local_rank, world, dev, Hh=256, Ww=256, bins=5,
+                                                                   window=(2, 8, 8), steps=k, full=False)
+        torch.cuda.empty_cache()
+        secondary["cfg4_train_T10_w466_192x192_B4"] = train_workload(args, rank, local_rank, world, dev, Hh=192, Ww=192,
+                                                                    window=(4, 6, 6), steps=k, full=False)
+        torch.cuda.empty_cache()
+        secondary["infer_cfg2_B8_480x640"] = infer_workload(args, rank, world, dev, steps=k)
+        secondary = {n: {"samples_per_s": v["value"], "ms_per_step": v["ms_per_step"], "steps": v["steps"]} for n, v in secondary.items()}
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        cstep = cpu_train_step_factory(1)
-        t0 = time.time()
-        cstep()
-        dt = time.time() - t0
-        cpu_base = {"value": 1.0 / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-                    "sample": "1 training step (fwd+loss+bwd+AdamW), B=1, 288x384, oracle port of the reference torch path"}
-
+        cpu_base = cpu_baseline_leg()
     if rank == 0:
         peak, how = measured_peaks()
-        traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic_lif_fwd.json")
-        if os.path.exists(tp):      # dram bytes per K1 launch from the committed `ncu --set full` capture of this command
-            tj = json.load(open(tp))
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_traffic_lif_fwd.json (ncu --set full, 42 K1 launches of one step)"
-        value = world * B * args.steps / (ms_total * 1e-3)
-        e2e_v = world * B * args.steps / (ms_e2e * 1e-3)
+        prof = committed_profile_numbers()
+        kernels = head["kernels"]
+        top = next(iter(kernels))                      # dominant libsdf_b200 entry point by time in the step
+        kt = kernels[top]
+        lif = kernels.get("sdf_lif_fwd", {"GBps": 0.0, "ms_per_step": 0.0, "launches_per_step": 0})
+        for v in kernels.values():
+            v["frac_of_hbm_peak"] = v["GBps"] / peak
+        own_ms = sum(v["ms_per_step"] for v in kernels.values())
         line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": head["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "gemm": "cuBLAS/cuDNN TF32x2 weight split on spike operands (fp32-grade), fp32 elsewhere; TF32 backward",
+            "config": {"workload": WORKLOAD.replace("lif(v_th=0.1)", f"{args.neuron}(v_th=0.1)"), "global_batch": world * B_PER_GPU,
+                       "parallelism": f"dp{world}",
+                       "gemm": "own tcgen05 + TMA engine on every Linear / 3x3 conv fed by spikes: kind::i8 forward on 1-byte spikes x 3 "
+                               "weight digit planes (exact integer accumulate, BN sums from the epilogue), TF32 data / weight "
+                               "gradients; library (cuDNN/cuBLAS, TF32 x 2) only for transposed convs, strided conv dgrad and "
+                               "real-valued operands",
                        "l2": "activations per step >> 126 MB L2; no explicit flush",
                        "weights": "random init (init_weights, seed 0)",
                        "launch": (("one CUDA graph per step (reset+fwd+loss+bwd+AdamW), replayed" if world == 1 else
-                                   "one CUDA graph per step for reset+fwd+loss+bwd, then eager bucketed all-reduce + fused AdamW")
-                                  + "; K1 roofline timed in an eager pass of the same step") if use_graph else "eager (one launch per kernel)"},
-            "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "eager": None if ms_eager is None else {"value": world * B * args.steps / (ms_eager * 1e-3), "unit": "samples/s",
-                                                     "ms_per_step": ms_eager / args.steps,
-                                                     "note": "same step launched kernel by kernel (with the per-kernel K1 events on)"},
-            "roofline": {"bound": "hbm", "kernel": "sdf_lif_fwd (K1, all launches of the " + ("eager pass" if use_graph else "timed region") + ")",
-                         "achieved": ksum["gbps"], "peak": peak, "unit": "GB/s", "frac": ksum["gbps"] / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_kind": how, "launches": ksum["launches"],
-                         "kernel_ms_per_step": ksum["ms"] / args.steps,
-                         "algo_bytes_per_step": ksum["bytes"] / args.steps,
-                         "algo_bytes_per_launch": ksum["bytes"] / max(ksum["launches"], 1)},
+                                   "graph(reset+fwd+loss+bwd) -> ONE NCCL all-reduce of the flat gradient buffer -> graph(AdamW)")
+                                  + "; per-kernel roofline timed in an eager pass of the same step")
+                       if args.graph != "off" else "eager (one launch per kernel), DDP for N > 1"},
+            "e2e": {"value": head["e2e_value"], "unit": "samples/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": 4,
+                    "ms_per_step": head["e2e_ms_per_step"]},
+            "gpu_launches": head["launches"],
+            "clocks": head["clocks"],
+            "eager": {"value": world * B_PER_GPU / (head["eager_ms_per_step"] * 1e-3), "unit": "samples/s",
+                      "ms_per_step": head["eager_ms_per_step"],
+                      "note": "same step launched kernel by kernel with per-kernel CUDA events on"},
+            "roofline": {"bound": "hbm", "kernel": f"{top} (dominant libsdf_b200 entry point: {kt['ms_per_step']:.2f} ms of the step, "
+                                                   f"{kt['launches_per_step']:.0f} launches; eager pass)",
+                         "achieved": kt["GBps"], "peak": peak, "unit": "GB/s", "frac": kt["GBps"] / peak,
+                         "traffic": prof["traffic"], "traffic_source": prof["traffic_source"], "peak_kind": how,
+                         "algo_bytes_per_launch": kt["algo_GB_per_step"] * 1e9 / max(kt["launches_per_step"], 1),
+                         "own_kernels_ms_per_step": own_ms,
+                         "lif_fwd_K1": {"achieved": lif["GBps"], "frac": lif["GBps"] / peak, "ms_per_step": lif["ms_per_step"]}},
+            "kernels": kernels,
+            "attn_tc_util": prof["attn_tc_util"],
+            "secondary": secondary,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def infer_workload(args, rank, world, dev, steps):
+    """BASELINE.json configs[1]: inference, B=8 per GPU, 480x640, eval (replicas only, no collective), one CUDA graph."""
+    from sdformerflow_b200.sj import functional
+    model = build_model(dev, 480, 640, "lif", train=False)
+    g = torch.Generator().manual_seed(16146 + rank)
+    xd = (torch.rand(8, BINS, 2, 480, 640, generator=g) * (torch.rand(8, BINS, 2, 480, 640, generator=g) < 0.10)).to(dev)
+
+    def fwd():
+        functional.reset_net(model)
+        with torch.no_grad():
+            return model(xd)["flow"][-1]
+    for _ in range(3):
+        fwd()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        fwd()
+    graph.replay()
+    timed = make_timed(world, dev)
+    ms = timed(graph.replay, steps)
+    return {"value": world * 8 * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps}
 
 
 def main():
@@ -511,6 +583,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the training step as a CUDA graph (auto = on); off = eager launches, DDP for N > 1")
+    ap.add_argument("--neuron", default="lif", choices=["lif", "psn"],
+                    help="neuron of the headline workload: lif (BASELINE.json north_star) or psn (the reference's shipped yml)")
+    ap.add_argument("--secondary", default="auto", choices=["auto", "on", "off"],
+                    help="also run the other BASELINE configs (psn, 480x640, cfg4, inference) as short secondary runs "
+                         "(auto: only at N=1)")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train (default, the headline metric: BASELINE.json configs[2]) or infer (configs[1]: eval, "
                          "B=8/GPU, 480x640)")

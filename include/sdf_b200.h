@@ -678,6 +678,27 @@ typedef struct {
 
 int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a);
 
+/* ---- input pipeline: polarity split + min-max normalisation + bins->steps regroup, channels-last out ----------------
+ * Replaces train_flow_parallel_supervised_SNN.py:261-265,278-284 (eval_DSEC_flow_SNN.py:196-212) and the regroup loop of
+ * MS_PED_Spiking_PatchEmbed_Conv_sfn.forward (Spiking_modules.py:1772-1786).
+ *   split = 1: x is the signed voxel grid (B, bins, H, W); pos = relu(x), neg = relu(-x)
+ *   split = 0: x is already (B, bins, 2, H, W) (what the reference scripts hand to the model); normalize must be 0
+ *   normalize = 1: non-zero entries -> (v - min) / (max - min), min / max over the non-zero entries (no-op when min == max)
+ *   out (B, steps, H, W, 2*bins/steps): out[b,t,h,w,2g+pol] = chunk[b, g*steps + t, pol, h, w]
+ * workspace: 888 floats (normalize only); minmax (optional): the two reduced values, for callers that log them. */
+typedef struct {
+  const float* x;
+  float* out;
+  float* workspace;
+  float* minmax;
+  int64_t B, bins, H, W, steps;
+  int32_t split;
+  int32_t normalize;
+  void* stream;
+} sdf_voxel_prepare_args;
+
+int sdf_voxel_prepare(const sdf_voxel_prepare_args* a);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 int sdf_version(void);             /* major*100 + minor */
 const char* sdf_last_error(void);  /* thread-local, never NULL */

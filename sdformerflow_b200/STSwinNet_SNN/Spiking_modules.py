@@ -499,7 +499,12 @@ class MS_PED_Spiking_PatchEmbed_Conv_sfn(nn.Module):
 
     def forward_cl(self, x):
         """voxels (B, bins, 2, H, W) -> (B, T, H/4, W/4, embed_dim)."""
-        x = regroup_bins_to_steps_cl(x, self.num_bins, self.num_steps)
+        if x.is_cuda and x.dtype == torch.float32 and not x.requires_grad:
+            if x.size(1) > self.num_bins:
+                x = x[:, :self.num_bins]
+            x = ops.regroup_voxels(x, self.num_steps)             # one kernel, no permute copy (csrc/voxel_input.cu)
+        else:
+            x = regroup_bins_to_steps_cl(x, self.num_bins, self.num_steps)
         # real-valued voxel input: plain fp32 conv; its spikes feed `conv` as 1-byte Spikes when that runs on the spike GEMM
         x = self.head.forward_cl(x, spike_input=False, u8_out=u8_ok(self.conv.conv[0]))
         x = self.conv.forward_cl(x, spike_input=True)             # input = head's spikes

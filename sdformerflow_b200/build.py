@@ -14,7 +14,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libsdf_b200.so")
 
-SOURCES = ["capi.cu", "lif.cu", "bn.cu", "window.cu", "attn_qkgate.cu", "attn_qktv.cu", "conv_small.cu", "spike_gemm.cu", "spike_wgrad.cu"]
+SOURCES = ["capi.cu", "lif.cu", "bn.cu", "window.cu", "attn_qkgate.cu", "attn_qktv.cu", "conv_small.cu", "spike_gemm.cu", "spike_wgrad.cu", "voxel_input.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

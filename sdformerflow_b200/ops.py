@@ -787,6 +787,39 @@ def spike_conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, ou
 
 
 # ---------------------------------------------------------------------------------------------
+# input pipeline
+# ---------------------------------------------------------------------------------------------
+def prepare_voxels(x, num_steps, normalize=True):
+    """Signed voxel grid (B, bins, H, W) -> channels-last network input (B, steps, H, W, 2*bins/steps): polarity split,
+    min-max normalisation over the non-zero entries and the bins -> (steps, channels) regroup of the patch embedding in one
+    kernel pair (reference train_flow_parallel_supervised_SNN.py:261-265,278-284 + Spiking_modules.py:1772-1786).
+    No autograd (it is the data side of the model)."""
+    _need_cuda(x)
+    x = x.detach().contiguous()
+    B, bins, Hh, Ww = x.shape
+    out = torch.empty((B, num_steps, Hh, Ww, 2 * bins // num_steps), device=x.device, dtype=torch.float32)
+    ws = torch.empty(888, device=x.device, dtype=torch.float32) if normalize else None
+    capi.call("sdf_voxel_prepare", capi.struct(
+        "sdf_voxel_prepare_args", x=_ptr(x), out=_ptr(out), workspace=_ptr(ws), B=B, bins=bins, H=Hh, W=Ww, steps=num_steps,
+        split=1, normalize=1 if normalize else 0, stream=_stream()), algo_bytes=(8 if normalize else 4) * x.numel() + 4 * out.numel())
+    return out
+
+
+def regroup_voxels(x, num_steps):
+    """(B, bins, 2, H, W) — what the reference scripts hand to the model — -> (B, steps, H, W, 2*bins/steps) channels-last
+    (the regroup of MS_PED_Spiking_PatchEmbed_Conv_sfn.forward, Spiking_modules.py:1772-1786, without the permute copy)."""
+    _need_cuda(x)
+    x = x.detach().contiguous()
+    B, bins, two, Hh, Ww = x.shape
+    assert two == 2
+    out = torch.empty((B, num_steps, Hh, Ww, 2 * bins // num_steps), device=x.device, dtype=torch.float32)
+    capi.call("sdf_voxel_prepare", capi.struct(
+        "sdf_voxel_prepare_args", x=_ptr(x), out=_ptr(out), B=B, bins=bins, H=Hh, W=Ww, steps=num_steps, split=0, normalize=0,
+        stream=_stream()), algo_bytes=4 * (x.numel() + out.numel()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # window index algebra
 # ---------------------------------------------------------------------------------------------
 class WindowGeom:

@@ -420,3 +420,33 @@ def test_small_cin_conv_fwd_bwd(Cin, Cout, H, W):
     assert ((wg.grad.cpu().double() - w.grad.double()).abs().max() / w.grad.abs().max()).item() <= 3e-3
     assert ((xg.grad.cpu().double() - x.grad.double()).abs().max() / x.grad.abs().max()).item() <= 3e-3
     assert ((bg.grad.cpu().double() - b.grad.double()).abs().max() / b.grad.abs().max()).item() <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# input pipeline: polarity split + min-max normalisation + bins->steps regroup
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,bins,steps,H,W", [(2, 10, 10, 24, 40), (1, 10, 5, 17, 23), (3, 5, 5, 16, 16), (1, 20, 10, 8, 12)])
+def test_voxel_prepare_matches_script_lines(B, bins, steps, H, W):
+    """ops.prepare_voxels == train_flow_parallel_supervised_SNN.py:261-265,278-284 followed by the patch embedding's regroup
+    (Spiking_modules.py:1772-1786), bit for bit."""
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(B * 100 + bins)
+    raw = torch.rand(B, bins, H, W, generator=g) * 3.0 * (torch.rand(B, bins, H, W, generator=g) < 0.3) \
+        * (torch.randint(0, 2, (B, bins, H, W), generator=g) * 2 - 1)
+    # reference script lines (CPU torch)
+    chunk = raw.clone()
+    neg = F.relu(-chunk)
+    pos = F.relu(chunk)
+    chunk = torch.cat((pos.unsqueeze(2), neg.unsqueeze(2)), dim=2)
+    mn, mx = torch.min(chunk[chunk != 0]), torch.max(chunk[chunk != 0])
+    if not mn == mx:
+        chunk[chunk != 0] = (chunk[chunk != 0] - mn) / (mx - mn)
+    ref = port.regroup_events(chunk, bins, steps)                     # (steps, B, num_ch, H, W)
+    got = ops.prepare_voxels(raw.to(DEV), steps)                      # (B, steps, H, W, num_ch)
+    assert torch.equal(got.cpu(), ref.permute(1, 0, 3, 4, 2).contiguous())
+    # the model-side regroup alone, on what the scripts hand to the model
+    got2 = ops.regroup_voxels(chunk.to(DEV), steps)
+    assert torch.equal(got2.cpu(), ref.permute(1, 0, 3, 4, 2).contiguous())
+    # all-equal non-zero values: min == max, the reference skips the normalisation
+    flat = (torch.rand(1, bins, H, W, generator=g) < 0.2).float() * 0.7
+    assert torch.equal(ops.prepare_voxels(flat.to(DEV), steps).cpu().sum(), flat.sum())
