@@ -120,6 +120,10 @@ typedef struct {
   float* bn_partials;   /* optional [n_partial_blocks, 2, C]: per-block sum(dx), sum(dx*u) */
   int64_t n_partial_blocks; /* in: capacity; the launcher uses min(capacity, its grid) and zero-fills the rest */
   float* plif_partials; /* optional [n_partial_blocks]: PLIF d(1/tau) partial sums */
+  const float* bn_coef; /* optional [3, C] from sdf_bn_bwd_finalize: the BatchNorm backward is applied in this pass,
+                           grad_u = a[c]*dx + b[c]*u + c0[c].  Two-phase use: call once with grad_u = grad_x = NULL and
+                           bn_partials (statistics only, nothing written), finalize, call again with bn_coef + grad_u:
+                           20 B per neuron-timestep instead of 24 B for K2 + a separate sdf_bn_bwd_apply. */
   int64_t C;
   int64_t hw;
   sdf_seq_layout lay;

@@ -34,6 +34,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "sdf_common.cuh"
+#include "tc_ptx.cuh"   // TMA (cp.async.bulk.tensor) wrappers + the host tensor-map encoder, used by the v2 forward
 
 namespace sdf {
 
@@ -77,6 +78,13 @@ __device__ __forceinline__ void mma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+// u8 x u8 -> s32 (kind::i8), overwrite D
+__device__ __forceinline__ void mma_ss_i8_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, 0, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
       : "memory");
 }
 template <bool ACC>
@@ -462,6 +470,11 @@ __global__ void __launch_bounds__(kSlotThreads * NSLOT, NSLOT == 2 ? 1 : 4) qktv
 //   * Bias_h is fixed per CTA (fixed pseudo-head): it is built once, split hi + lo in fp16 (22 significant
 //     bits) and stays RESIDENT in TMEM as the A operand of two more MMAs per key chunk;
 //   * the shift mask only ever adds -100 * (number of spiking keys of the other regions): 27 region sums of V.
+// Operand staging (round 2): Q and K are NOT converted any more — one TMA box each ([npad rows x 32 B] of the raw 1-byte
+// spikes, SWIZZLE_32B K-major) lands them in shared memory and the first contraction S = Q K^T runs in tcgen05.mma kind::i8
+// (u8 x u8 -> s32, one MMA per tile since K = 32 bytes is exactly one i8 K step); the conversion warps turn the exact integer
+// counts into fp16 in place.  Only V (the MN-major B operand of the fp16 second contraction) is still expanded by the
+// producer warps — a third of the former staging work.
 // Roles: warps 0-3 epilogue (one per TMEM lane quarter), warp 4 MMA issuer, warps 5-8 producers (global ->
 // fp16 canonical shared-memory layouts, double buffered).  All hand-offs are mbarriers; S is double buffered in
 // TMEM so MMA 1 of item i+1 and MMA 2 of item i overlap the conversion of item i.
@@ -471,7 +484,7 @@ constexpr int kV2Producers = 256;
 constexpr int kV2KT = 64;
 constexpr int kV2S0 = 352, kV2S1 = 416, kV2O = 480;
 constexpr int kV2Regions = 27;
-constexpr int kV2Loads = (6 * 176 + kV2Producers - 1) / kV2Producers;   // 16-byte loads in flight per producer thread
+constexpr int kV2Loads = (2 * 176 + kV2Producers - 1) / kV2Producers;   // 16-byte loads of V in flight per producer thread
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -499,17 +512,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 
 struct V2Plan {
-  uint32_t op[2];       // operand buffers: Q | K | V, each Rpad*64 B
+  uint32_t op[2];       // operand buffers: Q (u8, Rpad*32 B) | K (u8, Rpad*32 B) | V (fp16, Rpad*64 B)
   uint32_t rsum;        // 4 output warps x (kV2Regions + 1) x 32 ints: per-warp region sums of V, last row = the warp's total
   uint32_t reg;         // Rpad bytes: region id of every token of the current window
   uint32_t rowoff;      // Rpad x int64: element offset of token row i inside a window's output rows
   uint32_t ostage;      // 4 output warps x 32 rows x 144 B (128 B + 16 B pad: conflict-free both ways)
   uint32_t lin, tab, bars, tmem_slot, total;
 };
-__host__ __device__ inline V2Plan plan_v2(int Rpad, int tab) {
+// op_row_bytes: 128 for the forward (Q, K as raw bytes + fp16 V), 192 for the backward (three 16-bit operand slots)
+__host__ __device__ inline V2Plan plan_v2(int Rpad, int tab, int op_row_bytes = 192) {
   V2Plan s;
   uint32_t o = 0;
-  for (int b = 0; b < 2; ++b) { s.op[b] = o; o += (uint32_t)Rpad * 64 * 3; }
+  for (int b = 0; b < 2; ++b) { s.op[b] = o; o += (uint32_t)Rpad * op_row_bytes; }
   s.rsum = o; o += (4 * (kV2Regions + 1) + kV2Regions) * 32 * 4;   // + combined table: keys outside region r, per dim
   s.reg = o; o += (uint32_t)((Rpad + 15) / 16 * 16);
   s.rowoff = o; o += (uint32_t)Rpad * 8;
@@ -530,9 +544,10 @@ __device__ long long g_v2_trace[16 * 64];
 #endif
 
 template <int NPAD, bool MASK>
-__global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
+__global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                             const __grid_constant__ CUtensorMap tmK, const QktvP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const V2Plan sp = plan_v2(p.Rpad, p.tab);
+  const V2Plan sp = plan_v2(p.Rpad, p.tab, 128);
   int* lin_s = reinterpret_cast<int*>(smem + sp.lin);
   float* tab_s = reinterpret_cast<float*>(smem + sp.tab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
@@ -567,7 +582,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
   const float inv_scale = 1.f / p.scale;
   for (int i = tid; i < p.tab; i += kV2Threads) tab_s[i] = __ldg(p.bias_table + (int64_t)i * p.nH + head) * inv_scale;
   if (tid == 0) {
-    mbar_init(&full[0], kV2Producers / 32); mbar_init(&full[1], kV2Producers / 32);
+    mbar_init(&full[0], kV2Producers / 32 + 1); mbar_init(&full[1], kV2Producers / 32 + 1);   // + the TMA transaction
     mbar_init(&empty[0], 5); mbar_init(&empty[1], 5);
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
     mbar_init(&s16_full[0], 4); mbar_init(&s16_full[1], 4);
@@ -625,27 +640,27 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
       if (pt == 0) V2_TR(10, pi);
       mbar_wait(&empty[b], ((pi >> 1) & 1) ^ 1);
       if (pt == 0) V2_TR(11, pi);
-      // all 16-byte half-rows of Q, K and V of this pair: issue every load first, then convert and store
-      const uint8_t* src = p.q + pair * N * 32;
-      const int64_t kq = (p.k - p.q), vq = (p.v - p.q);
-      const int per = 2 * N, n_it = 3 * per;
+      // Q and K: one TMA box each of the raw spike bytes (rows [pair*N, pair*N + npad) of the [M*nH*N, 32] views; rows past
+      // N belong to the next pair and only ever meet zero rows of V / zero bias columns, rows past the tensor are zero-filled)
+      if (pt == 0) {
+        tc::mbar_expect_tx(&full[b], 2u * npad * 32u);
+        tc::tma_load_2d(&tmQ, &full[b], smem_u32(smem + sp.op[b]), 0, (int)(pair * N));
+        tc::tma_load_2d(&tmK, &full[b], smem_u32(smem + sp.op[b]) + (uint32_t)Rpad * 32u, 0, (int)(pair * N));
+      }
+      // V: all 16-byte half-rows of this pair, every load issued first, then expanded to fp16 and stored
+      const uint8_t* src = p.v + pair * N * 32;
+      const int n_it = 2 * N;
       uint4 w[kV2Loads];
 #pragma unroll
       for (int u = 0; u < kV2Loads; ++u) {
         const int g = pt + u * kV2Producers;
-        if (g < n_it) {
-          const int a = g >= 2 * per ? 2 : (g >= per ? 1 : 0);
-          const int i = g - a * per;
-          w[u] = __ldg(reinterpret_cast<const uint4*>(src + (a == 0 ? 0 : (a == 1 ? kq : vq)) + (int64_t)i * 16));
-        }
+        if (g < n_it) w[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)g * 16));
       }
 #pragma unroll
       for (int u = 0; u < kV2Loads; ++u) {
         const int g = pt + u * kV2Producers;
         if (g < n_it) {
-          const int a = g >= 2 * per ? 2 : (g >= per ? 1 : 0);
-          const int i = g - a * per;
-          const int r = i >> 1, hf = i & 1;
+          const int r = g >> 1, hf = g & 1;
           const uint32_t ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
           uint32_t o[8];
 #pragma unroll
@@ -654,7 +669,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
             o[2 * j] = __byte_perm(ws[j], 0, 0x4140) * 0x3C00u;
             o[2 * j + 1] = __byte_perm(ws[j], 0, 0x4342) * 0x3C00u;
           }
-          const uint32_t base = sp.op[b] + (uint32_t)a * Rpad * 64;
+          const uint32_t base = sp.op[b] + (uint32_t)Rpad * 64;
           *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<uint4*>(smem + base + plain_off(Rpad, r, hf * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
@@ -678,24 +693,25 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
         const int b = pi & 1;
         mbar_wait(&full[b], (pi >> 1) & 1);
         tc_fence_after();
+        // Q, K: u8 rows of 32 B, SWIZZLE_32B K-major (8-row groups 256 B apart); V: fp16 rows of 64 B, SWIZZLE_64B
         const uint32_t q_lo = ((smem_u32(smem + sp.op[b]) & 0x3FFFF) >> 4) | (1u << 16);
-        const uint32_t k_lo = q_lo + (uint32_t)((Rpad * 64) >> 4), v_lo = k_lo + (uint32_t)((Rpad * 64) >> 4);
+        const uint32_t k_lo = q_lo + (uint32_t)((Rpad * 32) >> 4), v_lo = k_lo + (uint32_t)((Rpad * 32) >> 4);
+        constexpr uint32_t kDescHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);
 #pragma unroll
         for (int li = 0; li < n_items; ++li, ++item) {
           const int sb = item & 1;
           const uint32_t s_cur = tm + kV2S0 + (uint32_t)sb * 64u, s_nxt = tm + kV2S0 + (uint32_t)(sb ^ 1) * 64u;
           V2_TR(0, item);
-          // MMA 1 of this item (first item of the pair only) and of the next one
+          // MMA 1 of this item (first item of the pair only) and of the next one: kind::i8, u8 x u8 -> s32, K = 32
 #pragma unroll
           for (int lj = (li == 0 ? 0 : li + 1); lj <= li + 1 && lj < n_items; ++lj) {
             const int mt1 = lj / n_kt, kt1 = lj % n_kt;
             const int key1 = kt1 * kV2KT;
             const int nk1 = (npad - key1) < kV2KT ? (npad - key1) : kV2KT;
-            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(nk1 >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc1 = (2u << 4) | ((uint32_t)(nk1 >> 3) << 17) | ((128u >> 4) << 24);   // S32 accum, u8 x u8
             const uint32_t d1 = lj == li ? s_cur : s_nxt;
             if (elect_one()) {
-              mma_ss_lh<false>(d1, q_lo + (uint32_t)(mt1 * 128 * 64 >> 4), k_lo + (uint32_t)(key1 * 64 >> 4), kDescHi, idesc1);
-              mma_ss_lh<true>(d1, q_lo + (uint32_t)(mt1 * 128 * 64 >> 4) + 2, k_lo + (uint32_t)(key1 * 64 >> 4) + 2, kDescHi, idesc1);
+              mma_ss_i8_lh(d1, q_lo + (uint32_t)(mt1 * 128 * 32 >> 4), k_lo + (uint32_t)(key1 * 32 >> 4), kDescHiSw32, idesc1);
               tc_commit(&s_full[lj == li ? sb : sb ^ 1]);
             }
             __syncwarp();
@@ -753,15 +769,18 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
         mbar_wait(&s_full[sb], (item >> 1) & 1);
         tc_fence_after();
         if (tid == 0) V2_TR(5, item);
-        // S (fp32 exact integers) -> fp16 pairs, in place: this warp is the only one touching these lanes
+        // S (s32 exact counts 0..32) -> fp16 pairs, in place: this warp is the only one touching these lanes.
+        // int -> float without I2F: as_float(n + 0x4B400000) - 1.5 * 2^23 (exact for |n| < 2^22)
         uint32_t r0[32], o[32];
         tmem_ld32(scol, r0);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] = pack2<0>(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+        for (int c = 0; c < 16; ++c)
+          o[c] = pack2<0>(__uint_as_float(r0[2 * c] + 0x4B400000u) - 12582912.f, __uint_as_float(r0[2 * c + 1] + 0x4B400000u) - 12582912.f);
         if (nk > 32) {
           tmem_ld32(scol + 32, r0);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) o[16 + c] = pack2<0>(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1]));
+          for (int c = 0; c < 16; ++c)
+            o[16 + c] = pack2<0>(__uint_as_float(r0[2 * c] + 0x4B400000u) - 12582912.f, __uint_as_float(r0[2 * c + 1] + 0x4B400000u) - 12582912.f);
         } else {
 #pragma unroll
           for (int c = 0; c < 16; ++c) o[16 + c] = 0;
@@ -809,7 +828,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) qktv2_kernel(const QktvP p) {
         if (otid == 0) V2_TR(14, pi);
         // rows in groups of 8 (one swizzle period): the four chunk offsets are lane constants
         const int per_w = (((N + 3) >> 2) + 7) & ~7, j0 = qw * per_w, j1 = min((N + 7) & ~7, j0 + per_w);
-        const uint8_t* vb = smem + sp.op[b] + 2u * Rpad * 64 + (lane & 7) * 2;
+        const uint8_t* vb = smem + sp.op[b] + (uint32_t)Rpad * 64 + (lane & 7) * 2;
         const int c = lane >> 3;
         const uint32_t o0 = (uint32_t)(c ^ 0) << 4, o1 = (uint32_t)(c ^ 1) << 4, o2 = (uint32_t)(c ^ 2) << 4, o3 = (uint32_t)(c ^ 3) << 4;
         int cur = j0 < j1 ? (int)rg[j0] : 0, acc = 0, tot = 0;
@@ -1393,28 +1412,38 @@ static void launch_v2_bwd(int npad, bool mask, int grid, uint32_t smem_bytes, cu
 }
 
 template <int NPAD>
-static void launch_v2_npad(bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
+static int launch_v2_npad(bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
+  // Q / K as [M*nH*N rows, 32 bytes] tensors; one box = the npad rows of a (window, pseudo-head) pair
+  CUtensorMap tmQ, tmK;
+  const uint64_t dims[2] = {32, (uint64_t)(p.M * p.nH * p.N)};
+  const uint64_t str[1] = {32};
+  const uint32_t box[2] = {32, (uint32_t)NPAD};
+  int st = make_tmap(&tmQ, 0, 2, p.q, dims, str, box, nullptr, 32);
+  if (st) return st;
+  st = make_tmap(&tmK, 0, 2, p.k, dims, str, box, nullptr, 32);
+  if (st) return st;
   if (mask) {
     cudaFuncSetAttribute(qktv2_kernel<NPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    qktv2_kernel<NPAD, true><<<grid, kV2Threads, smem_bytes, stream>>>(p);
+    qktv2_kernel<NPAD, true><<<grid, kV2Threads, smem_bytes, stream>>>(tmQ, tmK, p);
   } else {
     cudaFuncSetAttribute(qktv2_kernel<NPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    qktv2_kernel<NPAD, false><<<grid, kV2Threads, smem_bytes, stream>>>(p);
+    qktv2_kernel<NPAD, false><<<grid, kV2Threads, smem_bytes, stream>>>(tmQ, tmK, p);
   }
+  return SDF_OK;
 }
-static void launch_v2(int npad, bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
+static int launch_v2(int npad, bool mask, int grid, uint32_t smem_bytes, cudaStream_t stream, const QktvP& p) {
   switch (npad) {
-    case 16: launch_v2_npad<16>(mask, grid, smem_bytes, stream, p); break;
-    case 32: launch_v2_npad<32>(mask, grid, smem_bytes, stream, p); break;
-    case 48: launch_v2_npad<48>(mask, grid, smem_bytes, stream, p); break;
-    case 64: launch_v2_npad<64>(mask, grid, smem_bytes, stream, p); break;
-    case 80: launch_v2_npad<80>(mask, grid, smem_bytes, stream, p); break;
-    case 96: launch_v2_npad<96>(mask, grid, smem_bytes, stream, p); break;
-    case 112: launch_v2_npad<112>(mask, grid, smem_bytes, stream, p); break;
-    case 128: launch_v2_npad<128>(mask, grid, smem_bytes, stream, p); break;
-    case 144: launch_v2_npad<144>(mask, grid, smem_bytes, stream, p); break;
-    case 160: launch_v2_npad<160>(mask, grid, smem_bytes, stream, p); break;
-    default: launch_v2_npad<176>(mask, grid, smem_bytes, stream, p); break;
+    case 16: return launch_v2_npad<16>(mask, grid, smem_bytes, stream, p);
+    case 32: return launch_v2_npad<32>(mask, grid, smem_bytes, stream, p);
+    case 48: return launch_v2_npad<48>(mask, grid, smem_bytes, stream, p);
+    case 64: return launch_v2_npad<64>(mask, grid, smem_bytes, stream, p);
+    case 80: return launch_v2_npad<80>(mask, grid, smem_bytes, stream, p);
+    case 96: return launch_v2_npad<96>(mask, grid, smem_bytes, stream, p);
+    case 112: return launch_v2_npad<112>(mask, grid, smem_bytes, stream, p);
+    case 128: return launch_v2_npad<128>(mask, grid, smem_bytes, stream, p);
+    case 144: return launch_v2_npad<144>(mask, grid, smem_bytes, stream, p);
+    case 160: return launch_v2_npad<160>(mask, grid, smem_bytes, stream, p);
+    default: return launch_v2_npad<176>(mask, grid, smem_bytes, stream, p);
   }
 }
 #ifdef SDF_V2_TRACE
@@ -1471,12 +1500,13 @@ extern "C" int sdf_attn_qktv_fwd(const sdf_attn_qktv_fwd_args* a) {
     // v2 (warp-specialised, bias resident in TMEM) when both M-tiles' fp16 hi/lo bias fit in 352 columns
     static const int use_v2 = [] { const char* e = getenv("SDF_QKTV_V2"); return e ? atoi(e) : 1; }();
     const int npad = (p.N + 15) & ~15;
-    const V2Plan vp = plan_v2(p.Rpad, p.tab);
+    const V2Plan vp = plan_v2(p.Rpad, p.tab, 128);
     if (use_v2 && !dbg && p.n_mt * npad <= 352 && vp.total <= 200 * 1024 && a->scale != 0.0) {
       int g = kNumSMs / (int)a->nH * (int)a->nH;
       if (g < a->nH) g = (int)a->nH;
       if ((int64_t)g > a->M * a->nH) g = (int)(a->M * a->nH);
-      launch_v2(npad, p.has_mask != 0, g, vp.total, stream, p);
+      int st2 = launch_v2(npad, p.has_mask != 0, g, vp.total, stream, p);
+      if (st2) return st2;
       return finish_launch("sdf_attn_qktv_fwd(v2)");
     }
   }

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(512, (T > 0 && T <= 10 && DT != SDF_SPIKE_F32)
 struct LifBwdP {
   const float* u; const float* gs; float* gu; float* gx; const float* v_init;
   const float* scale; const float* shift;
+  const float* coef;      // optional [3, C]: BatchNorm backward folded in, gu = a[c]*dx + b[c]*u + c0[c] (channels-last only)
   float* bn_partials; float* plif_partials;
   SeqP s; NeuronP nrn;
 };
@@ -169,6 +170,13 @@ __global__ void __launch_bounds__(288, (V == 2) ? (PRE ? 2 : 3) : (PRE ? 1 : 2))
   const int64_t col = (int64_t)blockIdx.y * s.tile_w + (int64_t)rx * V;
   float sc[V], sh[V];
   init_affine<V>(s, p.scale, p.shift, col, sc, sh);
+  float ca[V], cb[V], cc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { ca[i] = 0.f; cb[i] = 0.f; cc[i] = 0.f; }
+  if (p.coef) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) { ca[i] = p.coef[col + i]; cb[i] = p.coef[s.C + col + i]; cc[i] = p.coef[2 * s.C + col + i]; }
+  }
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float plif_acc = 0.f;
   const float dh_dx = neuron_dh_dx(nrn), dh_dv = neuron_dh_dv(nrn);
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(288, (V == 2) ? (PRE ? 2 : 3) : (PRE ? 1 : 2))
           float gh = neuron_grad_h_t<SIMPLE>(nrn, h[t][i], g[i], gv[i]);
           dx[i] = gh * dh_dx;
           gv[i] = gh * dh_dv;
-          du[i] = dx[i] * sc[i];
+          du[i] = p.coef ? fmaf(ca[i], dx[i], fmaf(cb[i], u[t][i], cc[i])) : dx[i] * sc[i];
           if (s.chan_mode == 1) {
             acc[0][i] += dx[i];
             acc[1][i] += dx[i] * u[t][i];
@@ -524,7 +532,8 @@ extern "C" int sdf_lif_fwd(const sdf_lif_fwd_args* a) {
 }
 
 extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
-  SDF_REQUIRE(a && a->u && a->grad_spike && (a->grad_u || a->grad_x), "sdf_lif_bwd: null argument");
+  SDF_REQUIRE(a && a->u && a->grad_spike && (a->grad_u || a->grad_x || a->bn_partials), "sdf_lif_bwd: null argument");
+  SDF_REQUIRE(!a->bn_coef || (a->grad_u && a->scale && a->hw == 1), "sdf_lif_bwd: bn_coef needs grad_u and a channels-last BN site");
   int st = validate_neuron(a->neuron);
   if (st) return st;
   const bool affine = a->scale != nullptr;
@@ -534,6 +543,7 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   LifBwdP p;
   p.u = a->u; p.gs = (const float*)a->grad_spike; p.gu = a->grad_u; p.gx = a->grad_x; p.v_init = a->v_init;
   p.scale = a->scale; p.shift = a->shift; p.bn_partials = a->bn_partials; p.plif_partials = a->plif_partials;
+  p.coef = a->bn_coef;
   p.nrn = make_neuron(a->neuron);
   const void* ptrs[] = {a->u, a->grad_spike, a->grad_u, a->grad_x, a->v_init};
   const int T = (int)a->lay.T;

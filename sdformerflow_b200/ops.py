@@ -181,9 +181,9 @@ def _bn_forward_affine(u2d, rows, C, ld, bn: BNParams, partials=None):
     return scale, shift, mean, rstd
 
 
-def _bn_backward(partials, dy, u2d, ld_u, rows, C, weight, mean, rstd, training, need_du=True, du_ld=None):
-    """partials = per-block (sum dy, sum dy*u).  -> du [rows, C], grad_weight, grad_bias."""
-    dev = dy.device
+def _bn_bwd_coef(partials, rows, C, weight, mean, rstd, training):
+    """partials = per-block (sum dy, sum dy*u) -> (coef [3, C] of du = a*dy + b*u + c, grad_weight, grad_bias)."""
+    dev = partials.device
     gw = torch.empty(C, device=dev, dtype=torch.float32)
     gb = torch.empty_like(gw)
     coef = torch.empty((3, C), device=dev, dtype=torch.float32)
@@ -191,6 +191,13 @@ def _bn_backward(partials, dy, u2d, ld_u, rows, C, weight, mean, rstd, training,
         "sdf_bn_bwd_finalize_args", partials=_ptr(partials), n_partial_blocks=N_PARTIAL, count=rows, C=C,
         weight=_ptr(weight), mean=_ptr(mean), rstd=_ptr(rstd), grad_weight=_ptr(gw), grad_bias=_ptr(gb),
         coef=_ptr(coef), training=1 if training else 0, stream=_stream()))
+    return coef, gw, gb
+
+
+def _bn_backward(partials, dy, u2d, ld_u, rows, C, weight, mean, rstd, training, need_du=True, du_ld=None):
+    """partials = per-block (sum dy, sum dy*u).  -> du [rows, C], grad_weight, grad_bias."""
+    dev = dy.device
+    coef, gw, gb = _bn_bwd_coef(partials, rows, C, weight, mean, rstd, training)
     du = None
     if need_du:
         du = torch.empty((rows, C), device=dev, dtype=torch.float32)
@@ -328,7 +335,9 @@ class _PSNFn(torch.autograd.Function):
             "sdf_psn_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=_ptr(gu), grad_h=_ptr(gh),
             x_out=None if ctx.lay["stride_b"] == 0 else _ptr(xo), weight=_ptr(w), bias=_ptr(b), C=0, hw=1,
             lay=ctx.lay, surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
-        return gu, gh @ xo.t(), gh.sum(1, keepdim=True), None, None, None
+        with _tf32(True):          # [T, n] x [n, T] over the huge neuron axis: tensor cores (TF32), like every other weight gradient
+            g_w = gh @ xo.t()
+        return gu, g_w, gh.sum(1, keepdim=True), None, None, None
 
 
 def _check_psn(weight, bias, lay):
@@ -388,12 +397,16 @@ class _BNNeuronFn(torch.autograd.Function):
         rows, C = ctx.rows, ctx.C
         dev = u.device
         partials = torch.empty((N_PARTIAL, 2, C), device=dev, dtype=torch.float32)
-        dx = torch.empty_like(u)
         g_psn_w = g_psn_b = g_plif = None
         if psn_w is None:
+            # (a two-phase variant — statistics-only pass, then a second walk of the recurrence applying the BatchNorm
+            # backward in registers via sdf_lif_bwd_args.bn_coef, 20 B instead of 24 B per neuron-timestep — measured
+            # SLOWER on B200: K2 is register/latency bound at T = 10, sdf_lif_bwd 4.5 -> 7.7 ms vs sdf_bn_bwd_apply
+            # 4.6 -> 2.6 ms per step; kept in the C-ABI, not used here)
             plif_part = None
             if ctx.cfg.kind == capi.SDF_NEURON_PLIF:
                 plif_part = torch.empty(N_PARTIAL, device=dev, dtype=torch.float32)
+            dx = torch.empty_like(u)
             capi.call("sdf_lif_bwd", capi.struct(
                 "sdf_lif_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=None, grad_x=_ptr(dx), scale=_ptr(scale),
                 shift=_ptr(shift), bn_partials=_ptr(partials), plif_partials=_ptr(plif_part), n_partial_blocks=N_PARTIAL,
@@ -401,7 +414,10 @@ class _BNNeuronFn(torch.autograd.Function):
             if plif_part is not None:
                 sg = torch.sigmoid(plif_w.detach())
                 g_plif = (plif_part.sum() * sg * (1 - sg)).reshape(plif_w.shape)
-        else:
+            du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, weight, mean, rstd, ctx.training)
+            return du.view(u.shape), gw, gb, None, None, None, g_psn_w, g_psn_b, g_plif, None, None
+        dx = torch.empty_like(u)
+        if True:
             T, n = ctx.lay["T"], ctx.lay["n_neurons"]
             gh = torch.empty((T, n), device=dev, dtype=torch.float32)
             xo = torch.empty((T, n), device=dev, dtype=torch.float32)
@@ -410,7 +426,8 @@ class _BNNeuronFn(torch.autograd.Function):
                 x_out=_ptr(xo), weight=_ptr(psn_w), bias=_ptr(psn_b), scale=_ptr(scale), shift=_ptr(shift),
                 bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=ctx.lay,
                 surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
-            g_psn_w = gh @ xo.t()
+            with _tf32(True):
+                g_psn_w = gh @ xo.t()
             g_psn_b = gh.sum(1, keepdim=True)
         du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, weight, mean, rstd, ctx.training)
         return du.view(u.shape), gw, gb, None, None, None, g_psn_w, g_psn_b, g_plif, None, None
@@ -1266,7 +1283,8 @@ class _QKTVFn(torch.autograd.Function):
                     weight=_ptr(pw), bias=_ptr(pb), scale=_ptr(sc), shift=_ptr(sh), bn_partials=_ptr(partials),
                     n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=lay, surrogate=cfg.surrogate, sg_alpha=float(cfg.sg_alpha),
                     stream=_stream()))
-                psn_grads += [gh @ xo.t(), gh.sum(1, keepdim=True)]
+                with _tf32(True):
+                    psn_grads += [gh @ xo.t(), gh.sum(1, keepdim=True)]
             du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, ws_bn[i], mean, rstd, trains[i])
             outs.append(du.view(u.shape))
             bn_grads += [gw, gb]

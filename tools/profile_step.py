@@ -18,6 +18,9 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda")
 mc, sc = bench.model_cfg()
+for a in sys.argv[1:]:
+    if a in ("lif", "psn", "plif"):
+        mc["spiking_neuron"]["neuron_type"] = a
 torch.manual_seed(0)
 model = getattr(prod, mc["name"])(copy.deepcopy(mc), copy.deepcopy(sc))
 model.init_weights()

@@ -1,0 +1,53 @@
+"""One small launch of every hand-written tensor-core / TMA kernel family (and K1/K2/K5), for
+    compute-sanitizer --tool memcheck  python tools/sanitizer_targets.py
+    compute-sanitizer --tool racecheck python tools/sanitizer_targets.py
+Logs go to profiles/r02_sanitizer_*.txt (tools/sanitize.sh)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from sdformerflow_b200 import gemm, ops, capi  # noqa: E402
+
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def spikes(*shape, rate=0.3):
+    return (torch.rand(*shape, device=dev) < rate).to(torch.uint8)
+
+
+# G1 / G2 / G3: linear
+a = spikes(700, 96)
+w = torch.randn(192, 96, device=dev) * 0.05
+pw = gemm.pack_weight(w, need_wt=True)
+y, part = gemm.spike_gemm_fwd(a, pw, None, want_stats=True, a_max=1)
+g = torch.randn_like(y)
+gemm.gemm_tf32(g, pw.wt)
+gemm.spike_wgrad(g, a)
+# conv (stride 1 and 2)
+x = spikes(2, 20, 27, 96, rate=0.25)
+wc = torch.randn(96, 96, 3, 3, device=dev) * 0.03
+pc = gemm.pack_weight(wc, "conv", need_wt=True)
+yc, _ = gemm.spike_conv_fwd(x, pc, None, 3, 3, 1, 1, want_stats=True, a_max=1)
+gc = torch.randn_like(yc)
+gemm.conv_dgrad_tf32(gc, wc, 20, 27, 1, pc.wt)
+gemm.spike_conv_wgrad(gc, x, 3, 3, 1, 1)
+y2, _ = gemm.spike_conv_fwd(x, pc, None, 3, 3, 2, 1)
+gemm.spike_conv_wgrad(torch.randn_like(y2), x, 3, 3, 2, 1)
+# K3 / K4 (v2 pipeline, masked and unmasked) on a (2,3,4) window
+wd, wh, ww, nH, M = 2, 3, 4, 3, 8
+N = wd * wh * ww
+q, k, v = (spikes(M * nH * N, 32, rate=0.2) for _ in range(3))
+table = torch.randn((2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1), nH, device=dev) * 0.02
+region = torch.randint(0, 3, (4 * N,), device=dev, dtype=torch.uint8)
+for reg, nW in ((None, 1), (region, 4)):
+    out, _, _ = ops.qktv_debug(q, k, v, table, reg, M, nH, nW, (wd, wh, ww), 0.125, debug=False)
+    ops.qktv_bwd_debug(q, k, v, table, reg, torch.randn_like(out), M, nH, nW, (wd, wh, ww), 0.125)
+# K1 / K2
+cfg = ops.NeuronCfg(kind=capi.SDF_NEURON_LIF, v_th=0.1, v_reset=None, tau=2.0, detach_reset=True)
+u = torch.randn(10, 4096, device=dev, requires_grad=True)
+s = ops.neuron(u, cfg)
+s.sum().backward()
+torch.cuda.synchronize()
+print("sanitizer targets done")
