@@ -180,6 +180,20 @@ typedef struct {
 
 int sdf_psn_bwd(const sdf_psn_bwd_args* a);
 
+/* PSN parameter gradients from the outputs of sdf_psn_bwd: dW[t,k] = sum_n grad_h[t,n] * x[k,n], db[t] = sum_n grad_h[t,n]
+ * (autograd of the addmm in Spiking_submodules.py:207-211).  partials: [n_partial_blocks, T*T + T] per-block sums (the
+ * caller adds them up; unused rows are zero-filled).  T in {2, 4, 5, 10}. */
+typedef struct {
+  const float* grad_h;   /* [T, n_neurons] */
+  const float* x;        /* [T, n_neurons] */
+  float* partials;
+  int64_t n_partial_blocks;
+  int64_t T, n_neurons;
+  void* stream;
+} sdf_psn_wgrad_args;
+
+int sdf_psn_wgrad(const sdf_psn_wgrad_args* a);
+
 /* ---- K6: BatchNorm statistics over channels-last rows ---------------------------------------
  * Replaces the statistics half of sj_layer.BatchNorm2d on permuted views
  * (Spiking_swin_transformer3D.py:153,159,310,314,318,367,673,677,714,933,972). */

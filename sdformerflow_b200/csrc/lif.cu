@@ -669,3 +669,67 @@ extern "C" int sdf_psn_bwd(const sdf_psn_bwd_args* a) {
   }
   return finish_launch("sdf_psn_bwd");
 }
+
+// ---- PSN parameter gradients: dW[t,k] = sum_n gh[t,n] * x[k,n],  db[t] = sum_n gh[t,n] ------------------------------------
+// The reference gets them from autograd through addmm (Spiking_submodules.py:207-211): a [T, n] x [n, T] product with T <= 10
+// and n ~ 1e8, which library GEMMs handle badly (cuBLAS picks a large-K SIMT / unsplit kernel: 55-72 ms per training step).
+// Here: one thread walks a strided set of neurons with the T x T outer product in registers; per-block partials, summed by
+// the caller.  HBM-bound: 8*T bytes per neuron.
+namespace sdf {
+template <int T>
+__global__ void __launch_bounds__(256) psn_wgrad_kernel(const float* __restrict__ gh, const float* __restrict__ x, int64_t n,
+                                                        float* __restrict__ partial) {
+  float acc[T][T], accb[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    accb[t] = 0.f;
+#pragma unroll
+    for (int k = 0; k < T; ++k) acc[t][k] = 0.f;
+  }
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    float g[T], xv[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { g[t] = ld_stream1(gh + (int64_t)t * n + j); xv[t] = ld_stream1(x + (int64_t)t * n + j); }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      accb[t] += g[t];
+#pragma unroll
+      for (int k = 0; k < T; ++k) acc[t][k] = fmaf(g[t], xv[k], acc[t][k]);
+    }
+  }
+  __shared__ float red[8];
+  float* out = partial + (int64_t)blockIdx.x * (T * T + T);
+#pragma unroll
+  for (int e = 0; e < T * T + T; ++e) {
+    float v = e < T * T ? acc[e / T][e % T] : accb[e - T * T];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i];
+      out[e] = s;
+    }
+    __syncthreads();
+  }
+}
+}  // namespace sdf
+
+extern "C" int sdf_psn_wgrad(const sdf_psn_wgrad_args* a) {
+  SDF_REQUIRE(a && a->grad_h && a->x && a->partials, "sdf_psn_wgrad: null argument");
+  SDF_REQUIRE(a->n_neurons > 0 && a->n_partial_blocks >= 1, "sdf_psn_wgrad: empty problem");
+  int64_t blocks = (a->n_neurons + 255) / 256;
+  if (blocks > a->n_partial_blocks) blocks = a->n_partial_blocks;
+  if (blocks > sdf::kNumSMs * 4) blocks = sdf::kNumSMs * 4;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const int64_t per = a->T * a->T + a->T;
+  if (a->n_partial_blocks > blocks) cudaMemsetAsync(a->partials + blocks * per, 0, sizeof(float) * (a->n_partial_blocks - blocks) * per, st);
+  switch (a->T) {
+    case 2: sdf::psn_wgrad_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(a->grad_h, a->x, a->n_neurons, a->partials); break;
+    case 4: sdf::psn_wgrad_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(a->grad_h, a->x, a->n_neurons, a->partials); break;
+    case 5: sdf::psn_wgrad_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(a->grad_h, a->x, a->n_neurons, a->partials); break;
+    case 10: sdf::psn_wgrad_kernel<10><<<(unsigned)blocks, 256, 0, st>>>(a->grad_h, a->x, a->n_neurons, a->partials); break;
+    default: sdf::set_error("sdf_psn_wgrad: T=%lld not built (2, 4, 5, 10)", (long long)a->T); return SDF_ERR_UNSUPPORTED;
+  }
+  return sdf::finish_launch("sdf_psn_wgrad");
+}

@@ -335,9 +335,23 @@ class _PSNFn(torch.autograd.Function):
             "sdf_psn_bwd_args", u=_ptr(u), grad_spike=_ptr(gs), grad_u=_ptr(gu), grad_h=_ptr(gh),
             x_out=None if ctx.lay["stride_b"] == 0 else _ptr(xo), weight=_ptr(w), bias=_ptr(b), C=0, hw=1,
             lay=ctx.lay, surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
-        with _tf32(True):          # [T, n] x [n, T] over the huge neuron axis: tensor cores (TF32), like every other weight gradient
-            g_w = gh @ xo.t()
-        return gu, g_w, gh.sum(1, keepdim=True), None, None, None
+        g_w, g_b = _psn_param_grads(gh, xo.contiguous() if not xo.is_contiguous() else xo)
+        return gu, g_w, g_b, None, None, None
+
+
+def _psn_param_grads(gh, xo):
+    """(dW [T,T], db [T,1]) of a PSN from the kernel's grad_h and x: own strided-reduction kernel for the T the models use
+    (a [T, n] x [n, T] library GEMM with n ~ 1e8 cost 55-72 ms per training step), library fallback otherwise."""
+    T, n = gh.shape
+    if T in (2, 4, 5, 10):
+        part = torch.empty((N_PARTIAL, T * T + T), device=gh.device, dtype=torch.float32)
+        capi.call("sdf_psn_wgrad", capi.struct("sdf_psn_wgrad_args", grad_h=_ptr(gh), x=_ptr(xo), partials=_ptr(part),
+                                               n_partial_blocks=N_PARTIAL, T=T, n_neurons=n, stream=_stream()),
+                  algo_bytes=8 * T * n)
+        tot = part.sum(0)
+        return tot[:T * T].view(T, T), tot[T * T:].view(T, 1)
+    with _tf32(True):
+        return gh @ xo.t(), gh.sum(1, keepdim=True)
 
 
 def _check_psn(weight, bias, lay):
@@ -426,9 +440,7 @@ class _BNNeuronFn(torch.autograd.Function):
                 x_out=_ptr(xo), weight=_ptr(psn_w), bias=_ptr(psn_b), scale=_ptr(scale), shift=_ptr(shift),
                 bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=ctx.lay,
                 surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
-            with _tf32(True):
-                g_psn_w = gh @ xo.t()
-            g_psn_b = gh.sum(1, keepdim=True)
+            g_psn_w, g_psn_b = _psn_param_grads(gh, xo)
         du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, weight, mean, rstd, ctx.training)
         return du.view(u.shape), gw, gb, None, None, None, g_psn_w, g_psn_b, g_plif, None, None
 
@@ -1283,8 +1295,7 @@ class _QKTVFn(torch.autograd.Function):
                     weight=_ptr(pw), bias=_ptr(pb), scale=_ptr(sc), shift=_ptr(sh), bn_partials=_ptr(partials),
                     n_partial_blocks=N_PARTIAL, C=C, hw=1, lay=lay, surrogate=cfg.surrogate, sg_alpha=float(cfg.sg_alpha),
                     stream=_stream()))
-                with _tf32(True):
-                    psn_grads += [gh @ xo.t(), gh.sum(1, keepdim=True)]
+                psn_grads += list(_psn_param_grads(gh, xo))
             du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, ws_bn[i], mean, rstd, trains[i])
             outs.append(du.view(u.shape))
             bn_grads += [gw, gb]

@@ -51,17 +51,19 @@ def test_graphed_step_matches_eager(nt):
                 for v in st.values():
                     if torch.is_tensor(v):
                         v.zero_()
-        losses = [step(*inp).item() for _ in range(2)]
-        runs[graph] = (losses, {k: v.detach().clone() for k, v in model.named_parameters()}, step)
+        losses = [step(*inp).item()]
+        after1 = {k: v.detach().clone() for k, v in model.named_parameters()}
+        losses.append(step(*inp).item())
+        runs[graph] = (losses, after1, step)
     (le, pe, _), (lg, pg, sg) = runs[False], runs[True]
-    # step 1: the same computation from the same state.  Step 2 starts from weights that differ where a ~0 gradient changed
-    # sign between the runs (atomics order in the bias / table reductions; Adam's first step is +-lr whatever the magnitude),
-    # and a spiking net amplifies that: looser.
+    # step 1: the same computation from the same state (same loss, same updated weights).  Step 2 starts from weights that
+    # differ wherever a ~0 gradient changed sign between the runs (atomics order in the bias / table reductions; Adam's first
+    # step is +-lr whatever the magnitude) and a spiking net amplifies that: only its loss is compared, loosely.
     assert abs(le[0] - lg[0]) <= 1e-5 * abs(le[0]), (le, lg)
     assert abs(le[1] - lg[1]) <= 1e-2 * abs(le[1]), (le, lg)
     assert lg[1] != lg[0]                              # the weights really moved between replays
-    n_bad = sum(((pe[k] - pg[k]).abs() > 1e-4).sum().item() for k in pe)
-    assert n_bad <= 0.05 * sum(v.numel() for v in pe.values())
+    n_bad = sum(((pe[k] - pg[k]).abs() > 2e-5).sum().item() for k in pe)
+    assert n_bad <= 0.01 * sum(v.numel() for v in pe.values())
     n_params = sum(1 for p in sg.model.parameters() if p.requires_grad)
     if nt == "psn":
         assert len(sg.grads.params) < n_params        # dead attn_sn parameters are not in the optimizer
