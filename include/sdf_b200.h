@@ -673,7 +673,7 @@ typedef struct {
   int64_t workspace_bytes;
   int64_t rows, Cout, K, ldg;
   int32_t accumulate;
-  int32_t _pad;
+  int32_t s_max;       /* largest value in s: 1 = binary spikes (cheaper expansion), 0 = any u8 */
   void* stream;
 } sdf_spike_wgrad_args;
 
@@ -690,7 +690,7 @@ typedef struct {
   int64_t Nimg, H, W, Cin, Cout, Ho, Wo;
   int64_t kh, kw, stride, pad;
   int32_t accumulate;
-  int32_t _pad;
+  int32_t s_max;       /* largest value in x: 1 = binary spikes, 0 = any u8 */
   void* stream;
 } sdf_spike_conv_wgrad_args;
 

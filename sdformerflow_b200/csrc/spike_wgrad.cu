@@ -8,12 +8,15 @@
 //
 // D[M = co, N = (tap, ci)] accumulates in TMEM over a slab of pixels; both operands are "MN-major" for the MMA (the
 // contraction index is the slow one in memory), which tcgen05 takes directly through the descriptor major bits — no transposes.
-//   A = G, fp32, read as TF32: TMA boxes of [32 pixels][32 channels] land in the MN-major layout as they are.  MN-major TF32
-//       operands exist in one shared-memory layout only, SWIZZLE_128B with 32-byte atoms (UMMA layout type 1 = TMA
-//       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunk index XOR (row & 3), K groups of 4 rows (SBO = 512 B).
+// The MMA kind is f16 with bf16 operands: MN-major 16-bit operands use the ordinary SWIZZLE_128B layout and run at the full
+// bf16 rate (MN-major TF32, the first version of this kernel, exists only in the 32-byte-atom layout and measured 45 % of the
+// TF32 rate: the whole kernel was bound by it).
+//   A = G, fp32 in HBM: ONE TMA box of [32 pixels][128 channels] per stage lands raw; the converter warps split every value
+//       into bf16 hi + bf16 lo (hi = rn(g), lo = rn(g - hi): 16 significant bits, more than TF32's 11) and both planes are
+//       multiplied into the same accumulator.
 //   B = S, 1-byte spikes: TMA brings the raw bytes (4-D box shifted by the tap offset, zero fill outside the image = the
-//       convolution padding); four converter warps expand them to fp32 {0,1} in the same MN-major layout (exact in TF32).
-// One CTA = one (128-channel M tile, <= 256-column N tile, pixel slab); partial tiles go to a workspace and a second kernel
+//       convolution padding); the converter warps expand them to bf16 (exact) in the MN-major layout.
+// One CTA = one (128-channel M tile, <= 384-column N tile, pixel slab); partial tiles go to a workspace and a second kernel
 // reduces the slabs in a fixed order (deterministic) into the parameter's own layout (Linear [Cout,K], Conv OIHW).
 #include <cstdlib>
 #include "sdf_common.cuh"
@@ -22,14 +25,16 @@
 namespace sdf {
 using namespace tc;
 
-constexpr int kWgThreads = 320;      // warps 0-7: converters, then epilogue (warps 0-3); warp 8: TMA producer; warp 9: MMA issuer
-constexpr int kWgConv = 256;         // converter threads
+constexpr int kWgConv = 512;         // converter threads (16 warps: the conversion is latency-bound, 8 warps left it exposed)
+constexpr int kWgThreads = kWgConv + 64;   // warps 0-15: converters, then epilogue (warps 0-3); then the TMA producer warp and the MMA issuer warp
+constexpr int kWgProdWarp = kWgConv / 32, kWgMmaWarp = kWgConv / 32 + 1;
 constexpr int kWgRB = 32;            // pixels (GEMM K) per pipeline stage
 constexpr int kWgM = 128;            // output channels per tile
 constexpr int kWgMaxN = 384;         // columns per tile (TMEM columns of the accumulator; issued as <= 2 MMAs of N <= 256)
-constexpr int kWgMaxStages = 8;      // TMA ring (G tile + raw spike bytes): deep, the L2/HBM round trip is ~2 us under load
-constexpr int kWgBSlots = 2;         // converted-B ring
+constexpr int kWgMaxStages = 8;      // TMA ring (raw G tile + raw spike bytes): deep, the L2/HBM round trip is ~2 us under load
+constexpr int kWgBSlots = 2;         // converted-operand ring (A planes + B)
 constexpr int kWgPatchW = 16, kWgPatchH = 2;
+constexpr uint32_t kWgBlk = kWgRB * 128;   // one 64-column MN block of bf16: 32 pixel rows x 128 B
 
 struct WgradP {
   int n_chunks;            // pixel chunks (of 32) in the whole problem
@@ -47,18 +52,23 @@ struct WgradP {
   int conv, tiles_h, tiles_w, stride;
   int dh[9], dw[9];
   float* partial;          // [n_slabs][Cout][ncols_total]
+  int halo;                // stride-1 conv, one kernel row per tile: ONE spike box [2][16 + kw - 1][Cin] serves the kw taps
+  int binary;              // spikes are 0/1 (cheaper byte -> bf16 expansion)
+  int stg_bytes;           // raw spike bytes per stage
   int debug;               // timing experiments (SDF_WGRAD_DEBUG): 1 skip conversion, 2 also skip MMA, 3 MMA only (no TMA)
 };
 
-struct WgSmem { uint32_t a, stg, b, bars, tmem_slot, a_stage, b_slot, stg_stage, total; };
-__host__ __device__ inline WgSmem wg_smem_plan(int max_cols, int stages) {
+struct WgSmem { uint32_t a, b, g, stg, bars, tmem_slot, a_slot, b_slot, g_stage, stg_stage, total; };
+__host__ __device__ inline WgSmem wg_smem_plan(int max_cols, int stages, int stg_bytes) {
   WgSmem s;
   uint32_t o = 0;
-  s.a_stage = kWgM * kWgRB * 4;                            // 16 KB
-  s.b_slot = (uint32_t)((max_cols + 31) / 32) * (kWgRB * 128);   // fp32 B in whole 32-column MN blocks, <= 48 KB
-  s.stg_stage = ((uint32_t)max_cols * kWgRB + 1023) / 1024 * 1024;
-  s.a = o; o += stages * s.a_stage;
+  s.a_slot = 2 * (kWgM / 64) * kWgBlk;                              // bf16 hi + lo planes of the G tile: 16 KB
+  s.b_slot = (uint32_t)((max_cols + 63) / 64) * kWgBlk;             // bf16 spikes in whole 64-column MN blocks, <= 24 KB
+  s.g_stage = kWgM * kWgRB * 4;                                     // raw fp32 G box: 16 KB
+  s.stg_stage = ((uint32_t)stg_bytes + 1023) / 1024 * 1024;         // raw spike bytes
+  s.a = o; o += kWgBSlots * s.a_slot;
   s.b = o; o += kWgBSlots * s.b_slot;
+  s.g = o; o += stages * s.g_stage;
   s.stg = o; o += stages * s.stg_stage;
   s.bars = o; o += (2 * kWgMaxStages + 2 * kWgBSlots + 1) * 8;
   s.tmem_slot = o; o += 16;
@@ -66,16 +76,42 @@ __host__ __device__ inline WgSmem wg_smem_plan(int max_cols, int stages) {
   return s;
 }
 
+// two fp32 -> packed bf16x2 (x in the low half), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16(float x, float y) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+  return d;
+}
+// hi / lo bf16 split of two values: hi = rn(v), lo = rn(v - hi)
+__device__ __forceinline__ void split_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(x, y);
+  lo = pack_bf16(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xFFFF0000u));
+}
+// four spike bytes -> four bf16 (exact for 0..255): 0x4B000000 | b is 2^23 + b in fp32; the top half of (that - 2^23) is bf16(b)
+__device__ __forceinline__ uint2 bytes_to_bf16(uint32_t w) {
+  const uint32_t f0 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - 8388608.f);
+  const uint32_t f1 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - 8388608.f);
+  const uint32_t f2 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - 8388608.f);
+  const uint32_t f3 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - 8388608.f);
+  return make_uint2(__byte_perm(f0, f1, 0x7632), __byte_perm(f2, f3, 0x7632));
+}
+
+// the same for 0/1 bytes: bf16(1) = 0x3F80, so the high bytes are w * 0x3F and the low bytes w << 7 (no carries between bytes)
+__device__ __forceinline__ uint2 bits_to_bf16(uint32_t w) {
+  const uint32_t h = w * 0x3Fu, l = w << 7;
+  return make_uint2(__byte_perm(l, h, 0x5140), __byte_perm(l, h, 0x7362));
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS, const WgradP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const WgSmem sp = wg_smem_plan(p.max_cols, p.stages);
+  const WgSmem sp = wg_smem_plan(p.max_cols, p.stages, p.stg_bytes);
   const int kWgStages = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
-  uint64_t* full_tma = bars;                                   // TMA landed (A + raw spike bytes)            [stages]
-  uint64_t* empty = bars + kWgMaxStages;                       // MMAs reading A of the stage retired         [stages]
-  uint64_t* full_b = bars + 2 * kWgMaxStages;                  // converters finished a B slot                [kWgBSlots]
-  uint64_t* empty_b = bars + 2 * kWgMaxStages + kWgBSlots;     // MMAs reading the B slot retired             [kWgBSlots]
+  uint64_t* full_tma = bars;                                   // TMA landed (raw G + raw spike bytes)         [stages]
+  uint64_t* empty = bars + kWgMaxStages;                       // converters finished reading the raw stage   [stages]
+  uint64_t* full_b = bars + 2 * kWgMaxStages;                  // converters finished an operand slot         [kWgBSlots]
+  uint64_t* empty_b = bars + 2 * kWgMaxStages + kWgBSlots;     // MMAs reading the operand slot retired       [kWgBSlots]
   uint64_t* done = bars + 2 * kWgMaxStages + 2 * kWgBSlots;    // accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_slot);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -94,50 +130,49 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     ci0 = 0; width = p.Cin;
   }
   const int ncols = ntap * width;               // multiple of 16 (host-checked), <= kWgMaxN
-  // <= 2 MMAs per K step: N0 + N1 = ncols, both multiples of 16 and <= 256, N0 a multiple of 32 (whole MN blocks)
-  const int N0 = ncols <= 256 ? ncols : ((ncols / 2 + 31) / 32) * 32;
+  // <= 2 MMAs per K step: N0 + N1 = ncols, both multiples of 16 and <= 256, N0 a multiple of 64 (whole MN blocks)
+  const int N0 = ncols <= 256 ? ncols : ((ncols / 2 + 63) / 64) * 64;
   const int N1 = ncols - N0;
   const int c_begin = slab * p.chunks_per_slab;
   const int c_end = min(p.n_chunks, c_begin + p.chunks_per_slab);
   const int n_iter = c_end - c_begin;
 
   if (tid == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_tma[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_tma[i], 1); mbar_init(&empty[i], kWgConv / 32); }
     for (int i = 0; i < kWgBSlots; ++i) { mbar_init(&full_b[i], kWgConv / 32); mbar_init(&empty_b[i], 1); }
     mbar_init(done, 1);
     mbar_fence_init();
   }
-  if (warp == 8 && elect_one()) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmS); }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == kWgProdWarp && elect_one()) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmS); }
+  if (warp == kWgMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b), stg_base = smem_u32(smem + sp.stg);
-  const uint32_t kAStage = sp.a_stage, kBSlot = sp.b_slot, kStgStage = sp.stg_stage;
-  constexpr uint32_t kBlk = kWgRB * 128;        // one 32-column MN block: 32 pixel rows x 128 B
+  const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b);
+  const uint32_t g_base = smem_u32(smem + sp.g), stg_base = smem_u32(smem + sp.stg);
+  const uint32_t kASlot = sp.a_slot, kBSlot = sp.b_slot, kGStage = sp.g_stage, kStgStage = sp.stg_stage;
 
-  if (warp == 8) {
-    // ===== TMA producer: lane 0 waits for the stage and posts the byte count, then every lane issues ONE box of the stage
-    // (a bulk-tensor copy costs its issuing thread a few hundred cycles; seven boxes per stage issued serially were the
-    // bottleneck of the whole kernel) =====
+  if (warp == kWgProdWarp) {
+    // ===== TMA producer: lane 0 waits for the stage, posts the byte count and issues the G box; lanes 4.. issue ONE spike box
+    // each (a bulk-tensor copy costs its issuing thread a few hundred cycles) =====
     const int lane = tid & 31;
     const int per_img = p.tiles_h * p.tiles_w;
-    const int n_sbox = ntap * p.nbox;
+    const int n_sbox = p.halo ? 1 : ntap * p.nbox;
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kWgStages;
       const uint32_t ph = (it / kWgStages) & 1;
       if (lane == 0) {
         mbar_wait(&empty[s], ph ^ 1);
         if (p.debug == 3) mbar_arrive(&full_tma[s]);
-        else mbar_expect_tx(&full_tma[s], kAStage + (uint32_t)(n_sbox * p.box_w * kWgRB));
+        else mbar_expect_tx(&full_tma[s], kGStage + (uint32_t)(p.halo ? p.stg_bytes : n_sbox * p.box_w * kWgRB));
       }
       __syncwarp();
       if (p.debug == 3) continue;
       const int chunk = c_begin + it;
       if (!p.conv) {
-        if (lane < 4) tma_load_2d(&tmG, &full_tma[s], a_base + s * kAStage + lane * kBlk, m_tile * kWgM + lane * 32, chunk * kWgRB);
-        else if (lane - 4 < p.nbox) {
+        if (lane == 0) tma_load_2d(&tmG, &full_tma[s], g_base + s * kGStage, m_tile * kWgM, chunk * kWgRB);
+        else if (lane >= 4 && lane - 4 < p.nbox) {
           const int j = lane - 4;
           tma_load_2d(&tmS, &full_tma[s], stg_base + s * kStgStage + j * (p.box_w * kWgRB), ci0 + j * p.box_w, chunk * kWgRB);
         }
@@ -145,8 +180,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         const int img = chunk / per_img, rem = chunk - img * per_img;
         const int py = rem / p.tiles_w, px = rem - py * p.tiles_w;
         const int w0 = px * kWgPatchW, h0 = py * kWgPatchH;
-        if (lane < 4) tma_load_4d(&tmG, &full_tma[s], a_base + s * kAStage + lane * kBlk, m_tile * kWgM + lane * 32, w0, h0, img);
-        else if (lane - 4 < n_sbox) {
+        if (lane == 0) tma_load_4d(&tmG, &full_tma[s], g_base + s * kGStage, m_tile * kWgM, w0, h0, img);
+        else if (p.halo) {
+          if (lane == 4) tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage, ci0, w0 + p.dw[tap0], h0 + p.dh[tap0], img);
+        } else if (lane >= 4 && lane - 4 < n_sbox) {
           const int b = lane - 4, t = b / p.nbox, j = b - t * p.nbox;
           tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage + b * (p.box_w * kWgRB), ci0 + j * p.box_w,
                       w0 * p.stride + p.dw[tap0 + t], h0 * p.stride + p.dh[tap0 + t], img);
@@ -154,69 +191,90 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       }
       __syncwarp();
     }
-  } else if (warp == 9) {
+  } else if (warp == kWgMmaWarp) {
     if (elect_one()) {
-      const uint32_t idesc0 = idesc_tf32(kWgM, N0, 1, 1);
-      const uint32_t idesc1 = idesc_tf32(kWgM, N1 > 0 ? N1 : 16, 1, 1);
-      constexpr uint32_t hi = desc_hi_sw128_base32(512);
+      const uint32_t idesc0 = idesc_bf16(kWgM, N0, 1, 1);
+      const uint32_t idesc1 = idesc_bf16(kWgM, N1 > 0 ? N1 : 16, 1, 1);
+      constexpr uint32_t hi = desc_hi_sw128(1024);     // K groups of 8 pixels are 8 x 128 B apart
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kWgStages, bs = it % kWgBSlots;
-        const uint32_t ph = (it / kWgStages) & 1, bph = (it / kWgBSlots) & 1;
-        mbar_wait(&full_tma[s], ph);
+        const int bs = it % kWgBSlots;
+        const uint32_t bph = (it / kWgBSlots) & 1;
         mbar_wait(&full_b[bs], bph);
         tc_fence_after();
+        if (p.debug != 2) {
 #pragma unroll
-        for (int g = 0; g < kWgRB / 8; ++g) {   // one MMA (pair) per 8 pixels (K = 8 for TF32): the 8-row group is 1024 B further
-          const uint32_t a_lo = desc_lo(a_base + s * kAStage + g * 1024, kBlk);
-          const uint32_t b_lo = desc_lo(b_base + bs * kBSlot + g * 1024, kBlk);
-          if (p.debug != 2) {
-            mma_ss<KIND_TF32>(tmem_base, a_lo, b_lo, hi, idesc0, (it | g) != 0 ? 1u : 0u);
-            if (N1 > 0) mma_ss<KIND_TF32>(tmem_base + N0, a_lo, b_lo + (uint32_t)(N0 / 32) * (kBlk >> 4), hi, idesc1, (it | g) != 0 ? 1u : 0u);
+          for (int g = 0; g < kWgRB / 16; ++g) {       // bf16 MMA: K = 16 pixels = two 8-row groups, 2048 B per step
+            const uint32_t b_lo = desc_lo(b_base + bs * kBSlot + g * 2048, kWgBlk);
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {           // G hi plane, then G lo plane, into the same accumulator
+              const uint32_t a_lo = desc_lo(a_base + bs * kASlot + pl * (2 * kWgBlk) + g * 2048, kWgBlk);
+              const uint32_t acc = (it | g | pl) != 0 ? 1u : 0u;
+              mma_ss<KIND_F16>(tmem_base, a_lo, b_lo, hi, idesc0, acc);
+              if (N1 > 0) mma_ss<KIND_F16>(tmem_base + N0, a_lo, b_lo + (uint32_t)(N0 / 64) * (kWgBlk >> 4), hi, idesc1, acc);
+            }
           }
         }
-        tc_commit(&empty[s]);
         tc_commit(&empty_b[bs]);
       }
       tc_commit(done);
     }
   } else {
-    // ===== converters: raw spike bytes -> fp32 {0,1} in the MN-major SWIZZLE_128B (32-byte atom) layout =====
-    // Thread -> (fixed 4-spike word q of the tile row, row sub-phase): no divisions inside the loop.
-    const int q_per_row = ncols >> 2;           // u32 words (4 spikes) per pixel row, <= 96
-    const int rows_par = kWgConv / q_per_row;   // pixel rows converted in parallel (>= 2)
+    // ===== converters: raw fp32 G -> bf16 hi/lo planes, raw spike bytes -> bf16, both in the MN-major SWIZZLE_128B layout
+    // (64-column blocks of [32 pixels][128 B], 16-byte chunk index XOR (pixel & 7)) =====
+    // spikes: thread -> (fixed 8-spike word q of the tile row, row sub-phase): no divisions inside the loop.
+    const int q_per_row = ncols >> 3;           // 8-spike words per pixel row, <= 48
+    const int rows_par = kWgConv / q_per_row;   // pixel rows converted in parallel (>= 5)
     const int q = tid % q_per_row, rsub = tid / q_per_row;
-    const int wq4 = width >> 2;
-    const int tq = q / wq4, qc = q - tq * wq4;  // tap-local index, word within the tap's channels
-    const int ch = qc * 4, bj = ch / p.box_w;   // channel within the tap slice -> (spike box, offset in the box row)
-    const uint32_t src_off = (uint32_t)((tq * p.nbox + bj) * (p.box_w * kWgRB) + (ch - bj * p.box_w));
-    const int nb = q >> 3, c = q & 7;
-    const uint32_t dst_blk = (uint32_t)nb * kBlk;
+    const int wq8 = width >> 3;
+    const int tq = q / wq8, qc = q - tq * wq8;  // tap-local index, word within the tap's channels
+    const int ch = qc * 8, bj = ch / p.box_w;   // channel within the tap slice -> (spike box, offset in the box row)
+    // halo box: pixel (h, w) of tap tq is row h * (16 + ntap - 1) + w + tq of the one staged box
+    const uint32_t src_off = p.halo ? (uint32_t)(tq * p.box_w + ch)
+                                    : (uint32_t)((tq * p.nbox + bj) * (p.box_w * kWgRB) + (ch - bj * p.box_w));
+    const int halo_extra = p.halo ? ntap - 1 : 0;
+    const int c = q & 7;
+    const uint32_t dst_blk = (uint32_t)(q >> 3) * kWgBlk;
     const bool conv_thread = rsub < rows_par;
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kWgStages, bs = it % kWgBSlots;
       const uint32_t ph = (it / kWgStages) & 1, bph = (it / kWgBSlots) & 1;
-      if ((tid & 31) == 0) {                    // one polling lane per warp: 256 threads spinning on the barrier that the
-        mbar_wait(&empty_b[bs], bph ^ 1);       // TMA completions update slowed the copies down
-        mbar_wait(&full_tma[s], ph);            // (empty_b: the MMAs that read this B slot two iterations ago have retired)
+      if ((tid & 31) == 0) {                    // one polling lane per warp
+        mbar_wait(&empty_b[bs], bph ^ 1);       // the MMAs that read this operand slot two iterations ago have retired
+        mbar_wait(&full_tma[s], ph);
       }
       __syncwarp();
-      const uint8_t* stg = smem + sp.stg + s * kStgStage + src_off;
-      uint8_t* bdst = smem + sp.b + bs * kBSlot + dst_blk;
-      if (conv_thread && p.debug == 0) {
+      if (p.debug == 0) {
+        // G: 32 pixels x 16 chunks of 8 channels = 512 tasks
+        const uint8_t* gsrc = smem + sp.g + s * kGStage;
+        uint8_t* adst = smem + sp.a + bs * kASlot;
+#pragma unroll
+        for (int j = 0; j < 512 / kWgConv; ++j) {
+          const int task = tid + j * kWgConv, r = task >> 4, cg = task & 15;
+          const float4 v0 = *reinterpret_cast<const float4*>(gsrc + r * 512 + cg * 32);
+          const float4 v1 = *reinterpret_cast<const float4*>(gsrc + r * 512 + cg * 32 + 16);
+          uint4 h, l;
+          split_bf16(v0.x, v0.y, h.x, l.x);
+          split_bf16(v0.z, v0.w, h.y, l.y);
+          split_bf16(v1.x, v1.y, h.z, l.z);
+          split_bf16(v1.z, v1.w, h.w, l.w);
+          uint8_t* d = adst + (cg >> 3) * kWgBlk + r * 128 + (((cg & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(d) = h;
+          *reinterpret_cast<uint4*>(d + 2 * kWgBlk) = l;
+        }
+        if (conv_thread) {
+          const uint8_t* stg = smem + sp.stg + s * kStgStage + src_off;
+          uint8_t* bdst = smem + sp.b + bs * kBSlot + dst_blk;
 #pragma unroll 4
-        for (int r = rsub; r < kWgRB; r += rows_par) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + r * p.box_w);
-          // byte b -> float(b) without I2F: 0x4B000000 | b is 2^23 + b
-          const float4 v = make_float4(__uint_as_float(0x4B000000u | (w & 0xFF)) - 8388608.f,
-                                       __uint_as_float(0x4B000000u | ((w >> 8) & 0xFF)) - 8388608.f,
-                                       __uint_as_float(0x4B000000u | ((w >> 16) & 0xFF)) - 8388608.f,
-                                       __uint_as_float(0x4B000000u | (w >> 24)) - 8388608.f);
-          *reinterpret_cast<float4*>(bdst + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))) = v;
+          for (int r = rsub; r < kWgRB; r += rows_par) {
+            const uint2 w = *reinterpret_cast<const uint2*>(stg + (r + (r >> 4) * halo_extra) * p.box_w);
+            const uint2 lo = p.binary ? bits_to_bf16(w.x) : bytes_to_bf16(w.x), hi2 = p.binary ? bits_to_bf16(w.y) : bytes_to_bf16(w.y);
+            *reinterpret_cast<uint4*>(bdst + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(lo.x, lo.y, hi2.x, hi2.y);
+          }
         }
       }
       fence_async_smem();
       __syncwarp();
-      if (elect_one()) mbar_arrive(&full_b[bs]);
+      if (elect_one()) { mbar_arrive(&full_b[bs]); mbar_arrive(&empty[s]); }
     }
     // ===== epilogue (warps 0-3): TMEM -> this slab's partial tile =====
     if (warp < 4) {
@@ -243,7 +301,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+  if (warp == kWgMmaWarp) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
 // dW[co*s_co + ci*s_ci + tap*s_tap] (+)= sum_s partial[s][co][tap*Cin + ci], slabs added in index order
@@ -319,11 +377,12 @@ static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tm
               (long long)p.n_slabs * p.Cout * p.ncols_total * 4);
   p.max_cols = p.ci_tiles > 1 ? p.ci_width : p.taps_per_tile * p.Cin;
   SDF_REQUIRE(p.max_cols % 16 == 0 && p.max_cols <= kWgMaxN && p.box_w % 16 == 0, "%s: unsupported column tiling (%d columns, box %d)", what, p.max_cols, p.box_w);
+  if (!p.halo) p.stg_bytes = p.max_cols * kWgRB;
   p.stages = 2;
   for (int st_ = kWgMaxStages; st_ >= 2; --st_)
-    if (wg_smem_plan(p.max_cols, st_).total <= 220 * 1024) { p.stages = st_; break; }
+    if (wg_smem_plan(p.max_cols, st_, p.stg_bytes).total <= 220 * 1024) { p.stages = st_; break; }
   static bool attr_done = false;
-  const WgSmem sp = wg_smem_plan(p.max_cols, p.stages);
+  const WgSmem sp = wg_smem_plan(p.max_cols, p.stages, p.stg_bytes);
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return SDF_ERR_CUDA; }
@@ -349,14 +408,15 @@ extern "C" int sdf_spike_wgrad(const sdf_spike_wgrad_args* a) {
   wgrad_tiles(p.Cin, 1, &p.taps_per_tile, &p.ci_tiles, &p.ci_width, &p.n_ntiles);
   p.n_chunks = (int)((a->rows + kWgRB - 1) / kWgRB);
   p.partial = a->workspace;
+  p.binary = a->s_max == 1;
   p.nbox = p.ci_width > 256 ? 2 : 1;
   p.box_w = p.ci_width / p.nbox;
   CUtensorMap tmG, tmS;
   {
     const uint64_t dims[2] = {(uint64_t)a->Cout, (uint64_t)a->rows};
     const uint64_t str[1] = {(uint64_t)a->ldg * 4};
-    const uint32_t box[2] = {32, (uint32_t)kWgRB};
-    int st = make_tmap(&tmG, 1, 2, a->g, dims, str, box, nullptr, 12832);
+    const uint32_t box[2] = {(uint32_t)kWgM, (uint32_t)kWgRB};
+    int st = make_tmap(&tmG, 1, 2, a->g, dims, str, box, nullptr, 0);
     if (st) return st;
   }
   {
@@ -387,21 +447,26 @@ extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
   p.stride = (int)a->stride;
   for (int i = 0; i < p.taps; ++i) { p.dh[i] = i / (int)a->kw - (int)a->pad; p.dw[i] = i % (int)a->kw - (int)a->pad; }
   p.partial = a->workspace;
+  p.binary = a->s_max == 1;
   p.nbox = p.ci_width > 256 ? 2 : 1;
   p.box_w = p.ci_width / p.nbox;
+  // one kernel row per N tile at stride 1: the kw taps of the row read overlapping pixels, one box with a (kw - 1)-pixel halo
+  p.halo = a->stride == 1 && a->kw > 1 && p.ci_tiles == 1 && p.nbox == 1 && p.taps_per_tile == (int)a->kw;
+  if (p.halo) p.stg_bytes = kWgPatchH * (kWgPatchW + (int)a->kw - 1) * p.box_w;
   CUtensorMap tmG, tmS;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
     const uint64_t str[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->Wo * a->Cout * 4, (uint64_t)a->Ho * a->Wo * a->Cout * 4};
-    const uint32_t box[4] = {32, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
-    int st = make_tmap(&tmG, 1, 4, a->g, dims, str, box, nullptr, 12832);
+    const uint32_t box[4] = {(uint32_t)kWgM, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
+    int st = make_tmap(&tmG, 1, 4, a->g, dims, str, box, nullptr, 0);
     if (st) return st;
   }
   {
     const int width = p.box_w;
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
     const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
-    const uint32_t box[4] = {(uint32_t)width, (uint32_t)(kWgPatchW * a->stride), (uint32_t)(kWgPatchH * a->stride), 1};
+    const uint32_t box[4] = {(uint32_t)width, (uint32_t)(p.halo ? kWgPatchW + a->kw - 1 : kWgPatchW * a->stride),
+                             (uint32_t)(kWgPatchH * a->stride), 1};
     const uint32_t es[4] = {1, (uint32_t)a->stride, (uint32_t)a->stride, 1};
     int st = make_tmap(&tmS, 0, 4, a->x, dims, str, box, es, 0);
     if (st) return st;

@@ -87,7 +87,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
 
-enum MmaKind { KIND_I8 = 0, KIND_TF32 = 1 };
+enum MmaKind { KIND_I8 = 0, KIND_TF32 = 1, KIND_F16 = 2 };   // KIND_F16 covers fp16 and bf16 operands (a/b_format)
 // D[tmem] (+)= A[smem] * B[smem]; descriptors as (lo word, shared hi word); acc = 0 overwrites D
 template <int KIND>
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
@@ -96,10 +96,15 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t 
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
         : "memory");
-  } else {
+  } else if (KIND == KIND_TF32) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
         : "memory");
   }
 }
@@ -144,6 +149,11 @@ __host__ __device__ constexpr uint32_t desc_hi_sw128_base32(uint32_t sbo_bytes) 
 // kind::i8 0 = u8, 1 = s8; kind::tf32 2 = TF32; a_major bit 15, b_major bit 16 (1 = MN-major); N >> 3 in [17,23); M >> 4 in [24,29).
 __host__ __device__ constexpr uint32_t idesc_i8_u8s8(int M, int N) {
   return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// kind::f16 with bf16 operands (format 1), fp32 accumulate
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |

@@ -594,7 +594,7 @@ class _PlainLinearFn(torch.autograd.Function):
 class _SpikeGemmFn(torch.autograd.Function):
     """y = spikes @ W^T (+ b) on the tcgen05 engine: kind::i8 forward on the 1-byte spikes (gemm.spike_gemm_fwd, exact
     integer accumulation of three weight digit planes, BN partial sums from the epilogue), TF32 data gradient
-    (gemm.gemm_tf32) and MN-major TF32 weight gradient (gemm.spike_wgrad).  Reference: sj_layer.Linear on spike tensors,
+    (gemm.gemm_tf32) and MN-major bf16 hi/lo weight gradient (gemm.spike_wgrad).  Reference: sj_layer.Linear on spike tensors,
     Spiking_swin_transformer3D.py:126-131,267-290,632-652,909."""
 
     @staticmethod
@@ -625,7 +625,7 @@ class _SpikeGemmFn(torch.autograd.Function):
             holder.add_grad(gemm.gemm_tf32(g2, wt).view(a.shape))
             gtok = _zero_token(gy.device)
         if ctx.needs_input_grad[1]:
-            gw = gemm.spike_wgrad(g2, a.view(-1, K))
+            gw = gemm.spike_wgrad(g2, a.view(-1, K), s_max=1)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2.sum(0)
         return gtok, gw, gb, None, None
@@ -782,7 +782,7 @@ class _SpikeConvGemmFn(torch.autograd.Function):
             holder.add_grad(gx.view(x.shape))
             gtok = _zero_token(gy.device)
         if ctx.needs_input_grad[1]:
-            gw = gemm.spike_conv_wgrad(g4, x.view(-1, H, W, Cin), kh, kw, stride, padding)
+            gw = gemm.spike_conv_wgrad(g4, x.view(-1, H, W, Cin), kh, kw, stride, padding, s_max=1)
         if has_bias and ctx.needs_input_grad[2]:
             gb = g4.sum((0, 1, 2))
         return gtok, gw, gb, None, None, None, None

@@ -134,7 +134,11 @@ def test_spike_wgrad(rows, K, Cout):
     dw = gemm.spike_wgrad(g, s)
     ref = g.double().t() @ s.double()
     err = (dw.double() - ref).abs().max().item() / ref.abs().max().item()
-    assert err <= 2e-3, err          # G enters as TF32 (truncated 10-bit mantissa); spikes are exact
+    assert err <= 1e-4, err          # G enters as bf16 hi + bf16 lo (16 significant bits); spikes are exact
+    assert torch.equal(dw, gemm.spike_wgrad(g, s, s_max=1))     # the 0/1 expansion produces the same bf16 operand
+    s3 = (s * torch.randint(1, 4, s.shape, device=DEV, dtype=torch.uint8))       # general path: small integers
+    ref3 = g.double().t() @ s3.double()
+    assert (gemm.spike_wgrad(g, s3).double() - ref3).abs().max().item() <= 1e-4 * ref3.abs().max().item()
     # exact-operand case: fp32-grade
     g2 = (torch.randint(-512, 512, (rows, Cout)).float() / 256).to(DEV)
     dw2 = gemm.spike_wgrad(g2, s)
@@ -157,6 +161,7 @@ def test_spike_conv_wgrad(Nimg, H, W, Cin, Cout, k, stride, pad):
     (ref,) = torch.autograd.grad(y, wr, g.permute(0, 3, 1, 2).double())
     assert dw.shape == ref.shape
     assert (dw.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert torch.equal(dw, gemm.spike_conv_wgrad(g, x, k, k, stride, pad, s_max=1))
 
 
 @pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,pad", [(3, 24, 32, 96, 96, 3, 1), (2, 20, 27, 96, 96, 3, 1), (5, 9, 12, 768, 768, 3, 1),
