@@ -11,9 +11,11 @@
 // The MMA kind is f16 with bf16 operands: MN-major 16-bit operands use the ordinary SWIZZLE_128B layout and run at the full
 // bf16 rate (MN-major TF32, the first version of this kernel, exists only in the 32-byte-atom layout and measured 45 % of the
 // TF32 rate: the whole kernel was bound by it).
-//   A = G, fp32 in HBM: ONE TMA box of [32 pixels][128 channels] per stage lands raw; the converter warps split every value
-//       into bf16 hi + bf16 lo (hi = rn(g), lo = rn(g - hi): 16 significant bits, more than TF32's 11) and both planes are
-//       multiplied into the same accumulator.
+//   A = G, fp32 in HBM: ONE TMA box of [32 pixels][128 channels] per stage lands raw; four converter warps (thread = output
+//       channel = TMEM lane) split every value into bf16 hi + bf16 lo (hi = rn(g), lo = rn(g - hi): 16 significant bits,
+//       more than TF32's 11) and write both planes to TENSOR MEMORY (tcgen05.st): the MMA takes A from TMEM, so G costs no
+//       shared-memory store and no shared-memory operand read (the kernel is bound by shared-memory bandwidth otherwise);
+//       both planes are multiplied into the same accumulator.
 //   B = S, 1-byte spikes: TMA brings the raw bytes (4-D box shifted by the tap offset, zero fill outside the image = the
 //       convolution padding); the converter warps expand them to bf16 (exact) in the MN-major layout.
 // One CTA = one (128-channel M tile, <= 384-column N tile, pixel slab); partial tiles go to a workspace and a second kernel
@@ -32,7 +34,10 @@ constexpr int kWgRB = 32;            // pixels (GEMM K) per pipeline stage
 constexpr int kWgM = 128;            // output channels per tile
 constexpr int kWgMaxN = 384;         // columns per tile (TMEM columns of the accumulator; issued as <= 2 MMAs of N <= 256)
 constexpr int kWgMaxStages = 8;      // TMA ring (raw G tile + raw spike bytes): deep, the L2/HBM round trip is ~2 us under load
-constexpr int kWgBSlots = 2;         // converted-operand ring (A planes + B)
+constexpr int kWgBSlots = 2;         // converted-operand ring (A planes in TMEM + B in shared memory)
+constexpr int kWgGConv = 128;        // threads 0..127 convert G (one output channel = one TMEM lane each), the rest convert spikes
+                                     // (8 G warps, 16 pixels each, measured 5-10 % slower: the spike side is the critical one)
+constexpr int kWgACols = 32;         // TMEM columns of one A slot: [hi px 0-15 | hi px 16-31 | lo px 0-15 | lo px 16-31], 8 columns each
 constexpr int kWgPatchW = 16, kWgPatchH = 2;
 constexpr uint32_t kWgBlk = kWgRB * 128;   // one 64-column MN block of bf16: 32 pixel rows x 128 B
 
@@ -58,15 +63,13 @@ struct WgradP {
   int debug;               // timing experiments (SDF_WGRAD_DEBUG): 1 skip conversion, 2 also skip MMA, 3 MMA only (no TMA)
 };
 
-struct WgSmem { uint32_t a, b, g, stg, bars, tmem_slot, a_slot, b_slot, g_stage, stg_stage, total; };
+struct WgSmem { uint32_t b, g, stg, bars, tmem_slot, b_slot, g_stage, stg_stage, total; };
 __host__ __device__ inline WgSmem wg_smem_plan(int max_cols, int stages, int stg_bytes) {
   WgSmem s;
   uint32_t o = 0;
-  s.a_slot = 2 * (kWgM / 64) * kWgBlk;                              // bf16 hi + lo planes of the G tile: 16 KB
   s.b_slot = (uint32_t)((max_cols + 63) / 64) * kWgBlk;             // bf16 spikes in whole 64-column MN blocks, <= 24 KB
   s.g_stage = kWgM * kWgRB * 4;                                     // raw fp32 G box: 16 KB
   s.stg_stage = ((uint32_t)stg_bytes + 1023) / 1024 * 1024;         // raw spike bytes
-  s.a = o; o += kWgBSlots * s.a_slot;
   s.b = o; o += kWgBSlots * s.b_slot;
   s.g = o; o += stages * s.g_stage;
   s.stg = o; o += stages * s.stg_stage;
@@ -149,9 +152,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_base = smem_u32(smem + sp.a), b_base = smem_u32(smem + sp.b);
+  const uint32_t b_base = smem_u32(smem + sp.b);
   const uint32_t g_base = smem_u32(smem + sp.g), stg_base = smem_u32(smem + sp.stg);
-  const uint32_t kASlot = sp.a_slot, kBSlot = sp.b_slot, kGStage = sp.g_stage, kStgStage = sp.stg_stage;
+  const uint32_t kBSlot = sp.b_slot, kGStage = sp.g_stage, kStgStage = sp.stg_stage;
 
   if (warp == kWgProdWarp) {
     // ===== TMA producer: lane 0 waits for the stage, posts the byte count and issues the G box; lanes 4.. issue ONE spike box
@@ -193,8 +196,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     }
   } else if (warp == kWgMmaWarp) {
     if (elect_one()) {
-      const uint32_t idesc0 = idesc_bf16(kWgM, N0, 1, 1);
-      const uint32_t idesc1 = idesc_bf16(kWgM, N1 > 0 ? N1 : 16, 1, 1);
+      const uint32_t idesc0 = idesc_bf16(kWgM, N0, 0, 1);      // A: TMEM (K-major by construction), B: MN-major
+      const uint32_t idesc1 = idesc_bf16(kWgM, N1 > 0 ? N1 : 16, 0, 1);
       constexpr uint32_t hi = desc_hi_sw128(1024);     // K groups of 8 pixels are 8 x 128 B apart
       for (int it = 0; it < n_iter; ++it) {
         const int bs = it % kWgBSlots;
@@ -207,10 +210,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
             const uint32_t b_lo = desc_lo(b_base + bs * kBSlot + g * 2048, kWgBlk);
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {           // G hi plane, then G lo plane, into the same accumulator
-              const uint32_t a_lo = desc_lo(a_base + bs * kASlot + pl * (2 * kWgBlk) + g * 2048, kWgBlk);
+              const uint32_t a_t = tmem_base + kWgMaxN + bs * kWgACols + pl * 16 + g * 8;
               const uint32_t acc = (it | g | pl) != 0 ? 1u : 0u;
-              mma_ss<KIND_F16>(tmem_base, a_lo, b_lo, hi, idesc0, acc);
-              if (N1 > 0) mma_ss<KIND_F16>(tmem_base + N0, a_lo, b_lo + (uint32_t)(N0 / 64) * (kWgBlk >> 4), hi, idesc1, acc);
+              mma_ts_f16(tmem_base, a_t, b_lo, hi, idesc0, acc);
+              if (N1 > 0) mma_ts_f16(tmem_base + N0, a_t, b_lo + (uint32_t)(N0 / 64) * (kWgBlk >> 4), hi, idesc1, acc);
             }
           }
         }
@@ -219,12 +222,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       tc_commit(done);
     }
   } else {
-    // ===== converters: raw fp32 G -> bf16 hi/lo planes, raw spike bytes -> bf16, both in the MN-major SWIZZLE_128B layout
-    // (64-column blocks of [32 pixels][128 B], 16-byte chunk index XOR (pixel & 7)) =====
-    // spikes: thread -> (fixed 8-spike word q of the tile row, row sub-phase): no divisions inside the loop.
+    // ===== converters =====
+    // threads 0..127 (warps 0-3): G.  Thread = output channel = TMEM lane: 32 pixel values of the raw box (a warp reads 128
+    //   contiguous bytes per pixel row) -> bf16 hi / lo pairs -> 2 x 16 TMEM columns of the A slot.
+    // threads 128..511: spikes.  Raw bytes -> bf16 in the MN-major SWIZZLE_128B layout (64-column blocks of [32 pixels][128 B],
+    //   16-byte chunk index XOR (pixel & 7)); thread -> (fixed 8-spike word q of the tile row, row sub-phase).
+    const bool g_thread = tid < kWgGConv;
+    const int tid2 = tid - kWgGConv;
     const int q_per_row = ncols >> 3;           // 8-spike words per pixel row, <= 48
-    const int rows_par = kWgConv / q_per_row;   // pixel rows converted in parallel (>= 5)
-    const int q = tid % q_per_row, rsub = tid / q_per_row;
+    const int rows_par = (kWgConv - kWgGConv) / q_per_row;   // pixel rows converted in parallel (>= 8)
+    const int q = g_thread ? 0 : tid2 % q_per_row, rsub = g_thread ? kWgRB : tid2 / q_per_row;
     const int wq8 = width >> 3;
     const int tq = q / wq8, qc = q - tq * wq8;  // tap-local index, word within the tap's channels
     const int ch = qc * 8, bj = ch / p.box_w;   // channel within the tap slice -> (spike box, offset in the box row)
@@ -234,7 +241,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     const int halo_extra = p.halo ? ntap - 1 : 0;
     const int c = q & 7;
     const uint32_t dst_blk = (uint32_t)(q >> 3) * kWgBlk;
-    const bool conv_thread = rsub < rows_par;
+    const bool conv_thread = !g_thread && rsub < rows_par;
+    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kWgMaxN;
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kWgStages, bs = it % kWgBSlots;
       const uint32_t ph = (it / kWgStages) & 1, bph = (it / kWgBSlots) & 1;
@@ -244,24 +252,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       }
       __syncwarp();
       if (p.debug == 0) {
-        // G: 32 pixels x 16 chunks of 8 channels = 512 tasks
-        const uint8_t* gsrc = smem + sp.g + s * kGStage;
-        uint8_t* adst = smem + sp.a + bs * kASlot;
+        if (g_thread) {
+          tc_fence_after();
+          const uint8_t* gsrc = smem + sp.g + s * kGStage + tid * 4;
+          uint32_t h[16], l[16];
 #pragma unroll
-        for (int j = 0; j < 512 / kWgConv; ++j) {
-          const int task = tid + j * kWgConv, r = task >> 4, cg = task & 15;
-          const float4 v0 = *reinterpret_cast<const float4*>(gsrc + r * 512 + cg * 32);
-          const float4 v1 = *reinterpret_cast<const float4*>(gsrc + r * 512 + cg * 32 + 16);
-          uint4 h, l;
-          split_bf16(v0.x, v0.y, h.x, l.x);
-          split_bf16(v0.z, v0.w, h.y, l.y);
-          split_bf16(v1.x, v1.y, h.z, l.z);
-          split_bf16(v1.z, v1.w, h.w, l.w);
-          uint8_t* d = adst + (cg >> 3) * kWgBlk + r * 128 + (((cg & 7) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(d) = h;
-          *reinterpret_cast<uint4*>(d + 2 * kWgBlk) = l;
-        }
-        if (conv_thread) {
+          for (int j = 0; j < 16; ++j)
+            split_bf16(*reinterpret_cast<const float*>(gsrc + (2 * j) * 512), *reinterpret_cast<const float*>(gsrc + (2 * j + 1) * 512),
+                       h[j], l[j]);
+          tmem_st16(a_lane + bs * kWgACols, h);
+          tmem_st16(a_lane + bs * kWgACols + 16, l);
+          tmem_st_wait_all();
+          tc_fence_before();
+        } else if (conv_thread) {
           const uint8_t* stg = smem + sp.stg + s * kStgStage + src_off;
           uint8_t* bdst = smem + sp.b + bs * kBSlot + dst_blk;
 #pragma unroll 4
