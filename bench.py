@@ -306,7 +306,7 @@ def run_infer(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def build_model(dev, Hh, Ww, neuron="lif", bins=BINS, window=(2, 9, 9), train=True):
+def build_model(dev, Hh, Ww, neuron="lif", bins=BINS, window=(2, 9, 9), train=True, name=None):
     import copy
     from sdformerflow_b200.sj import functional
     from sdformerflow_b200.STSwinNet_SNN import Spiking_STSwinNet as prod
@@ -316,6 +316,10 @@ def build_model(dev, Hh, Ww, neuron="lif", bins=BINS, window=(2, 9, 9), train=Tr
     mc["spiking_neuron"]["num_steps"] = bins
     sc["input_size"] = [Hh, Ww]
     sc["window_size"] = list(window)
+    if name == "SpikingformerFlowNet":
+        # the SEW-shortcut family (reference Spiking_STSwinNet.py:254-311): 3 encoder stages, Q K^T V window attention (K3/K4)
+        mc["name"] = name
+        sc["swin_depths"], sc["swin_num_heads"], sc["swin_out_indices"] = [2, 2, 6], [3, 6, 12], [0, 1, 2]
     torch.manual_seed(0)
     model = getattr(prod, mc["name"])(copy.deepcopy(mc), copy.deepcopy(sc))
     model.init_weights()
@@ -356,13 +360,13 @@ def make_timed(world, dev):
 
 
 def train_workload(args, rank, local_rank, world, dev, Hh=H, Ww=W, B=B_PER_GPU, neuron="lif", bins=BINS, window=(2, 9, 9),
-                   steps=None, full=True):
+                   steps=None, full=True, name=None):
     """One training workload (reset + fwd + loss + bwd + AdamW, data parallel over `world` ranks) -> dict of measurements.
     full=True adds the eager pass with per-kernel events (roofline table) and the end-to-end (host buffers) measurement."""
     from sdformerflow_b200 import capi, train as sdtrain, distributed as sdist
     from sdformerflow_b200.sj import functional
     steps = steps or args.steps
-    model = build_model(dev, Hh, Ww, neuron, bins, window)
+    model = build_model(dev, Hh, Ww, neuron, bins, window, name=name)
     xh, gth, mh = synth_batch_shape(B, 16146 + rank, bins, Hh, Ww)
     xh, gth, mh = xh.pin_memory(), gth.pin_memory(), mh.pin_memory()
     xd, gtd, md = xh.to(dev), gth.to(dev), mh.to(dev)
@@ -493,6 +497,13 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.empty_cache()
         secondary["infer_cfg2_B8_480x640"] = infer_workload(args, rank, world, dev, steps=k)
         secondary = {n: {"samples_per_s": v["value"], "ms_per_step": v["ms_per_step"], "steps": v["steps"]} for n, v in secondary.items()}
+        torch.cuda.empty_cache()
+        try:    # SEW family with the Q K^T V window attention (K3/K4) inside a whole training step; not a shipped config
+            v = train_workload(args, rank, local_rank, world, dev, steps=k, full=False, name="SpikingformerFlowNet")
+            secondary["train_sew_SpikingformerFlowNet_qktv_288x384_B4"] = {
+                "samples_per_s": v["value"], "ms_per_step": v["ms_per_step"], "steps": v["steps"]}
+        except Exception as e:  # noqa: BLE001 — a secondary line must not cost the headline
+            secondary["train_sew_SpikingformerFlowNet_qktv_288x384_B4"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_leg()

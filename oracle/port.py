@@ -10,7 +10,7 @@ SURVEY.md Appendix A.
 Pinning: the reference ships no tests or golden vectors, so this port is pinned
 against outputs of the reference's own modules imported in the build container through
 ``oracle/standin`` (see ``oracle/make_golden.py`` -> ``tests/golden/*.pt`` and
-``tests/test_oracle_vs_reference.py``).  The stand-in itself cannot be diffed against the real
+``tests/test_oracle_golden.py``, which checks this port against those fixtures).  The stand-in itself cannot be diffed against the real
 spikingjelly package offline; that residual risk is stated in DESIGN.md.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.

@@ -25,12 +25,14 @@ def _activate():
     for p in (_STANDIN, REFERENCE_ROOT):
         if p not in sys.path:
             sys.path.insert(0, p)
-    # the product ships a top-level ``models`` shim with the same import path; make sure the
-    # reference's own package wins inside this process.
-    m = sys.modules.get("models")
-    if m is not None and not getattr(m, "__file__", "").startswith(REFERENCE_ROOT):
-        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
-            del sys.modules[k]
+    # sdformerflow_b200.dropin.install() registers the product under the reference's import path (``models``,
+    # ``spikingjelly``) in sys.modules; if a test did that earlier in this process, drop those aliases so that the
+    # reference's own package is what gets imported here.
+    for top, home in (("models", REFERENCE_ROOT), ("spikingjelly", _STANDIN)):
+        m = sys.modules.get(top)
+        if m is not None and not (getattr(m, "__file__", None) or "").startswith(home):
+            for k in [k for k in sys.modules if k == top or k.startswith(top + ".")]:
+                del sys.modules[k]
 
 
 def default_config(neuron_type="lif", v_th=0.1, num_steps=10, window_size=(2, 9, 9),

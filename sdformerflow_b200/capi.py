@@ -168,11 +168,23 @@ def set_timer(timer):
     _timer = timer
 
 
+NVTX = os.environ.get("SDF_NVTX", "0") not in ("", "0")
+
+
 def call(fn_name, args_struct, algo_bytes=0):
     """Calls an ``int sdf_*(const args*)`` entry point; raises with sdf_last_error() on failure."""
     L = lib()
     t = _timer
-    if t is not None and t.wants(fn_name):
+    if NVTX:
+        # SDF_NVTX=1: one NVTX range per C-ABI call, so that a timeline (nsys / torch.profiler) shows the entry points by
+        # name around their kernels; off by default (two extra Python calls per launch)
+        import torch
+        torch.cuda.nvtx.range_push(fn_name)
+        try:
+            rc = getattr(L, fn_name)(ctypes.byref(args_struct))
+        finally:
+            torch.cuda.nvtx.range_pop()
+    elif t is not None and t.wants(fn_name):
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -99,56 +99,57 @@ struct FinP {
   const float* mean_in; const float* rstd_in; float* gw; float* gb; float* coef;
 };
 
-// one warp per channel: lanes stride over the per-block partials, fixed-order shuffle tree in double
-// (deterministic; the single rounding to fp32 at the end keeps mean/var within 1 ulp of exact).
-__device__ __forceinline__ void warp_sum_partials(const float* partials, int64_t nblk, int64_t C, int64_t c, double& s0, double& s1) {
-  const int lane = threadIdx.x & 31;
-  double a = 0.0, b = 0.0, a2 = 0.0, b2 = 0.0;
-  int64_t blk = lane;
-  for (; blk + 32 < nblk; blk += 64) {           // two independent chains per lane, fixed order
-    const float x0 = partials[(blk * 2 + 0) * C + c], y0 = partials[(blk * 2 + 1) * C + c];
-    const float x1 = partials[((blk + 32) * 2 + 0) * C + c], y1 = partials[((blk + 32) * 2 + 1) * C + c];
-    a += (double)x0; b += (double)y0; a2 += (double)x1; b2 += (double)y1;
+// Block of 32 channels x 32 row groups: thread (rg, cl) sums the partial rows rg, rg + 32, ... of channel c0 + cl (a warp
+// reads 32 consecutive channels of one row: coalesced; ~14 independent loads per thread instead of a serial chain of 14 per
+// lane), the 32 row-group sums are then added in index order by the rg == 0 threads.  Everything in double, fixed order:
+// deterministic, and the single rounding to fp32 at the end keeps mean/var within 1 ulp of exact.
+constexpr int kFinThreads = 1024;
+__device__ __forceinline__ void block_sum_partials(const float* partials, int64_t nblk, int64_t C, int64_t c, double& s0, double& s1) {
+  __shared__ double sh[2][32][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int64_t blk = rg; blk < nblk; blk += 32) {
+      a += (double)partials[(blk * 2 + 0) * C + c];
+      b += (double)partials[(blk * 2 + 1) * C + c];
+    }
   }
-  for (; blk < nblk; blk += 32) {
-    a += (double)partials[(blk * 2 + 0) * C + c];
-    b += (double)partials[(blk * 2 + 1) * C + c];
-  }
-  a += a2; b += b2;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
+  sh[0][rg][cl] = a;
+  sh[1][rg][cl] = b;
+  __syncthreads();
+  a = 0.0; b = 0.0;
+  if (rg == 0) {
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) { a += sh[0][r][cl]; b += sh[1][r][cl]; }
   }
   s0 = a; s1 = b;
 }
 
-__global__ void bn_finalize_kernel(const FinP p) {
-  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= p.C) return;
-  const int lane = threadIdx.x & 31;
-  float mean, var;
+__global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const FinP p) {
+  const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool lead = (threadIdx.x >> 5) == 0 && c < p.C;
+  float mean = 0.f, var = 1.f;
   if (p.training) {
     double s, ss;
-    warp_sum_partials(p.partials, p.nblk, p.C, c, s, ss);
+    block_sum_partials(p.partials, p.nblk, p.C, c, s, ss);
+    if (!lead) return;
     const double n = (double)p.count;
     const double m = s / n;
     double v = ss / n - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
-    if (lane == 0) {
-      if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
-      if (p.running_var) {
-        const float unbiased = (float)(v * (n / (n > 1.0 ? n - 1.0 : 1.0)));
-        p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
-      }
+    if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+    if (p.running_var) {
+      const float unbiased = (float)(v * (n / (n > 1.0 ? n - 1.0 : 1.0)));
+      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
     }
   } else {
+    if (!lead) return;
     mean = p.running_mean[c];
     var = p.running_var[c];
   }
-  if (lane != 0) return;
   const float rstd = 1.f / sqrtf(var + p.eps);
   const float w = p.weight ? p.weight[c] : 1.f;
   const float b = p.bias ? p.bias[c] : 0.f;
@@ -159,12 +160,11 @@ __global__ void bn_finalize_kernel(const FinP p) {
   if (p.rstd) p.rstd[c] = rstd;
 }
 
-__global__ void bn_bwd_finalize_kernel(const FinP p) {
-  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= p.C) return;
+__global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const FinP p) {
+  const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
   double s, su;
-  warp_sum_partials(p.partials, p.nblk, p.C, c, s, su);
-  if ((threadIdx.x & 31) != 0) return;
+  block_sum_partials(p.partials, p.nblk, p.C, c, s, su);
+  if ((threadIdx.x >> 5) != 0 || c >= p.C) return;
   const double mean = p.mean_in[c], rstd = p.rstd_in[c];
   const double w = p.weight ? (double)p.weight[c] : 1.0;
   const double dgamma = (su - mean * s) * rstd;  // sum dy * xhat
@@ -254,8 +254,7 @@ extern "C" int sdf_bn_finalize(const sdf_bn_finalize_args* a) {
   p.weight = a->weight; p.bias = a->bias; p.running_mean = a->running_mean; p.running_var = a->running_var;
   p.momentum = (float)a->momentum; p.eps = (float)a->eps; p.training = a->training;
   p.scale = a->scale; p.shift = a->shift; p.mean = a->mean; p.rstd = a->rstd;
-  const int threads = 256;   // 8 channels (warps) per block
-  bn_finalize_kernel<<<(unsigned)((a->C * 32 + threads - 1) / threads), threads, 0, (cudaStream_t)a->stream>>>(p);
+  bn_finalize_kernel<<<(unsigned)((a->C + 31) / 32), kFinThreads, 0, (cudaStream_t)a->stream>>>(p);
   return finish_launch("sdf_bn_finalize");
 }
 
@@ -265,8 +264,7 @@ extern "C" int sdf_bn_bwd_finalize(const sdf_bn_bwd_finalize_args* a) {
   p.partials = a->partials; p.nblk = a->n_partial_blocks; p.count = a->count; p.C = a->C;
   p.weight = a->weight; p.mean_in = a->mean; p.rstd_in = a->rstd; p.gw = a->grad_weight; p.gb = a->grad_bias;
   p.coef = a->coef; p.training = a->training;
-  const int threads = 256;
-  bn_bwd_finalize_kernel<<<(unsigned)((a->C * 32 + threads - 1) / threads), threads, 0, (cudaStream_t)a->stream>>>(p);
+  bn_bwd_finalize_kernel<<<(unsigned)((a->C + 31) / 32), kFinThreads, 0, (cudaStream_t)a->stream>>>(p);
   return finish_launch("sdf_bn_bwd_finalize");
 }
 

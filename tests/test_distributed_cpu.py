@@ -38,7 +38,8 @@ def _worker(rank, world, port, q):
         loss.backward()
         model[4].bias.grad = None if rank == 1 else model[4].bias.grad      # a rank with an "unused" parameter
         nb = sdist.allreduce_gradients(model.parameters(), world, bucket_bytes=8 * 1024)
-        q.put((rank, nb, [p.grad.clone() for p in model.parameters()]))
+        # plain arrays, pickled by value: a tensor would travel as a shared-memory handle that dies with this process
+        q.put((rank, nb, [p.grad.numpy().copy() for p in model.parameters()]))
     finally:
         dist.destroy_process_group()
 
@@ -70,7 +71,7 @@ def test_two_rank_gradient_allreduce_matches_full_batch():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=100) for _ in procs]
+    results = [(r, nb, [torch.from_numpy(g) for g in grads]) for r, nb, grads in (q.get(timeout=100) for _ in procs)]
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0

@@ -218,7 +218,23 @@ def test_small_model_train_step(golden):
     gt, mask = synth.synth_labels(B, 96, 128)
     loss = port.flow_loss(flows, gt.to(DEV), mask.to(DEV))
     assert torch.isfinite(loss)
-    assert abs(loss.item() - g["loss"]) <= 0.25 * abs(g["loss"])
+    # Bound: the reference's own sensitivity to rounding on this input — the oracle port run in float64 against the fp32
+    # reference fixture (free-running train-mode forward; spike flips cascade).  The product has to be as
+    # close to the reference as twice that, not within an arbitrary percentage.
+    sd = synth.synth_state_dict(model.state_dict(), 0)
+    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    port.KEEP_DTYPE = True
+    try:
+        with torch.no_grad():
+            f64 = port.ms_flownet_forward(x.double(), P64, port_cfg(mc, sc), port_spec(mc), port.BNMode(True),
+                                          drop_scales=[None if t is None else t.double() for t in scales])
+    finally:
+        port.KEEP_DTYPE = False
+    loss64 = port.flow_loss([f.float() for f in f64], gt, mask).item()
+    self_sens = abs(loss64 - g["loss"])
+    print(f"train-step loss: product {loss.item():.6f}, reference {g['loss']:.6f}, oracle fp64 {loss64:.6f} "
+          f"(reference self-sensitivity {self_sens:.2e})")
+    assert abs(loss.item() - g["loss"]) <= max(1e-3 * abs(g["loss"]), 2.0 * self_sens)
     loss.backward()
     named = dict(model.named_parameters())
     for k, gref in g["grads"].items():

@@ -123,7 +123,7 @@ def test_qktv_forward_fast_kernel_is_deterministic():
         assert torch.equal(first, again)
 
 
-@pytest.mark.parametrize("case", CASES[:5])
+@pytest.mark.parametrize("case", CASES)
 def test_qktv_backward(case):
     from sdformerflow_b200 import ops
     wd, wh, ww, nH, B, nW, masked = case

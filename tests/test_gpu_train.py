@@ -102,7 +102,9 @@ def _ddp_worker(rank, world, port, q):
                         v.zero_()
         step(*inp)
         torch.cuda.synchronize()
-        q.put((rank, step.grads.flat.detach().cpu(), torch.cat([p.detach().reshape(-1) for p in step.grads.params]).cpu()))
+        # numpy arrays are pickled by value; a CPU tensor would travel as a shared-memory handle that dies with this process
+        q.put((rank, step.grads.flat.detach().cpu().numpy(),
+               torch.cat([p.detach().reshape(-1) for p in step.grads.params]).cpu().numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -120,7 +122,7 @@ def test_two_rank_step_equals_mean_of_single_gpu_gradients():
     got = dict()
     for _ in range(2):
         r, flat, w = q.get(timeout=600)
-        got[r] = (flat, w)
+        got[r] = (torch.from_numpy(flat), torch.from_numpy(w))
     for p in procs:
         p.join(timeout=60)
     assert torch.equal(got[0][0], got[1][0])           # both ranks hold the same reduced gradient ...

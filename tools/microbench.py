@@ -70,6 +70,24 @@ def main():
             del gs, gx
         del x
         torch.cuda.empty_cache()
+    # PSN (the shipped en4 configs' neuron, reference Spiking_submodules.py:196-211): forward, backward, parameter gradients
+    T, Np = 10, 4 * 144 * 192 * 96
+    xp = (torch.randn(T, Np, device=dev) * 0.2).requires_grad_(True)
+    wp = (torch.eye(T, device=dev) + torch.randn(T, T, device=dev) * 0.05).requires_grad_(True)
+    bp = torch.full((T, 1), -0.1, device=dev).requires_grad_(True)
+    pcfg = ops.NeuronCfg(kind=capi.SDF_NEURON_LIF, v_th=0.1, v_reset=None, tau=2.0, detach_reset=True)   # surrogate settings only
+    with torch.no_grad():
+        ms = timeit(lambda: ops.psn(xp, wp, bp, pcfg, 0))
+    report("psn_fwd T=10 out=f32", T * Np * 8, ms, T=T, N=Np)
+    sp = ops.psn(xp, wp, bp, pcfg, 0)
+    gsp = torch.randn_like(sp)
+    ms = timeit(lambda: torch.autograd.grad(sp, (xp, wp, bp), gsp, retain_graph=True))
+    report("psn_bwd T=10 (grad_x + dW/db kernel)", T * Np * 12 + T * Np * 8, ms, T=T, N=Np)
+    gh = torch.randn(T, Np, device=dev)
+    ms = timeit(lambda: ops._psn_param_grads(gh, xp.detach()))
+    report("psn_wgrad T=10 (dW [T,T], db)", T * Np * 8, ms, T=T, N=Np)
+    del xp, sp, gsp, gh
+    torch.cuda.empty_cache()
     # time-strided (B, D, H, W, C) layout, the MLP sn1 site of cfg2 stage 1
     x = torch.randn(8, 10, 120, 160, 96, device=dev) * 0.1
     lay = ops.seq_layout(x.shape, 1)

@@ -60,3 +60,15 @@ for k, v in tot.most_common(45):
 if "--ops" in sys.argv:
     print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=28, max_name_column_width=40,
                                                              max_shapes_column_width=90))
+
+if "--aten" in sys.argv:
+    rows = [(e.self_device_time_total / 2e3, e.count // 2, e.key) for e in prof.key_averages() if e.key.startswith("aten::") or "Backward" in e.key or e.key.startswith("_")]
+    for t, n, k in sorted(rows, reverse=True)[:40]:
+        print(f"{t:8.3f} ms/step  n={n:5d}  {k}")
+
+if "--shapes" in sys.argv:
+    rows = [(e.self_device_time_total / 2e3, e.count // 2, e.key, str(e.input_shapes)[:110]) for e in prof.key_averages(group_by_input_shape=True)
+            if e.key in ("aten::add_", "aten::add", "aten::sum", "aten::cat", "aten::copy_", "aten::mm", "aten::addmm", "aten::addmm_",
+                         "aten::fill_", "aten::mul", "aten::convolution_backward", "aten::cudnn_convolution_transpose", "aten::cudnn_convolution")]
+    for t, n, k, sh in sorted(rows, reverse=True)[:45]:
+        print(f"{t:8.3f} ms/step  n={n:4d}  {k:34s} {sh}")
