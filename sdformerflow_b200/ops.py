@@ -203,7 +203,7 @@ def _bn_backward(partials, dy, u2d, ld_u, rows, C, weight, mean, rstd, training,
         du = torch.empty((rows, C), device=dev, dtype=torch.float32)
         capi.call("sdf_bn_bwd_apply", capi.struct(
             "sdf_bn_bwd_apply_args", dy=_ptr(dy), u=_ptr(u2d), ld_u=ld_u, du=_ptr(du), ld_du=C, coef=_ptr(coef),
-            rows=rows, C=C, stream=_stream()))
+            rows=rows, C=C, stream=_stream()), algo_bytes=12 * rows * C)
     return du, gw, gb
 
 
@@ -350,7 +350,7 @@ def _psn_param_grads(gh, xo):
                   algo_bytes=8 * T * n)
         tot = part.sum(0)
         return tot[:T * T].view(T, T), tot[T * T:].view(T, 1)
-    with _tf32(True):
+    with _tf32(False):      # other T: rare (no shipped config), keep the library GEMM in true fp32
         return gh @ xo.t(), gh.sum(1, keepdim=True)
 
 
@@ -485,7 +485,7 @@ class _BNResidualFn(torch.autograd.Function):
             res = res.contiguous()
         capi.call("sdf_bn_apply", capi.struct(
             "sdf_bn_apply_args", u=_ptr(u), ld_u=C, res=_ptr(res), out=_ptr(out), scale=_ptr(scale), shift=_ptr(shift),
-            rows=rows, C=C, stream=_stream()))
+            rows=rows, C=C, stream=_stream()), algo_bytes=(8 if res is None else 12) * rows * C)
         ctx.save_for_backward(u, weight, mean, rstd)
         ctx.training, ctx.rows, ctx.C, ctx.has_res = bn.training, rows, C, res is not None
         return out
@@ -498,7 +498,7 @@ class _BNResidualFn(torch.autograd.Function):
         partials = torch.empty((N_PARTIAL, 2, C), device=u.device, dtype=torch.float32)
         capi.call("sdf_bn_bwd_reduce", capi.struct(
             "sdf_bn_bwd_reduce_args", dy=_ptr(go), u=_ptr(u), ld_u=C, rows=rows, C=C, partials=_ptr(partials),
-            n_partial_blocks=N_PARTIAL, stream=_stream()))
+            n_partial_blocks=N_PARTIAL, stream=_stream()), algo_bytes=8 * rows * C)
         du, gw, gb = _bn_backward(partials, go, u, C, rows, C, weight, mean, rstd, ctx.training)
         return du.view(u.shape), (go if ctx.has_res else None), gw, gb, None, None
 
@@ -1009,7 +1009,7 @@ class _WindowScatterFn(torch.autograd.Function):
         capi.call("sdf_window_scatter", capi.struct(
             "sdf_window_scatter_args", y=_ptr(y), res=_ptr(res), out=_ptr(out), win2x=_ptr(geom.win2x),
             scale=_ptr(scale), shift=_ptr(shift), alpha=_ptr(alpha), rows=rows, rows_per_sample=geom.nW * geom.N, C=C,
-            stream=_stream()))
+            stream=_stream()), algo_bytes=4 * rows * C + (4 if res is None else 8) * out.numel())
         ctx.save_for_backward(y, weight, mean, rstd, alpha)
         ctx.geom, ctx.C, ctx.has_bn, ctx.training = geom, C, bn is not None, (bn.training if bn is not None else False)
         ctx.has_res = res is not None
@@ -1026,7 +1026,8 @@ class _WindowScatterFn(torch.autograd.Function):
         capi.call("sdf_window_scatter_bwd", capi.struct(
             "sdf_window_scatter_bwd_args", dout=_ptr(go), dy=_ptr(dy), u=_ptr(y) if ctx.has_bn else None,
             win2x=_ptr(geom.win2x), alpha=_ptr(alpha), bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL,
-            rows=rows, rows_per_sample=geom.nW * geom.N, C=C, stream=_stream()))
+            rows=rows, rows_per_sample=geom.nW * geom.N, C=C, stream=_stream()),
+            algo_bytes=4 * go.numel() + (8 if ctx.has_bn else 4) * rows * C)
         gw = gb = None
         if ctx.has_bn:
             dy, gw, gb = _bn_backward(partials, dy, y, C, rows, C, weight, mean, rstd, ctx.training)
@@ -1165,7 +1166,7 @@ class _QKGateFn(torch.autograd.Function):
                 coef=_ptr(coef), training=1 if tr else 0, stream=_stream()))
             capi.call("sdf_bn_bwd_apply", capi.struct(
                 "sdf_bn_bwd_apply_args", dy=_ptr(g), u=_ptr(u), ld_u=2 * C, du=_ptr(dqk[:, half * C:]), ld_du=2 * C,
-                coef=_ptr(coef), rows=rows, C=C, stream=_stream()))
+                coef=_ptr(coef), rows=rows, C=C, stream=_stream()), algo_bytes=12 * rows * C)
             outs += [gw, gb]
         return (dqk, outs[0], outs[1], outs[2], outs[3], gpos.view(pos.shape), None, None, None, None, None, None, None,
                 None, None, None)
