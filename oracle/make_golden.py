@@ -90,6 +90,52 @@ def golden_small_model(neuron_type, train):
     return out
 
 
+def golden_small_train_sensitivity(n_samples=4, log2_jitter=-21):
+    """How far the reference's OWN train-mode loss (same model / input / DropPath masks as small_lif_train.pt) moves when
+    every weight matrix is jittered by a relative +-2^-21 (4 ulp): the yardstick for the free-running train-step test.
+    The product's arithmetic is a few ulp away from torch's per pre-activation (BatchNorm as one fused affine
+    scale*x + shift, spike-GEMM weights in 23-bit fixed point relative to the channel maximum), each within the per-layer
+    bars, so the reference's response to a perturbation of that size is what the product's loss can be held to."""
+    from spikingjelly.activation_based import functional
+    mc, sc = synth.small_config("lif")
+    model = rl.build_reference_model(mc, sc, seed=0, train=True)
+    B = 2
+    x = synth.synth_voxels(B, 10, 96, 128)
+    scales = synth.synth_drop_scales(sc["swin_depths"], B)
+    blocks = [b for lyr in model.sttmultires_unet.encoders.swin3d.layers for b in lyr.swin_blocks]
+
+    class Forced(torch.nn.Module):
+        def __init__(self, s):
+            super().__init__()
+            self.s = s
+
+        def forward(self, t):
+            return t if self.s is None else t * self.s.view(-1, 1, 1, 1, 1)
+
+    for b, s in zip(blocks, scales):
+        b.drop_path = Forced(s)
+    gt, mask = synth.synth_labels(B, 96, 128)
+    sys.path.insert(0, rl.REFERENCE_ROOT)
+    from loss.flow_supervised import flow_loss_supervised
+    crit = flow_loss_supervised({"metrics": {"flow_scaling": 1}, "loss": {"lambda_mod": 1, "lambda_ang": 0}}, "cpu")
+
+    def loss_with(sd):
+        model.load_state_dict(sd, strict=True)
+        functional.reset_net(model)
+        with torch.no_grad():
+            return crit(model(x)["flow"], gt, mask).item()
+
+    sd0 = synth.synth_state_dict(model.state_dict(), 0)
+    out = {"loss": loss_with(sd0), "log2_jitter": log2_jitter, "jittered": []}
+    for seed in range(n_samples):
+        g = torch.Generator().manual_seed(200 + seed)
+        sd = {k: (v * (1 + (torch.randint(0, 2, v.shape, generator=g).float() * 2 - 1) * 2.0 ** log2_jitter)
+                  if v.is_floating_point() and v.dim() >= 2 else v.clone()) for k, v in sd0.items()}
+        out["jittered"].append(loss_with(sd))
+        print("jitter sample", seed, out["jittered"][-1] - out["loss"], flush=True)
+    return out
+
+
 def golden_en4(neuron_type="lif"):
     """The shipped model/config (MS en4, window (2,9,9)) at its smallest legal size 288x384, eval."""
     from spikingjelly.activation_based import functional
@@ -191,6 +237,7 @@ def main():
         "small_psn_eval.pt": lambda: golden_small_model("psn", False),
         "small_lif_train.pt": lambda: golden_small_model("lif", True),
         "small_psn_train.pt": lambda: golden_small_model("psn", True),
+        "small_lif_train_sensitivity.pt": golden_small_train_sensitivity,
         "en4_lif_eval.pt": lambda: golden_en4("lif"),
         "sew_stage.pt": golden_sew_stage,
         "cfg4_lif_eval.pt": golden_cfg4,

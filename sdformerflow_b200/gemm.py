@@ -4,6 +4,8 @@ Forward: u8 spikes x 3 signed 8-bit weight digit planes (tcgen05.mma kind::i8, e
 Data gradient: fp32 x fp32 read as TF32.  Weight gradient: G^T S with a split over the row (pixel) axis.
 Autograd wrappers live in ops.py; this module only allocates outputs and calls the C-ABI.
 """
+import weakref
+
 import torch
 
 from . import capi
@@ -21,10 +23,11 @@ def _stream():
 
 class PackedWeight:
     """Digit planes + scales of one Linear / Conv weight, valid for one (data_ptr, _version) of the fp32 parameter."""
-    __slots__ = ("wq", "wscale", "wt", "Cout", "Cin", "taps", "key")
+    __slots__ = ("wq", "wscale", "wt", "Cout", "Cin", "taps", "key", "owner")
 
-    def __init__(self, wq, wscale, wt, Cout, Cin, taps, key):
+    def __init__(self, wq, wscale, wt, Cout, Cin, taps, key, owner=None):
         self.wq, self.wscale, self.wt, self.Cout, self.Cin, self.taps, self.key = wq, wscale, wt, Cout, Cin, taps, key
+        self.owner = owner          # weakref to the parameter this pack belongs to (None: not cached)
 
 
 _pack_cache = {}
@@ -34,7 +37,10 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
     """fp32 weight -> PackedWeight.  layout: 'linear' (Cout, K), 'conv' (Cout, Cin, kh, kw) OIHW.
     Cached per parameter version (optimizer steps bump ``_version``) for nn.Parameters (or when cache=True: the caller
     keeps `w` alive and unchanged); never cached while a CUDA graph is being captured, so a captured training step
-    re-packs inside the graph on every replay."""
+    re-packs inside the graph on every replay.  A cache entry belongs to ONE live tensor object (weak reference): the
+    id / address / version of a freed parameter can all recur in the next model built by the same code, which must not
+    get the old model's planes.  Weights changed behind autograd's back (``w.data.copy_()``, raw pointers) do not bump
+    ``_version``: call ``invalidate_pack_cache()`` after such an edit."""
     capturing = torch.cuda.is_current_stream_capturing()
     if cache is None:
         cache = isinstance(w, torch.nn.Parameter)
@@ -43,7 +49,7 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
     key = (w.data_ptr(), w._version, tuple(w.shape), layout, bool(w.requires_grad or need_wt))
     if not capturing:
         hit = _pack_cache.get(id(w))
-        if hit is not None and hit.key == key:
+        if hit is not None and hit.key == key and hit.owner is not None and hit.owner() is w:
             return hit
     wd = w.detach()
     if not wd.is_contiguous():
@@ -68,8 +74,16 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
         taps=taps, s_co=s_co, s_ci=s_ci, s_tap=s_tap, tap_map=list(range(9)), stream=_stream()))
     pw = PackedWeight(wq, wscale, wt, Cout, Cin, taps, key)
     if not capturing:
-        _pack_cache[id(w)] = pw
+        wid = id(w)
+        pw.owner = weakref.ref(w, lambda _r, wid=wid: _pack_cache.pop(wid, None) if (_pack_cache.get(wid) is not None
+                                                                                     and _pack_cache[wid].owner is _r) else None)
+        _pack_cache[wid] = pw
     return pw
+
+
+def invalidate_pack_cache():
+    """Drop every cached weight pack (after editing weights through .data / raw pointers)."""
+    _pack_cache.clear()
 
 
 def spike_gemm_fwd(a_u8, pw, bias=None, want_stats=False, a_max=0):

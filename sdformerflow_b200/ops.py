@@ -7,6 +7,8 @@ lines each operator replaces.
 """
 from dataclasses import dataclass
 import math
+import weakref
+
 import torch
 
 from . import capi, gemm
@@ -272,16 +274,23 @@ def plif_tau(plif_w):
     parameter version, so PLIF models are not CUDA-graph capturable; lif / if / psn never come here."""
     key = (plif_w.data_ptr(), plif_w._version)
     hit = _plif_tau_cache.get(id(plif_w))
-    if hit is not None and hit[0] == key:
+    if hit is not None and hit[0] == key and hit[2]() is plif_w:       # the entry of THIS live tensor, not of a freed one
         return hit[1]
     tau = 1.0 / torch.sigmoid(plif_w.detach()).item()
-    _plif_tau_cache[id(plif_w)] = (key, tau)
+    wid = id(plif_w)
+    _plif_tau_cache[wid] = (key, tau, weakref.ref(plif_w, lambda _r, wid=wid: _plif_tau_cache.pop(wid, None)
+                                                  if (wid in _plif_tau_cache and _plif_tau_cache[wid][2] is _r) else None))
     return tau
 
 
 def neuron(u, cfg: NeuronCfg, time_dim=0, plif_w=None, v_init=None, want_state=False, u8=False):
     """spikes of a multi-step neuron over dim `time_dim` — fp32 {0,1}, or a Spikes (1 byte each) with u8=True;
     optionally the final membrane."""
+    if v_init is not None and v_init.requires_grad:
+        # the kernels treat the carried membrane as a constant; silently dropping its gradient would be a wrong answer.
+        # The reference never needs it: functional.reset_net runs before every forward (train_…_SNN.py:247).
+        raise RuntimeError("ops.neuron: gradient w.r.t. the initial membrane (state carried across calls) is not "
+                           "implemented; detach() the state or reset the net between calls")
     holder = Spikes() if u8 else None
     spike, v = _NeuronFn.apply(u, plif_w, cfg, time_dim, v_init, want_state, holder)
     if u8:

@@ -72,6 +72,25 @@ def test_spike_gemm_integer_operand_and_exactness():
     assert torch.equal(y.double(), ref.float().double())
 
 
+def test_pack_cache_never_serves_a_freed_parameters_planes():
+    """A new parameter that recycles the id, the address and the version of a freed one (what the next model built by the
+    same code does) must get its own digit planes, not the cached ones of the dead tensor."""
+    gemm = _gemm()
+    a = _spikes((256, 96), 0.3, 1)
+    recycled = 0
+    seen = set()
+    for seed in range(8):
+        torch.manual_seed(seed)
+        w = torch.nn.Parameter(torch.randn(192, 96, device=DEV) * 0.05)
+        recycled += (id(w), w.data_ptr()) in seen
+        seen.add((id(w), w.data_ptr()))
+        y, _ = gemm.spike_gemm_fwd(a, gemm.pack_weight(w), None, False, a_max=1)
+        ref = a.double() @ w.detach().double().t()
+        assert (y.double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item(), seed
+        del w
+    print("recycled (id, address) pairs:", recycled)
+
+
 @pytest.mark.parametrize("rows,K,N", [(1000, 192, 96), (4099, 96, 96), (700, 768, 384), (513, 3072, 768), (300, 768, 3072),
                                      (2000, 384, 96), (200, 96, 48), (333, 4, 96), (260, 100, 20)])
 def test_gemm_tf32(rows, K, N):

@@ -218,23 +218,17 @@ def test_small_model_train_step(golden):
     gt, mask = synth.synth_labels(B, 96, 128)
     loss = port.flow_loss(flows, gt.to(DEV), mask.to(DEV))
     assert torch.isfinite(loss)
-    # Bound: the reference's own sensitivity to rounding on this input — the oracle port run in float64 against the fp32
-    # reference fixture (free-running train-mode forward; spike flips cascade).  The product has to be as
-    # close to the reference as twice that, not within an arbitrary percentage.
-    sd = synth.synth_state_dict(model.state_dict(), 0)
-    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-    port.KEEP_DTYPE = True
-    try:
-        with torch.no_grad():
-            f64 = port.ms_flownet_forward(x.double(), P64, port_cfg(mc, sc), port_spec(mc), port.BNMode(True),
-                                          drop_scales=[None if t is None else t.double() for t in scales])
-    finally:
-        port.KEEP_DTYPE = False
-    loss64 = port.flow_loss([f.float() for f in f64], gt, mask).item()
-    self_sens = abs(loss64 - g["loss"])
-    print(f"train-step loss: product {loss.item():.6f}, reference {g['loss']:.6f}, oracle fp64 {loss64:.6f} "
-          f"(reference self-sensitivity {self_sens:.2e})")
-    assert abs(loss.item() - g["loss"]) <= max(1e-3 * abs(g["loss"]), 2.0 * self_sens)
+    # Bound: the reference's OWN sensitivity on this input.  tests/golden/small_lif_train_sensitivity.pt (oracle/make_golden.py
+    # ::golden_small_train_sensitivity) holds the unmodified reference's loss with every weight matrix jittered by a relative
+    # +-2^-21 (4 ulp), four samples: free-running, a handful of flipped spikes cascade, and its loss moves by
+    # 3e-3 .. 3e-2.  The product's arithmetic is a few ulp away from torch's per pre-activation (fused BN affine, 23-bit
+    # fixed-point weights; per-layer bars asserted teacher-forced), so it must stay inside the range the reference itself spans.
+    sens = golden("small_lif_train_sensitivity.pt")
+    assert abs(sens["loss"] - g["loss"]) <= 1e-6 * abs(g["loss"])
+    spread = max(abs(v - sens["loss"]) for v in sens["jittered"])
+    print(f"train-step loss: product {loss.item():.6f}, reference {g['loss']:.6f}; reference under 2^{sens['log2_jitter']} weight "
+          f"jitter moves by up to {spread:.2e}")
+    assert abs(loss.item() - g["loss"]) <= spread
     loss.backward()
     named = dict(model.named_parameters())
     for k, gref in g["grads"].items():
