@@ -662,8 +662,10 @@ typedef struct {
 int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a);
 
 /* ---- G3: weight gradient dW = G^T S of a Linear / convolution on a spike operand (csrc/spike_wgrad.cu) -------------
- * G fp32 [rows, Cout] (read as TF32), S u8 spikes [rows, K]; contraction over the rows on tcgen05 (both operands MN-major),
- * split over row slabs into `workspace`, reduced in slab order (deterministic).  accumulate != 0: dw += result.
+ * G fp32 [rows, Cout] (split into bf16 hi + lo, A operand through tensor memory), S u8 spikes [rows, K] (expanded to bf16,
+ * MN-major B operand); contraction over the rows on tcgen05, split over row slabs into `workspace`, reduced in slab order
+ * (deterministic).  accumulate != 0: dw += result.  db (optional): the bias gradient sum_rows G[:, co] from the same pass over
+ * G (replaces the reference's separate g.sum(0) reduction in the autograd of F.linear / conv2d with bias).
  * workspace_bytes >= sdf_spike_wgrad_workspace_bytes(rows (conv: Nimg*Ho*Wo + partial-patch slack), Cout, Cin, taps). */
 typedef struct {
   const float* g;
@@ -675,6 +677,7 @@ typedef struct {
   int32_t accumulate;
   int32_t s_max;       /* largest value in s: 1 = binary spikes (cheaper expansion), 0 = any u8 */
   void* stream;
+  float* db;           /* [Cout] or NULL */
 } sdf_spike_wgrad_args;
 
 int sdf_spike_wgrad(const sdf_spike_wgrad_args* a);
@@ -692,6 +695,7 @@ typedef struct {
   int32_t accumulate;
   int32_t s_max;       /* largest value in x: 1 = binary spikes, 0 = any u8 */
   void* stream;
+  float* db;           /* [Cout] or NULL */
 } sdf_spike_conv_wgrad_args;
 
 int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a);

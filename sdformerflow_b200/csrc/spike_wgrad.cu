@@ -57,6 +57,7 @@ struct WgradP {
   int conv, tiles_h, tiles_w, stride;
   int dh[9], dw[9];
   float* partial;          // [n_slabs][Cout][ncols_total]
+  float* db_partial;       // [n_slabs][Cout] bias-gradient partial sums (column sums of G), or nullptr
   int halo;                // stride-1 conv, one kernel row per tile: ONE spike box [2][16 + kw - 1][Cin] serves the kw taps
   int binary;              // spikes are 0/1 (cheaper byte -> bf16 expansion)
   int stg_bytes;           // raw spike bytes per stage
@@ -243,6 +244,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     const uint32_t dst_blk = (uint32_t)(q >> 3) * kWgBlk;
     const bool conv_thread = !g_thread && rsub < rows_par;
     const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kWgMaxN;
+    float bsum = 0.f;                           // G threads: column sum of this slab's G (bias gradient), fixed order
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % kWgStages, bs = it % kWgBSlots;
       const uint32_t ph = (it / kWgStages) & 1, bph = (it / kWgBSlots) & 1;
@@ -257,9 +259,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
           const uint8_t* gsrc = smem + sp.g + s * kGStage + tid * 4;
           uint32_t h[16], l[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            split_bf16(*reinterpret_cast<const float*>(gsrc + (2 * j) * 512), *reinterpret_cast<const float*>(gsrc + (2 * j + 1) * 512),
-                       h[j], l[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float x0 = *reinterpret_cast<const float*>(gsrc + (2 * j) * 512);
+            const float x1 = *reinterpret_cast<const float*>(gsrc + (2 * j + 1) * 512);
+            bsum += x0 + x1;
+            split_bf16(x0, x1, h[j], l[j]);
+          }
           tmem_st16(a_lane + bs * kWgACols, h);
           tmem_st16(a_lane + bs * kWgACols + 16, l);
           tmem_st_wait_all();
@@ -284,6 +289,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       mbar_wait(done, 0);
       tc_fence_after();
       const int co = m_tile * kWgM + tid;
+      if (p.db_partial != nullptr && n_tile == 0 && co < p.Cout) p.db_partial[(int64_t)slab * p.Cout + co] = bsum;
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
       float* dst = p.partial + ((int64_t)slab * p.Cout + co) * p.ncols_total + (int64_t)tap0 * p.Cin + ci0;
       for (int cc = 0; cc < ncols; cc += 16) {
@@ -309,9 +315,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
 
 // dW[co*s_co + ci*s_ci + tap*s_tap] (+)= sum_s partial[s][co][tap*Cin + ci], slabs added in index order
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n_slabs, int Cout, int Cin,
-                                    int taps, int64_t s_co, int64_t s_ci, int64_t s_tap, int accumulate) {
+                                    int taps, int64_t s_co, int64_t s_ci, int64_t s_tap, int accumulate,
+                                    const float* __restrict__ db_partial, float* __restrict__ db) {
   const int64_t total = (int64_t)Cout * taps * Cin;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t total_all = total + (db != nullptr ? Cout : 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_all; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= total) {                           // bias gradient: slabs added in index order
+      const int64_t co = i - total;
+      float acc = 0.f;
+      for (int s = 0; s < n_slabs; ++s) acc += __ldg(db_partial + (int64_t)s * Cout + co);
+      db[co] = accumulate ? db[co] + acc : acc;
+      continue;
+    }
     float acc = 0.f;
     for (int s = 0; s < n_slabs; ++s) acc += __ldg(partial + (int64_t)s * total + i);
     const int64_t co = i / ((int64_t)taps * Cin);
@@ -364,7 +379,7 @@ extern "C" int64_t sdf_spike_wgrad_workspace_bytes(int64_t rows_or_pixels, int64
   p.n_chunks = (int)((rows_or_pixels + kWgRB - 1) / kWgRB);   // conv callers pass whole 2 x 16 patches
   wgrad_slabs(p);
   const int64_t slabs = p.n_slabs;
-  return slabs * Cout * taps * Cin * 4;
+  return slabs * Cout * (taps * Cin + 1) * 4;     // partial tiles + the bias-gradient partial sums
 }
 
 static int wgrad_debug_mode() {
@@ -373,11 +388,12 @@ static int wgrad_debug_mode() {
 }
 
 static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tmS, float* dw, int64_t s_co, int64_t s_ci,
-                        int64_t s_tap, int accumulate, int64_t ws_bytes, cudaStream_t st, const char* what) {
+                        int64_t s_tap, int accumulate, int64_t ws_bytes, cudaStream_t st, const char* what, float* db) {
   wgrad_slabs(p);
   p.debug = wgrad_debug_mode();
-  SDF_REQUIRE((int64_t)p.n_slabs * p.Cout * p.ncols_total * 4 <= ws_bytes, "%s: workspace too small (%lld needed)", what,
-              (long long)p.n_slabs * p.Cout * p.ncols_total * 4);
+  SDF_REQUIRE((int64_t)p.n_slabs * p.Cout * (p.ncols_total + 1) * 4 <= ws_bytes, "%s: workspace too small (%lld needed)", what,
+              (long long)p.n_slabs * p.Cout * (p.ncols_total + 1) * 4);
+  p.db_partial = db != nullptr ? p.partial + (int64_t)p.n_slabs * p.Cout * p.ncols_total : nullptr;
   p.max_cols = p.ci_tiles > 1 ? p.ci_width : p.taps_per_tile * p.Cin;
   SDF_REQUIRE(p.max_cols % 16 == 0 && p.max_cols <= kWgMaxN && p.box_w % 16 == 0, "%s: unsupported column tiling (%d columns, box %d)", what, p.max_cols, p.box_w);
   if (!p.halo) p.stg_bytes = p.max_cols * kWgRB;
@@ -394,9 +410,10 @@ static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tm
   wgrad_kernel<<<p.n_slabs * p.n_mtiles * p.n_ntiles, kWgThreads, sp.total, st>>>(tmG, tmS, p);
   int r = finish_launch(what);
   if (r) return r;
-  const int64_t total = (int64_t)p.Cout * p.ncols_total;
+  const int64_t total = (int64_t)p.Cout * (p.ncols_total + 1);
   const int blocks = (int)((total + 255) / 256 < 4 * num_sms() ? (total + 255) / 256 : 4 * num_sms());
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, p.n_slabs, p.Cout, p.Cin, p.taps, s_co, s_ci, s_tap, accumulate);
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, p.n_slabs, p.Cout, p.Cin, p.taps, s_co, s_ci, s_tap, accumulate,
+                                              p.db_partial, db);
   return finish_launch(what);
 }
 
@@ -430,7 +447,8 @@ extern "C" int sdf_spike_wgrad(const sdf_spike_wgrad_args* a) {
     int st = make_tmap(&tmS, 0, 2, a->s, dims, str, box, nullptr, 0);
     if (st) return st;
   }
-  return wgrad_launch(p, tmG, tmS, a->dw, a->K, 1, 0, a->accumulate, a->workspace_bytes, (cudaStream_t)a->stream, "sdf_spike_wgrad");
+  return wgrad_launch(p, tmG, tmS, a->dw, a->K, 1, 0, a->accumulate, a->workspace_bytes, (cudaStream_t)a->stream, "sdf_spike_wgrad",
+                      a->db);
 }
 
 extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
@@ -476,5 +494,5 @@ extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
   }
   // parameter layout OIHW: (co, ci, tap) at co*Cin*taps + ci*taps + tap
   return wgrad_launch(p, tmG, tmS, a->dw, (int64_t)p.Cin * p.taps, p.taps, 1, a->accumulate, a->workspace_bytes,
-                      (cudaStream_t)a->stream, "sdf_spike_conv_wgrad");
+                      (cudaStream_t)a->stream, "sdf_spike_conv_wgrad", a->db);
 }

@@ -142,9 +142,10 @@ def _workspace(nbytes, device):
     return ws
 
 
-def spike_wgrad(g, s_u8, out=None, s_max=0):
+def spike_wgrad(g, s_u8, out=None, s_max=0, want_db=False):
     """dW [Cout, K] = g[rows, Cout]^T @ s_u8[rows, K]; g fp32 (split into bf16 hi + lo operands), s uint8 (s_max = 1: the
-    caller guarantees 0/1 spikes, which expand to bf16 with fewer instructions; 0: any byte value)."""
+    caller guarantees 0/1 spikes, which expand to bf16 with fewer instructions; 0: any byte value).
+    want_db: also return the bias gradient g.sum(0) [Cout], accumulated by the same pass over g -> (dW, db)."""
     rows, Cout = g.shape
     K = s_u8.shape[1]
     assert s_u8.shape[0] == rows and s_u8.dtype == torch.uint8 and s_u8.is_contiguous() and g.stride(1) == 1
@@ -152,14 +153,15 @@ def spike_wgrad(g, s_u8, out=None, s_max=0):
     ws = _workspace(nbytes, g.device)
     acc = out is not None
     dw = out if acc else torch.empty((Cout, K), device=g.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=g.device, dtype=torch.float32) if want_db else None
     capi.call("sdf_spike_wgrad", capi.struct(
         "sdf_spike_wgrad_args", g=_ptr(g), s=_ptr(s_u8), dw=_ptr(dw), workspace=_ptr(ws), workspace_bytes=ws.numel() * 4,
-        rows=rows, Cout=Cout, K=K, ldg=g.stride(0), accumulate=1 if acc else 0, s_max=s_max, stream=_stream()),
-        algo_bytes=rows * (4 * Cout + K))
-    return dw
+        rows=rows, Cout=Cout, K=K, ldg=g.stride(0), accumulate=1 if acc else 0, s_max=s_max, stream=_stream(),
+        db=_ptr(db)), algo_bytes=rows * (4 * Cout + K))
+    return (dw, db) if want_db else dw
 
 
-def spike_conv_wgrad(g, x_u8, kh, kw, stride, pad, s_max=0):
+def spike_conv_wgrad(g, x_u8, kh, kw, stride, pad, s_max=0, want_db=False):
     """dW (Cout, Cin, kh, kw) of a convolution: g fp32 NHWC (Nimg, Ho, Wo, Cout), x_u8 NHWC (Nimg, H, W, Cin)."""
     Nimg, Ho, Wo, Cout = g.shape
     _, H, W, Cin = x_u8.shape
@@ -168,11 +170,12 @@ def spike_conv_wgrad(g, x_u8, kh, kw, stride, pad, s_max=0):
     nbytes = int(capi.lib().sdf_spike_wgrad_workspace_bytes(pixels, Cout, Cin, kh * kw))
     ws = _workspace(nbytes, g.device)
     dw = torch.empty((Cout, Cin, kh, kw), device=g.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=g.device, dtype=torch.float32) if want_db else None
     capi.call("sdf_spike_conv_wgrad", capi.struct(
         "sdf_spike_conv_wgrad_args", g=_ptr(g), x=_ptr(x_u8), dw=_ptr(dw), workspace=_ptr(ws), workspace_bytes=ws.numel() * 4,
         Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo, kh=kh, kw=kw, stride=stride, pad=pad, accumulate=0,
-        s_max=s_max, stream=_stream()), algo_bytes=4 * g.numel() + x_u8.numel())
-    return dw
+        s_max=s_max, stream=_stream(), db=_ptr(db)), algo_bytes=4 * g.numel() + x_u8.numel())
+    return (dw, db) if want_db else dw
 
 
 def conv_dgrad_tf32(g, weight, H, W, pad, wd=None):

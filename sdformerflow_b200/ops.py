@@ -633,9 +633,12 @@ class _SpikeGemmFn(torch.autograd.Function):
             wt = ctx.wt if ctx.wt is not None else weight.detach().t().contiguous()
             holder.add_grad(gemm.gemm_tf32(g2, wt).view(a.shape))
             gtok = _zero_token(gy.device)
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            gw = gemm.spike_wgrad(g2, a.view(-1, K), s_max=1)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gw = gemm.spike_wgrad(g2, a.view(-1, K), s_max=1, want_db=want_gb)     # bias gradient from the same pass over g
+            if want_gb:
+                gw, gb = gw
+        elif want_gb:
             gb = g2.sum(0)
         return gtok, gw, gb, None, None
 
@@ -790,9 +793,12 @@ class _SpikeConvGemmFn(torch.autograd.Function):
                 gx = gx.permute(0, 2, 3, 1).contiguous()      # no-op when cuDNN returned NHWC
             holder.add_grad(gx.view(x.shape))
             gtok = _zero_token(gy.device)
+        want_gb = has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            gw = gemm.spike_conv_wgrad(g4, x.view(-1, H, W, Cin), kh, kw, stride, padding, s_max=1)
-        if has_bias and ctx.needs_input_grad[2]:
+            gw = gemm.spike_conv_wgrad(g4, x.view(-1, H, W, Cin), kh, kw, stride, padding, s_max=1, want_db=want_gb)
+            if want_gb:
+                gw, gb = gw
+        elif want_gb:
             gb = g4.sum((0, 1, 2))
         return gtok, gw, gb, None, None, None, None
 

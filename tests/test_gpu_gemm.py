@@ -164,6 +164,12 @@ def test_spike_wgrad(rows, K, Cout):
     ref2 = g2.double().t() @ s.double()
     assert (dw2.double() - ref2).abs().max().item() <= 2e-5 * ref2.abs().max().item()
     assert torch.equal(dw2, gemm.spike_wgrad(g2, s))            # fixed reduction order
+    # bias gradient from the same pass over g
+    dw3, db = gemm.spike_wgrad(g, s, want_db=True)
+    assert torch.equal(dw3, dw)
+    refb = g.double().sum(0)
+    assert (db.double() - refb).abs().max().item() <= 1e-5 * g.double().abs().sum(0).max().item()
+    assert torch.equal(db, gemm.spike_wgrad(g, s, want_db=True)[1])
 
 
 @pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,stride,pad", CONV_CASES)
@@ -180,7 +186,10 @@ def test_spike_conv_wgrad(Nimg, H, W, Cin, Cout, k, stride, pad):
     (ref,) = torch.autograd.grad(y, wr, g.permute(0, 3, 1, 2).double())
     assert dw.shape == ref.shape
     assert (dw.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
-    assert torch.equal(dw, gemm.spike_conv_wgrad(g, x, k, k, stride, pad, s_max=1))
+    dw3, db = gemm.spike_conv_wgrad(g, x, k, k, stride, pad, s_max=1, want_db=True)
+    assert torch.equal(dw, dw3)
+    refb = g.double().sum((0, 1, 2))
+    assert (db.double() - refb).abs().max().item() <= 1e-5 * g.double().abs().sum((0, 1, 2)).max().item()
 
 
 @pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,pad", [(3, 24, 32, 96, 96, 3, 1), (2, 20, 27, 96, 96, 3, 1), (5, 9, 12, 768, 768, 3, 1),

@@ -167,9 +167,11 @@ def test_model_teacher_forced_every_module(nt, train):
         seen += 1
     print(f"[{nt} train={train}] teacher-forced mismatch fractions:", {k: round(v, 5) for k, v in worst.items()})
     for name, bad in worst.items():
-        # a flipped spike inside a multi-layer module touches a neighbourhood of outputs; late, small stages have
-        # few rows, so one flip is a larger fraction
-        assert bad <= 2e-2, (name, bad)
+        # a flipped spike inside a multi-layer module touches a neighbourhood of outputs (measured: <= 1.1e-3 everywhere but
+        # the last stage); the last stage has 8x12 tokens, so ONE flip there is already a 1e-2 fraction of the block's output.
+        # The per-neuron-layer bars (flip rate <= 1e-4, membranes <= 1e-4) are asserted in
+        # test_every_neuron_layer_membrane_and_flip_rate.
+        assert bad <= (2e-2 if name.startswith("layers.2") else 5e-3), (name, bad)
     assert seen == 5 + 6 + 2 + 2 + 3 + 3
 
 
