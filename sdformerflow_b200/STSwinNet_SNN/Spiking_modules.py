@@ -153,9 +153,12 @@ def from_cl(y):
 
 def u8_ok(conv, transposed=False):
     """Does this convolution run on the tcgen05 spike GEMM engine when fed 1-byte spikes?"""
-    return (ops.spike_gemm_on() and not transposed and isinstance(conv, nn.Conv2d)
-            and conv.groups == 1 and tuple(conv.dilation) == (1, 1)
-            and ops.spike_conv_supported(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding))
+    if not (ops.spike_gemm_on() and not transposed and isinstance(conv, nn.Conv2d) and conv.groups == 1
+            and tuple(conv.dilation) == (1, 1)):
+        return False
+    if (tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)) == ((1, 1), (1, 1), (0, 0)) and conv.in_channels % 16 == 0:
+        return True          # 1x1 = Linear on the rows; any Cout (ops.spike_linear pads the 2-channel heads)
+    return ops.spike_conv_supported(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding)
 
 
 def bn_training(norm_layer):
@@ -329,7 +332,7 @@ class MS_SpikingPredLayer(nn.Module):
         self.conv = _conv(in_channels, out_channels, kernel_size, stride, kernel_size // 2, True)
 
     def forward_cl(self, x):
-        return conv_cl(self.sn(x, 1), self.conv[0], True)
+        return conv_cl(self.sn(x, 1, u8=u8_ok(self.conv[0])), self.conv[0], True)
 
     def forward(self, x):
         return from_cl(self.forward_cl(to_cl(x)))

@@ -650,7 +650,19 @@ def spike_linear(s, weight, bias=None, exact_input=True, stats=None):
     path.  stats (bool, optional): when given the result is (y, partials) — the BN partial sums of y from the GEMM
     epilogue if stats is True and the tcgen05 path ran, else None."""
     if isinstance(s, Spikes):
-        y, part = _SpikeGemmFn.apply(s.token, weight, bias, s, bool(stats))
+        Cout = weight.shape[0]
+        if Cout % 4:
+            # the 2-channel flow heads (reference Spiking_modules.py:607-647): the engine's output rows are 16-byte pitched, so
+            # the weight gets zero rows up to a multiple of 4 and the result is a view of the first Cout columns; autograd
+            # pads / slices the (tiny) gradients accordingly
+            padn = 4 - Cout % 4
+            wp = torch.nn.functional.pad(weight, (0, 0, 0, padn))
+            bp = None if bias is None else torch.nn.functional.pad(bias, (0, padn))
+            y, part = _SpikeGemmFn.apply(s.token, wp, bp, s, bool(stats))
+            y = y[..., :Cout]
+            part = None if part is None else part[..., :Cout].contiguous()
+        else:
+            y, part = _SpikeGemmFn.apply(s.token, weight, bias, s, bool(stats))
         return y if stats is None else (y, part)
     if stats is not None:
         return spike_linear(s, weight, bias, exact_input), None
