@@ -17,12 +17,19 @@ def skip_concat(x1, x2, dim=1):
     return torch.cat([F.pad(x1, (dX // 2, dX - dX // 2, dY // 2, dY - dY // 2)), x2], dim=dim)
 
 
-def skip_concat_cl(x1, x2):
-    """skip_concat on channels-last (B, T, H, W, C) tensors: pad x1's H, W to x2's, concatenate channels."""
+def skip_concat_cl(x1, x2, align=1):
+    """skip_concat on channels-last (B, T, H, W, C) tensors: pad x1's H, W to x2's, concatenate channels.
+    align > 1: zero channels are appended up to a multiple of `align` in the same pass (the consumer pads its weight with
+    zero input slices: Spiking_modules.padded_in_weight) — 770 / 386 / 194-channel decoder inputs otherwise cost cuDNN a
+    padding copy of the whole tensor per convolution call."""
     dY, dX = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
     if dY or dX:
         x1 = F.pad(x1, (0, 0, dX // 2, dX - dX // 2, dY // 2, dY - dY // 2))
-    return torch.cat([x1, x2], dim=-1)
+    parts = [x1, x2]
+    extra = -(x1.size(-1) + x2.size(-1)) % align
+    if extra:
+        parts.append(x2.new_zeros(*x2.shape[:-1], extra))
+    return torch.cat(parts, dim=-1)
 
 
 def skip_sum(x1, x2, dim=None):

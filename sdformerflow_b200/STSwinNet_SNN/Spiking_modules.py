@@ -167,20 +167,38 @@ def bn_training(norm_layer):
     return isinstance(bn, nn.modules.batchnorm._BatchNorm) and (bn.training or bn.running_mean is None)
 
 
-def conv_cl(x, conv, spike_input, transposed=False, stats=None):
+def conv_cl(x, conv, spike_input, transposed=False, stats=None, weight=None):
     """x (B, T, H, W, Cin) fp32 or ops.Spikes -> (B, T, H', W', Cout); `conv` is an nn.Conv2d / nn.ConvTranspose2d parameter
-    holder.  stats (bool, optional): when given, returns (y, BN partial sums of y or None) as ops.spike_linear does."""
+    holder.  stats (bool, optional): when given, returns (y, BN partial sums of y or None) as ops.spike_linear does.
+    weight: use this tensor instead of conv.weight (library path only; see padded_in_weight)."""
     if isinstance(x, ops.Spikes):
         sh = conv.stride[0]
         if tuple(conv.kernel_size) == (1, 1) and sh == 1:
             return ops.spike_linear(x, conv.weight.view(conv.weight.shape[0], -1), conv.bias, stats=stats)
         return ops.spike_conv_gemm(x, conv.weight, conv.bias, sh, conv.padding[0], stats=stats)
-    y = _conv_cl_lib(x, conv, spike_input, transposed)
+    y = _conv_cl_lib(x, conv, spike_input, transposed, weight)
     return y if stats is None else (y, None)
 
 
-def _conv_cl_lib(x, conv, spike_input, transposed=False):
+def padded_in_weight(conv, cin, transposed):
+    """conv.weight with zero input-channel slices appended up to `cin` (the decoder input is concatenated with zero channels
+    up to a multiple of 4 so that cuDNN's NHWC kernels take it without their own padding copy); autograd slices the gradient."""
+    w = conv.weight
+    have = w.shape[0] if transposed else w.shape[1]
+    if cin == have:
+        return None
+    pad = (0, 0, 0, 0, 0, 0, 0, cin - have) if transposed else (0, 0, 0, 0, 0, cin - have)
+    return F.pad(w, pad)
+
+
+def _conv_cl_lib(x, conv, spike_input, transposed=False, weight=None):
     B, T, H, W, C = x.shape
+    if weight is not None:
+        x4 = x.view(B * T, H, W, C).permute(0, 3, 1, 2)
+        y4 = ops.spike_conv2d(x4, weight, conv.bias, conv.stride, conv.padding, transposed,
+                              conv.output_padding if transposed else 0, exact_input=spike_input)
+        y = y4.permute(0, 2, 3, 1).contiguous()
+        return y.view(B, T, y.shape[1], y.shape[2], y.shape[3])
     if (not transposed and not spike_input and C <= 4 and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1)
             and tuple(conv.padding) == (1, 1) and conv.weight.shape[0] % 4 == 0 and ops.GEMM_MODE != "fp32"):
         y = ops.conv3x3_small_cin(x.view(B * T, H, W, C), conv.weight, conv.bias)     # patch-embed head: direct kernel
@@ -290,7 +308,7 @@ class SpikingTransposeDecoderLayer(nn.Module):
         self.sn = Spiking_neuron(**spiking_kwargs)
 
     def forward_cl(self, x, spike_input=True):
-        h = conv_cl(x, self.deconv[0], spike_input, transposed=True)
+        h = conv_cl(x, self.deconv[0], spike_input, transposed=True, weight=padded_in_weight(self.deconv[0], x.shape[-1], True))
         if self.norm is not None:
             return _bn_sn(h, self.norm_layer, self.sn)
         return self.sn(h, 1)
@@ -303,7 +321,8 @@ class MS_SpikingTransposeDecoderLayer(SpikingTransposeDecoderLayer):
     """neuron -> deconv -> norm (reference :461-474)."""
 
     def forward_cl(self, x):
-        h = conv_cl(self.sn(x, 1), self.deconv[0], True, transposed=True)
+        h = conv_cl(self.sn(x, 1), self.deconv[0], True, transposed=True,
+                    weight=padded_in_weight(self.deconv[0], x.shape[-1], True))
         return ops.bn_residual(h, self.norm_layer.norm_layer) if self.norm is not None else h
 
 
