@@ -567,6 +567,23 @@ typedef struct {
 
 int sdf_conv3x3_cl_fwd(const sdf_conv3x3_cl_args* a);
 
+/* weight and bias gradient of the same convolution (autograd of that nn.Conv2d: the voxel input needs no gradient):
+ * dw (Cout, Cin, 3, 3) = sum over pixels of g (N, H, W, Cout) x the 3x3 input patch, db [Cout] = sum of g (optional).
+ * Per-block partial sums in `workspace` (>= sdf_conv3x3_cl_wgrad_workspace_bytes), reduced in block order: deterministic. */
+typedef struct {
+  const float* x;      /* (N, H, W, Cin) */
+  const float* g;      /* (N, H, W, Cout) */
+  float* dw;           /* (Cout, Cin, 3, 3), overwritten */
+  float* db;           /* [Cout] or NULL */
+  float* workspace;
+  int64_t workspace_bytes;
+  int64_t N, H, W, Cin, Cout;
+  void* stream;
+} sdf_conv3x3_cl_wgrad_args;
+
+int sdf_conv3x3_cl_wgrad(const sdf_conv3x3_cl_wgrad_args* a);
+int64_t sdf_conv3x3_cl_wgrad_workspace_bytes(int64_t Cin, int64_t Cout);
+
 /* ---- G1/G2: spike GEMM / implicit-GEMM convolution on tcgen05 + TMA (csrc/spike_gemm.cu) -----------
  * Replaces the cuBLAS / cuDNN calls behind sj_layer.Linear / sj_layer.Conv2d on spike operands:
  * Spiking_swin_transformer3D.py:126-131 (fc1/fc2), :267-290 and :632-652 (linear_q/k/v, proj), :909 (reduction);

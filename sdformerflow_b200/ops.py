@@ -726,7 +726,8 @@ class _PlainConvFn(torch.autograd.Function):
 
 class _SmallCinConvFn(torch.autograd.Function):
     """3x3 / stride 1 / pad 1 conv with Cin <= 4 on a channels-last (N, H, W, Cin) tensor: direct fp32 kernel forward
-    (patch-embed head, reference Spiking_modules.py:1737-1745), library TF32 weight/input gradients backward."""
+    (patch-embed head, reference Spiking_modules.py:1737-1745) and direct fp32 weight / bias gradient kernel; the library
+    (TF32) only when the input itself needs a gradient."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -746,6 +747,20 @@ class _SmallCinConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
+        if not ctx.needs_input_grad[0] and weight.shape[0] <= 128:
+            # the model's case (the voxel input needs no gradient): own direct kernel for dW and db, true fp32
+            g = g.contiguous()
+            N, H, W, Cin = x.shape
+            Cout = weight.shape[0]
+            gw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+            gb = torch.empty(Cout, device=g.device, dtype=torch.float32) if ctx.has_bias else None
+            nbytes = int(capi.lib().sdf_conv3x3_cl_wgrad_workspace_bytes(Cin, Cout))
+            ws = torch.empty(nbytes // 4, device=g.device, dtype=torch.float32)
+            capi.call("sdf_conv3x3_cl_wgrad", capi.struct(
+                "sdf_conv3x3_cl_wgrad_args", x=_ptr(x), g=_ptr(g), dw=_ptr(gw), db=_ptr(gb), workspace=_ptr(ws),
+                workspace_bytes=nbytes, N=N, H=H, W=W, Cin=Cin, Cout=Cout, stream=_stream()),
+                algo_bytes=4 * (x.numel() + g.numel()))
+            return None, (gw if ctx.needs_input_grad[1] else None), (gb if ctx.has_bias and ctx.needs_input_grad[2] else None)
         g4 = g.contiguous().permute(0, 3, 1, 2)           # logical NCHW, channels_last strides
         x4 = x.permute(0, 3, 1, 2)
         with _tf32(True):

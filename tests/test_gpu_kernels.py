@@ -402,7 +402,7 @@ def test_spike_linear_and_conv_are_fp32_grade(mode):
         ops.GEMM_MODE = old
 
 
-@pytest.mark.parametrize("Cin,Cout,H,W", [(2, 48, 17, 23), (1, 8, 5, 4), (4, 64, 9, 16)])
+@pytest.mark.parametrize("Cin,Cout,H,W", [(2, 48, 17, 23), (1, 8, 5, 4), (4, 64, 9, 16), (2, 48, 96, 128), (3, 128, 7, 9)])
 def test_small_cin_conv_fwd_bwd(Cin, Cout, H, W):
     """Direct 3x3 conv of the patch-embed head vs F.conv2d (fp64 reference), and its gradients."""
     ops, capi = _ops()
@@ -420,6 +420,15 @@ def test_small_cin_conv_fwd_bwd(Cin, Cout, H, W):
     assert ((wg.grad.cpu().double() - w.grad.double()).abs().max() / w.grad.abs().max()).item() <= 3e-3
     assert ((xg.grad.cpu().double() - x.grad.double()).abs().max() / x.grad.abs().max()).item() <= 3e-3
     assert ((bg.grad.cpu().double() - b.grad.double()).abs().max() / b.grad.abs().max()).item() <= 1e-4
+    # the model's case: the input needs no gradient -> dW / db from the library's own direct fp32 kernel, deterministic
+    grads = []
+    for _ in range(2):
+        w2, b2 = (t.detach().to(DEV).requires_grad_(True) for t in (w, b))
+        ops.conv3x3_small_cin(x.detach().to(DEV), w2, b2).backward(go.to(DEV))
+        grads.append((w2.grad.clone(), b2.grad.clone()))
+    assert ((grads[0][0].cpu().double() - w.grad.double()).abs().max() / w.grad.abs().max()).item() <= 1e-5
+    assert ((grads[0][1].cpu().double() - b.grad.double()).abs().max() / b.grad.abs().max()).item() <= 1e-5
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
 
 
 # ---------------------------------------------------------------------------------------------
