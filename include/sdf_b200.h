@@ -650,6 +650,29 @@ typedef struct {
 
 int sdf_spike_conv_fwd(const sdf_spike_conv_fwd_args* a);
 
+/* ConvTranspose2d(kernel 3, stride 2, padding 1, output_padding 1) on 1-byte spikes — the x2 up-sampling of the decoder
+ * (SpikingTransposeDecoderLayer / MS_SpikingTransposeDecoderLayer, Spiking_modules.py:398-474): x u8 NHWC (Nimg, H, W, Cin) ->
+ * out fp32 NHWC (Nimg, 2H, 2W, Cout).  Computed as four stride-1 implicit GEMMs, one per output parity class
+ * cls = 2*(row parity) + (column parity), with the 1 / 2 / 2 / 4 kernel taps that land on that class; wq[cls] / wscale[cls] =
+ * the planes of sdf_spike_gemm_pack run with taps = sdf_spike_deconv_class_taps(cls, tap_map, dh, dw) and the IOHW strides
+ * (s_ci = Cout*9, s_co = 9, s_tap = 1).  bn_partials (optional): [4 * n_partial_blocks, 2, Cout], one slab per class. */
+typedef struct {
+  const uint8_t* x;
+  const int8_t* wq[4];
+  const float* wscale[4];
+  const float* bias;        /* optional [Cout] */
+  float* out;
+  float* bn_partials;
+  int64_t n_partial_blocks;
+  int64_t Nimg, H, W, Cin, Cout;
+  int64_t a_max;
+  void* stream;
+} sdf_spike_deconv_fwd_args;
+
+int sdf_spike_deconv_fwd(const sdf_spike_deconv_fwd_args* a);
+/* taps of parity class cls (0..3): fills src_tap (kh*3 + kw of the 3x3 kernel), dh, dw (input offsets); returns their number */
+int64_t sdf_spike_deconv_class_taps(int64_t cls, int64_t* src_tap, int64_t* dh, int64_t* dw);
+
 /* out[rows, N] = a[rows, K] @ b[N, K]^T (+ bias[N]) with fp32 operands read as TF32 (tcgen05.mma kind::tf32), fp32
  * accumulate: the data-gradient GEMM dS = G @ W of every Linear above (b = W^T stored [Cin, Cout]).  lda / ldb / ld_out in
  * elements, multiples of 4. */

@@ -97,7 +97,7 @@ class Spikingformer_MultiResUNet(SpikingMultiResUNet):
         for i, (decoder, pred) in enumerate(zip(self.decoders, self.preds)):
             x = skip_concat_cl(x, blocks[self.num_encoders - i - 1])
             if i > 0:
-                x = skip_concat_cl(predictions[-1], x, align=4)
+                x = skip_concat_cl(predictions[-1], x, align=16)     # 16: the TMA pixel pitch of the 1-byte spike operand
             x = decoder.forward_cl(x)
             predictions.append(pred.forward_cl(x))
         return predictions

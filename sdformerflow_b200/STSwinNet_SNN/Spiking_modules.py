@@ -321,8 +321,15 @@ class MS_SpikingTransposeDecoderLayer(SpikingTransposeDecoderLayer):
     """neuron -> deconv -> norm (reference :461-474)."""
 
     def forward_cl(self, x):
-        h = conv_cl(self.sn(x, 1), self.deconv[0], True, transposed=True,
-                    weight=padded_in_weight(self.deconv[0], x.shape[-1], True))
+        dc = self.deconv[0]
+        if ops.spike_gemm_on() and ops.spike_deconv_supported(dc, x.shape[-1]):
+            # own engine: 1-byte spikes -> four parity-class implicit GEMMs, BN sums from their epilogues
+            s = self.sn(x, 1, u8=True)
+            if self.norm is None:
+                return ops.spike_deconv(s, dc.weight, dc.bias)
+            h, part = ops.spike_deconv(s, dc.weight, dc.bias, stats=bn_training(self.norm_layer))
+            return ops.bn_residual(h, self.norm_layer.norm_layer, partials=part)
+        h = conv_cl(self.sn(x, 1), dc, True, transposed=True, weight=padded_in_weight(dc, x.shape[-1], True))
         return ops.bn_residual(h, self.norm_layer.norm_layer) if self.norm is not None else h
 
 

@@ -18,7 +18,7 @@ from torch import nn
 
 from ..sj import layer as sj_layer
 from ..sj import surrogate, neuron  # noqa: F401
-from .. import ops
+from .. import gemm, ops
 from .Spiking_modules import *  # noqa: F401,F403
 from .Spiking_modules import Spiking_neuron, SpikingNormLayer, MS_PED_Spiking_PatchEmbed_Conv_sfn, bn_training  # noqa: F401
 
@@ -188,7 +188,7 @@ class Spiking_QK_WindowAttention3D(_WindowAttentionBase):
         wq, wk = self.linear_q.weight, self.linear_k.weight
         if torch.is_grad_enabled() and (wq.requires_grad or wk.requires_grad):
             return torch.cat([wq, wk], 0)
-        key = (wq.data_ptr(), wq._version, wk.data_ptr(), wk._version)
+        key = (wq.data_ptr(), wq._version, wk.data_ptr(), wk._version, gemm.weights_epoch())
         hit = self.__dict__.get("_wqk_cache")
         if hit is None or hit[0] != key or torch.cuda.is_current_stream_capturing():
             w = torch.cat([wq.detach(), wk.detach()], 0)

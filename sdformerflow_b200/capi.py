@@ -107,6 +107,8 @@ def lib():
                 m = re.match(r"const\s+(\w+)\s*\*", a)
                 if m and m.group(1) in st:
                     argtypes.append(ctypes.POINTER(st[m.group(1)]["ctype"]))
+                elif re.match(r"int64_t\s*\*", a):
+                    argtypes.append(ctypes.POINTER(ctypes.c_int64))
                 elif a.startswith("int64_t"):
                     argtypes.append(ctypes.c_int64)
                 else:

@@ -535,6 +535,65 @@ extern "C" int sdf_gemm_tf32(const sdf_gemm_tf32_args* a) {
   return launch_gemm<KIND_TF32>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_gemm_tf32");
 }
 
+namespace sdf {
+// One implicit-GEMM launch of the spike convolution: `taps` taps with input offsets (dh, dw) and the packed weights `wq`
+// (tap order of the pack); output pixel (h, w) of the (Ho, Wo) tile grid is written at out_base + ((h*osh)*ld_row + w*osw)*Cout
+// (osh = osw = 1, ld_row = Wo: an ordinary convolution; 2, 2 and a parity offset in out_base: one phase of a transposed one).
+struct ConvLaunch {
+  const uint8_t* x; int64_t Nimg, H, W, Cin;
+  const int8_t* wq; const float* wscale; const float* bias;
+  float* out_base; int64_t Ho, Wo, Cout, osh, osw, out_ld_row, out_img_elems;
+  int taps, stride; int dh[kMaxTaps], dw[kMaxTaps];
+  float* bn_partials; int64_t n_partial_blocks; int64_t a_max;
+  cudaStream_t stream;
+};
+static int conv_fwd_launch(const ConvLaunch& c, const char* what) {
+  GemmP p{};
+  p.conv = 1;
+  p.nt = pick_nt((int)c.Cout, 64);
+  p.n_ntiles = ((int)c.Cout + p.nt - 1) / p.nt;
+  p.ncols = 3 * p.nt;
+  p.Cout = (int)c.Cout;
+  p.Ho = (int)c.Ho; p.Wo = (int)c.Wo;
+  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
+  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
+  p.n_mtiles = (int)c.Nimg * p.tiles_h * p.tiles_w;
+  p.stride = c.stride;
+  p.taps = c.taps;
+  p.cpt = (int)((c.Cin + kChunkBytes - 1) / kChunkBytes);
+  p.n_kchunks = p.taps * p.cpt;
+  p.kc_elems = kChunkBytes;
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = c.dh[i]; p.dw[i] = c.dw[i]; }
+  p.wscale = c.wscale; p.bias = c.bias; p.bn_partials = c.bn_partials; p.n_partial_cap = (int)c.n_partial_blocks;
+  p.fast_cvt = (c.a_max > 0 && c.Cin * c.taps * c.a_max < 32768) ? 1 : 0;
+  const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t dims[4] = {(uint64_t)c.Cin, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.Nimg};
+    const uint64_t str[3] = {(uint64_t)c.Cin, (uint64_t)c.W * c.Cin, (uint64_t)c.H * c.W * c.Cin};
+    const uint32_t box[4] = {(uint32_t)kChunkBytes, (uint32_t)(kPatchW * c.stride), (uint32_t)(kPatchH * c.stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
+    int st = make_tmap(&tmA, 0, 4, c.x, dims, str, box, es, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)Kpad, (uint64_t)p.n_ntiles * p.ncols};
+    const uint64_t str[1] = {(uint64_t)Kpad};
+    const uint32_t box[2] = {(uint32_t)kChunkBytes, (uint32_t)p.ncols};
+    int st = make_tmap(&tmB, 0, 2, c.wq, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)c.Cout, (uint64_t)c.Wo, (uint64_t)c.Ho, (uint64_t)c.Nimg};
+    const uint64_t str[3] = {(uint64_t)c.osw * c.Cout * 4, (uint64_t)c.osh * c.out_ld_row * c.Cout * 4, (uint64_t)c.out_img_elems * 4};
+    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    int st = make_tmap(&tmO, 1, 4, c.out_base, dims, str, box, nullptr, 64);
+    if (st) return st;
+  }
+  return launch_gemm<KIND_I8>(p, tmA, tmB, tmO, c.stream, what);
+}
+}  // namespace sdf
+
 extern "C" int sdf_spike_conv_fwd(const sdf_spike_conv_fwd_args* a) {
   SDF_REQUIRE(a->x && a->wq && a->wscale && a->out, "spike_conv_fwd: null pointer");
   SDF_REQUIRE(a->Nimg > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "spike_conv_fwd: empty problem");
@@ -545,49 +604,62 @@ extern "C" int sdf_spike_conv_fwd(const sdf_spike_conv_fwd_args* a) {
   SDF_REQUIRE(a->Ho == (a->H + 2 * a->pad - a->kh) / a->stride + 1 && a->Wo == (a->W + 2 * a->pad - a->kw) / a->stride + 1,
               "spike_conv_fwd: output size does not match the geometry");
   SDF_REQUIRE(aligned16(a->x) && aligned16(a->out) && aligned16(a->wq), "spike_conv_fwd: pointers must be 16-byte aligned");
-  GemmP p{};
-  p.conv = 1;
-  p.nt = pick_nt((int)a->Cout, 64);
-  p.n_ntiles = ((int)a->Cout + p.nt - 1) / p.nt;
-  p.ncols = 3 * p.nt;
-  p.Cout = (int)a->Cout;
-  p.Ho = (int)a->Ho; p.Wo = (int)a->Wo;
-  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
-  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
-  p.n_mtiles = (int)a->Nimg * p.tiles_h * p.tiles_w;
-  p.stride = (int)a->stride;
-  p.taps = (int)(a->kh * a->kw);
-  p.cpt = (int)((a->Cin + kChunkBytes - 1) / kChunkBytes);
-  p.n_kchunks = p.taps * p.cpt;
-  p.kc_elems = kChunkBytes;
-  for (int i = 0; i < p.taps; ++i) { p.dh[i] = i / (int)a->kw - (int)a->pad; p.dw[i] = i % (int)a->kw - (int)a->pad; }
-  p.wscale = a->wscale; p.bias = a->bias; p.bn_partials = a->bn_partials; p.n_partial_cap = (int)a->n_partial_blocks;
-  p.fast_cvt = (a->a_max > 0 && a->Cin * a->kh * a->kw * a->a_max < 32768) ? 1 : 0;
-  const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
-  CUtensorMap tmA, tmB, tmO;
-  {
-    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
-    const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
-    const uint32_t box[4] = {(uint32_t)kChunkBytes, (uint32_t)(kPatchW * a->stride), (uint32_t)(kPatchH * a->stride), 1};
-    const uint32_t es[4] = {1, (uint32_t)a->stride, (uint32_t)a->stride, 1};
-    int st = make_tmap(&tmA, 0, 4, a->x, dims, str, box, es, 128);
+  ConvLaunch c{};
+  c.x = a->x; c.Nimg = a->Nimg; c.H = a->H; c.W = a->W; c.Cin = a->Cin;
+  c.wq = a->wq; c.wscale = a->wscale; c.bias = a->bias;
+  c.out_base = a->out; c.Ho = a->Ho; c.Wo = a->Wo; c.Cout = a->Cout; c.osh = 1; c.osw = 1; c.out_ld_row = a->Wo;
+  c.out_img_elems = a->Ho * a->Wo * a->Cout;
+  c.taps = (int)(a->kh * a->kw); c.stride = (int)a->stride;
+  for (int i = 0; i < c.taps; ++i) { c.dh[i] = i / (int)a->kw - (int)a->pad; c.dw[i] = i % (int)a->kw - (int)a->pad; }
+  c.bn_partials = a->bn_partials; c.n_partial_blocks = a->n_partial_blocks; c.a_max = a->a_max;
+  c.stream = (cudaStream_t)a->stream;
+  return conv_fwd_launch(c, "sdf_spike_conv_fwd");
+}
+
+// ConvTranspose2d(k = 3, stride 2, padding 1, output_padding 1) on spikes: out (Nimg, 2H, 2W, Cout).  The output pixels of
+// parity (a, b) are an ordinary stride-1 convolution of the input with the kernel taps that land on that parity
+//   a = 0: kh = 1 (input row i);          a = 1: kh = 2 (row i) and kh = 0 (row i + 1)          (same for columns)
+// i.e. 1 + 2 + 2 + 4 = 9 taps over four launches of the same implicit-GEMM kernel, each writing its quarter of the output
+// through a strided TMA tensor map (no zero-stuffed input, no scatter pass; rows past the image are the TMA zero fill).
+extern "C" int64_t sdf_spike_deconv_class_taps(int64_t cls, int64_t* src_tap, int64_t* dh, int64_t* dw) {
+  const int a = (int)(cls >> 1), b = (int)(cls & 1);
+  const int kh_list[2][2] = {{1, -1}, {2, 0}}, d_list[2][2] = {{0, 0}, {0, 1}};
+  int n = 0;
+  for (int i = 0; i < (a ? 2 : 1); ++i)
+    for (int j = 0; j < (b ? 2 : 1); ++j) {
+      src_tap[n] = kh_list[a][i] * 3 + kh_list[b][j];
+      dh[n] = d_list[a][i];
+      dw[n] = d_list[b][j];
+      ++n;
+    }
+  return n;
+}
+
+extern "C" int sdf_spike_deconv_fwd(const sdf_spike_deconv_fwd_args* a) {
+  SDF_REQUIRE(a->x && a->out, "spike_deconv_fwd: null pointer");
+  SDF_REQUIRE(a->Nimg > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "spike_deconv_fwd: empty problem");
+  SDF_REQUIRE(a->Cin % 16 == 0 && a->Cout % 4 == 0, "spike_deconv_fwd: Cin %% 16 and Cout %% 4 must be 0");
+  SDF_REQUIRE(aligned16(a->x) && aligned16(a->out), "spike_deconv_fwd: pointers must be 16-byte aligned");
+  const int64_t Ho = 2 * a->H, Wo = 2 * a->W;
+  for (int cls = 0; cls < 4; ++cls) {
+    SDF_REQUIRE(a->wq[cls] && a->wscale[cls] && aligned16(a->wq[cls]), "spike_deconv_fwd: null / unaligned weight planes of class %d", cls);
+    ConvLaunch c{};
+    c.x = a->x; c.Nimg = a->Nimg; c.H = a->H; c.W = a->W; c.Cin = a->Cin;
+    c.wq = a->wq[cls]; c.wscale = a->wscale[cls]; c.bias = a->bias;
+    const int pa = cls >> 1, pb = cls & 1;
+    c.out_base = a->out + ((int64_t)pa * Wo + pb) * a->Cout;
+    c.Ho = a->H; c.Wo = a->W; c.Cout = a->Cout; c.osh = 2; c.osw = 2; c.out_ld_row = Wo; c.out_img_elems = Ho * Wo * a->Cout;
+    int64_t src[4], dh[4], dw[4];
+    c.taps = (int)sdf_spike_deconv_class_taps(cls, src, dh, dw);
+    for (int i = 0; i < c.taps; ++i) { c.dh[i] = (int)dh[i]; c.dw[i] = (int)dw[i]; }
+    c.stride = 1;
+    c.bn_partials = a->bn_partials ? a->bn_partials + (int64_t)cls * a->n_partial_blocks * 2 * a->Cout : nullptr;
+    c.n_partial_blocks = a->n_partial_blocks; c.a_max = a->a_max;
+    c.stream = (cudaStream_t)a->stream;
+    int st = conv_fwd_launch(c, "sdf_spike_deconv_fwd");
     if (st) return st;
   }
-  {
-    const uint64_t dims[2] = {(uint64_t)Kpad, (uint64_t)p.n_ntiles * p.ncols};
-    const uint64_t str[1] = {(uint64_t)Kpad};
-    const uint32_t box[2] = {(uint32_t)kChunkBytes, (uint32_t)p.ncols};
-    int st = make_tmap(&tmB, 0, 2, a->wq, dims, str, box, nullptr, 128);
-    if (st) return st;
-  }
-  {
-    const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
-    const uint64_t str[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->Wo * a->Cout * 4, (uint64_t)a->Ho * a->Wo * a->Cout * 4};
-    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
-    int st = make_tmap(&tmO, 1, 4, a->out, dims, str, box, nullptr, 64);
-    if (st) return st;
-  }
-  return launch_gemm<KIND_I8>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_spike_conv_fwd");
+  return SDF_OK;
 }
 
 // Data gradient of a stride-1 NHWC convolution: dX[n,h,w,ci] = sum_{kh,kw,co} G[n, h+pad-kh, w+pad-kw, co] * W[co,ci,kh,kw],

@@ -32,6 +32,29 @@ class PackedWeight:
 
 _pack_cache = {}
 
+# Every cache of a weight-derived quantity (digit planes, concatenated q|k weight, PLIF 1/tau) is keyed by the parameter's
+# (data_ptr, _version) AND by this epoch.  ``_version`` alone is not enough: fused / foreach optimizers update parameters
+# without bumping it (torch 2.11 _fused_adamw_), so a global optimizer-step hook bumps the epoch after ANY optimizer.step(),
+# and train.GraphedStep bumps it after every replay (an optimizer captured in a CUDA graph runs no Python hook).  Weights
+# edited through .data / raw pointers, or by a user-made graph that contains the optimizer: call invalidate_pack_cache().
+_epoch = [0]
+_CACHE_OK = True
+
+
+def bump_weights_epoch():
+    _epoch[0] += 1
+
+
+def weights_epoch():
+    return _epoch[0]
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(lambda _opt, _args, _kwargs: bump_weights_epoch())
+except ImportError:          # no global hook on this torch: never cache
+    _CACHE_OK = False
+
 
 def pack_weight(w, layout="linear", cache=None, need_wt=False):
     """fp32 weight -> PackedWeight.  layout: 'linear' (Cout, K), 'conv' (Cout, Cin, kh, kw) OIHW.
@@ -44,9 +67,9 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
     capturing = torch.cuda.is_current_stream_capturing()
     if cache is None:
         cache = isinstance(w, torch.nn.Parameter)
-    if not cache:
+    if not cache or not _CACHE_OK:
         capturing = True            # same effect: neither look up nor store
-    key = (w.data_ptr(), w._version, tuple(w.shape), layout, bool(w.requires_grad or need_wt))
+    key = (w.data_ptr(), w._version, _epoch[0], tuple(w.shape), layout, bool(w.requires_grad or need_wt))
     if not capturing:
         hit = _pack_cache.get(id(w))
         if hit is not None and hit.key == key and hit.owner is not None and hit.owner() is w:
@@ -81,9 +104,67 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
     return pw
 
 
+_deconv_cache = {}
+
+
+def pack_deconv_weight(w, cin=None):
+    """ConvTranspose2d weight (Cin, Cout, 3, 3) -> the four PackedWeights of sdf_spike_deconv_fwd (one per output parity
+    class).  cin > w.shape[0]: zero input slices are appended first (decoder inputs concatenated up to a multiple of 16
+    channels).  Cached per live parameter and version like pack_weight."""
+    import ctypes
+    cin = w.shape[0] if cin is None else cin
+    capturing = torch.cuda.is_current_stream_capturing() or not isinstance(w, torch.nn.Parameter) or not _CACHE_OK
+    key = (w.data_ptr(), w._version, _epoch[0], tuple(w.shape), cin)
+    if not capturing:
+        hit = _deconv_cache.get(id(w))
+        if hit is not None and hit[0] == key and hit[2]() is w:
+            return hit[1]
+    wd = w.detach()
+    if cin != wd.shape[0]:
+        wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, 0, 0, cin - wd.shape[0]))
+    wd = wd.contiguous()
+    Cin, Cout = wd.shape[0], wd.shape[1]
+    assert tuple(wd.shape[2:]) == (3, 3)
+    L = capi.lib()
+    packs = []
+    for cls in range(4):
+        src, dh, dw = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+        taps = int(L.sdf_spike_deconv_class_taps(cls, src, dh, dw))
+        nbytes = int(L.sdf_spike_gemm_wq_bytes(Cout, Cin, taps))
+        wq = torch.empty(nbytes, device=w.device, dtype=torch.int8)
+        wscale = torch.empty(Cout, device=w.device, dtype=torch.float32)
+        capi.call("sdf_spike_gemm_pack", capi.struct(
+            "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(wq), wscale=_ptr(wscale), wt=None, wq_bytes=nbytes, Cout=Cout, Cin=Cin,
+            taps=taps, s_co=9, s_ci=Cout * 9, s_tap=1, tap_map=[int(src[i]) for i in range(taps)] + [0] * (9 - taps),
+            stream=_stream()))
+        packs.append(PackedWeight(wq, wscale, None, Cout, Cin, taps, key))
+    if not capturing:
+        wid = id(w)
+        ref = weakref.ref(w, lambda _r, wid=wid: _deconv_cache.pop(wid, None) if (wid in _deconv_cache and _deconv_cache[wid][2] is _r) else None)
+        _deconv_cache[wid] = (key, packs, ref)
+    return packs
+
+
+def spike_deconv_fwd(x_u8, packs, bias, want_stats=False, a_max=0):
+    """ConvTranspose2d(k 3, stride 2, padding 1, output_padding 1) of 1-byte spikes (Nimg, H, W, Cin) -> fp32 (Nimg, 2H, 2W, Cout),
+    BN partial sums [4 * N_PARTIAL, 2, Cout] when want_stats (one slab per parity class)."""
+    Nimg, H, W, Cin = x_u8.shape
+    Cout = packs[0].Cout
+    assert x_u8.dtype == torch.uint8 and x_u8.is_contiguous() and packs[0].Cin == Cin
+    out = torch.empty((Nimg, 2 * H, 2 * W, Cout), device=x_u8.device, dtype=torch.float32)
+    part = torch.empty((4 * N_PARTIAL, 2, Cout), device=x_u8.device, dtype=torch.float32) if want_stats else None
+    capi.call("sdf_spike_deconv_fwd", capi.struct(
+        "sdf_spike_deconv_fwd_args", x=_ptr(x_u8), wq=[_ptr(p.wq) for p in packs], wscale=[_ptr(p.wscale) for p in packs],
+        bias=_ptr(bias), out=_ptr(out), bn_partials=_ptr(part), n_partial_blocks=N_PARTIAL, Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=Cout,
+        a_max=a_max, stream=_stream()), algo_bytes=x_u8.numel() + 4 * out.numel())
+    return out, part
+
+
 def invalidate_pack_cache():
     """Drop every cached weight pack (after editing weights through .data / raw pointers)."""
     _pack_cache.clear()
+    _deconv_cache.clear()
+    bump_weights_epoch()
 
 
 def spike_gemm_fwd(a_u8, pw, bias=None, want_stats=False, a_max=0):

@@ -170,12 +170,13 @@ def _bn_forward_affine(u2d, rows, C, ld, bn: BNParams, partials=None):
                                                   partials=_ptr(partials), n_partial_blocks=N_PARTIAL, stream=_stream()),
                       algo_bytes=4 * rows * C)
         else:
-            assert partials.shape == (N_PARTIAL, 2, C) and partials.is_contiguous()
+            # [k * N_PARTIAL, 2, C]: k = 1 for a GEMM / convolution, 4 for the parity classes of a transposed convolution
+            assert partials.shape[1:] == (2, C) and partials.shape[0] % N_PARTIAL == 0 and partials.is_contiguous()
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
     with torch.no_grad():
         capi.call("sdf_bn_finalize", capi.struct(
-            "sdf_bn_finalize_args", partials=_ptr(partials), n_partial_blocks=N_PARTIAL if bn.training else 0,
+            "sdf_bn_finalize_args", partials=_ptr(partials), n_partial_blocks=partials.shape[0] if bn.training else 0,
             count=rows, C=C, weight=_ptr(bn.weight), bias=_ptr(bn.bias),
             running_mean=_ptr(bn.running_mean), running_var=_ptr(bn.running_var),
             momentum=float(bn.momentum), eps=float(bn.eps), training=1 if bn.training else 0,
@@ -272,7 +273,7 @@ _plif_tau_cache = {}
 def plif_tau(plif_w):
     """1 / sigmoid(w) of a ParametricLIFNode as a host float (the kernels take tau by value).  One device->host read per
     parameter version, so PLIF models are not CUDA-graph capturable; lif / if / psn never come here."""
-    key = (plif_w.data_ptr(), plif_w._version)
+    key = (plif_w.data_ptr(), plif_w._version, gemm.weights_epoch())      # epoch: fused optimizers do not bump _version
     hit = _plif_tau_cache.get(id(plif_w))
     if hit is not None and hit[0] == key and hit[2]() is plif_w:       # the entry of THIS live tensor, not of a freed one
         return hit[1]
@@ -828,6 +829,66 @@ class _SpikeConvGemmFn(torch.autograd.Function):
         elif want_gb:
             gb = g4.sum((0, 1, 2))
         return gtok, gw, gb, None, None, None, None
+
+
+class _SpikeDeconvFn(torch.autograd.Function):
+    """ConvTranspose2d(3, stride 2, padding 1, output_padding 1) of 1-byte spikes on the tcgen05 engine (gemm.spike_deconv_fwd:
+    four parity-class implicit GEMMs, exact integer contraction, BN sums from the epilogue).  Backward: the library's (cuDNN,
+    TF32) on the spikes expanded to fp32 — the weight gradient of a transposed convolution needs the tap shift on the fp32
+    operand, which G3 does not have.  Reference: SpikingTransposeDecoderLayer.deconv, Spiking_modules.py:398-474."""
+
+    @staticmethod
+    def forward(ctx, token, weight, bias, holder, want_stats):
+        x = holder.data                                   # (..., H, W, Cin_padded) u8
+        H, W, Cin = x.shape[-3:]
+        packs = gemm.pack_deconv_weight(weight, cin=Cin)
+        y, part = gemm.spike_deconv_fwd(x.view(-1, H, W, Cin), packs, None if bias is None else bias.detach(), want_stats, a_max=1)
+        ctx.save_for_backward(weight)
+        ctx.holder, ctx.has_bias = holder, bias is not None
+        y = y.view(*x.shape[:-3], 2 * H, 2 * W, weight.shape[1])
+        if part is not None:
+            ctx.mark_non_differentiable(part)
+        return y, part
+
+    @staticmethod
+    def backward(ctx, gy, _gp):
+        (weight,) = ctx.saved_tensors
+        holder = ctx.holder
+        x = holder.data
+        H, W, Cin = x.shape[-3:]
+        g4 = gy.contiguous().view(-1, *gy.shape[-3:]).permute(0, 3, 1, 2)      # logical NCHW, channels-last strides
+        x4 = x.view(-1, H, W, Cin).float().permute(0, 3, 1, 2)
+        w = weight.detach()
+        if Cin != w.shape[0]:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, Cin - w.shape[0]))
+        with _tf32(True):
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                g4, x4, w, [w.shape[1]] if ctx.has_bias else None, [2, 2], [1, 1], [1, 1], True, [1, 1], 1,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]])
+        gtok = None
+        if gx is not None:
+            holder.add_grad(gx.permute(0, 2, 3, 1).contiguous().view(x.shape))
+            gtok = _zero_token(gy.device)
+        if gw is not None and Cin != weight.shape[0]:
+            gw = gw[:weight.shape[0]]
+        return gtok, gw, gb, None, None
+
+
+USE_SPIKE_DECONV = True      # False: transposed convolutions stay on the library path (debug switch)
+
+
+def spike_deconv_supported(conv, cin):
+    """Geometries gemm.spike_deconv_fwd takes: the x2 decoder up-sampling of every shipped model."""
+    return (USE_SPIKE_DECONV and isinstance(conv, torch.nn.ConvTranspose2d) and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (2, 2)
+            and tuple(conv.padding) == (1, 1) and tuple(conv.output_padding) == (1, 1) and conv.groups == 1
+            and tuple(conv.dilation) == (1, 1) and cin % 16 == 0 and cin >= conv.in_channels and conv.out_channels % 4 == 0)
+
+
+def spike_deconv(s: "Spikes", weight, bias=None, stats=None):
+    """conv_transpose2d (3, stride 2, padding 1, output_padding 1) on a Spikes tensor (..., H, W, Cin) -> fp32 (..., 2H, 2W, Cout);
+    `stats` as in spike_linear.  s may carry more channels than the weight (zero channels appended by the caller)."""
+    y, part = _SpikeDeconvFn.apply(s.token, weight, bias, s, bool(stats))
+    return y if stats is None else (y, part)
 
 
 def spike_conv_supported(Cin, Cout, kernel_size, stride, padding):

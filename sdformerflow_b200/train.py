@@ -29,6 +29,7 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import gemm
 from .sj import functional
 
 
@@ -156,6 +157,7 @@ class GraphedStep:
         if self.world > 1:
             self.grads.allreduce(self.group)
             self._opt_graph.replay()
+        gemm.bump_weights_epoch()       # the captured AdamW ran no Python hook: weight-derived caches are stale now
         return self.loss
 
 

@@ -91,6 +91,33 @@ def test_pack_cache_never_serves_a_freed_parameters_planes():
     print("recycled (id, address) pairs:", recycled)
 
 
+def test_pack_cache_follows_a_fused_optimizer_step():
+    """torch's fused AdamW updates parameters WITHOUT bumping their _version: the pack caches are also keyed by an epoch that a
+    global optimizer-step hook bumps, so the step after an update must use the new weights (Linear and transposed-conv packs)."""
+    gemm = _gemm()
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(64, 32, device=DEV) * 0.1)
+    wd = torch.nn.Parameter(torch.randn(32, 8, 3, 3, device=DEV) * 0.1)
+    opt = torch.optim.AdamW([w, wd], lr=1e-1, fused=True)
+    a = _spikes((200, 32), 0.3, 3)
+    x = _spikes((1, 4, 4, 32), 0.3, 4)
+
+    def check():
+        y, _ = gemm.spike_gemm_fwd(a, gemm.pack_weight(w), None, False, a_max=1)
+        ref = a.double() @ w.detach().double().t()
+        assert (y.double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+        yd, _ = gemm.spike_deconv_fwd(x, gemm.pack_deconv_weight(wd), None, a_max=1)
+        refd = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), wd.detach().double(), None, stride=2, padding=1,
+                                  output_padding=1).permute(0, 2, 3, 1)
+        assert (yd.double() - refd).abs().max().item() <= 2e-6 * refd.abs().max().item()
+
+    check()
+    assert gemm.pack_weight(w) is gemm.pack_weight(w)          # cached while nothing changes
+    w.grad, wd.grad = torch.ones_like(w), torch.ones_like(wd)
+    opt.step()
+    check()
+
+
 @pytest.mark.parametrize("rows,K,N", [(1000, 192, 96), (4099, 96, 96), (700, 768, 384), (513, 3072, 768), (300, 768, 3072),
                                      (2000, 384, 96), (200, 96, 48), (333, 4, 96), (260, 100, 20)])
 def test_gemm_tf32(rows, K, N):
@@ -190,6 +217,36 @@ def test_spike_conv_wgrad(Nimg, H, W, Cin, Cout, k, stride, pad):
     assert torch.equal(dw, dw3)
     refb = g.double().sum((0, 1, 2))
     assert (db.double() - refb).abs().max().item() <= 1e-5 * g.double().abs().sum((0, 1, 2)).max().item()
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,Cout", [(2, 9, 12, 1536, 384), (3, 18, 24, 784, 192), (2, 36, 48, 400, 96), (2, 20, 27, 208, 96),
+                                                (1, 8, 16, 16, 4), (2, 5, 7, 32, 8)])
+def test_spike_deconv_fwd_fp32_grade(Nimg, H, W, Cin, Cout):
+    """ConvTranspose2d(3, stride 2, padding 1, output_padding 1) on spikes as four parity-class implicit GEMMs vs F.conv_transpose2d
+    in fp64 (decoder shapes of the model incl. the channel counts padded to 16), BN partial sums of the four slabs."""
+    gemm = _gemm()
+    torch.manual_seed(H * W + Cin)
+    x = _spikes((Nimg, H, W, Cin), 0.25, H + 5)
+    w = (torch.randn(Cin, Cout, 3, 3) * 0.03).to(DEV)
+    b = torch.randn(Cout).to(DEV)
+    packs = gemm.pack_deconv_weight(w)
+    y, part = gemm.spike_deconv_fwd(x, packs, b, want_stats=True, a_max=1)
+    ref = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=1,
+                             output_padding=1).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert ((y.double() - ref).abs().max() / ref.abs().max()).item() <= 2e-6
+    yy = y.double().reshape(-1, Cout)
+    assert torch.allclose(part[:, 0].double().sum(0), yy.sum(0), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(part[:, 1].double().sum(0), (yy ** 2).sum(0), rtol=1e-5, atol=1e-2)
+    # zero input slices appended by the packer (decoder inputs concatenated up to a multiple of 16 channels)
+    if Cin >= 32:
+        packs2 = gemm.pack_deconv_weight(w[:Cin - 14], cin=Cin)
+        x2 = x.clone()
+        x2[..., Cin - 14:] = 0
+        y2, _ = gemm.spike_deconv_fwd(x2, packs2, b, a_max=1)
+        ref2 = F.conv_transpose2d(x2[..., :Cin - 14].permute(0, 3, 1, 2).double(), w[:Cin - 14].double(), b.double(), stride=2,
+                                  padding=1, output_padding=1).permute(0, 2, 3, 1)
+        assert ((y2.double() - ref2).abs().max() / ref2.abs().max()).item() <= 2e-6
 
 
 @pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,pad", [(3, 24, 32, 96, 96, 3, 1), (2, 20, 27, 96, 96, 3, 1), (5, 9, 12, 768, 768, 3, 1),
