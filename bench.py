@@ -525,7 +525,8 @@ def run_b200(args, rank, local_rank, world):
                        "parallelism": f"dp{world}",
                        "gemm": "own tcgen05 + TMA engine on every Linear / 3x3 conv fed by spikes: kind::i8 forward on 1-byte spikes x 3 "
                                "weight digit planes (exact integer accumulate, BN sums from the epilogue), TF32 data / weight "
-                               "gradients; library (cuDNN/cuBLAS, TF32 x 2) only for transposed convs, strided conv dgrad and "
+                               "gradients; decoder transposed convs forward as four parity-class implicit GEMMs; library (cuDNN/cuBLAS) only for the "
+                               "backward of the transposed convs, strided conv dgrad and "
                                "real-valued operands",
                        "l2": "activations per step >> 126 MB L2; no explicit flush",
                        "weights": "random init (init_weights, seed 0)",
