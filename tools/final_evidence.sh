@@ -11,6 +11,7 @@ python bench.py --workload infer --steps 5 --warmup 3 2>/dev/null | tail -1 > gp
 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${R}_bench_reference_arm.json
 python tools/microbench.py 2>/dev/null > gpurun_out/${R}_microbench.jsonl
 python tools/bench_gemm.py 2>/dev/null > gpurun_out/${R}_bench_gemm.jsonl
+python tools/bench_small_conv.py 2>/dev/null > gpurun_out/${R}_bench_small_conv.txt
 for m in 0 1 2; do SDF_WGRAD_DEBUG=$m python tools/bench_wgrad_dbg.py 2>/dev/null | grep case; done > gpurun_out/${R}_bench_wgrad_modes.jsonl
 ./tools/ubench/tma_stream > gpurun_out/${R}_ubench_tma_stream.jsonl 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --secondary off --graph off > gpurun_out/${R}_ncu_bench.log 2>&1
@@ -34,6 +35,7 @@ cap ${R}_ncu_lin_dgrad gemm_kernel 2 1 python tools/ncu_gemm_targets.py lin_dgra
 cap ${R}_ncu_conv_dgrad gemm_kernel 2 1 python tools/ncu_gemm_targets.py conv_dgrad
 cap ${R}_ncu_lin_wgrad wgrad_kernel 2 1 python tools/ncu_gemm_targets.py lin_wgrad
 cap ${R}_ncu_conv_wgrad wgrad_kernel 2 1 python tools/ncu_gemm_targets.py conv_wgrad
+cap ${R}_ncu_deconv_fwd gemm_kernel 8 4 python tools/ncu_gemm_targets.py deconv_fwd
 ls -la gpurun_out/ | grep ${R}_ | tail -40
 cat gpurun_out/${R}_pytest_gpu.txt gpurun_out/${R}_smoke.txt
 cut -c1-700 gpurun_out/${R}_bench_n1.json
