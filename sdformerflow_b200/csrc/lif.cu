@@ -160,7 +160,7 @@ struct LifBwdP {
 // PRE = 1: all grad loads issued up front (max loads in flight, ~190 regs, 1 CTA/SM);
 // PRE = 0: grad loads streamed inside the adjoint loop (128 regs, 2 CTAs/SM).
 template <int T, int V, int PRE, bool SIMPLE>
-__global__ void __launch_bounds__(288, (V == 2) ? (PRE ? 2 : 3) : (PRE ? 1 : 2)) lif_bwd_kernel(const LifBwdP p) {
+__global__ void __launch_bounds__(288, (T >= 16) ? 1 : ((V == 2) ? (PRE ? 2 : 3) : (PRE ? 1 : 2))) lif_bwd_kernel(const LifBwdP p) {
   constexpr int TM = T > 0 ? T : 32;
   extern __shared__ float smem[];
   const SeqP& s = p.s;
@@ -547,19 +547,19 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   p.nrn = make_neuron(a->neuron);
   const void* ptrs[] = {a->u, a->grad_spike, a->grad_u, a->grad_x, a->v_init};
   const int T = (int)a->lay.T;
-  const bool fastT = (T == 2 || T == 4 || T == 5 || T == 10);
+  const bool fastT = (T == 2 || T == 4 || T == 5 || T == 10 || T == 20);
   const bool parts = a->bn_partials || a->plif_partials;
   int64_t max_blocks = (int64_t)kNumSMs * (T == 10 ? 3 : 2);
   if (parts) {
     SDF_REQUIRE(a->n_partial_blocks >= 1, "sdf_lif_bwd: n_partial_blocks < 1");
     if (a->n_partial_blocks < max_blocks) max_blocks = a->n_partial_blocks;
   }
-  if (a->bn_partials) SDF_REQUIRE(fastT, "sdf_lif_bwd: bn_partials supported for T in {2,4,5,10}");
+  if (a->bn_partials) SDF_REQUIRE(fastT, "sdf_lif_bwd: bn_partials supported for T in {2,4,5,10,20}");
   SeqLaunch L;
   // T = 10 keeps u, h (and the preloaded grads) in registers: 2 neurons per thread there, 4 otherwise
   static const int v4_t10 = [] { const char* e = getenv("SDF_LIF_BWD_V4"); return e ? atoi(e) : 1; }();
   // T = 10 with 4 neurons/thread keeps u, h and the preloaded grads in ~220 registers: 288-thread CTAs, one per SM
-  st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, fastT ? ((T == 10 && !v4_t10) ? 2 : 4) : 1,
+  st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, fastT ? (((T == 10 && !v4_t10) || T == 20) ? 2 : 4) : 1,
                  (T == 10 && v4_t10) ? 288 : 256, max_blocks, &L);
   if (st) return st;
   p.s = L.s;
@@ -586,6 +586,10 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
         else lif_bwd_kernel<5, 4, 1, false><<<L.grid, L.threads, smem, stream>>>(p);
         break;
     }
+  } else if (L.V == 2 && T == 20) {
+    // T = 20 (20-bin inputs): u and h of 2 neurons x 20 steps stay in registers (vector path; grads streamed), one CTA per SM
+    if (simple) lif_bwd_kernel<20, 2, 0, true><<<L.grid, L.threads, smem, stream>>>(p);
+    else lif_bwd_kernel<20, 2, 0, false><<<L.grid, L.threads, smem, stream>>>(p);
   } else if (L.V == 2) {
     static const int pre_mode = [] { const char* e = getenv("SDF_LIF_BWD_PRELOAD"); return e ? atoi(e) : 1; }();
     if (simple && pre_mode) lif_bwd_kernel<10, 2, 1, true><<<L.grid, L.threads, smem, stream>>>(p);

@@ -140,14 +140,15 @@ def _bn(C, seed, train):
     return bn
 
 
-@pytest.mark.parametrize("C", [96, 384, 3072])
+@pytest.mark.parametrize("C,T", [(96, 10), (384, 10), (3072, 10), (96, 20), (192, 5)])
 @pytest.mark.parametrize("train", [False, True])
-def test_bn_neuron_fwd_bwd(C, train):
-    """neuron(BN(u)) on channels-last rows vs sn(bn(u.permute(0,1,4,2,3)).permute(0,1,3,4,2))."""
+def test_bn_neuron_fwd_bwd(C, T, train):
+    """neuron(BN(u)) on channels-last rows vs sn(bn(u.permute(0,1,4,2,3)).permute(0,1,3,4,2)); T = 20 is the 20-bin input of
+    the reference's MDR configs (vector path of K2 with the BN partial sums)."""
     ops, capi = _ops()
     import copy
     g = torch.Generator().manual_seed(C)
-    T, B, H, W = 10, 2, 3, 5
+    B, H, W = 2, 3, 5
     u = (torch.randn(T, B, H, W, C, generator=g) * 0.8 + 0.2).requires_grad_(True)
     go = torch.randn(T, B, H, W, C, generator=g)
     bn_ref = _bn(C, 1, train)

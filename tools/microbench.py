@@ -54,7 +54,7 @@ def main():
         scale, shift = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1
         ms = timeit(lambda: ops._lif_fwd_raw(x, lay, cfg.c(), capi.SDF_SPIKE_U8, scale, shift, C, 1))
         report(f"lif_fwd+bn T={T} out=u8", T * N * 5, ms, T=T, N=N)
-        if T <= 10:
+        if T <= 20:          # T = 20: the vector path added in round 2 (u, h of 2 neurons x 20 steps in registers)
             gs = torch.randn(T, N, device=dev)
             gx = torch.empty_like(x)
             part = torch.empty(ops.N_PARTIAL, 2, C, device=dev)
