@@ -161,7 +161,7 @@ typedef struct {
   const float* grad_spike;
   float* grad_u;       /* optional: dL/du = dL/dx * scale[c] */
   float* grad_x;       /* optional: dL/dx (BN-train backward needs it before the scale multiply) */
-  float* grad_h;       /* [T, n_neurons] contiguous: dL/dh, consumed by the host for dW = dh x^T, db */
+  float* grad_h;       /* [T, n_neurons] contiguous: dL/dh, for sdf_psn_wgrad (optional when wgrad_partials is given) */
   float* x_out;        /* optional [T, n_neurons] contiguous: the post-affine input x (for dW) */
   const float* weight;
   const float* bias;
@@ -176,6 +176,10 @@ typedef struct {
   int32_t _pad;
   double sg_alpha;
   void* stream;
+  float* wgrad_partials;    /* optional [n_wgrad_blocks, T*T + T]: per-block partial sums of dW[t][k] = sum_n dh[t,n] x[k,n] and
+                               db[t] = sum_n dh[t,n], accumulated in this pass (T in {2,4,5,10}, 16-byte aligned layout); with
+                               it grad_h / x_out may be NULL: dh and x never go to HBM (12 B instead of 28 B per neuron-step) */
+  int64_t n_wgrad_blocks;
 } sdf_psn_bwd_args;
 
 int sdf_psn_bwd(const sdf_psn_bwd_args* a);

@@ -274,6 +274,7 @@ struct PsnP {
   const float* weight; const float* bias;
   const float* scale; const float* shift;
   float* bn_partials;
+  float* wg_partials;   // backward, optional: per-block partial sums of dW [T*T] and db [T] (see psn_bwd_kernel<.., WG = true>)
   SeqP s; NeuronP nrn;  // nrn: only sg / sg_alpha used (threshold is 0)
 };
 
@@ -330,9 +331,13 @@ __global__ void __launch_bounds__(512) psn_fwd_kernel(const PsnP p) {
   }
 }
 
-template <int T, int V>
+// WG = true: the parameter gradients dW[t][k] = sum_n dh[t,n] * x[k,n], db[t] = sum_n dh[t,n] are accumulated in registers
+// over the thread's neurons and reduced per block — dh and x never go to HBM (the separate sdf_psn_wgrad pass re-read
+// 8 B per neuron-timestep that this kernel had to write first: 28 B -> 12 B per neuron-timestep).
+template <int T, int V, bool WG = false>
 __global__ void __launch_bounds__(256) psn_bwd_kernel(const PsnP p) {
   constexpr int TM = T > 0 ? T : 32;
+  constexpr int TW = WG ? TM : 1;
   extern __shared__ float smem[];
   __shared__ float sw[32 * 32 + 32];
   const SeqP& s = p.s;
@@ -346,6 +351,13 @@ __global__ void __launch_bounds__(256) psn_bwd_kernel(const PsnP p) {
   float sc[V], sh[V];
   init_affine<V>(s, p.scale, p.shift, col, sc, sh);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float wacc[TW][TW], wb[TW];
+#pragma unroll
+  for (int t = 0; t < TW; ++t) {
+    wb[t] = 0.f;
+#pragma unroll
+    for (int k = 0; k < TW; ++k) wacc[t][k] = 0.f;
+  }
   for (int64_t row = (int64_t)blockIdx.x * s.k + ry; row < s.n_rows; row += (int64_t)gridDim.x * s.k) {
     const int64_t n = row * s.row_w + col;
     if (n >= s.n_neurons) continue;
@@ -384,8 +396,24 @@ __global__ void __launch_bounds__(256) psn_bwd_kernel(const PsnP p) {
           }
 #pragma unroll
         for (int i = 0; i < V; ++i) dh[t][i] *= surrogate_grad(nrn, h[i] + sw[1024 + t]);
-        stv<V>(p.gh + (int64_t)t * s.n_neurons + n, dh[t]);
+        if (p.gh) stv<V>(p.gh + (int64_t)t * s.n_neurons + n, dh[t]);
       }
+    }
+    if (WG) {
+#pragma unroll
+      for (int k = 0; k < TW; ++k) {
+        float xk[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) xk[i] = fmaf(u[k][i], sc[i], sh[i]);
+#pragma unroll
+        for (int t = 0; t < TW; ++t)
+#pragma unroll
+          for (int i = 0; i < V; ++i) wacc[t][k] = fmaf(dh[t][i], xk[i], wacc[t][k]);
+      }
+#pragma unroll
+      for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int i = 0; i < V; ++i) wb[t] += dh[t][i];
     }
     // dx_k = sum_t W[t][k] dh_t
 #pragma unroll
@@ -416,6 +444,27 @@ __global__ void __launch_bounds__(256) psn_bwd_kernel(const PsnP p) {
   }
   if (p.bn_partials && s.chan_mode == 1 && V == 4)
     block_reduce_rows_to_partials<2>(acc, smem, p.bn_partials, s.R, s.k, s.C, (int64_t)blockIdx.y * s.tile_w);
+  if (WG) {
+    // block sum of the T*T + T accumulators: warp shuffles, then one pass over the 8 warp rows (fixed order)
+    __shared__ float wred[8][TW * TW + TW];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < TW * TW + TW; ++e) {
+      float v = e < TW * TW ? wacc[e / TW][e % TW] : wb[e - TW * TW];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) wred[wp][e] = v;
+    }
+    __syncthreads();
+    float* out = p.wg_partials + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (TW * TW + TW);
+    const int nwarps = blockDim.x >> 5;        // host-checked: blockDim.x is a multiple of 32, <= 256
+    for (int e = threadIdx.x; e < TW * TW + TW; e += blockDim.x) {
+      float sum = 0.f;
+      for (int w = 0; w < nwarps; ++w) sum += wred[w][e];
+      out[e] = sum;
+    }
+  }
 }
 
 // ---- host: tiling and dispatch --------------------------------------------------------------
@@ -633,13 +682,15 @@ extern "C" int sdf_psn_fwd(const sdf_psn_fwd_args* a) {
 }
 
 extern "C" int sdf_psn_bwd(const sdf_psn_bwd_args* a) {
-  SDF_REQUIRE(a && a->u && a->grad_spike && (a->grad_u || a->grad_x) && a->grad_h && a->weight && a->bias, "sdf_psn_bwd: null argument");
+  SDF_REQUIRE(a && a->u && a->grad_spike && (a->grad_u || a->grad_x) && (a->grad_h || a->wgrad_partials) && a->weight && a->bias,
+              "sdf_psn_bwd: null argument");
   const bool affine = a->scale != nullptr;
   SDF_REQUIRE(!affine || a->shift, "sdf_psn_bwd: scale without shift");
   if (a->lay.n_neurons == 0) return SDF_OK;
   PsnP p = {};
   p.u = a->u; p.gs = a->grad_spike; p.gu = a->grad_u; p.gx = a->grad_x; p.gh = a->grad_h; p.x_out = a->x_out;
   p.weight = a->weight; p.bias = a->bias; p.scale = a->scale; p.shift = a->shift; p.bn_partials = a->bn_partials;
+  p.wg_partials = a->wgrad_partials;
   sdf_neuron_cfg nc = {};
   nc.kind = SDF_NEURON_IF; nc.surrogate = a->surrogate; nc.sg_alpha = a->sg_alpha; nc.tau = 2.0; nc.v_th = 0.0;
   p.nrn = make_neuron(nc);
@@ -661,7 +712,20 @@ extern "C" int sdf_psn_bwd(const sdf_psn_bwd_args* a) {
     cudaMemsetAsync(a->bn_partials + (int64_t)L.grid.x * 2 * a->C, 0,
                     sizeof(float) * (a->n_partial_blocks - L.grid.x) * 2 * a->C, stream);
   const size_t smem = sizeof(float) * 4 * (size_t)L.threads;
-  if (L.V == 4) {
+  if (a->wgrad_partials) {
+    // parameter gradients accumulated in the same pass: vector path only, 256-thread blocks (8 warps in the block reduce)
+    const int64_t nb = (int64_t)L.grid.x * L.grid.y, per = (int64_t)T * T + T;
+    SDF_REQUIRE(L.V == 4 && fastT && L.threads % 32 == 0 && L.threads <= 256,
+                "sdf_psn_bwd: wgrad_partials need the vector path (T in {2,4,5,10}, 16-byte aligned layout, whole warps)");
+    SDF_REQUIRE(a->n_wgrad_blocks >= nb, "sdf_psn_bwd: wgrad_partials too small (%lld blocks needed)", (long long)nb);
+    if (a->n_wgrad_blocks > nb) cudaMemsetAsync(a->wgrad_partials + nb * per, 0, sizeof(float) * (a->n_wgrad_blocks - nb) * per, stream);
+    switch (T) {
+      case 2: psn_bwd_kernel<2, 4, true><<<L.grid, L.threads, smem, stream>>>(p); break;
+      case 4: psn_bwd_kernel<4, 4, true><<<L.grid, L.threads, smem, stream>>>(p); break;
+      case 5: psn_bwd_kernel<5, 4, true><<<L.grid, L.threads, smem, stream>>>(p); break;
+      default: psn_bwd_kernel<10, 4, true><<<L.grid, L.threads, smem, stream>>>(p); break;
+    }
+  } else if (L.V == 4) {
     switch (T) {
       case 2: psn_bwd_kernel<2, 4><<<L.grid, L.threads, smem, stream>>>(p); break;
       case 4: psn_bwd_kernel<4, 4><<<L.grid, L.threads, smem, stream>>>(p); break;

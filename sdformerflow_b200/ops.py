@@ -339,6 +339,12 @@ class _PSNFn(torch.autograd.Function):
         gs = gs.contiguous() if ctx.holder is None else ctx.holder.take_grad()
         T, n = ctx.lay["T"], ctx.lay["n_neurons"]
         gu = torch.empty_like(u)
+        if _psn_fused_wgrad_ok(ctx.lay, u, gs, gu):
+            pg = _psn_bwd_fused(T, u, dict(
+                u=_ptr(u), grad_spike=_ptr(gs), grad_u=_ptr(gu), grad_h=None, x_out=None, weight=_ptr(w), bias=_ptr(b), C=0, hw=1,
+                lay=ctx.lay, surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
+            if pg is not None:
+                return gu, pg[0], pg[1], None, None, None
         gh = torch.empty((T, n), device=u.device, dtype=torch.float32)
         xo = u.view(T, n) if ctx.lay["stride_b"] == 0 else torch.empty((T, n), device=u.device, dtype=torch.float32)
         capi.call("sdf_psn_bwd", capi.struct(
@@ -347,6 +353,31 @@ class _PSNFn(torch.autograd.Function):
             lay=ctx.lay, surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
         g_w, g_b = _psn_param_grads(gh, xo.contiguous() if not xo.is_contiguous() else xo)
         return gu, g_w, g_b, None, None, None
+
+
+N_PSN_WG = 2048      # rows of the PSN parameter-gradient partial buffer (>= blocks of any sdf_psn_bwd launch)
+
+
+def _psn_bwd_fused(T, u, kw):
+    """sdf_psn_bwd with the parameter gradients accumulated in the same pass -> (dW [T,T], db [T,1]), or None when the launch
+    geometry of this layout cannot take it (the caller then runs the two-kernel path; nothing was launched)."""
+    wpart = torch.empty((N_PSN_WG, T * T + T), device=u.device, dtype=torch.float32)
+    try:
+        capi.call("sdf_psn_bwd", capi.struct("sdf_psn_bwd_args", wgrad_partials=_ptr(wpart), n_wgrad_blocks=N_PSN_WG, **kw),
+                  algo_bytes=12 * u.numel())
+    except RuntimeError as e:
+        if "wgrad_partials" not in str(e):
+            raise
+        return None
+    tot = wpart.sum(0)
+    return tot[:T * T].view(T, T), tot[T * T:].view(T, 1)
+
+
+def _psn_fused_wgrad_ok(lay, *tensors):
+    """Can sdf_psn_bwd accumulate dW / db itself (its vector path: T in {2,4,5,10}, every stride a multiple of 4 elements,
+    16-byte aligned buffers)?  Otherwise grad_h / x go through HBM to sdf_psn_wgrad."""
+    return (lay["T"] in (2, 4, 5, 10) and lay["n_neurons"] % 4 == 0 and lay["inner"] % 4 == 0 and lay["stride_b"] % 4 == 0
+            and lay["stride_t"] % 4 == 0 and all(t.data_ptr() % 16 == 0 for t in tensors))
 
 
 def _psn_param_grads(gh, xo):
@@ -441,8 +472,16 @@ class _BNNeuronFn(torch.autograd.Function):
             du, gw, gb = _bn_backward(partials, dx, u, C, rows, C, weight, mean, rstd, ctx.training)
             return du.view(u.shape), gw, gb, None, None, None, g_psn_w, g_psn_b, g_plif, None, None
         dx = torch.empty_like(u)
-        if True:
-            T, n = ctx.lay["T"], ctx.lay["n_neurons"]
+        T, n = ctx.lay["T"], ctx.lay["n_neurons"]
+        pg = None
+        if _psn_fused_wgrad_ok(ctx.lay, u, gs, dx):
+            pg = _psn_bwd_fused(T, u, dict(
+                u=_ptr(u), grad_spike=_ptr(gs), grad_u=None, grad_x=_ptr(dx), grad_h=None, x_out=None, weight=_ptr(psn_w),
+                bias=_ptr(psn_b), scale=_ptr(scale), shift=_ptr(shift), bn_partials=_ptr(partials), n_partial_blocks=N_PARTIAL,
+                C=C, hw=1, lay=ctx.lay, surrogate=ctx.cfg.surrogate, sg_alpha=float(ctx.cfg.sg_alpha), stream=_stream()))
+        if pg is not None:
+            g_psn_w, g_psn_b = pg
+        else:
             gh = torch.empty((T, n), device=dev, dtype=torch.float32)
             xo = torch.empty((T, n), device=dev, dtype=torch.float32)
             capi.call("sdf_psn_bwd", capi.struct(

@@ -82,10 +82,10 @@ def main():
     sp = ops.psn(xp, wp, bp, pcfg, 0)
     gsp = torch.randn_like(sp)
     ms = timeit(lambda: torch.autograd.grad(sp, (xp, wp, bp), gsp, retain_graph=True))
-    report("psn_bwd T=10 (grad_x + dW/db kernel)", T * Np * 12 + T * Np * 8, ms, T=T, N=Np)
+    report("psn_bwd T=10 (grad_x, dW / db accumulated in the same pass)", T * Np * 12, ms, T=T, N=Np)
     gh = torch.randn(T, Np, device=dev)
     ms = timeit(lambda: ops._psn_param_grads(gh, xp.detach()))
-    report("psn_wgrad T=10 (dW [T,T], db)", T * Np * 8, ms, T=T, N=Np)
+    report("psn_wgrad T=10 (dW [T,T], db; stand-alone kernel for layouts the fused path does not take)", T * Np * 8, ms, T=T, N=Np)
     del xp, sp, gsp, gh
     torch.cuda.empty_cache()
     # time-strided (B, D, H, W, C) layout, the MLP sn1 site of cfg2 stage 1
