@@ -35,6 +35,24 @@ gemm.conv_dgrad_tf32(gc, wc, 20, 27, 1, pc.wt)
 gemm.spike_conv_wgrad(gc, x, 3, 3, 1, 1)
 y2, _ = gemm.spike_conv_fwd(x, pc, None, 3, 3, 2, 1)
 gemm.spike_conv_wgrad(torch.randn_like(y2), x, 3, 3, 2, 1)
+gemm.spike_wgrad(g, a, s_max=1, want_db=True)                       # 0/1 expansion + bias gradient
+gemm.spike_conv_wgrad(gc, x, 3, 3, 1, 1, s_max=1, want_db=True)     # halo box (stride 1, one kernel row per tile)
+# G1t: transposed convolution as four parity-class launches (208 = 194 channels padded to the TMA pitch)
+xd = spikes(2, 9, 12, 208, rate=0.25)
+wdc = torch.randn(208, 96, 3, 3, device=dev) * 0.03
+gemm.spike_deconv_fwd(xd, gemm.pack_deconv_weight(wdc), None, want_stats=True, a_max=1)
+# head convolution (2 real-valued channels): forward + dW / db
+xv = torch.rand(3, 17, 23, 2, device=dev)
+wh_ = (torch.randn(48, 2, 3, 3, device=dev) * 0.3).requires_grad_(True)
+bh_ = torch.zeros(48, device=dev, requires_grad=True)
+ops.conv3x3_small_cin(xv, wh_, bh_).sum().backward()
+# PSN forward / backward with the parameter gradients accumulated in the same pass; T = 20 vector path of K2
+pw_ = (torch.eye(10, device=dev) + 0.05 * torch.randn(10, 10, device=dev)).requires_grad_(True)
+pb_ = torch.full((10, 1), -0.1, device=dev).requires_grad_(True)
+up = torch.randn(10, 4096, device=dev, requires_grad=True)
+ops.psn(up, pw_, pb_, ops.NeuronCfg(kind=capi.SDF_NEURON_LIF, v_th=0.1, v_reset=None, tau=2.0, detach_reset=True), 0).sum().backward()
+u20 = torch.randn(20, 4096, device=dev, requires_grad=True)
+ops.neuron(u20, ops.NeuronCfg(kind=capi.SDF_NEURON_LIF, v_th=0.1, v_reset=None, tau=2.0, detach_reset=True)).sum().backward()
 # K3 / K4 (v2 pipeline, masked and unmasked) on a (2,3,4) window
 wd, wh, ww, nH, M = 2, 3, 4, 3, 8
 N = wd * wh * ww
