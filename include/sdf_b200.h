@@ -705,6 +705,35 @@ typedef struct {
 
 int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a);
 
+/* Data gradient of a 3x3 / stride-2 / padding-1 NHWC convolution (the strided convolutions of the patch embedding, reference
+ * Spiking_modules.py:1710-1790; autograd of sj_layer.Conv2d(stride=2)): the input pixels of each parity class are a stride-1
+ * convolution of g with the taps landing on that parity, i.e. four launches of the TF32 implicit GEMM writing their quarter
+ * of `out` through strided TMA tensor maps.  wd as for sdf_conv_dgrad_tf32 ([Cin][9*Cout], PackedWeight.wt); Cout % 32 == 0. */
+typedef struct {
+  const float* g;      /* (Nimg, Ho, Wo, Cout) */
+  const float* wd;     /* [Cin][9 * Cout]: wd[ci][tap*Cout + co] = W[co, ci, kh, kw], tap = kh*3 + kw */
+  float* out;          /* (Nimg, H, W, Cin) */
+  int64_t Nimg, H, W, Cin, Cout, Ho, Wo;
+  void* stream;
+} sdf_conv_dgrad_s2_tf32_args;
+
+int sdf_conv_dgrad_s2_tf32(const sdf_conv_dgrad_s2_tf32_args* a);
+
+/* Data gradient of ConvTranspose2d(k 3, stride 2, padding 1, output_padding 1) (decoder up-sampling, reference
+ * Spiking_modules.py:398-474): a stride-2 / padding-1 convolution of g, one launch of the TF32 implicit GEMM with the tapped
+ * operand read through an element-stride-2 TMA tensor map.
+ *   wd [Cin_w][9 * Cpad], Cpad = Cout rounded up to a multiple of 32: wd[ci][tap*Cpad + co] = W[ci, co, kh, kw], zero padded.
+ *   out channels Cin_w .. Cin-1 (operand channels the caller appended as padding) are written as zeros. */
+typedef struct {
+  const float* g;      /* (Nimg, 2H, 2W, Cout) */
+  const float* wd;
+  float* out;          /* (Nimg, H, W, Cin) */
+  int64_t Nimg, H, W, Cin, Cin_w, Cout;
+  void* stream;
+} sdf_deconv_dgrad_tf32_args;
+
+int sdf_deconv_dgrad_tf32(const sdf_deconv_dgrad_tf32_args* a);
+
 /* ---- G3: weight gradient dW = G^T S of a Linear / convolution on a spike operand (csrc/spike_wgrad.cu) -------------
  * G fp32 [rows, Cout] (split into bf16 hi + lo, A operand through tensor memory), S u8 spikes [rows, K] (expanded to bf16,
  * MN-major B operand); contraction over the rows on tcgen05, split over row slabs into `workspace`, reduced in slab order
@@ -743,6 +772,29 @@ typedef struct {
 } sdf_spike_conv_wgrad_args;
 
 int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a);
+
+/* Weight (+ bias) gradient of ConvTranspose2d(k 3, stride 2, padding 1, output_padding 1) on 1-byte spikes (reference
+ * Spiking_modules.py:398-474, autograd of the decoder's sj_layer.ConvTranspose2d):
+ *   dW[ci, co, kh, kw] = sum S[n, i, j, ci] * G[n, 2i - 1 + kh, 2j - 1 + kw, co]
+ * as four launches of the G3 kernel, one per output parity class: G of a class is a strided TMA view on the input grid, the
+ * class's taps shift the spike operand by 0 / 1 pixels.  dw is the parameter layout (Cin_w, Cout, 3, 3); x may carry
+ * Cin >= Cin_w channels (zero channels appended by the caller), whose gradients are dropped.  db (optional) = sum of g.
+ * workspace_bytes >= sdf_spike_deconv_wgrad_workspace_bytes(Nimg, H, W, Cout, Cin). */
+typedef struct {
+  const float* g;      /* (Nimg, 2H, 2W, Cout) */
+  const uint8_t* x;    /* (Nimg, H, W, Cin) */
+  float* dw;           /* (Cin_w, Cout, 3, 3) */
+  float* workspace;
+  int64_t workspace_bytes;
+  int64_t Nimg, H, W, Cin, Cin_w, Cout;
+  int32_t s_max;       /* 1 = binary spikes, 0 = any u8 */
+  int32_t reserved;
+  void* stream;
+  float* db;           /* [Cout] or NULL */
+} sdf_spike_deconv_wgrad_args;
+
+int sdf_spike_deconv_wgrad(const sdf_spike_deconv_wgrad_args* a);
+int64_t sdf_spike_deconv_wgrad_workspace_bytes(int64_t Nimg, int64_t H, int64_t W, int64_t Cout, int64_t Cin);
 
 /* ---- input pipeline: polarity split + min-max normalisation + bins->steps regroup, channels-last out ----------------
  * Replaces train_flow_parallel_supervised_SNN.py:261-265,278-284 (eval_DSEC_flow_SNN.py:196-212) and the regroup loop of

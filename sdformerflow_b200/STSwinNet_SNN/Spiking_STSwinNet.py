@@ -175,10 +175,17 @@ class SpikingformerFlowNet(nn.Module):
             raise NotImplementedError("log=True (attention-score dump) is not built; see Spiking_SwinTransformerBlock3D")
         H, W = x.shape[-2], x.shape[-1]
         flow_list = []
-        for pred in self.sttmultires_unet.forward_cl(x):               # (B, T, h, w, 2)
-            flow = torch.sum(pred, dim=1).permute(0, 3, 1, 2)           # sum over time -> (B, 2, h, w)
-            flow_list.append(torch.nn.functional.interpolate(
-                flow, scale_factor=(H / flow.shape[-2], W / flow.shape[-1])))
+        # The reference trainer enters the model under torch.cuda.amp.autocast when a GradScaler is configured
+        # (train_flow_parallel_supervised_SNN.py:248).  This path has nothing for autocast to down-cast: membranes integrate
+        # in fp32 and the spike contractions are exact integer GEMMs, so autocast is switched off for the model's extent
+        # (the scripts run unmodified; losses / GradScaler see fp32 flows, which autocast would have produced for the
+        # final sum / interpolate anyway).
+        with torch.autocast(device_type=x.device.type, enabled=False):
+            x = x.float()
+            for pred in self.sttmultires_unet.forward_cl(x):               # (B, T, h, w, 2)
+                flow = torch.sum(pred, dim=1).permute(0, 3, 1, 2)           # sum over time -> (B, 2, h, w)
+                flow_list.append(torch.nn.functional.interpolate(
+                    flow, scale_factor=(H / flow.shape[-2], W / flow.shape[-1])))
         return {"flow": flow_list, "attn": None}
 
     def __str__(self):

@@ -104,15 +104,26 @@ struct FinP {
 // lane), the 32 row-group sums are then added in index order by the rg == 0 threads.  Everything in double, fixed order:
 // deterministic, and the single rounding to fp32 at the end keeps mean/var within 1 ulp of exact.
 constexpr int kFinThreads = 1024;
-__device__ __forceinline__ void block_sum_partials(const float* partials, int64_t nblk, int64_t C, int64_t c, double& s0, double& s1) {
+constexpr int kFinRows = 14;    // partial rows per thread and round: 32 row groups x 14 = 448 >= the 444-row workspaces
+__device__ __forceinline__ void block_sum_partials(const float* __restrict__ partials, int64_t nblk, int64_t C, int64_t c, double& s0,
+                                                   double& s1) {
   __shared__ double sh[2][32][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   double a = 0.0, b = 0.0;
   if (c < C) {
-#pragma unroll 4
-    for (int64_t blk = rg; blk < nblk; blk += 32) {
-      a += (double)partials[(blk * 2 + 0) * C + c];
-      b += (double)partials[(blk * 2 + 1) * C + c];
+    // all the loads of a round are issued before the first add (one memory round trip per 448 rows, not one per 4 rows:
+    // these kernels are pure latency — a few CTAs reading ~100 KB that the producer has just written)
+    for (int64_t base = rg; base < nblk; base += 32 * kFinRows) {
+      float va[kFinRows], vb[kFinRows];
+#pragma unroll
+      for (int i = 0; i < kFinRows; ++i) {
+        const int64_t blk = base + 32 * i;
+        const bool ok = blk < nblk;
+        va[i] = ok ? __ldg(partials + (blk * 2 + 0) * C + c) : 0.f;
+        vb[i] = ok ? __ldg(partials + (blk * 2 + 1) * C + c) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kFinRows; ++i) { a += (double)va[i]; b += (double)vb[i]; }
     }
   }
   sh[0][rg][cl] = a;
@@ -129,6 +140,15 @@ __device__ __forceinline__ void block_sum_partials(const float* partials, int64_
 __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const FinP p) {
   const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
   const bool lead = (threadIdx.x >> 5) == 0 && c < p.C;
+  // parameters and running statistics are read BEFORE the reduction, so that their (cold) round trips overlap with it
+  // instead of forming a chain of dependent load -> store pairs behind it
+  float w = 1.f, b = 0.f, rm = 0.f, rv = 1.f;
+  if (lead) {
+    if (p.weight) w = p.weight[c];
+    if (p.bias) b = p.bias[c];
+    if (p.running_mean) rm = p.running_mean[c];
+    if (p.running_var) rv = p.running_var[c];
+  }
   float mean = 0.f, var = 1.f;
   if (p.training) {
     double s, ss;
@@ -140,19 +160,17 @@ __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const FinP p) 
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
-    if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+    if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * rm + p.momentum * mean;
     if (p.running_var) {
       const float unbiased = (float)(v * (n / (n > 1.0 ? n - 1.0 : 1.0)));
-      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
+      p.running_var[c] = (1.f - p.momentum) * rv + p.momentum * unbiased;
     }
   } else {
     if (!lead) return;
-    mean = p.running_mean[c];
-    var = p.running_var[c];
+    mean = rm;
+    var = rv;
   }
   const float rstd = 1.f / sqrtf(var + p.eps);
-  const float w = p.weight ? p.weight[c] : 1.f;
-  const float b = p.bias ? p.bias[c] : 0.f;
   const float sc = w * rstd;
   p.scale[c] = sc;
   p.shift[c] = b - mean * sc;
@@ -162,11 +180,15 @@ __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const FinP p) 
 
 __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const FinP p) {
   const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool lead = (threadIdx.x >> 5) == 0 && c < p.C;
+  double mean = 0.0, rstd = 1.0, w = 1.0;
+  if (lead) {                     // issued before the reduction (see bn_finalize_kernel)
+    mean = p.mean_in[c]; rstd = p.rstd_in[c];
+    if (p.weight) w = (double)p.weight[c];
+  }
   double s, su;
   block_sum_partials(p.partials, p.nblk, p.C, c, s, su);
-  if ((threadIdx.x >> 5) != 0 || c >= p.C) return;
-  const double mean = p.mean_in[c], rstd = p.rstd_in[c];
-  const double w = p.weight ? (double)p.weight[c] : 1.0;
+  if (!lead) return;
   const double dgamma = (su - mean * s) * rstd;  // sum dy * xhat
   const double dbeta = s;
   if (p.gw) p.gw[c] = (float)dgamma;

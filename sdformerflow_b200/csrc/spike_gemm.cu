@@ -54,6 +54,8 @@ struct GemmP {
   // convolution geometry (conv = 1): output (Nimg, Ho, Wo), tiles_h x tiles_w patches per image
   int conv, tiles_h, tiles_w, Ho, Wo, stride, taps, cpt;   // cpt = K chunks per tap
   int dh[kMaxTaps], dw[kMaxTaps];                          // input offset of tap t (already includes -padding)
+  int btap[kMaxTaps];                                      // conv: tap t of this launch reads the B rows' K range of tap btap[t]
+                                                           // (identity unless the launch uses a subset of the packed taps)
   int out_sh, out_sw, out_oh, out_ow;                      // transposed conv: output pixel = patch pixel * out_s + out_o
 };
 
@@ -85,6 +87,12 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmP& p, int m_tile) {
   const int ph = rem / p.tiles_w, pw = rem - ph * p.tiles_w;
   t.c1 = pw * kPatchW; t.c2 = ph * kPatchH; t.c3 = img;
   return t;
+}
+// K coordinate (elements) of chunk kc in the B operand
+__device__ __forceinline__ int b_kcoord(const GemmP& p, int kc) {
+  if (!p.conv) return kc * p.kc_elems;
+  const int tap = kc / p.cpt, cc = kc - tap * p.cpt;
+  return (p.btap[tap] * p.cpt + cc) * p.kc_elems;
 }
 // number of valid rows mask: is tile row r inside the output?
 __device__ __forceinline__ bool row_valid(const GemmP& p, const TileCoord& t, int r) {
@@ -136,24 +144,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (elect_one()) {
       if (p.b_resident) {
         mbar_expect_tx(bres, (uint32_t)p.n_kchunks * bchunk);
-        for (int kc = 0; kc < p.n_kchunks; ++kc) tma_load_2d(&tmB, bres, b_base + kc * bchunk, kc * p.kc_elems, n_tile * p.ncols);
+        for (int kc = 0; kc < p.n_kchunks; ++kc) tma_load_2d(&tmB, bres, b_base + kc * bchunk, b_kcoord(p, kc), n_tile * p.ncols);
       }
-      uint32_t it = 0;
+      int s = 0;                                 // ring slot and its phase, advanced incrementally (no division per chunk)
+      uint32_t ph = 0;
+      const int n_taps = p.conv ? p.taps : 1, cpt = p.conv ? p.cpt : p.n_kchunks;
       for (int m = group; m < p.n_mtiles; m += p.n_groups) {
         const TileCoord t = tile_coord(p, m);
-        for (int kc = 0; kc < p.n_kchunks; ++kc, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], kAChunk + (p.b_resident ? 0u : bchunk));
-          if (!p.conv) {
-            tma_load_2d(&tmA, &full[s], a_base + s * kAChunk, kc * p.kc_elems, t.c1);
-          } else {
-            const int tap = kc / p.cpt, cc = kc - tap * p.cpt;
-            tma_load_4d(&tmA, &full[s], a_base + s * kAChunk, cc * p.kc_elems, t.c1 * p.stride + p.dw[tap],
-                        t.c2 * p.stride + p.dh[tap], t.c3);
+        for (int tap = 0; tap < n_taps; ++tap) {
+          // per-tap coordinates hoisted out of the chunk loop (no division on the issue path)
+          const int aw = p.conv ? t.c1 * p.stride + p.dw[tap] : 0, ah = p.conv ? t.c2 * p.stride + p.dh[tap] : 0;
+          const int bk0 = p.conv ? p.btap[tap] * cpt * p.kc_elems : 0;
+          for (int cc = 0; cc < cpt; ++cc) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], kAChunk + (p.b_resident ? 0u : bchunk));
+            if (!p.conv) tma_load_2d(&tmA, &full[s], a_base + s * kAChunk, cc * p.kc_elems, t.c1);
+            else tma_load_4d(&tmA, &full[s], a_base + s * kAChunk, cc * p.kc_elems, aw, ah, t.c3);
+            if (!p.b_resident) tma_load_2d(&tmB, &full[s], b_base + s * bchunk, bk0 + cc * p.kc_elems, n_tile * p.ncols);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
-          if (!p.b_resident) tma_load_2d(&tmB, &full[s], b_base + s * bchunk, kc * p.kc_elems, n_tile * p.ncols);
         }
       }
     }
@@ -163,15 +172,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t idesc = KIND == KIND_I8 ? idesc_i8_u8s8(kTileM, p.ncols) : idesc_tf32(kTileM, p.ncols);
       constexpr uint32_t hi = desc_hi_sw128(1024);
       if (p.b_resident) { mbar_wait(bres, 0); }
-      uint32_t it = 0, tile_i = 0;
+      uint32_t tile_i = 0, ph = 0;
+      int s = 0;
       for (int m = group; m < p.n_mtiles; m += p.n_groups, ++tile_i) {
         const uint32_t as = tile_i & 1, aph = (tile_i >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + as * (uint32_t)p.ncols;
-        for (int kc = 0; kc < p.n_kchunks; ++kc, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int kc = 0; kc < p.n_kchunks; ++kc) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_lo = desc_lo(a_base + s * kAChunk);
@@ -180,6 +188,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int ks = 0; ks < kChunkBytes / 32; ++ks)
             mma_ss<KIND>(d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc, (kc | ks) != 0 ? 1u : 0u);
           tc_commit(&empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         tc_commit(&tfull[as]);
       }
@@ -563,7 +572,7 @@ static int conv_fwd_launch(const ConvLaunch& c, const char* what) {
   p.cpt = (int)((c.Cin + kChunkBytes - 1) / kChunkBytes);
   p.n_kchunks = p.taps * p.cpt;
   p.kc_elems = kChunkBytes;
-  for (int i = 0; i < p.taps; ++i) { p.dh[i] = c.dh[i]; p.dw[i] = c.dw[i]; }
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = c.dh[i]; p.dw[i] = c.dw[i]; p.btap[i] = i; }
   p.wscale = c.wscale; p.bias = c.bias; p.bn_partials = c.bn_partials; p.n_partial_cap = (int)c.n_partial_blocks;
   p.fast_cvt = (c.a_max > 0 && c.Cin * c.taps * c.a_max < 32768) ? 1 : 0;
   const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
@@ -688,7 +697,7 @@ extern "C" int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a) {
   p.cpt = (int)(a->Cout / 32);
   p.n_kchunks = p.taps * p.cpt;
   p.kc_elems = 32;
-  for (int i = 0; i < p.taps; ++i) { p.dh[i] = (int)a->pad - i / (int)a->kw; p.dw[i] = (int)a->pad - i % (int)a->kw; }
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = (int)a->pad - i / (int)a->kw; p.dw[i] = (int)a->pad - i % (int)a->kw; p.btap[i] = i; }
   CUtensorMap tmA, tmB, tmO;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
@@ -713,4 +722,118 @@ extern "C" int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a) {
     if (st) return st;
   }
   return launch_gemm<KIND_TF32>(p, tmA, tmB, tmO, (cudaStream_t)a->stream, "sdf_conv_dgrad_tf32");
+}
+
+namespace sdf {
+// One TF32 implicit-GEMM launch over a tapped fp32 NHWC operand `g` (Nimg, Hg, Wg, Cg), read with element stride `stride`:
+//   out[n, h, w, c] = sum_{t < taps} sum_{k < Cg} g[n, h*stride + dh[t], w*stride + dw[t], k] * wd[c][(btap[t]*cpt + k/32)*32 + k%32]
+// for the (Hc, Wc) grid of output pixels, written at out_base + (h*osh + w*osw + n*oimg) elements + c.  wd has n_brows valid
+// rows (rows beyond are TMA zero fill: output channels of zero-padded operand slices come out as zeros) of total_taps*cpt*32
+// floats, cpt = ceil(Cg / 32) (a tap's channels padded to whole 128-byte K chunks).
+struct ConvTf32Launch {
+  const float* g; int64_t Nimg, Hg, Wg, Cg; int stride;
+  const float* wd; int64_t n_brows; int total_taps;
+  float* out_base; int64_t Hc, Wc, N, osw, osh, oimg;
+  int taps; int dh[kMaxTaps], dw[kMaxTaps], btap[kMaxTaps];
+  cudaStream_t stream;
+};
+static int conv_tf32_launch(const ConvTf32Launch& c, const char* what) {
+  GemmP p{};
+  p.conv = 1;
+  // as few N tiles as possible (every N tile re-reads the tapped operand), each as narrow as that allows
+  const int tiles = (int)((c.N + 127) / 128);
+  p.nt = (int)(((c.N + tiles - 1) / tiles + 15) / 16 * 16);
+  p.n_ntiles = ((int)c.N + p.nt - 1) / p.nt;
+  p.ncols = p.nt;
+  p.Cout = (int)c.N;
+  p.Ho = (int)c.Hc; p.Wo = (int)c.Wc;
+  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
+  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
+  p.n_mtiles = (int)c.Nimg * p.tiles_h * p.tiles_w;
+  p.stride = c.stride;
+  p.taps = c.taps;
+  p.cpt = (int)((c.Cg + 31) / 32);
+  p.n_kchunks = p.taps * p.cpt;
+  p.kc_elems = 32;
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = c.dh[i]; p.dw[i] = c.dw[i]; p.btap[i] = c.btap[i]; }
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t dims[4] = {(uint64_t)c.Cg, (uint64_t)c.Wg, (uint64_t)c.Hg, (uint64_t)c.Nimg};
+    const uint64_t str[3] = {(uint64_t)c.Cg * 4, (uint64_t)c.Wg * c.Cg * 4, (uint64_t)c.Hg * c.Wg * c.Cg * 4};
+    const uint32_t box[4] = {32, (uint32_t)(kPatchW * c.stride), (uint32_t)(kPatchH * c.stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
+    int st = make_tmap(&tmA, 1, 4, c.g, dims, str, box, es, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t K = (uint64_t)c.total_taps * p.cpt * 32;
+    const uint64_t dims[2] = {K, (uint64_t)c.n_brows};
+    const uint64_t str[1] = {K * 4};
+    const uint32_t box[2] = {32, (uint32_t)p.nt};
+    int st = make_tmap(&tmB, 1, 2, c.wd, dims, str, box, nullptr, 128);
+    if (st) return st;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)c.N, (uint64_t)c.Wc, (uint64_t)c.Hc, (uint64_t)c.Nimg};
+    const uint64_t str[3] = {(uint64_t)c.osw * 4, (uint64_t)c.osh * 4, (uint64_t)c.oimg * 4};
+    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    int st = make_tmap(&tmO, 1, 4, c.out_base, dims, str, box, nullptr, 64);
+    if (st) return st;
+  }
+  return launch_gemm<KIND_TF32>(p, tmA, tmB, tmO, c.stream, what);
+}
+}  // namespace sdf
+
+// Data gradient of a 3x3, stride-2, padding-1 NHWC convolution (the strided convolutions of the patch embedding):
+//   dX[n, h, w, ci] = sum_{kh, kw, co : h + 1 - kh = 2 ho, w + 1 - kw = 2 wo} G[n, ho, wo, co] * W[co, ci, kh, kw]
+// The input pixels of parity (a, b) = (h & 1, w & 1) are an ordinary stride-1 convolution of G with the taps that land on that
+// parity — the classes of sdf_spike_deconv_class_taps (a strided convolution's data gradient IS a transposed convolution):
+// four launches of the TF32 implicit GEMM, each reading its taps' K range of wd and writing its quarter of dX through a
+// strided TMA tensor map.  Replaces cuDNN's strided_dgrad engine (+ its NHWC repacking) on this path.
+extern "C" int sdf_conv_dgrad_s2_tf32(const sdf_conv_dgrad_s2_tf32_args* a) {
+  SDF_REQUIRE(a->g && a->wd && a->out, "conv_dgrad_s2_tf32: null pointer");
+  SDF_REQUIRE(a->Nimg > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "conv_dgrad_s2_tf32: empty problem");
+  SDF_REQUIRE(a->Cout % 32 == 0, "conv_dgrad_s2_tf32: Cout=%lld must be a multiple of 32 (one 128-byte K chunk)", (long long)a->Cout);
+  SDF_REQUIRE(a->Cin % 4 == 0, "conv_dgrad_s2_tf32: Cin must be a multiple of 4");
+  SDF_REQUIRE(a->Ho == (a->H - 1) / 2 + 1 && a->Wo == (a->W - 1) / 2 + 1, "conv_dgrad_s2_tf32: 3x3 / stride 2 / padding 1 geometry expected");
+  SDF_REQUIRE(aligned16(a->g) && aligned16(a->wd) && aligned16(a->out), "conv_dgrad_s2_tf32: pointers must be 16-byte aligned");
+  for (int cls = 0; cls < 4; ++cls) {
+    const int pa = cls >> 1, pb = cls & 1;
+    ConvTf32Launch c{};
+    c.Hc = (a->H - pa + 1) / 2; c.Wc = (a->W - pb + 1) / 2;
+    if (c.Hc <= 0 || c.Wc <= 0) continue;
+    c.g = a->g; c.Nimg = a->Nimg; c.Hg = a->Ho; c.Wg = a->Wo; c.Cg = a->Cout; c.stride = 1;
+    c.wd = a->wd; c.n_brows = a->Cin; c.total_taps = 9;
+    c.out_base = a->out + ((int64_t)pa * a->W + pb) * a->Cin;
+    c.N = a->Cin; c.osw = 2 * a->Cin; c.osh = 2 * a->W * a->Cin; c.oimg = a->H * a->W * a->Cin;
+    int64_t src[4], dh[4], dw[4];
+    c.taps = (int)sdf_spike_deconv_class_taps(cls, src, dh, dw);
+    for (int i = 0; i < c.taps; ++i) { c.dh[i] = (int)dh[i]; c.dw[i] = (int)dw[i]; c.btap[i] = (int)src[i]; }
+    c.stream = (cudaStream_t)a->stream;
+    int st = conv_tf32_launch(c, "sdf_conv_dgrad_s2_tf32");
+    if (st) return st;
+  }
+  return SDF_OK;
+}
+
+// Data gradient of ConvTranspose2d(k = 3, stride 2, padding 1, output_padding 1):
+//   dX[n, i, j, ci] = sum_{kh, kw, co} G[n, 2i - 1 + kh, 2j - 1 + kw, co] * W[ci, co, kh, kw]
+// i.e. a stride-2, padding-1 convolution of G: ONE launch of the TF32 implicit GEMM whose tapped operand is read through a
+// TMA tensor map with element stride 2 (rows / columns -1 and 2H are the TMA zero fill).  Replaces cuDNN's fprop engine on
+// this path (reference: SpikingTransposeDecoderLayer.deconv backward, Spiking_modules.py:398-474).
+extern "C" int sdf_deconv_dgrad_tf32(const sdf_deconv_dgrad_tf32_args* a) {
+  SDF_REQUIRE(a->g && a->wd && a->out, "deconv_dgrad_tf32: null pointer");
+  SDF_REQUIRE(a->Nimg > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "deconv_dgrad_tf32: empty problem");
+  SDF_REQUIRE(a->Cout % 4 == 0 && a->Cin % 4 == 0, "deconv_dgrad_tf32: Cin, Cout must be multiples of 4");
+  SDF_REQUIRE(a->Cin_w >= 1 && a->Cin_w <= a->Cin, "deconv_dgrad_tf32: Cin_w=%lld outside [1, Cin]", (long long)a->Cin_w);
+  SDF_REQUIRE(aligned16(a->g) && aligned16(a->wd) && aligned16(a->out), "deconv_dgrad_tf32: pointers must be 16-byte aligned");
+  ConvTf32Launch c{};
+  c.g = a->g; c.Nimg = a->Nimg; c.Hg = 2 * a->H; c.Wg = 2 * a->W; c.Cg = a->Cout; c.stride = 2;
+  c.wd = a->wd; c.n_brows = a->Cin_w; c.total_taps = 9;
+  c.out_base = a->out; c.Hc = a->H; c.Wc = a->W; c.N = a->Cin;
+  c.osw = a->Cin; c.osh = a->W * a->Cin; c.oimg = a->H * a->W * a->Cin;
+  c.taps = 9;
+  for (int i = 0; i < 9; ++i) { c.dh[i] = i / 3 - 1; c.dw[i] = i % 3 - 1; c.btap[i] = i; }
+  c.stream = (cudaStream_t)a->stream;
+  return conv_tf32_launch(c, "sdf_deconv_dgrad_tf32");
 }

@@ -314,9 +314,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
 }
 
 // dW[co*s_co + ci*s_ci + tap*s_tap] (+)= sum_s partial[s][co][tap*Cin + ci], slabs added in index order
+// tap_map: destination tap of local tap t (a launch over a subset of a kernel's taps); channels ci >= cin_store are dropped
+// (operand channels appended as padding); db_accumulate: the bias gradient is added to db (dw is not)
+struct WgTapMap { int t[9]; };
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n_slabs, int Cout, int Cin,
                                     int taps, int64_t s_co, int64_t s_ci, int64_t s_tap, int accumulate,
-                                    const float* __restrict__ db_partial, float* __restrict__ db) {
+                                    const float* __restrict__ db_partial, float* __restrict__ db, const WgTapMap tap_map,
+                                    int cin_store, int db_accumulate) {
   const int64_t total = (int64_t)Cout * taps * Cin;
   const int64_t total_all = total + (db != nullptr ? Cout : 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_all; i += (int64_t)gridDim.x * blockDim.x) {
@@ -324,7 +328,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
       const int64_t co = i - total;
       float acc = 0.f;
       for (int s = 0; s < n_slabs; ++s) acc += __ldg(db_partial + (int64_t)s * Cout + co);
-      db[co] = accumulate ? db[co] + acc : acc;
+      db[co] = (accumulate || db_accumulate) ? db[co] + acc : acc;
       continue;
     }
     float acc = 0.f;
@@ -332,7 +336,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     const int64_t co = i / ((int64_t)taps * Cin);
     const int64_t rem = i - co * taps * Cin;
     const int64_t tap = rem / Cin, ci = rem - tap * Cin;
-    float* d = dw + co * s_co + ci * s_ci + tap * s_tap;
+    if (ci >= cin_store) continue;
+    float* d = dw + co * s_co + ci * s_ci + tap_map.t[tap] * s_tap;
     *d = accumulate ? *d + acc : acc;
   }
 }
@@ -388,7 +393,8 @@ static int wgrad_debug_mode() {
 }
 
 static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tmS, float* dw, int64_t s_co, int64_t s_ci,
-                        int64_t s_tap, int accumulate, int64_t ws_bytes, cudaStream_t st, const char* what, float* db) {
+                        int64_t s_tap, int accumulate, int64_t ws_bytes, cudaStream_t st, const char* what, float* db,
+                        const int* tap_map = nullptr, int cin_store = -1, int db_accumulate = 0) {
   wgrad_slabs(p);
   p.debug = wgrad_debug_mode();
   SDF_REQUIRE((int64_t)p.n_slabs * p.Cout * (p.ncols_total + 1) * 4 <= ws_bytes, "%s: workspace too small (%lld needed)", what,
@@ -412,8 +418,10 @@ static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tm
   if (r) return r;
   const int64_t total = (int64_t)p.Cout * (p.ncols_total + 1);
   const int blocks = (int)((total + 255) / 256 < 4 * num_sms() ? (total + 255) / 256 : 4 * num_sms());
+  WgTapMap tm;
+  for (int i = 0; i < 9; ++i) tm.t[i] = tap_map != nullptr && i < p.taps ? tap_map[i] : i;
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, p.n_slabs, p.Cout, p.Cin, p.taps, s_co, s_ci, s_tap, accumulate,
-                                              p.db_partial, db);
+                                              p.db_partial, db, tm, cin_store < 0 ? p.Cin : cin_store, db_accumulate);
   return finish_launch(what);
 }
 
@@ -495,4 +503,81 @@ extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
   // parameter layout OIHW: (co, ci, tap) at co*Cin*taps + ci*taps + tap
   return wgrad_launch(p, tmG, tmS, a->dw, (int64_t)p.Cin * p.taps, p.taps, 1, a->accumulate, a->workspace_bytes,
                       (cudaStream_t)a->stream, "sdf_spike_conv_wgrad", a->db);
+}
+
+// Weight (+ bias) gradient of ConvTranspose2d(k = 3, stride 2, padding 1, output_padding 1) on a spike operand:
+//   dW[ci, co, kh, kw] = sum_{n,i,j} S[n, i, j, ci] * G[n, 2i - 1 + kh, 2j - 1 + kw, co]
+// Per output parity class (a, b) the pixels G[2i + a, 2j + b] are a strided VIEW of G (a TMA tensor map with doubled pixel /
+// row strides and a parity base offset) on the input grid, and the class's taps read the spikes at (i + dh, j + dw),
+// dh, dw in {0, 1} (sdf_spike_deconv_class_taps): four launches of the G3 kernel, each producing the dW of its 1 / 2 / 2 / 4
+// taps — the tap shift stays on the 1-byte operand, G is never gathered or copied.  Replaces cuDNN's wgrad on fp32-expanded
+// spikes (reference: SpikingTransposeDecoderLayer.deconv backward, Spiking_modules.py:398-474).
+extern "C" int64_t sdf_spike_deconv_class_taps(int64_t cls, int64_t* src_tap, int64_t* dh, int64_t* dw);
+
+static void deconv_wgrad_class(WgradP& p, const sdf_spike_deconv_wgrad_args* a, int cls, int* tap_map) {
+  p = WgradP{};
+  int64_t src[4], dh[4], dw[4];
+  p.taps = (int)sdf_spike_deconv_class_taps(cls, src, dh, dw);
+  p.conv = 1;
+  p.Cout = (int)a->Cout; p.Cin = (int)a->Cin; p.ncols_total = p.taps * p.Cin;
+  p.n_mtiles = (p.Cout + kWgM - 1) / kWgM;
+  wgrad_tiles(p.Cin, p.taps, &p.taps_per_tile, &p.ci_tiles, &p.ci_width, &p.n_ntiles);
+  p.tiles_h = (int)((a->H + kWgPatchH - 1) / kWgPatchH);
+  p.tiles_w = (int)((a->W + kWgPatchW - 1) / kWgPatchW);
+  p.n_chunks = (int)a->Nimg * p.tiles_h * p.tiles_w;
+  p.stride = 1;
+  for (int i = 0; i < p.taps; ++i) { p.dh[i] = (int)dh[i]; p.dw[i] = (int)dw[i]; tap_map[i] = (int)src[i]; }
+  p.binary = a->s_max == 1;
+  p.nbox = p.ci_width > 256 ? 2 : 1;
+  p.box_w = p.ci_width / p.nbox;
+}
+
+extern "C" int64_t sdf_spike_deconv_wgrad_workspace_bytes(int64_t Nimg, int64_t H, int64_t W, int64_t Cout, int64_t Cin) {
+  sdf_spike_deconv_wgrad_args a{};
+  a.Nimg = Nimg; a.H = H; a.W = W; a.Cout = Cout; a.Cin = Cin;
+  int64_t best = 0;
+  for (int cls = 0; cls < 4; ++cls) {
+    WgradP p; int tm[9];
+    deconv_wgrad_class(p, &a, cls, tm);
+    wgrad_slabs(p);
+    const int64_t b = (int64_t)p.n_slabs * Cout * (p.ncols_total + 1) * 4;
+    if (b > best) best = b;
+  }
+  return best;
+}
+
+extern "C" int sdf_spike_deconv_wgrad(const sdf_spike_deconv_wgrad_args* a) {
+  SDF_REQUIRE(a->g && a->x && a->dw && a->workspace, "spike_deconv_wgrad: null pointer");
+  SDF_REQUIRE(a->Nimg > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "spike_deconv_wgrad: empty problem");
+  SDF_REQUIRE(a->Cin % 16 == 0 && a->Cout % 4 == 0, "spike_deconv_wgrad: Cin %% 16 and Cout %% 4 must be 0");
+  SDF_REQUIRE(a->Cin_w >= 1 && a->Cin_w <= a->Cin, "spike_deconv_wgrad: Cin_w=%lld outside [1, Cin]", (long long)a->Cin_w);
+  SDF_REQUIRE(aligned16(a->g) && aligned16(a->x) && aligned16(a->workspace), "spike_deconv_wgrad: pointers must be 16-byte aligned");
+  const int64_t Ho = 2 * a->H, Wo = 2 * a->W;
+  for (int cls = 0; cls < 4; ++cls) {
+    WgradP p; int tap_map[9];
+    deconv_wgrad_class(p, a, cls, tap_map);
+    p.partial = a->workspace;
+    const int pa = cls >> 1, pb = cls & 1;
+    CUtensorMap tmG, tmS;
+    {
+      // the class's pixels of G on the input grid: (n, i, j) -> G[n, 2i + pa, 2j + pb, :]
+      const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
+      const uint64_t str[3] = {(uint64_t)2 * a->Cout * 4, (uint64_t)2 * Wo * a->Cout * 4, (uint64_t)Ho * Wo * a->Cout * 4};
+      const uint32_t box[4] = {(uint32_t)kWgM, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
+      int st = make_tmap(&tmG, 1, 4, a->g + ((int64_t)pa * Wo + pb) * a->Cout, dims, str, box, nullptr, 0);
+      if (st) return st;
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
+      const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
+      const uint32_t box[4] = {(uint32_t)p.box_w, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
+      int st = make_tmap(&tmS, 0, 4, a->x, dims, str, box, nullptr, 0);
+      if (st) return st;
+    }
+    // parameter layout IOHW: (ci, co, tap) at ci*Cout*9 + co*9 + tap
+    int st = wgrad_launch(p, tmG, tmS, a->dw, 9, (int64_t)a->Cout * 9, 1, 0, a->workspace_bytes, (cudaStream_t)a->stream,
+                          "sdf_spike_deconv_wgrad", a->db, tap_map, (int)a->Cin_w, cls > 0 ? 1 : 0);
+    if (st) return st;
+  }
+  return SDF_OK;
 }

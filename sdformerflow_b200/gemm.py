@@ -272,3 +272,63 @@ def conv_dgrad_tf32(g, weight, H, W, pad, wd=None):
         "sdf_conv_dgrad_tf32_args", g=_ptr(g), wd=_ptr(wd), out=_ptr(out), Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=Cout, Ho=Ho,
         Wo=Wo, kh=kh, kw=kw, pad=pad, stream=_stream()), algo_bytes=4 * (g.numel() + out.numel()))
     return out
+
+
+def conv_dgrad_s2_tf32(g, weight, H, W, wd=None):
+    """dX (Nimg, H, W, Cin) of a 3x3 / stride-2 / padding-1 convolution: g fp32 NHWC (Nimg, Ho, Wo, Cout), weight (Cout, Cin, 3, 3)
+    (four parity-class launches of the TF32 implicit GEMM; wd as in conv_dgrad_tf32)."""
+    Nimg, Ho, Wo, Cout = g.shape
+    _, Cin, kh, kw = weight.shape
+    assert g.is_contiguous() and (kh, kw) == (3, 3)
+    if wd is None:
+        wd = weight.detach().permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).contiguous()
+    out = torch.empty((Nimg, H, W, Cin), device=g.device, dtype=torch.float32)
+    capi.call("sdf_conv_dgrad_s2_tf32", capi.struct(
+        "sdf_conv_dgrad_s2_tf32_args", g=_ptr(g), wd=_ptr(wd), out=_ptr(out), Nimg=Nimg, H=H, W=W, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo,
+        stream=_stream()), algo_bytes=4 * (g.numel() + out.numel()))
+    return out
+
+
+def deconv_dgrad_weight(weight):
+    """ConvTranspose2d weight (Cin, Cout, 3, 3) -> the B operand of deconv_dgrad_tf32: [Cin][9 * Cpad] with
+    [ci][tap*Cpad + co] = W[ci, co, kh, kw], Cpad = Cout rounded up to 32 (whole 128-byte K chunks per tap), zero padded."""
+    Cin, Cout = weight.shape[:2]
+    Cpad = -(-Cout // 32) * 32
+    wd = weight.detach().permute(0, 2, 3, 1)
+    if Cpad != Cout:
+        wd = torch.nn.functional.pad(wd, (0, Cpad - Cout))
+    return wd.reshape(Cin, 9 * Cpad).contiguous()
+
+
+def deconv_dgrad_tf32(g, weight, Cin=None, wd=None):
+    """dX (Nimg, H, W, Cin) of ConvTranspose2d(3, stride 2, padding 1, output_padding 1): g fp32 NHWC (Nimg, 2H, 2W, Cout),
+    weight (Cin_w, Cout, 3, 3); Cin > Cin_w: the extra (padding) channels of dX are zeros."""
+    Nimg, Ho, Wo, Cout = g.shape
+    Cin_w = weight.shape[0]
+    Cin = Cin_w if Cin is None else Cin
+    assert g.is_contiguous() and Ho % 2 == 0 and Wo % 2 == 0 and weight.shape[1] == Cout and tuple(weight.shape[2:]) == (3, 3)
+    if wd is None:
+        wd = deconv_dgrad_weight(weight)
+    out = torch.empty((Nimg, Ho // 2, Wo // 2, Cin), device=g.device, dtype=torch.float32)
+    capi.call("sdf_deconv_dgrad_tf32", capi.struct(
+        "sdf_deconv_dgrad_tf32_args", g=_ptr(g), wd=_ptr(wd), out=_ptr(out), Nimg=Nimg, H=Ho // 2, W=Wo // 2, Cin=Cin, Cin_w=Cin_w,
+        Cout=Cout, stream=_stream()), algo_bytes=4 * (g.numel() + out.numel()))
+    return out
+
+
+def spike_deconv_wgrad(g, x_u8, Cin_w=None, s_max=0, want_db=False):
+    """dW (Cin_w, Cout, 3, 3) of ConvTranspose2d(3, stride 2, padding 1, output_padding 1): g fp32 NHWC (Nimg, 2H, 2W, Cout),
+    x_u8 NHWC (Nimg, H, W, Cin >= Cin_w) spikes.  want_db: also the bias gradient g.sum((0, 1, 2))."""
+    Nimg, Ho, Wo, Cout = g.shape
+    _, H, W, Cin = x_u8.shape
+    Cin_w = Cin if Cin_w is None else Cin_w
+    assert g.is_contiguous() and x_u8.is_contiguous() and x_u8.dtype == torch.uint8 and (Ho, Wo) == (2 * H, 2 * W)
+    nbytes = int(capi.lib().sdf_spike_deconv_wgrad_workspace_bytes(Nimg, H, W, Cout, Cin))
+    ws = _workspace(nbytes, g.device)
+    dw = torch.empty((Cin_w, Cout, 3, 3), device=g.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=g.device, dtype=torch.float32) if want_db else None
+    capi.call("sdf_spike_deconv_wgrad", capi.struct(
+        "sdf_spike_deconv_wgrad_args", g=_ptr(g), x=_ptr(x_u8), dw=_ptr(dw), workspace=_ptr(ws), workspace_bytes=ws.numel() * 4,
+        Nimg=Nimg, H=H, W=W, Cin=Cin, Cin_w=Cin_w, Cout=Cout, s_max=s_max, stream=_stream(), db=_ptr(db)),
+        algo_bytes=4 * g.numel() + x_u8.numel())
+    return (dw, db) if want_db else dw

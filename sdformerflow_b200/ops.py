@@ -819,7 +819,7 @@ def conv3x3_small_cin(x, weight, bias=None):
 class _SpikeConvGemmFn(torch.autograd.Function):
     """NHWC convolution of 1-byte spikes as an implicit GEMM on the tcgen05 engine (gemm.spike_conv_fwd: per-tap TMA boxes,
     zero padding = TMA out-of-bounds fill), weight gradient (gemm.spike_conv_wgrad) and stride-1 data gradient
-    (gemm.conv_dgrad_tf32) on the same engine; the strided data gradient is the library's (cuDNN, TF32).  Reference: sj_layer.Conv2d on spike tensors, Spiking_modules.py:268,318,803,845-846."""
+    (gemm.conv_dgrad_tf32) and 3x3 / stride-2 data gradient (gemm.conv_dgrad_s2_tf32) on the same engine.  Reference: sj_layer.Conv2d on spike tensors, Spiking_modules.py:268,318,803,845-846."""
 
     @staticmethod
     def forward(ctx, token, weight, bias, holder, stride, padding, want_stats):
@@ -849,8 +849,10 @@ class _SpikeConvGemmFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if stride == 1 and weight.shape[0] % 32 == 0:
                 gx = gemm.conv_dgrad_tf32(g4, weight, H, W, padding, ctx.wt)      # own implicit GEMM (TF32)
+            elif stride == 2 and (kh, kw, padding) == (3, 3, 1) and weight.shape[0] % 32 == 0 and Cin % 4 == 0:
+                gx = gemm.conv_dgrad_s2_tf32(g4, weight, H, W, ctx.wt)            # four parity-class launches of the same GEMM
             else:
-                # strided dgrad stays cuDNN's; only the input SIZE and layout matter for a data gradient (channels-last,
+                # other geometries: cuDNN; only the input SIZE and layout matter for a data gradient (channels-last,
                 # so that cuDNN neither transposes g nor returns an NCHW result)
                 fake = g4.new_empty((g4.shape[0], H, W, Cin)).permute(0, 3, 1, 2)
                 with _tf32(True):
@@ -872,9 +874,10 @@ class _SpikeConvGemmFn(torch.autograd.Function):
 
 class _SpikeDeconvFn(torch.autograd.Function):
     """ConvTranspose2d(3, stride 2, padding 1, output_padding 1) of 1-byte spikes on the tcgen05 engine (gemm.spike_deconv_fwd:
-    four parity-class implicit GEMMs, exact integer contraction, BN sums from the epilogue).  Backward: the library's (cuDNN,
-    TF32) on the spikes expanded to fp32 — the weight gradient of a transposed convolution needs the tap shift on the fp32
-    operand, which G3 does not have.  Reference: SpikingTransposeDecoderLayer.deconv, Spiking_modules.py:398-474."""
+    four parity-class implicit GEMMs, exact integer contraction, BN sums from the epilogue).  Backward on the same engine:
+    data gradient = a stride-2 TF32 convolution of g (gemm.deconv_dgrad_tf32), weight + bias gradient = four parity-class
+    launches of G3 over strided views of g (gemm.spike_deconv_wgrad).  Reference: SpikingTransposeDecoderLayer.deconv,
+    Spiking_modules.py:398-474."""
 
     @staticmethod
     def forward(ctx, token, weight, bias, holder, want_stats):
@@ -895,21 +898,20 @@ class _SpikeDeconvFn(torch.autograd.Function):
         holder = ctx.holder
         x = holder.data
         H, W, Cin = x.shape[-3:]
-        g4 = gy.contiguous().view(-1, *gy.shape[-3:]).permute(0, 3, 1, 2)      # logical NCHW, channels-last strides
-        x4 = x.view(-1, H, W, Cin).float().permute(0, 3, 1, 2)
-        w = weight.detach()
-        if Cin != w.shape[0]:
-            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, Cin - w.shape[0]))
-        with _tf32(True):
-            gx, gw, gb = torch.ops.aten.convolution_backward(
-                g4, x4, w, [w.shape[1]] if ctx.has_bias else None, [2, 2], [1, 1], [1, 1], True, [1, 1], 1,
-                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]])
-        gtok = None
-        if gx is not None:
-            holder.add_grad(gx.permute(0, 2, 3, 1).contiguous().view(x.shape))
+        g4 = gy.contiguous().view(-1, *gy.shape[-3:])      # (Nimg, 2H, 2W, Cout) NHWC
+        gtok = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # a stride-2 convolution of g: one TF32 implicit GEMM reading g through an element-stride-2 TMA map; the
+            # gradient of the zero channels appended to the operand comes out as zeros
+            holder.add_grad(gemm.deconv_dgrad_tf32(g4, weight, Cin=Cin).view(x.shape))
             gtok = _zero_token(gy.device)
-        if gw is not None and Cin != weight.shape[0]:
-            gw = gw[:weight.shape[0]]
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            gw = gemm.spike_deconv_wgrad(g4, x.view(-1, H, W, Cin), Cin_w=weight.shape[0], s_max=1, want_db=want_gb)
+            if want_gb:
+                gw, gb = gw
+        elif want_gb:
+            gb = g4.sum((0, 1, 2))
         return gtok, gw, gb, None, None
 
 

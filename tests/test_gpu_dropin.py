@@ -69,25 +69,37 @@ def test_train_and_eval_script_sequence_shipped_config():
     label, mask = synth.synth_labels(B, H, W)
     losses = []
     model.train()
-    for _ in range(2):
+    for it in range(2):
+        # second iteration: the `use_amp` branch of the script (:50, :248, :314-315, :329-331) — GradScaler + autocast around
+        # forward and loss; the model switches autocast off for its own extent (fp32 membranes, exact integer spike GEMMs)
+        scaler = torch.amp.GradScaler("cuda") if it == 1 else None
         functional.reset_net(model)                                                                                   # :238
         functional.set_step_mode(model, config["data"]["step_mode"])                                                  # :239
         chunk = raw.to(device=device, dtype=torch.float32)                                                            # :241
         lab, msk = label.to(device), mask.to(device)
-        neg = torch.nn.functional.relu(-chunk)                                                                        # :261-265
-        pos = torch.nn.functional.relu(chunk)
-        chunk = torch.cat((torch.unsqueeze(pos, dim=2), torch.unsqueeze(neg, dim=2)), dim=2)
-        mn, mx = torch.min(chunk[chunk != 0]), torch.max(chunk[chunk != 0])                                           # :278-284
-        if not mn == mx:
-            chunk[chunk != 0] = (chunk[chunk != 0] - mn) / (mx - mn)
-        pred_list = model(chunk.to(device))                                                                           # :299
-        pred = pred_list["flow"]                                                                                      # :300
-        assert len(pred) == 4 and all(p.shape == (B, 2, H, W) for p in pred) and pred_list["attn"] is None
-        loss = port.flow_loss(pred, lab, msk)                                                                         # :308 (loss/flow_supervised.py)
+        with torch.autocast("cuda", enabled=scaler is not None):                                                      # :248
+            neg = torch.nn.functional.relu(-chunk)                                                                    # :261-265
+            pos = torch.nn.functional.relu(chunk)
+            chunk = torch.cat((torch.unsqueeze(pos, dim=2), torch.unsqueeze(neg, dim=2)), dim=2)
+            mn, mx = torch.min(chunk[chunk != 0]), torch.max(chunk[chunk != 0])                                       # :278-284
+            if not mn == mx:
+                chunk[chunk != 0] = (chunk[chunk != 0] - mn) / (mx - mn)
+            pred_list = model(chunk.to(device))                                                                       # :299
+            pred = pred_list["flow"]                                                                                  # :300
+            assert len(pred) == 4 and all(p.shape == (B, 2, H, W) and p.dtype == torch.float32 for p in pred)
+            assert pred_list["attn"] is None
+            loss = port.flow_loss(pred, lab, msk)                                                                     # :308 (loss/flow_supervised.py)
         assert torch.isfinite(loss)
-        loss.backward()                                                                                               # :315
+        if scaler is not None:
+            scaler.scale(loss).backward()                                                                             # :315
+        else:
+            loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), config["loss"]["clip_grad"])                               # :323-324
-        optimizer.step()                                                                                              # :327-330
+        if scaler is not None:
+            scaler.step(optimizer)                                                                                    # :329-331
+            scaler.update()
+        else:
+            optimizer.step()
         optimizer.zero_grad()
         losses.append(loss.item())
     scheduler.step()                                                                                                  # :488-489

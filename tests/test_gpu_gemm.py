@@ -249,6 +249,66 @@ def test_spike_deconv_fwd_fp32_grade(Nimg, H, W, Cin, Cout):
         assert ((y2.double() - ref2).abs().max() / ref2.abs().max()).item() <= 2e-6
 
 
+DECONV_BWD_CASES = [(2, 9, 12, 1536, 1536, 384), (2, 18, 24, 770, 784, 192), (1, 36, 48, 386, 400, 96), (2, 20, 27, 194, 208, 48),
+                    (1, 8, 16, 16, 16, 4), (2, 5, 7, 18, 32, 8)]
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin_w,Cin,Cout", DECONV_BWD_CASES)
+def test_deconv_dgrad_tf32(Nimg, H, W, Cin_w, Cin, Cout):
+    """Data gradient of ConvTranspose2d(3, stride 2, padding 1, output_padding 1) as ONE stride-2 TF32 implicit GEMM over g (decoder
+    shapes incl. operands padded to 16 channels: the padding channels get zero gradients) vs fp64 autograd; operands are
+    TF32-representable, so only the fp32 accumulation order differs."""
+    gemm = _gemm()
+    torch.manual_seed(H * W + Cin)
+    g = (torch.randint(-512, 512, (Nimg, 2 * H, 2 * W, Cout)).float() / 256).to(DEV)
+    w = (torch.randint(-512, 512, (Cin_w, Cout, 3, 3)).float() / 4096).to(DEV)
+    dx = gemm.deconv_dgrad_tf32(g, w, Cin=Cin)
+    xr = torch.zeros(Nimg, Cin_w, H, W, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose2d(xr, w.double(), None, stride=2, padding=1, output_padding=1)
+    (ref,) = torch.autograd.grad(y, xr, g.permute(0, 3, 1, 2).double())
+    ref = ref.permute(0, 2, 3, 1)
+    assert dx.shape == (Nimg, H, W, Cin)
+    assert (dx[..., :Cin_w].double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert not dx[..., Cin_w:].any()
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin_w,Cin,Cout", DECONV_BWD_CASES)
+def test_spike_deconv_wgrad(Nimg, H, W, Cin_w, Cin, Cout):
+    """Weight + bias gradient of the transposed convolution as four parity-class G3 launches over strided views of g."""
+    gemm = _gemm()
+    torch.manual_seed(H * W + Cin + 2)
+    x = _spikes((Nimg, H, W, Cin), 0.25, H + 7)
+    x[..., Cin_w:] = 0
+    g = (torch.randint(-512, 512, (Nimg, 2 * H, 2 * W, Cout)).float() / 256).to(DEV)
+    dw, db = gemm.spike_deconv_wgrad(g, x, Cin_w=Cin_w, s_max=1, want_db=True)
+    wr = torch.zeros(Cin_w, Cout, 3, 3, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose2d(x[..., :Cin_w].permute(0, 3, 1, 2).double(), wr, None, stride=2, padding=1, output_padding=1)
+    (ref,) = torch.autograd.grad(y, wr, g.permute(0, 3, 1, 2).double())
+    assert dw.shape == ref.shape
+    assert (dw.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    refb = g.double().sum((0, 1, 2))
+    assert (db.double() - refb).abs().max().item() <= 1e-5 * g.double().abs().sum((0, 1, 2)).max().item()
+    dw2 = gemm.spike_deconv_wgrad(g, x, Cin_w=Cin_w, s_max=0)             # general byte expansion, no bias gradient
+    assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,Cout", [(3, 24, 32, 96, 96), (2, 21, 27, 48, 96), (2, 16, 17, 96, 32), (1, 144, 192, 96, 96)])
+def test_conv_dgrad_s2_tf32(Nimg, H, W, Cin, Cout):
+    """Data gradient of a 3x3 / stride-2 / padding-1 convolution as four parity-class TF32 implicit GEMMs (odd sizes included)."""
+    gemm = _gemm()
+    torch.manual_seed(H + W + Cin)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    g = (torch.randint(-512, 512, (Nimg, Ho, Wo, Cout)).float() / 256).to(DEV)
+    w = (torch.randint(-512, 512, (Cout, Cin, 3, 3)).float() / 4096).to(DEV)
+    dx = gemm.conv_dgrad_s2_tf32(g, w, H, W)
+    xr = torch.zeros(Nimg, Cin, H, W, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xr, w.double(), None, stride=2, padding=1)
+    (ref,) = torch.autograd.grad(y, xr, g.permute(0, 3, 1, 2).double())
+    ref = ref.permute(0, 2, 3, 1)
+    assert dx.shape == ref.shape
+    assert (dx.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("Nimg,H,W,Cin,Cout,k,pad", [(3, 24, 32, 96, 96, 3, 1), (2, 20, 27, 96, 96, 3, 1), (5, 9, 12, 768, 768, 3, 1),
                                                     (2, 16, 16, 48, 96, 1, 0)])
 def test_conv_dgrad_tf32(Nimg, H, W, Cin, Cout, k, pad):
