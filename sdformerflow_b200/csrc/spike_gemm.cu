@@ -57,6 +57,9 @@ struct GemmP {
   int btap[kMaxTaps];                                      // conv: tap t of this launch reads the B rows' K range of tap btap[t]
                                                            // (identity unless the launch uses a subset of the packed taps)
   int out_sh, out_sw, out_oh, out_ow;                      // transposed conv: output pixel = patch pixel * out_s + out_o
+  int patch_h, patch_w;                                    // conv M tile = patch_h x patch_w output pixels (<= 128 of them: rows
+                                                           // beyond patch_h*patch_w of a tile are never loaded, counted or stored)
+  uint32_t a_tx;                                           // bytes one A chunk brings (patch rows * 128)
 };
 
 struct GemmSmem {
@@ -85,7 +88,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmP& p, int m_tile) {
   const int per_img = p.tiles_h * p.tiles_w;
   const int img = m_tile / per_img, rem = m_tile - img * per_img;
   const int ph = rem / p.tiles_w, pw = rem - ph * p.tiles_w;
-  t.c1 = pw * kPatchW; t.c2 = ph * kPatchH; t.c3 = img;
+  t.c1 = pw * p.patch_w; t.c2 = ph * p.patch_h; t.c3 = img;
   return t;
 }
 // K coordinate (elements) of chunk kc in the B operand
@@ -97,7 +100,8 @@ __device__ __forceinline__ int b_kcoord(const GemmP& p, int kc) {
 // number of valid rows mask: is tile row r inside the output?
 __device__ __forceinline__ bool row_valid(const GemmP& p, const TileCoord& t, int r) {
   if (!p.conv) return (int64_t)t.c1 + r < p.rows;
-  return (t.c2 + r / kPatchW) < p.Ho && (t.c1 + r % kPatchW) < p.Wo;
+  const int rh = r / p.patch_w;
+  return rh < p.patch_h && (t.c2 + rh) < p.Ho && (t.c1 + r - rh * p.patch_w) < p.Wo;
 }
 
 template <int KIND>
@@ -157,7 +161,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int bk0 = p.conv ? p.btap[tap] * cpt * p.kc_elems : 0;
           for (int cc = 0; cc < cpt; ++cc) {
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], kAChunk + (p.b_resident ? 0u : bchunk));
+            mbar_expect_tx(&full[s], p.a_tx + (p.b_resident ? 0u : bchunk));
             if (!p.conv) tma_load_2d(&tmA, &full[s], a_base + s * kAChunk, cc * p.kc_elems, t.c1);
             else tma_load_4d(&tmA, &full[s], a_base + s * kAChunk, cc * p.kc_elems, aw, ah, t.c3);
             if (!p.b_resident) tma_load_2d(&tmB, &full[s], b_base + s * bchunk, bk0 + cc * p.kc_elems, n_tile * p.ncols);
@@ -376,6 +380,26 @@ __global__ void pack_kernel(const PackP p) {
   }
 }
 
+// conv M tile: 8 x 16 output pixels unless that wastes more than 10 % of the tile rows on this image size (small feature maps:
+// 9 x 12 fills 42 % of two 8 x 16 patches but 84 % of one 9 x 12 patch) — then the patch_h x patch_w <= 128 with the fewest tiles
+static void pick_patch(GemmP& p) {
+  auto tiles = [&](int h, int w) { return (int64_t)((p.Ho + h - 1) / h) * ((p.Wo + w - 1) / w); };
+  int bh = kPatchH, bw = kPatchW;
+  int64_t best = tiles(bh, bw);
+  if ((double)p.Ho * p.Wo < 0.9 * (double)best * kTileM) {
+    for (int w = 4; w <= kTileM && w <= p.Wo; ++w) {
+      int h = kTileM / w;
+      if (h > p.Ho) h = p.Ho;
+      const int64_t t = tiles(h, w);
+      if (t < best || (t == best && h * w > bh * bw)) { best = t; bh = h; bw = w; }
+    }
+  }
+  p.patch_h = bh; p.patch_w = bw;
+  p.tiles_h = (p.Ho + bh - 1) / bh;
+  p.tiles_w = (p.Wo + bw - 1) / bw;
+  p.a_tx = (uint32_t)(bh * bw) * kChunkBytes;
+}
+
 // N tile width: multiple of 16, minimal padding then as wide as possible
 static int pick_nt(int C, int max_nt) {
   int best = 16, best_pad = 1 << 30;
@@ -478,6 +502,7 @@ extern "C" int sdf_spike_gemm_fwd(const sdf_spike_gemm_fwd_args* a) {
   p.kc_elems = kChunkBytes;
   p.wscale = a->wscale; p.bias = a->bias; p.bn_partials = a->bn_partials; p.n_partial_cap = (int)a->n_partial_blocks;
   p.fast_cvt = (a->a_max > 0 && a->K * a->a_max < 32768) ? 1 : 0;
+  p.a_tx = kAChunk;
   const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
   CUtensorMap tmA, tmB, tmO;
   {
@@ -518,6 +543,7 @@ extern "C" int sdf_gemm_tf32(const sdf_gemm_tf32_args* a) {
   p.n_mtiles = (int)((a->rows + kTileM - 1) / kTileM);
   p.n_kchunks = (int)((a->K + 31) / 32);
   p.kc_elems = 32;
+  p.a_tx = kAChunk;
   p.bias = a->bias;
   CUtensorMap tmA, tmB, tmO;
   {
@@ -564,8 +590,7 @@ static int conv_fwd_launch(const ConvLaunch& c, const char* what) {
   p.ncols = 3 * p.nt;
   p.Cout = (int)c.Cout;
   p.Ho = (int)c.Ho; p.Wo = (int)c.Wo;
-  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
-  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
+  pick_patch(p);
   p.n_mtiles = (int)c.Nimg * p.tiles_h * p.tiles_w;
   p.stride = c.stride;
   p.taps = c.taps;
@@ -580,7 +605,7 @@ static int conv_fwd_launch(const ConvLaunch& c, const char* what) {
   {
     const uint64_t dims[4] = {(uint64_t)c.Cin, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.Nimg};
     const uint64_t str[3] = {(uint64_t)c.Cin, (uint64_t)c.W * c.Cin, (uint64_t)c.H * c.W * c.Cin};
-    const uint32_t box[4] = {(uint32_t)kChunkBytes, (uint32_t)(kPatchW * c.stride), (uint32_t)(kPatchH * c.stride), 1};
+    const uint32_t box[4] = {(uint32_t)kChunkBytes, (uint32_t)(p.patch_w * c.stride), (uint32_t)(p.patch_h * c.stride), 1};
     const uint32_t es[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
     int st = make_tmap(&tmA, 0, 4, c.x, dims, str, box, es, 128);
     if (st) return st;
@@ -595,7 +620,7 @@ static int conv_fwd_launch(const ConvLaunch& c, const char* what) {
   {
     const uint64_t dims[4] = {(uint64_t)c.Cout, (uint64_t)c.Wo, (uint64_t)c.Ho, (uint64_t)c.Nimg};
     const uint64_t str[3] = {(uint64_t)c.osw * c.Cout * 4, (uint64_t)c.osh * c.out_ld_row * c.Cout * 4, (uint64_t)c.out_img_elems * 4};
-    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    const uint32_t box[4] = {16, (uint32_t)p.patch_w, (uint32_t)p.patch_h, 1};
     int st = make_tmap(&tmO, 1, 4, c.out_base, dims, str, box, nullptr, 64);
     if (st) return st;
   }
@@ -689,8 +714,7 @@ extern "C" int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a) {
   p.ncols = p.nt;
   p.Cout = (int)a->Cin;                         // GEMM N = input channels
   p.Ho = (int)a->H; p.Wo = (int)a->W;           // the output of this GEMM is the input image
-  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
-  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
+  pick_patch(p);
   p.n_mtiles = (int)a->Nimg * p.tiles_h * p.tiles_w;
   p.stride = 1;
   p.taps = (int)(a->kh * a->kw);
@@ -702,7 +726,7 @@ extern "C" int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a) {
   {
     const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->Wo, (uint64_t)a->Ho, (uint64_t)a->Nimg};
     const uint64_t str[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->Wo * a->Cout * 4, (uint64_t)a->Ho * a->Wo * a->Cout * 4};
-    const uint32_t box[4] = {32, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    const uint32_t box[4] = {32, (uint32_t)p.patch_w, (uint32_t)p.patch_h, 1};
     int st = make_tmap(&tmA, 1, 4, a->g, dims, str, box, nullptr, 128);
     if (st) return st;
   }
@@ -717,7 +741,7 @@ extern "C" int sdf_conv_dgrad_tf32(const sdf_conv_dgrad_tf32_args* a) {
   {
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
     const uint64_t str[3] = {(uint64_t)a->Cin * 4, (uint64_t)a->W * a->Cin * 4, (uint64_t)a->H * a->W * a->Cin * 4};
-    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    const uint32_t box[4] = {16, (uint32_t)p.patch_w, (uint32_t)p.patch_h, 1};
     int st = make_tmap(&tmO, 1, 4, a->out, dims, str, box, nullptr, 64);
     if (st) return st;
   }
@@ -747,8 +771,7 @@ static int conv_tf32_launch(const ConvTf32Launch& c, const char* what) {
   p.ncols = p.nt;
   p.Cout = (int)c.N;
   p.Ho = (int)c.Hc; p.Wo = (int)c.Wc;
-  p.tiles_h = (p.Ho + kPatchH - 1) / kPatchH;
-  p.tiles_w = (p.Wo + kPatchW - 1) / kPatchW;
+  pick_patch(p);
   p.n_mtiles = (int)c.Nimg * p.tiles_h * p.tiles_w;
   p.stride = c.stride;
   p.taps = c.taps;
@@ -760,7 +783,7 @@ static int conv_tf32_launch(const ConvTf32Launch& c, const char* what) {
   {
     const uint64_t dims[4] = {(uint64_t)c.Cg, (uint64_t)c.Wg, (uint64_t)c.Hg, (uint64_t)c.Nimg};
     const uint64_t str[3] = {(uint64_t)c.Cg * 4, (uint64_t)c.Wg * c.Cg * 4, (uint64_t)c.Hg * c.Wg * c.Cg * 4};
-    const uint32_t box[4] = {32, (uint32_t)(kPatchW * c.stride), (uint32_t)(kPatchH * c.stride), 1};
+    const uint32_t box[4] = {32, (uint32_t)(p.patch_w * c.stride), (uint32_t)(p.patch_h * c.stride), 1};
     const uint32_t es[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
     int st = make_tmap(&tmA, 1, 4, c.g, dims, str, box, es, 128);
     if (st) return st;
@@ -776,7 +799,7 @@ static int conv_tf32_launch(const ConvTf32Launch& c, const char* what) {
   {
     const uint64_t dims[4] = {(uint64_t)c.N, (uint64_t)c.Wc, (uint64_t)c.Hc, (uint64_t)c.Nimg};
     const uint64_t str[3] = {(uint64_t)c.osw * 4, (uint64_t)c.osh * 4, (uint64_t)c.oimg * 4};
-    const uint32_t box[4] = {16, (uint32_t)kPatchW, (uint32_t)kPatchH, 1};
+    const uint32_t box[4] = {16, (uint32_t)p.patch_w, (uint32_t)p.patch_h, 1};
     int st = make_tmap(&tmO, 1, 4, c.out_base, dims, str, box, nullptr, 64);
     if (st) return st;
   }

@@ -62,6 +62,10 @@ struct WgradP {
   int binary;              // spikes are 0/1 (cheaper byte -> bf16 expansion)
   int stg_bytes;           // raw spike bytes per stage
   int debug;               // timing experiments (SDF_WGRAD_DEBUG): 1 skip conversion, 2 also skip MMA, 3 MMA only (no TMA)
+  // tap tiles: N tile n = k * ci_tiles + (channel slice), tap tile k covers taps [tt_tap0[k], tt_tap0[k] + tt_ntap[k]) and reads G
+  // through tensor map tt_cls[k] (one map per output parity class of a transposed convolution; 0 otherwise)
+  int n_cls;
+  unsigned char tt_tap0[9], tt_ntap[9], tt_cls[9], tt_first[9];   // tt_first: this tap tile writes its class's bias-gradient partial
 };
 
 struct WgSmem { uint32_t b, g, stg, bars, tmem_slot, b_slot, g_stage, stg_stage, total; };
@@ -107,7 +111,8 @@ __device__ __forceinline__ uint2 bits_to_bf16(uint32_t w) {
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS, const WgradP p) {
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG1, const __grid_constant__ CUtensorMap tmG2,
+             const __grid_constant__ CUtensorMap tmG3, const __grid_constant__ CUtensorMap tmS, const WgradP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const WgSmem sp = wg_smem_plan(p.max_cols, p.stages, p.stg_bytes);
   const int kWgStages = p.stages;
@@ -124,15 +129,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   const int n_tile = blockIdx.x % p.n_ntiles;
   const int m_tile = (blockIdx.x / p.n_ntiles) % p.n_mtiles;
   const int slab = blockIdx.x / (p.n_ntiles * p.n_mtiles);
-  int tap0, ntap, ci0, width;                   // this tile's columns: taps [tap0, tap0+ntap) x channels [ci0, ci0+width)
-  if (p.ci_tiles > 1) {
-    tap0 = n_tile / p.ci_tiles; ntap = 1;
-    ci0 = (n_tile % p.ci_tiles) * p.ci_width;
-    width = min(p.ci_width, p.Cin - ci0);
-  } else {
-    tap0 = n_tile * p.taps_per_tile; ntap = min(p.taps_per_tile, p.taps - tap0);
-    ci0 = 0; width = p.Cin;
-  }
+  // this tile's columns: taps [tap0, tap0+ntap) x channels [ci0, ci0+width)
+  const int tk = n_tile / p.ci_tiles, cit = n_tile - tk * p.ci_tiles;
+  const int tap0 = p.tt_tap0[tk], ntap = p.tt_ntap[tk], cls = p.tt_cls[tk];
+  const int ci0 = cit * p.ci_width, width = min(p.ci_width, p.Cin - ci0);
+  const CUtensorMap* tmGc = cls == 0 ? &tmG : cls == 1 ? &tmG1 : cls == 2 ? &tmG2 : &tmG3;
   const int ncols = ntap * width;               // multiple of 16 (host-checked), <= kWgMaxN
   // <= 2 MMAs per K step: N0 + N1 = ncols, both multiples of 16 and <= 256, N0 a multiple of 64 (whole MN blocks)
   const int N0 = ncols <= 256 ? ncols : ((ncols / 2 + 63) / 64) * 64;
@@ -147,7 +148,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     mbar_init(done, 1);
     mbar_fence_init();
   }
-  if (warp == kWgProdWarp && elect_one()) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmS); }
+  if (warp == kWgProdWarp && elect_one()) { tma_prefetch_desc(tmGc); tma_prefetch_desc(&tmS); }
   if (warp == kWgMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -175,7 +176,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       if (p.debug == 3) continue;
       const int chunk = c_begin + it;
       if (!p.conv) {
-        if (lane == 0) tma_load_2d(&tmG, &full_tma[s], g_base + s * kGStage, m_tile * kWgM, chunk * kWgRB);
+        if (lane == 0) tma_load_2d(tmGc, &full_tma[s], g_base + s * kGStage, m_tile * kWgM, chunk * kWgRB);
         else if (lane >= 4 && lane - 4 < p.nbox) {
           const int j = lane - 4;
           tma_load_2d(&tmS, &full_tma[s], stg_base + s * kStgStage + j * (p.box_w * kWgRB), ci0 + j * p.box_w, chunk * kWgRB);
@@ -184,7 +185,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         const int img = chunk / per_img, rem = chunk - img * per_img;
         const int py = rem / p.tiles_w, px = rem - py * p.tiles_w;
         const int w0 = px * kWgPatchW, h0 = py * kWgPatchH;
-        if (lane == 0) tma_load_4d(&tmG, &full_tma[s], g_base + s * kGStage, m_tile * kWgM, w0, h0, img);
+        if (lane == 0) tma_load_4d(tmGc, &full_tma[s], g_base + s * kGStage, m_tile * kWgM, w0, h0, img);
         else if (p.halo) {
           if (lane == 4) tma_load_4d(&tmS, &full_tma[s], stg_base + s * kStgStage, ci0, w0 + p.dw[tap0], h0 + p.dh[tap0], img);
         } else if (lane >= 4 && lane - 4 < n_sbox) {
@@ -289,7 +290,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       mbar_wait(done, 0);
       tc_fence_after();
       const int co = m_tile * kWgM + tid;
-      if (p.db_partial != nullptr && n_tile == 0 && co < p.Cout) p.db_partial[(int64_t)slab * p.Cout + co] = bsum;
+      if (p.db_partial != nullptr && cit == 0 && p.tt_first[tk] && co < p.Cout)
+        p.db_partial[((int64_t)slab * p.n_cls + cls) * p.Cout + co] = bsum;
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
       float* dst = p.partial + ((int64_t)slab * p.Cout + co) * p.ncols_total + (int64_t)tap0 * p.Cin + ci0;
       for (int cc = 0; cc < ncols; cc += 16) {
@@ -314,21 +316,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
 }
 
 // dW[co*s_co + ci*s_ci + tap*s_tap] (+)= sum_s partial[s][co][tap*Cin + ci], slabs added in index order
-// tap_map: destination tap of local tap t (a launch over a subset of a kernel's taps); channels ci >= cin_store are dropped
-// (operand channels appended as padding); db_accumulate: the bias gradient is added to db (dw is not)
+// tap_map: destination tap of local tap t (the launch's tap order need not be the parameter's); channels ci >= cin_store are
+// dropped (operand channels appended as padding); n_cls: bias-gradient partial rows per slab (one per parity class)
 struct WgTapMap { int t[9]; };
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n_slabs, int Cout, int Cin,
                                     int taps, int64_t s_co, int64_t s_ci, int64_t s_tap, int accumulate,
                                     const float* __restrict__ db_partial, float* __restrict__ db, const WgTapMap tap_map,
-                                    int cin_store, int db_accumulate) {
+                                    int cin_store, int n_cls) {
   const int64_t total = (int64_t)Cout * taps * Cin;
   const int64_t total_all = total + (db != nullptr ? Cout : 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_all; i += (int64_t)gridDim.x * blockDim.x) {
     if (i >= total) {                           // bias gradient: slabs added in index order
       const int64_t co = i - total;
       float acc = 0.f;
-      for (int s = 0; s < n_slabs; ++s) acc += __ldg(db_partial + (int64_t)s * Cout + co);
-      db[co] = (accumulate || db_accumulate) ? db[co] + acc : acc;
+      for (int s = 0; s < n_slabs * n_cls; ++s) acc += __ldg(db_partial + (int64_t)s * Cout + co);
+      db[co] = accumulate ? db[co] + acc : acc;
       continue;
     }
     float acc = 0.f;
@@ -392,15 +394,30 @@ static int wgrad_debug_mode() {
   return m;
 }
 
-static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tmS, float* dw, int64_t s_co, int64_t s_ci,
+// uniform tap tiles of an ordinary launch: taps_per_tile taps each, one G map
+static void wgrad_default_tap_tiles(WgradP& p) {
+  if (p.n_cls > 0) return;                       // the caller filled the table (transposed convolution)
+  p.n_cls = 1;
+  const int n = p.ci_tiles > 1 ? p.taps : (p.taps + p.taps_per_tile - 1) / p.taps_per_tile;
+  for (int k = 0; k < n; ++k) {
+    const int tpt = p.ci_tiles > 1 ? 1 : p.taps_per_tile;
+    p.tt_tap0[k] = (unsigned char)(k * tpt);
+    p.tt_ntap[k] = (unsigned char)(p.taps - k * tpt < tpt ? p.taps - k * tpt : tpt);
+    p.tt_cls[k] = 0;
+    p.tt_first[k] = k == 0;
+  }
+}
+
+static int wgrad_launch(WgradP& p, const CUtensorMap* tmG, const CUtensorMap& tmS, float* dw, int64_t s_co, int64_t s_ci,
                         int64_t s_tap, int accumulate, int64_t ws_bytes, cudaStream_t st, const char* what, float* db,
-                        const int* tap_map = nullptr, int cin_store = -1, int db_accumulate = 0) {
+                        const int* tap_map = nullptr, int cin_store = -1) {
+  wgrad_default_tap_tiles(p);
   wgrad_slabs(p);
   p.debug = wgrad_debug_mode();
-  SDF_REQUIRE((int64_t)p.n_slabs * p.Cout * (p.ncols_total + 1) * 4 <= ws_bytes, "%s: workspace too small (%lld needed)", what,
-              (long long)p.n_slabs * p.Cout * (p.ncols_total + 1) * 4);
+  SDF_REQUIRE((int64_t)p.n_slabs * p.Cout * (p.ncols_total + p.n_cls) * 4 <= ws_bytes, "%s: workspace too small (%lld needed)", what,
+              (long long)p.n_slabs * p.Cout * (p.ncols_total + p.n_cls) * 4);
   p.db_partial = db != nullptr ? p.partial + (int64_t)p.n_slabs * p.Cout * p.ncols_total : nullptr;
-  p.max_cols = p.ci_tiles > 1 ? p.ci_width : p.taps_per_tile * p.Cin;
+  if (p.max_cols == 0) p.max_cols = p.ci_tiles > 1 ? p.ci_width : p.taps_per_tile * p.Cin;
   SDF_REQUIRE(p.max_cols % 16 == 0 && p.max_cols <= kWgMaxN && p.box_w % 16 == 0, "%s: unsupported column tiling (%d columns, box %d)", what, p.max_cols, p.box_w);
   if (!p.halo) p.stg_bytes = p.max_cols * kWgRB;
   p.stages = 2;
@@ -413,7 +430,8 @@ static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tm
     if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return SDF_ERR_CUDA; }
     attr_done = true;
   }
-  wgrad_kernel<<<p.n_slabs * p.n_mtiles * p.n_ntiles, kWgThreads, sp.total, st>>>(tmG, tmS, p);
+  wgrad_kernel<<<p.n_slabs * p.n_mtiles * p.n_ntiles, kWgThreads, sp.total, st>>>(tmG[0], tmG[p.n_cls > 1 ? 1 : 0], tmG[p.n_cls > 2 ? 2 : 0],
+                                                                                  tmG[p.n_cls > 3 ? 3 : 0], tmS, p);
   int r = finish_launch(what);
   if (r) return r;
   const int64_t total = (int64_t)p.Cout * (p.ncols_total + 1);
@@ -421,7 +439,7 @@ static int wgrad_launch(WgradP& p, const CUtensorMap& tmG, const CUtensorMap& tm
   WgTapMap tm;
   for (int i = 0; i < 9; ++i) tm.t[i] = tap_map != nullptr && i < p.taps ? tap_map[i] : i;
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, p.n_slabs, p.Cout, p.Cin, p.taps, s_co, s_ci, s_tap, accumulate,
-                                              p.db_partial, db, tm, cin_store < 0 ? p.Cin : cin_store, db_accumulate);
+                                              p.db_partial, db, tm, cin_store < 0 ? p.Cin : cin_store, p.n_cls);
   return finish_launch(what);
 }
 
@@ -455,7 +473,7 @@ extern "C" int sdf_spike_wgrad(const sdf_spike_wgrad_args* a) {
     int st = make_tmap(&tmS, 0, 2, a->s, dims, str, box, nullptr, 0);
     if (st) return st;
   }
-  return wgrad_launch(p, tmG, tmS, a->dw, a->K, 1, 0, a->accumulate, a->workspace_bytes, (cudaStream_t)a->stream, "sdf_spike_wgrad",
+  return wgrad_launch(p, &tmG, tmS, a->dw, a->K, 1, 0, a->accumulate, a->workspace_bytes, (cudaStream_t)a->stream, "sdf_spike_wgrad",
                       a->db);
 }
 
@@ -501,7 +519,7 @@ extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
     if (st) return st;
   }
   // parameter layout OIHW: (co, ci, tap) at co*Cin*taps + ci*taps + tap
-  return wgrad_launch(p, tmG, tmS, a->dw, (int64_t)p.Cin * p.taps, p.taps, 1, a->accumulate, a->workspace_bytes,
+  return wgrad_launch(p, &tmG, tmS, a->dw, (int64_t)p.Cin * p.taps, p.taps, 1, a->accumulate, a->workspace_bytes,
                       (cudaStream_t)a->stream, "sdf_spike_conv_wgrad", a->db);
 }
 
@@ -509,24 +527,43 @@ extern "C" int sdf_spike_conv_wgrad(const sdf_spike_conv_wgrad_args* a) {
 //   dW[ci, co, kh, kw] = sum_{n,i,j} S[n, i, j, ci] * G[n, 2i - 1 + kh, 2j - 1 + kw, co]
 // Per output parity class (a, b) the pixels G[2i + a, 2j + b] are a strided VIEW of G (a TMA tensor map with doubled pixel /
 // row strides and a parity base offset) on the input grid, and the class's taps read the spikes at (i + dh, j + dw),
-// dh, dw in {0, 1} (sdf_spike_deconv_class_taps): four launches of the G3 kernel, each producing the dW of its 1 / 2 / 2 / 4
-// taps — the tap shift stays on the 1-byte operand, G is never gathered or copied.  Replaces cuDNN's wgrad on fp32-expanded
-// spikes (reference: SpikingTransposeDecoderLayer.deconv backward, Spiking_modules.py:398-474).
+// dh, dw in {0, 1} (sdf_spike_deconv_class_taps).  ONE launch of the G3 kernel: its N tiles are the 1 + 2 + 2 + 4 taps grouped
+// per class, each tile reading G through its class's tensor map — the tap shift stays on the 1-byte operand, G is never
+// gathered or copied.  Replaces cuDNN's wgrad on fp32-expanded spikes (reference: SpikingTransposeDecoderLayer.deconv
+// backward, Spiking_modules.py:398-474).
 extern "C" int64_t sdf_spike_deconv_class_taps(int64_t cls, int64_t* src_tap, int64_t* dh, int64_t* dw);
 
-static void deconv_wgrad_class(WgradP& p, const sdf_spike_deconv_wgrad_args* a, int cls, int* tap_map) {
+static void deconv_wgrad_plan(WgradP& p, const sdf_spike_deconv_wgrad_args* a, int* tap_map) {
   p = WgradP{};
-  int64_t src[4], dh[4], dw[4];
-  p.taps = (int)sdf_spike_deconv_class_taps(cls, src, dh, dw);
   p.conv = 1;
-  p.Cout = (int)a->Cout; p.Cin = (int)a->Cin; p.ncols_total = p.taps * p.Cin;
+  p.Cout = (int)a->Cout; p.Cin = (int)a->Cin; p.taps = 9; p.ncols_total = 9 * p.Cin;
   p.n_mtiles = (p.Cout + kWgM - 1) / kWgM;
-  wgrad_tiles(p.Cin, p.taps, &p.taps_per_tile, &p.ci_tiles, &p.ci_width, &p.n_ntiles);
+  int dummy_tpt, dummy_nt;
+  wgrad_tiles(p.Cin, 1, &dummy_tpt, &p.ci_tiles, &p.ci_width, &dummy_nt);      // channel slicing only
+  const int max_tpt = p.ci_tiles > 1 ? 1 : (kWgMaxN / p.Cin < 1 ? 1 : kWgMaxN / p.Cin);
+  p.taps_per_tile = 1;
+  int t = 0, k = 0, widest = 1;
+  for (int cls = 0; cls < 4; ++cls) {
+    int64_t src[4], dh[4], dw[4];
+    const int n = (int)sdf_spike_deconv_class_taps(cls, src, dh, dw);
+    for (int i = 0; i < n; ++i) { p.dh[t + i] = (int)dh[i]; p.dw[t + i] = (int)dw[i]; tap_map[t + i] = (int)src[i]; }
+    const int groups = (n + max_tpt - 1) / max_tpt, per = (n + groups - 1) / groups;      // balanced tap groups of the class
+    for (int g = 0; g * per < n; ++g, ++k) {
+      p.tt_tap0[k] = (unsigned char)(t + g * per);
+      p.tt_ntap[k] = (unsigned char)(n - g * per < per ? n - g * per : per);
+      p.tt_cls[k] = (unsigned char)cls;
+      p.tt_first[k] = g == 0;
+      if (p.tt_ntap[k] > widest) widest = p.tt_ntap[k];
+    }
+    t += n;
+  }
+  p.n_cls = 4;
+  p.n_ntiles = k * p.ci_tiles;
+  p.max_cols = p.ci_tiles > 1 ? p.ci_width : widest * p.Cin;
   p.tiles_h = (int)((a->H + kWgPatchH - 1) / kWgPatchH);
   p.tiles_w = (int)((a->W + kWgPatchW - 1) / kWgPatchW);
   p.n_chunks = (int)a->Nimg * p.tiles_h * p.tiles_w;
   p.stride = 1;
-  for (int i = 0; i < p.taps; ++i) { p.dh[i] = (int)dh[i]; p.dw[i] = (int)dw[i]; tap_map[i] = (int)src[i]; }
   p.binary = a->s_max == 1;
   p.nbox = p.ci_width > 256 ? 2 : 1;
   p.box_w = p.ci_width / p.nbox;
@@ -535,15 +572,10 @@ static void deconv_wgrad_class(WgradP& p, const sdf_spike_deconv_wgrad_args* a, 
 extern "C" int64_t sdf_spike_deconv_wgrad_workspace_bytes(int64_t Nimg, int64_t H, int64_t W, int64_t Cout, int64_t Cin) {
   sdf_spike_deconv_wgrad_args a{};
   a.Nimg = Nimg; a.H = H; a.W = W; a.Cout = Cout; a.Cin = Cin;
-  int64_t best = 0;
-  for (int cls = 0; cls < 4; ++cls) {
-    WgradP p; int tm[9];
-    deconv_wgrad_class(p, &a, cls, tm);
-    wgrad_slabs(p);
-    const int64_t b = (int64_t)p.n_slabs * Cout * (p.ncols_total + 1) * 4;
-    if (b > best) best = b;
-  }
-  return best;
+  WgradP p; int tm[9];
+  deconv_wgrad_plan(p, &a, tm);
+  wgrad_slabs(p);
+  return (int64_t)p.n_slabs * Cout * (p.ncols_total + p.n_cls) * 4;
 }
 
 extern "C" int sdf_spike_deconv_wgrad(const sdf_spike_deconv_wgrad_args* a) {
@@ -553,31 +585,27 @@ extern "C" int sdf_spike_deconv_wgrad(const sdf_spike_deconv_wgrad_args* a) {
   SDF_REQUIRE(a->Cin_w >= 1 && a->Cin_w <= a->Cin, "spike_deconv_wgrad: Cin_w=%lld outside [1, Cin]", (long long)a->Cin_w);
   SDF_REQUIRE(aligned16(a->g) && aligned16(a->x) && aligned16(a->workspace), "spike_deconv_wgrad: pointers must be 16-byte aligned");
   const int64_t Ho = 2 * a->H, Wo = 2 * a->W;
+  WgradP p; int tap_map[9];
+  deconv_wgrad_plan(p, a, tap_map);
+  p.partial = a->workspace;
+  CUtensorMap tmG[4], tmS;
   for (int cls = 0; cls < 4; ++cls) {
-    WgradP p; int tap_map[9];
-    deconv_wgrad_class(p, a, cls, tap_map);
-    p.partial = a->workspace;
+    // the class's pixels of G on the input grid: (n, i, j) -> G[n, 2i + pa, 2j + pb, :]
     const int pa = cls >> 1, pb = cls & 1;
-    CUtensorMap tmG, tmS;
-    {
-      // the class's pixels of G on the input grid: (n, i, j) -> G[n, 2i + pa, 2j + pb, :]
-      const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
-      const uint64_t str[3] = {(uint64_t)2 * a->Cout * 4, (uint64_t)2 * Wo * a->Cout * 4, (uint64_t)Ho * Wo * a->Cout * 4};
-      const uint32_t box[4] = {(uint32_t)kWgM, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
-      int st = make_tmap(&tmG, 1, 4, a->g + ((int64_t)pa * Wo + pb) * a->Cout, dims, str, box, nullptr, 0);
-      if (st) return st;
-    }
-    {
-      const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
-      const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
-      const uint32_t box[4] = {(uint32_t)p.box_w, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
-      int st = make_tmap(&tmS, 0, 4, a->x, dims, str, box, nullptr, 0);
-      if (st) return st;
-    }
-    // parameter layout IOHW: (ci, co, tap) at ci*Cout*9 + co*9 + tap
-    int st = wgrad_launch(p, tmG, tmS, a->dw, 9, (int64_t)a->Cout * 9, 1, 0, a->workspace_bytes, (cudaStream_t)a->stream,
-                          "sdf_spike_deconv_wgrad", a->db, tap_map, (int)a->Cin_w, cls > 0 ? 1 : 0);
+    const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)2 * a->Cout * 4, (uint64_t)2 * Wo * a->Cout * 4, (uint64_t)Ho * Wo * a->Cout * 4};
+    const uint32_t box[4] = {(uint32_t)kWgM, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
+    int st = make_tmap(&tmG[cls], 1, 4, a->g + ((int64_t)pa * Wo + pb) * a->Cout, dims, str, box, nullptr, 0);
     if (st) return st;
   }
-  return SDF_OK;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->Nimg};
+    const uint64_t str[3] = {(uint64_t)a->Cin, (uint64_t)a->W * a->Cin, (uint64_t)a->H * a->W * a->Cin};
+    const uint32_t box[4] = {(uint32_t)p.box_w, (uint32_t)kWgPatchW, (uint32_t)kWgPatchH, 1};
+    int st = make_tmap(&tmS, 0, 4, a->x, dims, str, box, nullptr, 0);
+    if (st) return st;
+  }
+  // parameter layout IOHW: (ci, co, tap) at ci*Cout*9 + co*9 + tap
+  return wgrad_launch(p, tmG, tmS, a->dw, 9, (int64_t)a->Cout * 9, 1, 0, a->workspace_bytes, (cudaStream_t)a->stream,
+                      "sdf_spike_deconv_wgrad", a->db, tap_map, (int)a->Cin_w);
 }

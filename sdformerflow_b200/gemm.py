@@ -56,6 +56,107 @@ except ImportError:          # no global hook on this torch: never cache
     _CACHE_OK = False
 
 
+def _layout_dims(wd, layout):
+    if layout == "linear":
+        Cout, Cin = wd.shape
+        return Cout, Cin, 1, Cin, 1, 0
+    if layout == "conv":
+        Cout, Cin, kh, kw = wd.shape
+        taps = kh * kw
+        return Cout, Cin, taps, Cin * taps, taps, 1
+    raise ValueError(layout)
+
+
+def _pack_launch(wd, layout, wq, wscale, wt):
+    Cout, Cin, taps, s_co, s_ci, s_tap = _layout_dims(wd, layout)
+    capi.call("sdf_spike_gemm_pack", capi.struct(
+        "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(wq), wscale=_ptr(wscale), wt=_ptr(wt), wq_bytes=wq.numel(), Cout=Cout, Cin=Cin,
+        taps=taps, s_co=s_co, s_ci=s_ci, s_tap=s_tap, tap_map=list(range(9)), stream=_stream()))
+
+
+# ---- pre-packing plan (train.GraphedStep) ------------------------------------------------------------------------------
+# A captured training step re-packs every weight on every replay (the optimizer has just changed them).  Issued lazily, layer
+# by layer, those ~80 small kernels sit on the step's critical path one after the other; a PackPlan issues them all at the
+# START of the step on side streams (forked from the capturing stream, so they become parallel branches of the graph) into
+# persistent buffers, and the layers' pack_weight / pack_deconv_weight calls pick those buffers up (joining the branches at
+# the first hit) — the packs overlap with each other and with the head of the forward pass, which does not need them.
+_record = None      # list of jobs while start_recording() is active
+_pinned = {}        # id(parameter) -> (job key, result, weakref, plan): results an active PackPlan owns
+
+
+def start_recording():
+    global _record
+    _record = []
+
+
+def stop_recording():
+    global _record
+    jobs, _record = _record or [], None
+    seen, out = set(), []
+    for job in jobs:
+        k = (id(job[1]),) + tuple(job[2:])
+        if k not in seen:
+            seen.add(k)
+            out.append(job)
+    return out
+
+
+def _pinned_hit(w, jobkey):
+    hit = _pinned.get(id(w))
+    if hit is None or hit[0] != jobkey or hit[2]() is not w:
+        return None
+    hit[3].join()
+    return hit[1]
+
+
+class PackPlan:
+    """jobs: what stop_recording() returned for one forward pass of the model (parameters only)."""
+
+    def __init__(self, jobs, n_streams=4):
+        self.jobs = []
+        for kind, w, *rest in jobs:
+            if kind == "w":
+                layout, need_wt = rest
+                res = pack_weight(w, layout, cache=False, need_wt=need_wt)             # allocates the persistent buffers
+            else:
+                (cin,) = rest
+                res = pack_deconv_weight(w, cin=cin, cache=False)
+            self.jobs.append((kind, w, tuple(rest), res))
+        self.streams = [torch.cuda.Stream() for _ in range(max(1, n_streams))]
+        self.joined = True
+        self._main = None
+
+    def run(self):
+        """Re-pack every weight into the plan's buffers on the side streams and pin the results for the layers."""
+        self._main = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(self._main)
+        for j, (kind, w, rest, res) in enumerate(self.jobs):
+            with torch.cuda.stream(self.streams[j % len(self.streams)]):
+                if kind == "w":
+                    wd = w.detach()
+                    _pack_launch(wd if wd.is_contiguous() else wd.contiguous(), rest[0], res.wq, res.wscale, res.wt)
+                else:
+                    _deconv_pack_launch(w, rest[0], res)
+            _pinned[id(w)] = ((kind,) + rest, res, weakref.ref(w), self)
+        self.joined = False
+
+    def join(self):
+        if not self.joined:
+            cur = torch.cuda.current_stream()
+            for st in self.streams:
+                cur.wait_stream(st)
+            self.joined = True
+
+    def release(self):
+        """Un-pin (the buffers stay allocated for the next run())."""
+        self.join()
+        for kind, w, rest, res in self.jobs:
+            hit = _pinned.get(id(w))
+            if hit is not None and hit[3] is self:
+                del _pinned[id(w)]
+
+
 def pack_weight(w, layout="linear", cache=None, need_wt=False):
     """fp32 weight -> PackedWeight.  layout: 'linear' (Cout, K), 'conv' (Cout, Cin, kh, kw) OIHW.
     Cached per parameter version (optimizer steps bump ``_version``) for nn.Parameters (or when cache=True: the caller
@@ -64,12 +165,21 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
     id / address / version of a freed parameter can all recur in the next model built by the same code, which must not
     get the old model's planes.  Weights changed behind autograd's back (``w.data.copy_()``, raw pointers) do not bump
     ``_version``: call ``invalidate_pack_cache()`` after such an edit."""
+    is_param = isinstance(w, torch.nn.Parameter)
+    want_wt = bool(w.requires_grad or need_wt)
+    if is_param and cache is not False:
+        if _record is not None:
+            _record.append(("w", w, layout, want_wt))
+        if _pinned:
+            hit = _pinned_hit(w, ("w", layout, want_wt))
+            if hit is not None:
+                return hit
     capturing = torch.cuda.is_current_stream_capturing()
     if cache is None:
-        cache = isinstance(w, torch.nn.Parameter)
+        cache = is_param
     if not cache or not _CACHE_OK:
         capturing = True            # same effect: neither look up nor store
-    key = (w.data_ptr(), w._version, _epoch[0], tuple(w.shape), layout, bool(w.requires_grad or need_wt))
+    key = (w.data_ptr(), w._version, _epoch[0], tuple(w.shape), layout, want_wt)
     if not capturing:
         hit = _pack_cache.get(id(w))
         if hit is not None and hit.key == key and hit.owner is not None and hit.owner() is w:
@@ -77,24 +187,14 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
     wd = w.detach()
     if not wd.is_contiguous():
         wd = wd.contiguous()
-    if layout == "linear":
-        Cout, Cin = wd.shape
-        taps, s_co, s_ci, s_tap = 1, Cin, 1, 0
-    elif layout == "conv":
-        Cout, Cin, kh, kw = wd.shape
-        taps = kh * kw
-        s_co, s_ci, s_tap = Cin * taps, taps, 1
-    else:
-        raise ValueError(layout)
+    Cout, Cin, taps = _layout_dims(wd, layout)[:3]
     L = capi.lib()
     nbytes = int(L.sdf_spike_gemm_wq_bytes(Cout, Cin, taps))
     wq = torch.empty(nbytes, device=w.device, dtype=torch.int8)
     wscale = torch.empty(Cout, device=w.device, dtype=torch.float32)
     # transposed fp32 copy for the data-gradient GEMM, only when a backward pass can follow
-    wt = torch.empty((Cin, taps * Cout), device=w.device, dtype=torch.float32) if (w.requires_grad or need_wt) else None
-    capi.call("sdf_spike_gemm_pack", capi.struct(
-        "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(wq), wscale=_ptr(wscale), wt=_ptr(wt), wq_bytes=nbytes, Cout=Cout, Cin=Cin,
-        taps=taps, s_co=s_co, s_ci=s_ci, s_tap=s_tap, tap_map=list(range(9)), stream=_stream()))
+    wt = torch.empty((Cin, taps * Cout), device=w.device, dtype=torch.float32) if want_wt else None
+    _pack_launch(wd, layout, wq, wscale, wt)
     pw = PackedWeight(wq, wscale, wt, Cout, Cin, taps, key)
     if not capturing:
         wid = id(w)
@@ -107,24 +207,46 @@ def pack_weight(w, layout="linear", cache=None, need_wt=False):
 _deconv_cache = {}
 
 
-def pack_deconv_weight(w, cin=None):
-    """ConvTranspose2d weight (Cin, Cout, 3, 3) -> the four PackedWeights of sdf_spike_deconv_fwd (one per output parity
-    class).  cin > w.shape[0]: zero input slices are appended first (decoder inputs concatenated up to a multiple of 16
-    channels).  Cached per live parameter and version like pack_weight."""
+def _deconv_pack_launch(w, cin, packs):
+    """(Re-)pack the four parity classes of a ConvTranspose2d weight into the buffers of `packs`."""
     import ctypes
-    cin = w.shape[0] if cin is None else cin
-    capturing = torch.cuda.is_current_stream_capturing() or not isinstance(w, torch.nn.Parameter) or not _CACHE_OK
-    key = (w.data_ptr(), w._version, _epoch[0], tuple(w.shape), cin)
-    if not capturing:
-        hit = _deconv_cache.get(id(w))
-        if hit is not None and hit[0] == key and hit[2]() is w:
-            return hit[1]
     wd = w.detach()
     if cin != wd.shape[0]:
         wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, 0, 0, cin - wd.shape[0]))
     wd = wd.contiguous()
     Cin, Cout = wd.shape[0], wd.shape[1]
-    assert tuple(wd.shape[2:]) == (3, 3)
+    L = capi.lib()
+    for cls, pk in enumerate(packs):
+        src, dh, dw = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+        taps = int(L.sdf_spike_deconv_class_taps(cls, src, dh, dw))
+        capi.call("sdf_spike_gemm_pack", capi.struct(
+            "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(pk.wq), wscale=_ptr(pk.wscale), wt=None, wq_bytes=pk.wq.numel(), Cout=Cout,
+            Cin=Cin, taps=taps, s_co=9, s_ci=Cout * 9, s_tap=1, tap_map=[int(src[i]) for i in range(taps)] + [0] * (9 - taps),
+            stream=_stream()))
+
+
+def pack_deconv_weight(w, cin=None, cache=None):
+    """ConvTranspose2d weight (Cin, Cout, 3, 3) -> the four PackedWeights of sdf_spike_deconv_fwd (one per output parity
+    class).  cin > w.shape[0]: zero input slices are appended first (decoder inputs concatenated up to a multiple of 16
+    channels).  Cached per live parameter and version like pack_weight."""
+    import ctypes
+    cin = w.shape[0] if cin is None else cin
+    is_param = isinstance(w, torch.nn.Parameter)
+    if is_param and cache is not False:
+        if _record is not None:
+            _record.append(("deconv", w, cin))
+        if _pinned:
+            hit = _pinned_hit(w, ("deconv", cin))
+            if hit is not None:
+                return hit
+    capturing = torch.cuda.is_current_stream_capturing() or not is_param or not _CACHE_OK or cache is False
+    key = (w.data_ptr(), w._version, _epoch[0], tuple(w.shape), cin)
+    if not capturing:
+        hit = _deconv_cache.get(id(w))
+        if hit is not None and hit[0] == key and hit[2]() is w:
+            return hit[1]
+    assert tuple(w.shape[2:]) == (3, 3)
+    Cin, Cout = cin, w.shape[1]
     L = capi.lib()
     packs = []
     for cls in range(4):
@@ -133,11 +255,8 @@ def pack_deconv_weight(w, cin=None):
         nbytes = int(L.sdf_spike_gemm_wq_bytes(Cout, Cin, taps))
         wq = torch.empty(nbytes, device=w.device, dtype=torch.int8)
         wscale = torch.empty(Cout, device=w.device, dtype=torch.float32)
-        capi.call("sdf_spike_gemm_pack", capi.struct(
-            "sdf_spike_gemm_pack_args", w=_ptr(wd), wq=_ptr(wq), wscale=_ptr(wscale), wt=None, wq_bytes=nbytes, Cout=Cout, Cin=Cin,
-            taps=taps, s_co=9, s_ci=Cout * 9, s_tap=1, tap_map=[int(src[i]) for i in range(taps)] + [0] * (9 - taps),
-            stream=_stream()))
         packs.append(PackedWeight(wq, wscale, None, Cout, Cin, taps, key))
+    _deconv_pack_launch(w, cin, packs)
     if not capturing:
         wid = id(w)
         ref = weakref.ref(w, lambda _r, wid=wid: _deconv_cache.pop(wid, None) if (wid in _deconv_cache and _deconv_cache[wid][2] is _r) else None)

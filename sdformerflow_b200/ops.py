@@ -7,6 +7,7 @@ lines each operator replaces.
 """
 from dataclasses import dataclass
 import math
+import os
 import weakref
 
 import torch
@@ -898,6 +899,8 @@ class _SpikeDeconvFn(torch.autograd.Function):
         holder = ctx.holder
         x = holder.data
         H, W, Cin = x.shape[-3:]
+        if DECONV_BWD == "lib":
+            return _SpikeDeconvFn._backward_lib(ctx, gy)
         g4 = gy.contiguous().view(-1, *gy.shape[-3:])      # (Nimg, 2H, 2W, Cout) NHWC
         gtok = gw = gb = None
         if ctx.needs_input_grad[0]:
@@ -915,7 +918,34 @@ class _SpikeDeconvFn(torch.autograd.Function):
         return gtok, gw, gb, None, None
 
 
+    @staticmethod
+    def _backward_lib(ctx, gy):
+        """Comparison path (SDF_DECONV_BWD=lib): cuDNN (TF32) on the spikes expanded to fp32 — what tools/bench_conv_bwd.py
+        times the engine's kernels against."""
+        (weight,) = ctx.saved_tensors
+        holder = ctx.holder
+        x = holder.data
+        H, W, Cin = x.shape[-3:]
+        g4 = gy.contiguous().view(-1, *gy.shape[-3:]).permute(0, 3, 1, 2)      # logical NCHW, channels-last strides
+        x4 = x.view(-1, H, W, Cin).float().permute(0, 3, 1, 2)
+        w = weight.detach()
+        if Cin != w.shape[0]:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, Cin - w.shape[0]))
+        with _tf32(True):
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                g4, x4, w, [w.shape[1]] if ctx.has_bias else None, [2, 2], [1, 1], [1, 1], True, [1, 1], 1,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]])
+        gtok = None
+        if gx is not None:
+            holder.add_grad(gx.permute(0, 2, 3, 1).contiguous().view(x.shape))
+            gtok = _zero_token(gy.device)
+        if gw is not None and Cin != weight.shape[0]:
+            gw = gw[:weight.shape[0]]
+        return gtok, gw, gb, None, None
+
+
 USE_SPIKE_DECONV = True      # False: transposed convolutions stay on the library path (debug switch)
+DECONV_BWD = os.environ.get("SDF_DECONV_BWD", "own")     # "lib": backward of the transposed convolutions through cuDNN (comparison)
 
 
 def spike_deconv_supported(conv, cin):

@@ -82,7 +82,7 @@ class GraphedStep:
     loss_fn(flows, gt, mask) -> scalar.  `world` > 1 expects an initialised NCCL process group."""
 
     def __init__(self, model, loss_fn, example, lr=1e-4, weight_decay=0.01, world=1, group=None, warmup=3, clip_grad=None,
-                 graph=True, optimizer_cls=torch.optim.AdamW):
+                 graph=True, optimizer_cls=torch.optim.AdamW, prepack=True):
         if torch.is_autocast_enabled():
             raise RuntimeError("sdformerflow_b200.train: run the step in fp32 (membranes integrate in fp32, spike GEMMs are "
                                "exact integer contractions); torch.autocast is not supported on this path")
@@ -97,6 +97,7 @@ class GraphedStep:
 
         self.loss = None
         self._fwd_graph = self._opt_graph = None
+        self._plan = None
         # Everything that creates autograd state for the parameters (the probing pass, the flat gradient buffer, warm-up) runs
         # on ONE side stream, and the capture uses that same stream: autograd pins each AccumulateGrad node / .grad buffer to
         # the stream it was created on, and a captured backward must not have to synchronise with any other stream.
@@ -109,15 +110,27 @@ class GraphedStep:
             if self.graph_mode:
                 for _ in range(max(warmup, 3)):          # cudnn autotune, lazily built tables, optimizer state
                     self._eager()
+                # which parameters the layers pack (digit planes for the spike GEMMs): recorded over one more eager step, then
+                # re-packed at the START of every captured step on side streams instead of layer by layer (gemm.PackPlan)
+                gemm.start_recording()
+                try:
+                    self._eager()
+                finally:
+                    jobs = gemm.stop_recording()
+                self._plan = gemm.PackPlan(jobs) if (jobs and prepack) else None
         torch.cuda.current_stream().wait_stream(self.stream)
         torch.cuda.synchronize()
         if not self.graph_mode:
             return
         self._fwd_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._fwd_graph, stream=self.stream, capture_error_mode="thread_local"):
-            self.loss = self._fwd_bwd()
-            if world == 1:
-                self._update()
+        try:
+            with torch.cuda.graph(self._fwd_graph, stream=self.stream, capture_error_mode="thread_local"):
+                self.loss = self._fwd_bwd()
+                if world == 1:
+                    self._update()
+        finally:
+            if self._plan is not None:
+                self._plan.release()         # eager use of the model afterwards packs for itself
         if world > 1:
             self._opt_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._opt_graph, stream=self.stream, capture_error_mode="thread_local"):
@@ -125,9 +138,14 @@ class GraphedStep:
 
     # -- pieces -------------------------------------------------------------------------------------------------------
     def _fwd_bwd(self):
+        plan = self._plan if torch.cuda.is_current_stream_capturing() else None
+        if plan is not None:
+            plan.run()                       # forked branches of the graph; joined at the first layer that needs a pack
         self.grads.zero()
         functional.reset_net(self.model)
         loss = self.loss_fn(self.model(self.static[0])["flow"], *self.static[1:])
+        if plan is not None:
+            plan.join()
         (loss / self.world if self.world > 1 else loss).backward()
         return loss.detach()
 

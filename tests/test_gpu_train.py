@@ -62,6 +62,10 @@ def test_graphed_step_matches_eager(nt):
     assert abs(le[0] - lg[0]) <= 1e-5 * abs(le[0]), (le, lg)
     assert abs(le[1] - lg[1]) <= 1e-2 * abs(le[1]), (le, lg)
     assert lg[1] != lg[0]                              # the weights really moved between replays
+    # the captured step re-packs the weights up front on side streams (gemm.PackPlan): every Linear / conv parameter of the
+    # spike GEMMs is in the plan, and nothing stays pinned after the capture
+    from sdformerflow_b200 import gemm
+    assert sg._plan is not None and len(sg._plan.jobs) >= 20 and not gemm._pinned
     n_bad = sum(((pe[k] - pg[k]).abs() > 2e-5).sum().item() for k in pe)
     assert n_bad <= 0.01 * sum(v.numel() for v in pe.values())
     n_params = sum(1 for p in sg.model.parameters() if p.requires_grad)
