@@ -9,6 +9,7 @@ Drop-in surface: ``Model(config["model"].copy(), config["swin_transformer"].copy
 import torch
 from torch import nn
 
+from .. import ops
 from ..sj import layer, functional, neuron  # noqa: F401
 from .Spiking_swin_transformer3D import Spiking_SwinTransformer3D_v2, MS_Spiking_SwinTransformer3D_v2
 from .SNN_models import *  # noqa: F401,F403
@@ -180,7 +181,7 @@ class SpikingformerFlowNet(nn.Module):
         # in fp32 and the spike contractions are exact integer GEMMs, so autocast is switched off for the model's extent
         # (the scripts run unmodified; losses / GradScaler see fp32 flows, which autocast would have produced for the
         # final sum / interpolate anyway).
-        with torch.autocast(device_type=x.device.type, enabled=False):
+        with torch.autocast(device_type=x.device.type, enabled=False), ops.defer_nbt():
             x = x.float()
             for pred in self.sttmultires_unet.forward_cl(x):               # (B, T, h, w, 2)
                 flow = torch.sum(pred, dim=1).permute(0, 3, 1, 2)           # sum over time -> (B, 2, h, w)

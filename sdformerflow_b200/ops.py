@@ -153,6 +153,38 @@ class BNParams:
         self.training = bn.training or bn.running_mean is None
 
 
+NBT_DEFER = None      # list while a model forward collects its BatchNorm counters (defer_nbt): ~80 one-element adds -> one launch
+
+
+class defer_nbt:
+    """with ops.defer_nbt(): ... — the num_batches_tracked += 1 of every BatchNorm call inside is applied on exit as ONE
+    torch._foreach_add_ (reference semantics: nn.BatchNorm2d increments its counter per training call)."""
+
+    def __enter__(self):
+        global NBT_DEFER
+        self.outer = NBT_DEFER
+        if self.outer is None:
+            NBT_DEFER = []
+        return self
+
+    def __exit__(self, *exc):
+        global NBT_DEFER
+        if self.outer is None:
+            pending, NBT_DEFER = NBT_DEFER, None
+            if pending:
+                uniq, counts = {}, {}
+                for t in pending:
+                    uniq[id(t)] = t
+                    counts[id(t)] = counts.get(id(t), 0) + 1
+                once = [uniq[k] for k in uniq if counts[k] == 1]
+                if once:
+                    torch._foreach_add_(once, 1)
+                for k, c in counts.items():
+                    if c > 1:
+                        uniq[k].add_(c)
+        return False
+
+
 def _bn_forward_affine(u2d, rows, C, ld, bn: BNParams, partials=None):
     """-> scale, shift, mean, rstd (all [C]).  Train: batch stats + running update like torch.
     partials: per-block (sum, sum of squares) [N_PARTIAL, 2, C] already produced by the epilogue of the GEMM that wrote
@@ -174,7 +206,10 @@ def _bn_forward_affine(u2d, rows, C, ld, bn: BNParams, partials=None):
             # [k * N_PARTIAL, 2, C]: k = 1 for a GEMM / convolution, 4 for the parity classes of a transposed convolution
             assert partials.shape[1:] == (2, C) and partials.shape[0] % N_PARTIAL == 0 and partials.is_contiguous()
         if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            if NBT_DEFER is not None:
+                NBT_DEFER.append(bn.num_batches_tracked)      # one multi-tensor add at the end of the model's forward
+            else:
+                bn.num_batches_tracked.add_(1)
     with torch.no_grad():
         capi.call("sdf_bn_finalize", capi.struct(
             "sdf_bn_finalize_args", partials=_ptr(partials), n_partial_blocks=partials.shape[0] if bn.training else 0,
@@ -649,6 +684,7 @@ class _SpikeGemmFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, token, weight, bias, holder, want_stats):
+        ctx.set_materialize_grads(False)      # the BN partial sums get no gradient: do not zero-fill one per call
         a = holder.data
         K = a.shape[-1]
         pw = gemm.pack_weight(weight, cache=getattr(weight, "_sdf_cacheable", None))
@@ -662,6 +698,8 @@ class _SpikeGemmFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, _gp):
+        if gy is None:
+            return (None,) * 5
         (weight,) = ctx.saved_tensors
         holder = ctx.holder
         a = holder.data
@@ -824,6 +862,7 @@ class _SpikeConvGemmFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, token, weight, bias, holder, stride, padding, want_stats):
+        ctx.set_materialize_grads(False)      # the BN partial sums get no gradient: do not zero-fill one per call
         x = holder.data                                   # (..., H, W, Cin) u8, leading dims = images
         H, W, Cin = x.shape[-3:]
         kh, kw = weight.shape[2], weight.shape[3]
@@ -839,6 +878,8 @@ class _SpikeConvGemmFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, _gp):
+        if gy is None:
+            return (None,) * 7
         (weight,) = ctx.saved_tensors
         stride, padding, has_bias = ctx.cfg
         holder = ctx.holder
@@ -882,6 +923,7 @@ class _SpikeDeconvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, token, weight, bias, holder, want_stats):
+        ctx.set_materialize_grads(False)      # the BN partial sums get no gradient: do not zero-fill one per call
         x = holder.data                                   # (..., H, W, Cin_padded) u8
         H, W, Cin = x.shape[-3:]
         packs = gemm.pack_deconv_weight(weight, cin=Cin)
@@ -895,6 +937,8 @@ class _SpikeDeconvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, _gp):
+        if gy is None:
+            return (None,) * 5
         (weight,) = ctx.saved_tensors
         holder = ctx.holder
         x = holder.data
