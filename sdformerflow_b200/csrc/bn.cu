@@ -76,7 +76,28 @@ __global__ void __launch_bounds__(512) bn_rows_kernel(const RowsP p) {
   if (p.v1) c1 = *reinterpret_cast<const float4*>(p.v1 + col);
   if (p.v2) c2 = *reinterpret_cast<const float4*>(p.v2 + col);
   const int64_t stride = (int64_t)gridDim.x * p.k;
-  for (int64_t row = (int64_t)blockIdx.x * p.k + ry; row < p.rows; row += stride) {
+  int64_t row = (int64_t)blockIdx.x * p.k + ry;
+  // two rows per iteration: four 16-byte loads in flight per thread
+  for (; row + stride < p.rows; row += 2 * stride) {
+    const int64_t r1 = row + stride;
+    float4 x0 = ld_stream4(p.a + row * p.ld_a + col), x1 = ld_stream4(p.a + r1 * p.ld_a + col);
+    float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
+    if (p.b) { y0 = ld_stream4(p.b + row * p.ld_b + col); y1 = ld_stream4(p.b + r1 * p.ld_b + col); }
+    float4 o0, o1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (MODE == 0) {
+        f4(o0, i) = f4(y0, i) + fmaf(f4(x0, i), f4(c0, i), f4(c1, i));
+        f4(o1, i) = f4(y1, i) + fmaf(f4(x1, i), f4(c0, i), f4(c1, i));
+      } else {
+        f4(o0, i) = fmaf(f4(c0, i), f4(x0, i), fmaf(f4(c1, i), f4(y0, i), f4(c2, i)));
+        f4(o1, i) = fmaf(f4(c0, i), f4(x1, i), fmaf(f4(c1, i), f4(y1, i), f4(c2, i)));
+      }
+    }
+    st_stream4(p.out + row * p.ld_out + col, o0);
+    st_stream4(p.out + r1 * p.ld_out + col, o1);
+  }
+  for (; row < p.rows; row += stride) {
     float4 x = ld_stream4(p.a + row * p.ld_a + col);
     float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.b) y = ld_stream4(p.b + row * p.ld_b + col);

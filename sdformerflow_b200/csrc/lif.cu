@@ -267,6 +267,100 @@ __global__ void __launch_bounds__(288, (T >= 16) ? 1 : ((V == 2) ? (PRE ? 2 : 3)
   }
 }
 
+// ---- K2s: backward with the operands staged through shared memory by cp.async ------------------
+// The register-resident K2 above loads a row block (u and dL/ds of T steps), then computes for ~1 us with nothing in flight,
+// then stores: with one 288-thread CTA per SM (T = 10 needs ~220 registers) the memory pipe idles during every compute
+// phase (0.58-0.66 of the HBM roofline).  Here each thread's 2T 16-byte operands of the NEXT row block are copied into a
+// second shared-memory stage by cp.async while the current block is processed from the first (a thread only ever reads its
+// own slots: no block barrier in the loop), so 92 KB per SM are in flight during the compute phases; only h stays in
+// registers (u and dL/ds are re-read from the stage where needed).  Persistent grid (one CTA per SM).  Same arithmetic and
+// operation order per neuron as lif_bwd_kernel: identical gradients; the BN partial sums group the rows differently.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int T, bool SIMPLE>
+__global__ void __launch_bounds__(288, 1) lif_bwd_stream_kernel(const LifBwdP p) {
+  constexpr int V = 4;
+  extern __shared__ float4 stg4[];                 // [2 stages][2T slots][blockDim.x]
+  const SeqP& s = p.s;
+  const NeuronP nrn = p.nrn;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  const int rx = tid % s.R, ry = tid / s.R;
+  const int64_t col = (int64_t)blockIdx.y * s.tile_w + (int64_t)rx * V;
+  float sc[V], sh[V];
+  init_affine<V>(s, p.scale, p.shift, col, sc, sh);
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const float dh_dx = neuron_dh_dx(nrn), dh_dv = neuron_dh_dv(nrn);
+  const float vr = nrn.hard ? nrn.v_reset : 0.f;
+  const int64_t gstride = (int64_t)gridDim.x * s.k;
+  auto issue = [&](int64_t row, int stage) {
+    const int64_t n = row * s.row_w + col;
+    if (row < s.n_rows && n < s.n_neurons) {
+      const int64_t off = seq_base(s, n);
+      float4* dst = stg4 + (size_t)stage * 2 * T * nthr + tid;
+#pragma unroll
+      for (int t = 0; t < T; ++t) cp_async16(dst + t * nthr, p.u + off + t * s.stride_t);
+#pragma unroll
+      for (int t = 0; t < T; ++t) cp_async16(dst + (T + t) * nthr, p.gs + off + t * s.stride_t);
+    }
+    cp_async_commit();
+  };
+  int64_t row = (int64_t)blockIdx.x * s.k + ry;
+  issue(row, 0);
+  int stage = 0;
+  for (; row < s.n_rows; row += gstride, stage ^= 1) {
+    issue(row + gstride, stage ^ 1);
+    cp_async_wait<1>();                            // everything but the group just committed has landed
+    const int64_t n = row * s.row_w + col;
+    if (n >= s.n_neurons) continue;
+    const int64_t off = seq_base(s, n);
+    const float4* src = stg4 + (size_t)stage * 2 * T * nthr + tid;
+    if (s.chan_mode >= 2) load_affine<V>(s, p.scale, p.shift, n, sc, sh);
+    float h[T][V], v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = vr;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float4 u4 = src[t * nthr];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xx = fmaf(f4(u4, i), sc[i], sh[i]);
+        h[t][i] = neuron_charge_t<SIMPLE>(nrn, v[i], xx);
+        v[i] = neuron_reset_t<SIMPLE>(nrn, h[t][i], neuron_fire(nrn, h[t][i]));
+      }
+    }
+    float gv[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) gv[i] = 0.f;
+#pragma unroll
+    for (int t = T - 1; t >= 0; --t) {
+      const float4 g4 = src[(T + t) * nthr];
+      const float4 u4 = src[t * nthr];
+      float dx[V], du[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float gh = neuron_grad_h_t<SIMPLE>(nrn, h[t][i], f4(g4, i), gv[i]);
+        dx[i] = gh * dh_dx;
+        gv[i] = gh * dh_dv;
+        du[i] = dx[i] * sc[i];
+        if (s.chan_mode == 1) {
+          acc[0][i] += dx[i];
+          acc[1][i] += dx[i] * f4(u4, i);
+        }
+      }
+      if (p.gu) stv<V>(p.gu + off + t * s.stride_t, du);
+      if (p.gx) stv<V>(p.gx + off + t * s.stride_t, dx);
+    }
+  }
+  cp_async_wait<0>();
+  if (p.bn_partials && s.chan_mode == 1)
+    block_reduce_rows_to_partials<2, V>(acc, reinterpret_cast<float*>(stg4), p.bn_partials, s.R, s.k, s.C, (int64_t)blockIdx.y * s.tile_w);
+}
+
 // ---- K1p: PSN ---------------------------------------------------------------------------------
 struct PsnP {
   const float* u; void* spike; float* h_seq;
@@ -605,6 +699,31 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   }
   if (a->bn_partials) SDF_REQUIRE(fastT, "sdf_lif_bwd: bn_partials supported for T in {2,4,5,10,20}");
   SeqLaunch L;
+  // T = 10, the common sites (LIF / IF, zero initial state, no folded BN backward): operands staged through shared memory by
+  // cp.async, persistent grid (lif_bwd_stream_kernel)
+  static const int stream_mode = [] { const char* e = getenv("SDF_LIF_BWD_STREAM"); return e ? atoi(e) : 1; }();
+  if (stream_mode && T == 10 && !a->v_init && !a->bn_coef && !a->plif_partials && a->neuron.kind != SDF_NEURON_PLIF) {
+    int64_t mb = kNumSMs;
+    if (parts && a->n_partial_blocks < mb) mb = a->n_partial_blocks;
+    st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, 4, 288, mb, &L);
+    if (st) return st;
+    if (L.V == 4) {
+      p.s = L.s;
+      if (a->bn_partials && a->n_partial_blocks > (int64_t)L.grid.x)
+        cudaMemsetAsync(a->bn_partials + (int64_t)L.grid.x * 2 * a->C, 0,
+                        sizeof(float) * (a->n_partial_blocks - L.grid.x) * 2 * a->C, stream);
+      const size_t smem_s = (size_t)2 * 2 * 10 * L.threads * sizeof(float4);
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(lif_bwd_stream_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(lif_bwd_stream_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+      }
+      if (neuron_is_simple(p.nrn)) lif_bwd_stream_kernel<10, true><<<L.grid, L.threads, smem_s, stream>>>(p);
+      else lif_bwd_stream_kernel<10, false><<<L.grid, L.threads, smem_s, stream>>>(p);
+      return finish_launch("sdf_lif_bwd");
+    }
+  }
   // T = 10 keeps u, h (and the preloaded grads) in registers: 2 neurons per thread there, 4 otherwise
   static const int v4_t10 = [] { const char* e = getenv("SDF_LIF_BWD_V4"); return e ? atoi(e) : 1; }();
   // T = 10 with 4 neurons/thread keeps u, h and the preloaded grads in ~220 registers: 288-thread CTAs, one per SM
