@@ -561,6 +561,157 @@ __global__ void __launch_bounds__(256) psn_bwd_kernel(const PsnP p) {
   }
 }
 
+// ---- K1p backward, streamed: same staging as lif_bwd_stream_kernel -----------------------------------------------------
+// psn_bwd_kernel<.., WG = true> holds u, dL/ds -> dh and the T x T + T parameter-gradient accumulators in registers (255,
+// one 256-thread CTA per SM) and has nothing in flight while it computes: 0.43 of the HBM roofline.  Here the operands of the
+// next row block arrive by cp.async while the current one is processed; dh is written back over the thread's own dL/ds slots,
+// so the live registers are x (T x 4) + the accumulators in the parameter-gradient phase and dh + the accumulators in the
+// dx phase.  Per accumulator the additions happen in the same order as in psn_bwd_kernel.
+template <int T>
+__global__ void __launch_bounds__(256, 1) psn_bwd_stream_kernel(const PsnP p) {
+  constexpr int V = 4;
+  extern __shared__ float4 stg4[];                 // [2 stages][2T slots][blockDim.x]
+  __shared__ float sw[T * T + T];
+  __shared__ float wred[8][T * T + T];
+  const SeqP& s = p.s;
+  const NeuronP nrn = p.nrn;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  for (int i = tid; i < T * T; i += nthr) sw[i] = p.weight[i];
+  for (int i = tid; i < T; i += nthr) sw[T * T + i] = p.bias[i];
+  __syncthreads();
+  const int rx = tid % s.R, ry = tid / s.R;
+  const int64_t col = (int64_t)blockIdx.y * s.tile_w + (int64_t)rx * V;
+  float sc[V], sh[V];
+  init_affine<V>(s, p.scale, p.shift, col, sc, sh);
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float wacc[T][T], wb[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    wb[t] = 0.f;
+#pragma unroll
+    for (int k = 0; k < T; ++k) wacc[t][k] = 0.f;
+  }
+  const int64_t gstride = (int64_t)gridDim.x * s.k;
+  auto issue = [&](int64_t row, int stage) {
+    const int64_t n = row * s.row_w + col;
+    if (row < s.n_rows && n < s.n_neurons) {
+      const int64_t off = seq_base(s, n);
+      float4* dst = stg4 + (size_t)stage * 2 * T * nthr + tid;
+#pragma unroll
+      for (int t = 0; t < T; ++t) cp_async16(dst + t * nthr, p.u + off + t * s.stride_t);
+#pragma unroll
+      for (int t = 0; t < T; ++t) cp_async16(dst + (T + t) * nthr, p.gs + off + t * s.stride_t);
+    }
+    cp_async_commit();
+  };
+  int64_t row = (int64_t)blockIdx.x * s.k + ry;
+  issue(row, 0);
+  int stage = 0;
+  for (; row < s.n_rows; row += gstride, stage ^= 1) {
+    issue(row + gstride, stage ^ 1);
+    cp_async_wait<1>();
+    const int64_t n = row * s.row_w + col;
+    if (n >= s.n_neurons) continue;
+    const int64_t off = seq_base(s, n);
+    float4* src = stg4 + (size_t)stage * 2 * T * nthr + tid;
+    if (s.chan_mode >= 2) load_affine<V>(s, p.scale, p.shift, n, sc, sh);
+    {
+      float x[T][V];
+#pragma unroll
+      for (int k = 0; k < T; ++k) {
+        const float4 u4 = src[k * nthr];
+#pragma unroll
+        for (int i = 0; i < V; ++i) x[k][i] = fmaf(f4(u4, i), sc[i], sh[i]);
+        if (p.x_out) stv<V>(p.x_out + (int64_t)k * s.n_neurons + n, x[k]);
+      }
+      // dh_t = g_t * sg(h_t), h_t = sum_k W[t][k] x_k + b_t; written back over the thread's own dL/ds slot
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        float h[V], dh[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) h[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+          const float w = sw[t * T + k];
+#pragma unroll
+          for (int i = 0; i < V; ++i) h[i] = fmaf(w, x[k][i], h[i]);
+        }
+        const float4 g4 = src[(T + t) * nthr];
+#pragma unroll
+        for (int i = 0; i < V; ++i) dh[i] = f4(g4, i) * surrogate_grad(nrn, h[i] + sw[T * T + t]);
+        src[(T + t) * nthr] = make_float4(dh[0], dh[1], dh[2], dh[3]);
+        if (p.gh) stv<V>(p.gh + (int64_t)t * s.n_neurons + n, dh);
+      }
+      // parameter gradients: dW[t][k] += dh_t . x_k, db[t] += sum dh_t
+      if (p.wg_partials) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const float4 d4 = src[(T + t) * nthr];
+#pragma unroll
+          for (int k = 0; k < T; ++k)
+#pragma unroll
+            for (int i = 0; i < V; ++i) wacc[t][k] = fmaf(f4(d4, i), x[k][i], wacc[t][k]);
+#pragma unroll
+          for (int i = 0; i < V; ++i) wb[t] += f4(d4, i);
+        }
+      }
+    }
+    // dx_k = sum_t W[t][k] dh_t
+    float dh[T][V];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float4 d4 = src[(T + t) * nthr];
+#pragma unroll
+      for (int i = 0; i < V; ++i) dh[t][i] = f4(d4, i);
+    }
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      float dx[V], du[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) dx[i] = 0.f;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float w = sw[t * T + k];
+#pragma unroll
+        for (int i = 0; i < V; ++i) dx[i] = fmaf(w, dh[t][i], dx[i]);
+      }
+      const float4 u4 = src[k * nthr];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        du[i] = dx[i] * sc[i];
+        if (s.chan_mode == 1) {
+          acc[0][i] += dx[i];
+          acc[1][i] += dx[i] * f4(u4, i);
+        }
+      }
+      if (p.gu) stv<V>(p.gu + off + k * s.stride_t, du);
+      if (p.gx) stv<V>(p.gx + off + k * s.stride_t, dx);
+    }
+  }
+  cp_async_wait<0>();
+  if (p.bn_partials && s.chan_mode == 1)
+    block_reduce_rows_to_partials<2>(acc, reinterpret_cast<float*>(stg4), p.bn_partials, s.R, s.k, s.C, (int64_t)blockIdx.y * s.tile_w);
+  if (p.wg_partials) {
+    __syncthreads();
+    const int lane = tid & 31, wp = tid >> 5;
+#pragma unroll
+    for (int e = 0; e < T * T + T; ++e) {
+      float v = e < T * T ? wacc[e / T][e % T] : wb[e - T * T];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) wred[wp][e] = v;
+    }
+    __syncthreads();
+    float* out = p.wg_partials + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (T * T + T);
+    const int nwarps = nthr >> 5;
+    for (int e = tid; e < T * T + T; e += nthr) {
+      float sum = 0.f;
+      for (int w = 0; w < nwarps; ++w) sum += wred[w][e];
+      out[e] = sum;
+    }
+  }
+}
+
 // ---- host: tiling and dispatch --------------------------------------------------------------
 struct SeqLaunch {
   SeqP s;
@@ -702,25 +853,34 @@ extern "C" int sdf_lif_bwd(const sdf_lif_bwd_args* a) {
   // T = 10, the common sites (LIF / IF, zero initial state, no folded BN backward): operands staged through shared memory by
   // cp.async, persistent grid (lif_bwd_stream_kernel)
   static const int stream_mode = [] { const char* e = getenv("SDF_LIF_BWD_STREAM"); return e ? atoi(e) : 1; }();
-  if (stream_mode && T == 10 && !a->v_init && !a->bn_coef && !a->plif_partials && a->neuron.kind != SDF_NEURON_PLIF) {
+  if (stream_mode && (T == 10 || T == 20) && !a->v_init && !a->bn_coef && !a->plif_partials && a->neuron.kind != SDF_NEURON_PLIF) {
     int64_t mb = kNumSMs;
     if (parts && a->n_partial_blocks < mb) mb = a->n_partial_blocks;
-    st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, 4, 288, mb, &L);
+    // two stages of 2T 16-byte slots per thread: 288 threads at T = 10 (180 KB), 128 at T = 20 (160 KB)
+    st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 5, 4, T == 10 ? 288 : 128, mb, &L);
     if (st) return st;
     if (L.V == 4) {
       p.s = L.s;
       if (a->bn_partials && a->n_partial_blocks > (int64_t)L.grid.x)
         cudaMemsetAsync(a->bn_partials + (int64_t)L.grid.x * 2 * a->C, 0,
                         sizeof(float) * (a->n_partial_blocks - L.grid.x) * 2 * a->C, stream);
-      const size_t smem_s = (size_t)2 * 2 * 10 * L.threads * sizeof(float4);
+      const size_t smem_s = (size_t)2 * 2 * T * L.threads * sizeof(float4);
       static bool attr_done = false;
       if (!attr_done) {
         cudaFuncSetAttribute(lif_bwd_stream_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(lif_bwd_stream_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(lif_bwd_stream_kernel<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(lif_bwd_stream_kernel<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
       }
-      if (neuron_is_simple(p.nrn)) lif_bwd_stream_kernel<10, true><<<L.grid, L.threads, smem_s, stream>>>(p);
-      else lif_bwd_stream_kernel<10, false><<<L.grid, L.threads, smem_s, stream>>>(p);
+      const bool simple_s = neuron_is_simple(p.nrn);
+      if (T == 10) {
+        if (simple_s) lif_bwd_stream_kernel<10, true><<<L.grid, L.threads, smem_s, stream>>>(p);
+        else lif_bwd_stream_kernel<10, false><<<L.grid, L.threads, smem_s, stream>>>(p);
+      } else {
+        if (simple_s) lif_bwd_stream_kernel<20, true><<<L.grid, L.threads, smem_s, stream>>>(p);
+        else lif_bwd_stream_kernel<20, false><<<L.grid, L.threads, smem_s, stream>>>(p);
+      }
       return finish_launch("sdf_lif_bwd");
     }
   }
@@ -822,11 +982,37 @@ extern "C" int sdf_psn_bwd(const sdf_psn_bwd_args* a) {
     if (a->n_partial_blocks < max_blocks) max_blocks = a->n_partial_blocks;
   }
   SeqLaunch L;
-  int st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 6, fastT ? 4 : 1,
-                     256, max_blocks, &L);
+  int st;
+  cudaStream_t stream = (cudaStream_t)a->stream;
+  // T = 10 with the parameter gradients in the same pass (the training path of the shipped configuration): operands staged
+  // through shared memory by cp.async, persistent grid (psn_bwd_stream_kernel)
+  static const int stream_mode = [] { const char* e = getenv("SDF_PSN_BWD_STREAM"); return e ? atoi(e) : 1; }();
+  if (stream_mode && T == 10 && a->wgrad_partials) {
+    int64_t mb = kNumSMs;
+    if (a->bn_partials && a->n_partial_blocks < mb) mb = a->n_partial_blocks;
+    st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 6, 4, 256, mb, &L);
+    if (st) return st;
+    const int64_t nb = (int64_t)L.grid.x * L.grid.y, per = (int64_t)T * T + T;
+    if (L.V == 4 && L.threads % 32 == 0 && L.threads <= 256 && a->n_wgrad_blocks >= nb) {
+      p.s = L.s;
+      if (a->bn_partials && a->n_partial_blocks > (int64_t)L.grid.x)
+        cudaMemsetAsync(a->bn_partials + (int64_t)L.grid.x * 2 * a->C, 0,
+                        sizeof(float) * (a->n_partial_blocks - L.grid.x) * 2 * a->C, stream);
+      if (a->n_wgrad_blocks > nb) cudaMemsetAsync(a->wgrad_partials + nb * per, 0, sizeof(float) * (a->n_wgrad_blocks - nb) * per, stream);
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(psn_bwd_stream_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+        attr_done = true;
+      }
+      const size_t smem_s = (size_t)2 * 2 * 10 * L.threads * sizeof(float4);
+      psn_bwd_stream_kernel<10><<<L.grid, L.threads, smem_s, stream>>>(p);
+      return finish_launch("sdf_psn_bwd");
+    }
+  }
+  st = build_seq(a->lay, a->C, a->hw, affine, a->bn_partials != nullptr, ptrs, 6, fastT ? 4 : 1,
+                 256, max_blocks, &L);
   if (st) return st;
   p.s = L.s;
-  cudaStream_t stream = (cudaStream_t)a->stream;
   if (a->bn_partials && a->n_partial_blocks > (int64_t)L.grid.x)
     cudaMemsetAsync(a->bn_partials + (int64_t)L.grid.x * 2 * a->C, 0,
                     sizeof(float) * (a->n_partial_blocks - L.grid.x) * 2 * a->C, stream);
