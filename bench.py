@@ -13,9 +13,10 @@ bucketed, overlapped with backward).  Weak scaling: per-GPU batch fixed.
 
 Prints ONE JSON line on rank 0.  `value` is timed with inputs resident in HBM; `e2e` repeats the
 measurement through the public model API with pinned HOST buffers (H2D copy of the step's inputs
-and a D2H read of the loss inside the timed region).  `roofline` reports the dominant hand-written
-kernel (K1 sdf_lif_fwd): algorithmic bytes / CUDA-event time of every launch in the timed region
-against the measured HBM peak of MEASURED_PEAKS.json.  `cpu_baseline` is the oracle port timed on
+and a D2H read of the loss inside the timed region).  `roofline` reports the dominant libsdf_b200
+entry point of the step (by summed CUDA-event time over an eager pass of the same step): algorithmic
+bytes / event time of its launches against the measured HBM peak of MEASURED_PEAKS.json; `kernels`
+lists every entry point the same way.  `cpu_baseline` is the oracle port timed on
 the host cores in the same run.
 """
 import argparse
@@ -525,9 +526,10 @@ def run_b200(args, rank, local_rank, world):
                        "parallelism": f"dp{world}",
                        "gemm": "own tcgen05 + TMA engine on every Linear / 3x3 conv fed by spikes: kind::i8 forward on 1-byte spikes x 3 "
                                "weight digit planes (exact integer accumulate, BN sums from the epilogue), TF32 data / weight "
-                               "gradients; decoder transposed convs forward as four parity-class implicit GEMMs; library (cuDNN/cuBLAS) only for the "
-                               "backward of the transposed convs, strided conv dgrad and "
-                               "real-valued operands",
+                               "gradients; decoder transposed convs (forward as four parity-class implicit GEMMs, data gradient as a "
+                               "stride-2 TF32 implicit GEMM, weight gradient as one G3 launch over four class tensor maps) and the strided "
+                               "conv data gradient on the same engine; library (cuDNN/cuBLAS) only for real-valued operands (the 1x1 "
+                               "stride-2 PED shortcut)",
                        "l2": "activations per step >> 126 MB L2; no explicit flush",
                        "weights": "random init (init_weights, seed 0)",
                        "launch": (("one CUDA graph per step (reset+fwd+loss+bwd+AdamW), replayed" if world == 1 else
@@ -544,7 +546,9 @@ def run_b200(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": f"{top} (dominant libsdf_b200 entry point: {kt['ms_per_step']:.2f} ms of the step, "
                                                    f"{kt['launches_per_step']:.0f} launches; eager pass)",
                          "achieved": kt["GBps"], "peak": peak, "unit": "GB/s", "frac": kt["GBps"] / peak,
-                         "traffic": prof["traffic"], "traffic_source": prof["traffic_source"], "peak_kind": how,
+                         "traffic": (prof.get("traffic_by_entry") or {}).get(top, {}).get("dram_bytes_per_launch", prof["traffic"]),
+                         "traffic_source": (prof.get("traffic_by_entry") or {}).get(top, {}).get("source", prof["traffic_source"]),
+                         "peak_kind": how,
                          "algo_bytes_per_launch": kt["algo_GB_per_step"] * 1e9 / max(kt["launches_per_step"], 1),
                          "own_kernels_ms_per_step": own_ms,
                          "lif_fwd_K1": {"achieved": lif["GBps"], "frac": lif["GBps"] / peak, "ms_per_step": lif["ms_per_step"]}},

@@ -39,11 +39,16 @@ def main():
                            "python bench.py --steps 1 --warmup 3 --no-cpu-baseline --secondary off --graph off"])
     out = {"traffic": None, "traffic_source": None, "attn_tc_util": None}
     # dominant kernel's DRAM traffic: the 42 K2 launches of one training step, captured inside the bench
-    for kern, key in (("lif_bwd", "lif_bwd_K2"), ("lif_fwd", "lif_fwd_K1")):
+    out["traffic_by_entry"] = {}
+    for kern, key, entry, must in (("lif_bwd", "lif_bwd_K2", "sdf_lif_bwd", "lif_bwd"), ("lif_fwd", "lif_fwd_K1", "sdf_lif_fwd", "lif_fwd"),
+                                   ("bn_rows", "bn_bwd_apply", "sdf_bn_bwd_apply", "bn_rows_kernel<1>")):
         p = os.path.join(SRC, f"{R}_ncu_{kern}_in_bench.raw.csv")
         if not os.path.exists(p):
             continue
         names, rows = raw_rows(p)
+        rows = [r for r in rows if must in r[names.index("Kernel Name")].replace(" ", "").replace("(int)", "")]
+        if not rows:
+            continue
         rd, wr, tm = names.index("dram__bytes_read.sum"), names.index("dram__bytes_write.sum"), names.index("gpu__time_duration.sum")
         units = list(csv.reader(open(p)))[[i for i, r in enumerate(csv.reader(open(p))) if "Kernel Name" in r][0] + 1]
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
@@ -51,9 +56,13 @@ def main():
         per = tot / max(len(rows), 1)
         out[key] = {"launches": len(rows), "dram_bytes_per_launch": per, "dram_bytes_per_step": tot,
                     "sum_kernel_time_under_ncu": sum(num(r[tm]) for r in rows), "time_unit": units[tm]}
+        out["traffic_by_entry"][entry] = {
+            "dram_bytes_per_launch": per, "launches": len(rows),
+            "source": (f"profiles/{R}_ncu_numbers.json <- ncu --set full -k regex:{kern} python bench.py --steps 1 --warmup 3 --graph off "
+                       f"(dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(rows)} launches of {must} in one training step)")}
         if kern == "lif_bwd":
             out["traffic"] = per
-            out["traffic_source"] = (f"profiles/{R}_ncu_numbers.json <- ncu --set full -k regex:lif_bwd_kernel -s 126 -c 42 python bench.py "
+            out["traffic_source"] = (f"profiles/{R}_ncu_numbers.json <- ncu --set full -k regex:lif_bwd -s 126 -c 42 python bench.py "
                                      "--steps 1 --warmup 3 --graph off (dram__bytes_read.sum + dram__bytes_write.sum, mean over the 42 "
                                      "K2 launches of one training step)")
     p = os.path.join(SRC, f"{R}_ncu_qktv2_fwd.raw.csv")

@@ -12,6 +12,8 @@ python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gp
 python tools/microbench.py 2>/dev/null > gpurun_out/${R}_microbench.jsonl
 python tools/bench_gemm.py 2>/dev/null > gpurun_out/${R}_bench_gemm.jsonl
 python tools/bench_small_conv.py 2>/dev/null > gpurun_out/${R}_bench_small_conv.txt
+python tools/bench_conv_bwd.py 2>/dev/null > gpurun_out/${R}_bench_conv_bwd.jsonl
+python tools/profile_step.py lif --aten > gpurun_out/${R}_profile_step.txt 2>&1
 for m in 0 1 2; do SDF_WGRAD_DEBUG=$m python tools/bench_wgrad_dbg.py 2>/dev/null | grep case; done > gpurun_out/${R}_bench_wgrad_modes.jsonl
 ./tools/ubench/tma_stream > gpurun_out/${R}_ubench_tma_stream.jsonl 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --secondary off --graph off > gpurun_out/${R}_ncu_bench.log 2>&1
@@ -23,10 +25,11 @@ cap() {  # name, kernel regex, skip, count, command...
   rm -f /tmp/$name.ncu-rep
 }
 BENCH1="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --secondary off --graph off"
-cap ${R}_ncu_lif_bwd_in_bench lif_bwd_kernel 126 42 $BENCH1
+cap ${R}_ncu_lif_bwd_in_bench lif_bwd 126 42 $BENCH1
+cap ${R}_ncu_bn_rows_in_bench bn_rows_kernel 309 103 $BENCH1
 cap ${R}_ncu_lif_fwd_in_bench lif_fwd_kernel 126 42 $BENCH1
 cap ${R}_ncu_lif_fwd lif_fwd_kernel 2 1 python tools/ncu_targets.py lif_fwd
-cap ${R}_ncu_lif_bwd lif_bwd_kernel 1 1 python tools/ncu_targets.py lif_bwd
+cap ${R}_ncu_lif_bwd lif_bwd 1 1 python tools/ncu_targets.py lif_bwd
 cap ${R}_ncu_qktv2_fwd qktv2_kernel 1 2 python tools/ncu_targets.py qktv
 cap ${R}_ncu_qktv2_bwd qktv2_bwd_kernel 0 3 python tools/ncu_targets.py qktv
 cap ${R}_ncu_lin_fwd gemm_kernel 2 1 python tools/ncu_gemm_targets.py lin_fwd
