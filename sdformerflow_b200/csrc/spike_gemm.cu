@@ -60,6 +60,8 @@ struct GemmP {
   int patch_h, patch_w;                                    // conv M tile = patch_h x patch_w output pixels (<= 128 of them: rows
                                                            // beyond patch_h*patch_w of a tile are never loaded, counted or stored)
   uint32_t a_tx;                                           // bytes one A chunk brings (patch rows * 128)
+  int last_ks;                                             // 32-byte K steps of the LAST chunk of a tap / row that hold data (1..4):
+                                                           // the MMAs over the zero-filled tail of the chunk are not issued
 };
 
 struct GemmSmem {
@@ -178,21 +180,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (p.b_resident) { mbar_wait(bres, 0); }
       uint32_t tile_i = 0, ph = 0;
       int s = 0;
+      const int cpt_eff = p.conv ? p.cpt : p.n_kchunks;
+      const int last_ks = p.last_ks > 0 ? p.last_ks : kChunkBytes / 32;
       for (int m = group; m < p.n_mtiles; m += p.n_groups, ++tile_i) {
         const uint32_t as = tile_i & 1, aph = (tile_i >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + as * (uint32_t)p.ncols;
-        for (int kc = 0; kc < p.n_kchunks; ++kc) {
+        for (int kc = 0, cc = 0; kc < p.n_kchunks; ++kc) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_lo = desc_lo(a_base + s * kAChunk);
           const uint32_t b_lo = desc_lo(b_base + (p.b_resident ? kc : s) * bchunk);
+          const int nks = cc == cpt_eff - 1 ? last_ks : kChunkBytes / 32;
 #pragma unroll
           for (int ks = 0; ks < kChunkBytes / 32; ++ks)
-            mma_ss<KIND>(d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc, (kc | ks) != 0 ? 1u : 0u);
+            if (ks < nks) mma_ss<KIND>(d, a_lo + ks * 2, b_lo + ks * 2, hi, idesc, (kc | ks) != 0 ? 1u : 0u);
           tc_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
+          if (++cc == cpt_eff) cc = 0;
         }
         tc_commit(&tfull[as]);
       }
@@ -503,6 +509,7 @@ extern "C" int sdf_spike_gemm_fwd(const sdf_spike_gemm_fwd_args* a) {
   p.wscale = a->wscale; p.bias = a->bias; p.bn_partials = a->bn_partials; p.n_partial_cap = (int)a->n_partial_blocks;
   p.fast_cvt = (a->a_max > 0 && a->K * a->a_max < 32768) ? 1 : 0;
   p.a_tx = kAChunk;
+  p.last_ks = (int)((a->K - (int64_t)(p.n_kchunks - 1) * kChunkBytes + 31) / 32);
   const int64_t Kpad = (int64_t)p.n_kchunks * kChunkBytes;
   CUtensorMap tmA, tmB, tmO;
   {
@@ -544,6 +551,7 @@ extern "C" int sdf_gemm_tf32(const sdf_gemm_tf32_args* a) {
   p.n_kchunks = (int)((a->K + 31) / 32);
   p.kc_elems = 32;
   p.a_tx = kAChunk;
+  p.last_ks = (int)((a->K - (int64_t)(p.n_kchunks - 1) * 32 + 7) / 8);
   p.bias = a->bias;
   CUtensorMap tmA, tmB, tmO;
   {
@@ -597,6 +605,7 @@ static int conv_fwd_launch(const ConvLaunch& c, const char* what) {
   p.cpt = (int)((c.Cin + kChunkBytes - 1) / kChunkBytes);
   p.n_kchunks = p.taps * p.cpt;
   p.kc_elems = kChunkBytes;
+  p.last_ks = (int)((c.Cin - (int64_t)(p.cpt - 1) * kChunkBytes + 31) / 32);
   for (int i = 0; i < p.taps; ++i) { p.dh[i] = c.dh[i]; p.dw[i] = c.dw[i]; p.btap[i] = i; }
   p.wscale = c.wscale; p.bias = c.bias; p.bn_partials = c.bn_partials; p.n_partial_cap = (int)c.n_partial_blocks;
   p.fast_cvt = (c.a_max > 0 && c.Cin * c.taps * c.a_max < 32768) ? 1 : 0;
@@ -778,6 +787,7 @@ static int conv_tf32_launch(const ConvTf32Launch& c, const char* what) {
   p.cpt = (int)((c.Cg + 31) / 32);
   p.n_kchunks = p.taps * p.cpt;
   p.kc_elems = 32;
+  p.last_ks = (int)((c.Cg - (int64_t)(p.cpt - 1) * 32 + 7) / 8);
   for (int i = 0; i < p.taps; ++i) { p.dh[i] = c.dh[i]; p.dw[i] = c.dw[i]; p.btap[i] = c.btap[i]; }
   CUtensorMap tmA, tmB, tmO;
   {
