@@ -307,6 +307,14 @@ def run_infer(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def _free_gpu():
+    """Between workloads: collect Python cycles first (autograd nodes of eager warm-up steps can sit in reference cycles that
+    pin their tensors), then hand the cached blocks back."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 def build_model(dev, Hh, Ww, neuron="lif", bins=BINS, window=(2, 9, 9), train=True, name=None):
     import copy
     from sdformerflow_b200.sj import functional
@@ -485,20 +493,20 @@ def run_b200(args, rank, local_rank, world):
     if args.secondary == "on" or (args.secondary == "auto" and world == 1):
         # the other BASELINE.json configurations, short runs (3 timed steps each) in the same process
         k = 3
-        torch.cuda.empty_cache()
+        _free_gpu()
         secondary["train_psn_288x384_shipped_neuron"] = train_workload(args, rank, local_rank, world, dev, neuron="psn", steps=k, full=False)
-        torch.cuda.empty_cache()
+        _free_gpu()
         secondary["train_lif_480x640_B4"] = train_workload(args, rank, local_rank, world, dev, Hh=480, Ww=640, steps=k, full=False)
-        torch.cuda.empty_cache()
+        _free_gpu()
         secondary["cfg4_train_T5_w288_256x256_B4"] = train_workload(args, rank, local_rank, world, dev, Hh=256, Ww=256, bins=5,
                                                                    window=(2, 8, 8), steps=k, full=False)
-        torch.cuda.empty_cache()
+        _free_gpu()
         secondary["cfg4_train_T10_w466_192x192_B4"] = train_workload(args, rank, local_rank, world, dev, Hh=192, Ww=192,
                                                                     window=(4, 6, 6), steps=k, full=False)
-        torch.cuda.empty_cache()
+        _free_gpu()
         secondary["infer_cfg2_B8_480x640"] = infer_workload(args, rank, world, dev, steps=k)
         secondary = {n: {"samples_per_s": v["value"], "ms_per_step": v["ms_per_step"], "steps": v["steps"]} for n, v in secondary.items()}
-        torch.cuda.empty_cache()
+        _free_gpu()
         try:    # SEW family with the Q K^T V window attention (K3/K4) inside a whole training step; not a shipped config
             v = train_workload(args, rank, local_rank, world, dev, steps=k, full=False, name="SpikingformerFlowNet")
             secondary["train_sew_SpikingformerFlowNet_qktv_288x384_B4"] = {

@@ -38,6 +38,10 @@ class Spikes:
         self.grad = g if self.grad is None else self.grad + g
 
     def take_grad(self):
+        # called by the producer's backward, after every consumer's: the token is not needed any more, and dropping it breaks
+        # the reference cycle producer node -> ctx.holder -> token -> grad_fn (= the producer node), which otherwise keeps
+        # the 1-byte spikes of every eager step alive until Python's cyclic collector happens to run
+        self.token = None
         g, self.grad = self.grad, None
         if g is None:       # no consumer produced a gradient (e.g. frozen weights downstream): zero
             g = torch.zeros(self.data.shape, device=self.data.device, dtype=torch.float32)
