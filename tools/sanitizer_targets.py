@@ -67,5 +67,21 @@ cfg = ops.NeuronCfg(kind=capi.SDF_NEURON_LIF, v_th=0.1, v_reset=None, tau=2.0, d
 u = torch.randn(10, 4096, device=dev, requires_grad=True)
 s = ops.neuron(u, cfg)
 s.sum().backward()
+# backward of the transposed / strided convolutions (stride-2 TMA operand, parity-class tensor maps, strided output maps)
+gd = torch.randn(2, 18, 24, 96, device=dev)
+gemm.deconv_dgrad_tf32(gd, wdc[:194].contiguous(), Cin=208)
+gemm.spike_deconv_wgrad(gd, xd, Cin_w=194, s_max=1, want_db=True)
+gemm.conv_dgrad_s2_tf32(torch.randn_like(y2), wc, 20, 27, pc.wt)
+# small feature map: 9 x 12 M tile (rows past the patch are never loaded / stored)
+x9 = spikes(3, 9, 12, 96)
+y9, _ = gemm.spike_conv_fwd(x9, pc, None, 3, 3, 1, 1, want_stats=True, a_max=1)
+gemm.conv_dgrad_tf32(torch.randn_like(y9), wc, 9, 12, 1, pc.wt)
+# BN-fused neurons in training mode: streamed K2 / PSN backward with the BN partial sums
+bn = torch.nn.BatchNorm2d(96).to(dev).train()
+ub = torch.randn(2, 10, 6, 8, 96, device=dev, requires_grad=True)
+ops.bn_neuron(ub, bn, cfg, time_dim=1).sum().backward()
+ub2 = torch.randn(2, 10, 6, 8, 96, device=dev, requires_grad=True)
+import types  # noqa: E402
+ops.bn_neuron(ub2, bn, cfg, time_dim=1, psn=types.SimpleNamespace(weight=pw_, bias=pb_)).sum().backward()
 torch.cuda.synchronize()
 print("sanitizer targets done")
