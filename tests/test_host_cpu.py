@@ -144,3 +144,52 @@ def test_bins_to_steps_regroup_matches_reference_loop(bins, steps):
     ref = port.regroup_events(x, bins, steps)
     assert torch.equal(ref, m.regroup_bins_to_steps(x, bins, steps))
     assert torch.equal(m.to_cl(ref), m.regroup_bins_to_steps_cl(x, bins, steps))
+
+
+def test_deferred_batchnorm_counters():
+    """ops.defer_nbt: the num_batches_tracked += 1 of every BatchNorm call of a forward pass becomes one multi-tensor add on
+    exit — same counts as nn.BatchNorm2d's per-call increment, also for a module called more than once, nested scopes flush
+    once (at the outermost exit)."""
+    from sdformerflow_b200 import ops
+    a, b, c = (torch.zeros((), dtype=torch.long) for _ in range(3))
+    assert ops.NBT_DEFER is None
+    with ops.defer_nbt():
+        ops.NBT_DEFER.extend([a, b, b])
+        with ops.defer_nbt():
+            ops.NBT_DEFER.append(c)
+        assert int(c) == 0                      # the inner scope does not flush
+    assert (int(a), int(b), int(c)) == (1, 2, 1) and ops.NBT_DEFER is None
+    with pytest.raises(ZeroDivisionError):      # an exception inside still leaves the switch off
+        with ops.defer_nbt():
+            1 / 0
+    assert ops.NBT_DEFER is None
+
+
+def test_spikes_take_grad_drops_the_token():
+    """Spikes.take_grad (called by the producer's backward) returns the summed consumer gradients and releases the token:
+    the producer node -> holder -> token -> grad_fn cycle must not keep a step's spikes alive until a cyclic GC pass."""
+    from sdformerflow_b200 import ops
+    s = ops.Spikes()
+    s.data = torch.zeros(4, 8, dtype=torch.uint8)
+    s.token = torch.zeros(())
+    s.add_grad(torch.ones(4, 8))
+    s.add_grad(torch.full((4, 8), 2.0))
+    g = s.take_grad()
+    assert torch.equal(g, torch.full((4, 8), 3.0)) and s.token is None and s.grad is None
+    z = s.take_grad()                           # no consumer produced a gradient: zeros of the spike shape
+    assert z.shape == (4, 8) and not z.any()
+
+
+def test_pack_plan_recording_is_per_parameter():
+    """gemm.start_recording / stop_recording (what train.GraphedStep builds its PackPlan from): parameters only, one job per
+    (parameter, layout / padded width), in first-use order; nothing is recorded outside a recording."""
+    from sdformerflow_b200 import gemm
+    w1, w2 = torch.nn.Parameter(torch.zeros(8, 16)), torch.nn.Parameter(torch.zeros(16, 8, 3, 3))
+    assert gemm._record is None and gemm.stop_recording() == []
+    gemm.start_recording()
+    gemm._record.append(("w", w1, "linear", True))
+    gemm._record.append(("deconv", w2, 16))
+    gemm._record.append(("w", w1, "linear", True))
+    jobs = gemm.stop_recording()
+    assert [j[0] for j in jobs] == ["w", "deconv"] and jobs[0][1] is w1 and jobs[1][1] is w2
+    assert gemm._record is None and not gemm._pinned
