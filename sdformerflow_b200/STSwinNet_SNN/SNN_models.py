@@ -1,6 +1,6 @@
 """Multi-resolution spiking U-Net plumbing around the Swin encoder (host-side mirror of reference
 models/STSwinNet_SNN/SNN_models.py:12-216).  Thin glue: residual blocks, transposed-conv decoders
-and prediction layers built from Spiking_modules; convolutions are cuDNN calls."""
+and prediction layers built from Spiking_modules (their convolutions run on the spike GEMM engine, ops.spike_conv_gemm / spike_deconv)."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
