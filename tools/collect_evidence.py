@@ -58,7 +58,7 @@ def main():
                     "sum_kernel_time_under_ncu": sum(num(r[tm]) for r in rows), "time_unit": units[tm]}
         out["traffic_by_entry"][entry] = {
             "dram_bytes_per_launch": per, "launches": len(rows),
-            "source": (f"profiles/{R}_ncu_numbers.json <- ncu {'--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum' if kern == 'bn_rows' else '--set full'} -k regex:{kern} python bench.py --steps 1 --warmup 3 --graph off "
+            "source": (f"profiles/{R}_ncu_numbers.json <- ncu {'--set full' if 'sm__throughput.avg.pct_of_peak_sustained_elapsed' in names else '--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum'} -k regex:{kern} python bench.py --steps 1 --warmup 3 --graph off "
                        f"(dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(rows)} launches of {must} in one training step)")}
         if kern == "lif_bwd":
             out["traffic"] = per

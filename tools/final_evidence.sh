@@ -24,10 +24,18 @@ cap() {  # name, kernel regex, skip, count, command...
   ncu -i /tmp/$name.ncu-rep --page raw --csv > gpurun_out/$name.raw.csv 2>/dev/null
   rm -f /tmp/$name.ncu-rep
 }
+# in-bench captures (every launch of a kernel family over one training step): DRAM bytes + duration only — the full set on
+# 42-103 launches costs ~6 GPU-minutes per family (the first r02 run of this script hit its 25-minute limit there)
+cap_light() {  # name, kernel regex, skip, count, command...
+  local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:$rx -s $skip -c $cnt -o /tmp/$name "$@" > /dev/null 2>&1
+  ncu -i /tmp/$name.ncu-rep --page raw --csv > gpurun_out/$name.raw.csv 2>/dev/null
+  rm -f /tmp/$name.ncu-rep
+}
 BENCH1="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --secondary off --graph off"
-cap ${R}_ncu_lif_bwd_in_bench lif_bwd 126 42 $BENCH1
-cap ${R}_ncu_bn_rows_in_bench bn_rows_kernel 309 103 $BENCH1
-cap ${R}_ncu_lif_fwd_in_bench lif_fwd_kernel 126 42 $BENCH1
+cap_light ${R}_ncu_lif_bwd_in_bench lif_bwd 126 42 $BENCH1
+cap_light ${R}_ncu_bn_rows_in_bench bn_rows_kernel 309 103 $BENCH1
+cap_light ${R}_ncu_lif_fwd_in_bench lif_fwd_kernel 126 42 $BENCH1
 cap ${R}_ncu_lif_fwd lif_fwd_kernel 2 1 python tools/ncu_targets.py lif_fwd
 cap ${R}_ncu_lif_bwd lif_bwd 1 1 python tools/ncu_targets.py lif_bwd
 cap ${R}_ncu_qktv2_fwd qktv2_kernel 1 2 python tools/ncu_targets.py qktv
