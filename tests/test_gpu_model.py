@@ -64,9 +64,10 @@ def test_ms_block_fwd_bwd(train, shift):
         assert _frac_bad(a, b, 2e-2) <= 2e-2, name
 
 
-def _teacher_forced(model, mc, sc, x, train):
-    """Yields (name, product_output_cpu, oracle_output) for every top-level module, each fed the oracle's input."""
-    P = port.params_from_state_dict(synth.synth_state_dict(model.state_dict(), 0))
+def _teacher_forced(model, mc, sc, x, train, sd=None):
+    """Yields (name, product_output_cpu, oracle_output) for every top-level module, each fed the oracle's input.
+    sd: the state dict the model was loaded with (default: the synthetic one of oracle.synth)."""
+    P = port.params_from_state_dict(sd if sd is not None else synth.synth_state_dict(model.state_dict(), 0))
     Pprod = port.params_from_state_dict(synth.synth_state_dict(model.state_dict(), 0))  # running stats get updated in train
     del Pprod
     spec, cfg = port_spec(mc), port_cfg(mc, sc)
@@ -173,6 +174,28 @@ def test_model_teacher_forced_every_module(nt, train):
         # test_every_neuron_layer_membrane_and_flip_rate.
         assert bad <= (2e-2 if name.startswith("layers.2") else 5e-3), (name, bad)
     assert seen == 5 + 6 + 2 + 2 + 3 + 3
+
+
+def test_plif_model_teacher_forced_with_trained_tau():
+    """The reference's default neuron type (ParametricLIFNode) with w != 0 at every site, i.e. 1/tau = sigmoid(w) != 0.5 as in a
+    trained checkpoint: every module of the model, fed the oracle's input, must reproduce the oracle — the fused sites (BN +
+    neuron, window / merge / QK-gate fusions or their generic fall-backs) all have to read the parameter, not the constructor's
+    tau."""
+    mc, sc = synth.small_config("plif")
+    model = build_product(mc, sc, "cpu", train=False)
+    sd = synth.synth_state_dict(model.state_dict(), 0)
+    keys = [k for k in sd if k.endswith("spiking_neuron.w")]
+    assert len(keys) >= 20
+    for k, v in zip(keys, torch.linspace(-0.6, 0.6, len(keys))):
+        sd[k] = torch.full_like(sd[k], float(v))
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV)
+    x = synth.synth_voxels(2, 10, 96, 128)
+    worst = {name: _frac_bad(got, ref) for name, got, ref in _teacher_forced(model, mc, sc, x, False, sd=sd)}
+    print("[plif, w != 0] teacher-forced mismatch fractions:", {k: round(v, 5) for k, v in worst.items()})
+    assert len(worst) == 5 + 6 + 2 + 2 + 3 + 3
+    for name, bad in worst.items():
+        assert bad <= (2e-2 if name.startswith("layers.2") else 5e-3), (name, bad)
 
 
 @pytest.mark.parametrize("nt", ["lif", "psn"])
