@@ -21,8 +21,10 @@ rl._activate()  # puts oracle/standin and /root/reference on sys.path
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def _load_synth(model, seed=0):
+def _load_synth(model, seed=0, spread_plif=False):
     sd = synth.synth_state_dict(model.state_dict(), seed)
+    if spread_plif:
+        synth.spread_plif_w(sd)
     model.load_state_dict(sd, strict=True)
     return sd
 
@@ -38,7 +40,7 @@ def golden_small_model(neuron_type, train):
     from spikingjelly.activation_based import functional
     mc, sc = synth.small_config(neuron_type)
     model = rl.build_reference_model(mc, sc, seed=0, train=train)
-    _load_synth(model)
+    _load_synth(model, spread_plif=neuron_type == "plif")       # plif: every site's w away from 0 (synth.spread_plif_w)
     B = 2
     x = synth.synth_voxels(B, 10, 96, 128)
     out = {"neuron_type": neuron_type, "train": train}
@@ -80,7 +82,13 @@ def golden_small_model(neuron_type, train):
               "sttmultires_unet.encoders.swin3d.layers.1.swin_blocks.1.attn.proj.bias",
               "sttmultires_unet.encoders.swin3d.layers.0.downsample.reduction.weight",
               "sttmultires_unet.encoders.swin3d.patch_embed.head.conv.0.weight",
-              "sttmultires_unet.preds.2.conv.0.weight"]:
+              "sttmultires_unet.preds.2.conv.0.weight"] + (
+            # plif: the gradient of 1/tau's parameter at a plain, a BN-fused, a window-fused and a QK-gate site
+            ["sttmultires_unet.encoders.swin3d.patch_embed.head.sn.spiking_neuron.w",
+             "sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.0.mlp.sn1.spiking_neuron.w",
+             "sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.0.attn.proj_sn.spiking_neuron.w",
+             "sttmultires_unet.encoders.swin3d.layers.0.swin_blocks.1.attn.sn_k.spiking_neuron.w",
+             "sttmultires_unet.decoders.1.sn.spiking_neuron.w"] if neuron_type == "plif" else []):
         grads[k] = named[k].grad.clone()
     out["grads"] = grads
     out["running_mean_after"] = model.state_dict()[
@@ -237,6 +245,8 @@ def main():
         "small_psn_eval.pt": lambda: golden_small_model("psn", False),
         "small_lif_train.pt": lambda: golden_small_model("lif", True),
         "small_psn_train.pt": lambda: golden_small_model("psn", True),
+        "small_plif_eval.pt": lambda: golden_small_model("plif", False),
+        "small_plif_train.pt": lambda: golden_small_model("plif", True),
         "small_lif_train_sensitivity.pt": golden_small_train_sensitivity,
         "en4_lif_eval.pt": lambda: golden_en4("lif"),
         "sew_stage.pt": golden_sew_stage,

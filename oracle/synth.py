@@ -60,6 +60,16 @@ def synth_state_dict(template, seed=0):
     return {k: synth_tensor(k, v, seed).to(v.dtype) for k, v in template.items()}
 
 
+def spread_plif_w(sd, lo=-0.6, hi=0.6):
+    """PLIF parameters away from their initial value: the ParametricLIFNode `w` of every site set to a different value in
+    [lo, hi] (1/tau = sigmoid(w) in [0.35, 0.65]) in state_dict order, as in a trained checkpoint — synth_tensor leaves them
+    at 0 (tau = 2), where a site that ignored its parameter would go unnoticed.  In place; returns sd."""
+    keys = [k for k in sd if k.endswith("spiking_neuron.w")]
+    for k, v in zip(keys, torch.linspace(lo, hi, max(len(keys), 1))):
+        sd[k] = torch.full_like(sd[k], float(v))
+    return sd
+
+
 def synth_voxels(B, bins, H, W, seed=SEED_INPUT, density=0.10):
     """v = U(0,1) * [U(0,1) < density], (B, bins, 2, H, W) fp32 — post relu(+-chunk)+minmax look
     (train_flow_parallel_supervised_SNN.py:261-284)."""

@@ -183,11 +183,8 @@ def test_plif_model_teacher_forced_with_trained_tau():
     tau."""
     mc, sc = synth.small_config("plif")
     model = build_product(mc, sc, "cpu", train=False)
-    sd = synth.synth_state_dict(model.state_dict(), 0)
-    keys = [k for k in sd if k.endswith("spiking_neuron.w")]
-    assert len(keys) >= 20
-    for k, v in zip(keys, torch.linspace(-0.6, 0.6, len(keys))):
-        sd[k] = torch.full_like(sd[k], float(v))
+    sd = synth.spread_plif_w(synth.synth_state_dict(model.state_dict(), 0))      # the recipe of tests/golden/small_plif_*.pt
+    assert len({float(v) for k, v in sd.items() if k.endswith("spiking_neuron.w")}) >= 20
     model.load_state_dict(sd, strict=True)
     model.to(DEV)
     x = synth.synth_voxels(2, 10, 96, 128)

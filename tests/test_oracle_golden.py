@@ -10,10 +10,12 @@ from helpers import port_spec, port_cfg, product_template_sd
 
 def _params(mc, sc, requires_grad=False):
     sd = synth.synth_state_dict(product_template_sd(mc, sc), 0)
+    if mc["spiking_neuron"]["neuron_type"] == "plif":
+        synth.spread_plif_w(sd)          # every ParametricLIFNode's w away from 0, as make_golden.py loaded the reference
     return port.params_from_state_dict(sd, requires_grad)
 
 
-@pytest.mark.parametrize("nt", ["lif", "psn"])
+@pytest.mark.parametrize("nt", ["lif", "psn", "plif"])
 def test_small_model_eval_matches_reference(golden, nt):
     g = golden(f"small_{nt}_eval.pt")
     mc, sc = synth.small_config(nt)
@@ -27,7 +29,7 @@ def test_small_model_eval_matches_reference(golden, nt):
         assert torch.equal(a, b), f"max abs diff {(a - b).abs().max().item()}"
 
 
-@pytest.mark.parametrize("nt", ["lif", "psn"])
+@pytest.mark.parametrize("nt", ["lif", "psn", "plif"])
 def test_small_model_train_matches_reference(golden, nt):
     g = golden(f"small_{nt}_train.pt")
     mc, sc = synth.small_config(nt)
