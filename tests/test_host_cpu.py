@@ -193,3 +193,42 @@ def test_pack_plan_recording_is_per_parameter():
     jobs = gemm.stop_recording()
     assert [j[0] for j in jobs] == ["w", "deconv"] and jobs[0][1] is w1 and jobs[1][1] is w2
     assert gemm._record is None and not gemm._pinned
+
+
+def test_deconv_parity_class_taps_reproduce_conv_transpose():
+    """sdf_spike_deconv_class_taps (host logic shared by the transposed-conv forward, its weight gradient and the stride-2 data
+    gradient): output pixels of parity (a, b) = a stride-1 convolution of the input with the listed taps at shifts (dh, dw) in
+    {0, 1}, rows / columns past the image reading zeros.  Rebuilt here with plain tensor ops and compared with
+    F.conv_transpose2d(k 3, stride 2, padding 1, output_padding 1) — and, the same identity read backwards, with the data
+    gradient of a 3x3 / stride-2 / padding-1 convolution."""
+    import torch.nn.functional as F
+    from sdformerflow_b200 import capi
+    L = capi.lib()
+    g = torch.Generator().manual_seed(11)
+    N, H, W, Ci, Co = 2, 5, 7, 3, 4
+    x = torch.randn(N, Ci, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Ci, Co, 3, 3, generator=g, dtype=torch.float64)
+    out = torch.zeros(N, Co, 2 * H, 2 * W, dtype=torch.float64)
+    xp = F.pad(x, (0, 1, 0, 1))                     # the zero fill past the last row / column
+    seen = []
+    for cls in range(4):
+        src, dh, dw = ((ctypes.c_int64 * 4)() for _ in range(3))
+        n = int(L.sdf_spike_deconv_class_taps(cls, src, dh, dw))
+        a, b = cls >> 1, cls & 1
+        assert n == (2 if a else 1) * (2 if b else 1)
+        for t in range(n):
+            kh, kw = int(src[t]) // 3, int(src[t]) % 3
+            seen.append(int(src[t]))
+            assert dh[t] in (0, 1) and dw[t] in (0, 1)
+            xs = xp[:, :, dh[t]:dh[t] + H, dw[t]:dw[t] + W]
+            out[:, :, a::2, b::2] += torch.einsum("nihw,io->nohw", xs, w[:, :, kh, kw])
+    assert sorted(seen) == list(range(9))           # every kernel tap belongs to exactly one class
+    ref = F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=1)
+    assert torch.allclose(out, ref, atol=1e-12)
+    # the data gradient of conv2d(3x3, stride 2, padding 1) with weight w2 (Co2, Ci2, 3, 3) is that transposed convolution of
+    # the output gradient with w2 read as (in = Co2, out = Ci2)
+    w2 = torch.randn(Co, Ci, 3, 3, generator=g, dtype=torch.float64)
+    xin = torch.zeros(N, Ci, 2 * H, 2 * W, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(N, Co, H, W, generator=g, dtype=torch.float64)
+    (gx,) = torch.autograd.grad(F.conv2d(xin, w2, None, stride=2, padding=1), xin, gy)
+    assert torch.allclose(gx, F.conv_transpose2d(gy, w2, None, stride=2, padding=1, output_padding=1), atol=1e-12)
